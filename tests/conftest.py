@@ -1,0 +1,29 @@
+"""pytest configuration: the `gpu` marker and shared fixtures."""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import pyoracle
+    pyoracle.build()
+    return pyoracle.Oracle()
+
+
+@pytest.fixture(scope="session")
+def reference():
+    from oracle import pyoracle
+    pyoracle.build()
+    if not pyoracle.have_reference():
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    return pyoracle.Reference()
