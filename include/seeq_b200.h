@@ -1,0 +1,149 @@
+/*
+ * seeq_b200.h -- batch / device interface of the B200-native matcher.
+ *
+ * This is the thin C-ABI between the C host library (libseeq API, file
+ * driver) and the hand-written sm_100a kernels: plain pointers and sizes, no
+ * C++ or torch types.  It is also what a binding written in another language
+ * (ctypes, cgo, JNI ...) would bind, see INTEGRATION.md.
+ *
+ * The reference has no batch entry point: its unit of work is one line
+ * (seeqStringMatch, libseeq.c:171-352) driven by the getline loop of
+ * seeqFileMatch (seeq.c:293-392).  A batch call here computes exactly what
+ * that loop computes for every line of a buffer, in one pass on the GPU:
+ *
+ *   K1  newline / line-offset scan            replaces getline + '\n' strip +
+ *                                             FASTA header rule + line++
+ *                                             (seeq.c:361-377)
+ *   K2  forward bit-parallel matcher          replaces the forward loop of
+ *                                             seeqStringMatch + dfa_step
+ *                                             (libseeq.c:250-338, :779-786)
+ *   K3  reverse start-recovery pass           replaces libseeq.c:290-316
+ *   K4  ordered compaction of records         replaces seeqAddMatch + final
+ *                                             reversal (libseeq.c:427-443,
+ *                                             :345-349)
+ */
+#ifndef SEEQ_B200_H_
+#define SEEQ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sqb_engine sqb_engine_t;
+
+/* One match record, 16 bytes, in file order (by line, then by end).
+ * line is the 0-based index of the line among the COUNTED lines (FASTA
+ * headers excluded) of the scanned buffer; start/end/dist are match_t's. */
+typedef struct {
+   uint32_t line;
+   uint32_t start;
+   uint32_t end;
+   uint32_t dist;
+} sqb_rec_t;
+
+typedef struct {
+   uint64_t nbytes;     /* bytes scanned                                     */
+   uint64_t nlines;     /* counted lines                                     */
+   uint64_t nmatched;   /* lines with at least one match                     */
+   uint64_t nrecs;      /* records (SQ_FIRST/SQ_BEST: == nmatched)           */
+   double   device_ms;  /* CUDA-event time of the kernels of this scan       */
+   double   kernel_ms[4];/* K1, K2, scan+K3/K4, spare (only with SQB_TIMING) */
+   uint32_t launches;   /* kernels launched by this scan                     */
+   uint32_t reruns;     /* scans repeated because a capacity guess was low   */
+} sqb_stats_t;
+
+/* flags, OR-ed into `options` next to the SQ_* bits of libseeq.h */
+#define SQB_COUNT_ONLY   0x0100  /* no records: nmatched and nrecs only      */
+#define SQB_FASTA        0x0200  /* lines starting with '>' are headers      */
+#define SQB_SINGLE_LINE  0x0400  /* the buffer is ONE line (string API)      */
+#define SQB_TIMING       0x0800  /* fill kernel_ms[] (adds event records)    */
+#define SQB_KEEP_LINES   0x1000  /* sqbScanHost: also return line offsets    */
+
+/* ---- engine life cycle --------------------------------------------------- */
+/* keys: one class byte per pattern position as produced by the parser
+ * (bit0 A, bit1 C, bit2 G, bit3 T/U, 0x1F N); 0 <= tau < m.
+ * device < 0 selects $SEEQ_B200_DEVICE, else $LOCAL_RANK, else 0.
+ * Returns NULL on failure (no CUDA device, unsupported pattern length);
+ * sqbLastError() says why.  There is no CPU fallback. */
+sqb_engine_t * sqbEngineNew   (const unsigned char * keys, int m, int tau, int device);
+void           sqbEngineFree  (sqb_engine_t * e);
+const char   * sqbLastError   (void);
+int            sqbDeviceCount (void);
+int            sqbMaxPatternLength (void);
+
+/* ---- device-resident input ----------------------------------------------- */
+/* d_text: device pointer, 16-byte aligned, readable up to the next multiple of
+ * 16 bytes past nbytes; nbytes < 4 GiB.  stream: a cudaStream_t (NULL = the
+ * engine's own stream).  Blocks until the results are ready.
+ * Returns 0, or -1 with sqbLastError(). */
+int sqbScanDevice (sqb_engine_t * e, const void * d_text, size_t nbytes,
+                   int options, void * stream, sqb_stats_t * stats);
+
+/* results of the last sqbScanDevice, resident on the device */
+const sqb_rec_t * sqbDeviceRecords    (sqb_engine_t * e);
+const uint32_t  * sqbDeviceLineStarts (sqb_engine_t * e);   /* nlines+1 entries */
+int sqbFetchRecords    (sqb_engine_t * e, sqb_rec_t * dst, uint64_t first, uint64_t count);
+int sqbFetchLineStarts (sqb_engine_t * e, uint32_t * dst, uint64_t first, uint64_t count);
+
+/* ---- host-resident input (the end-to-end path) ---------------------------- */
+/* Scans a host buffer of any size: newline-aligned chunks are copied to the
+ * device and matched in a software pipeline (copy of chunk k+1 overlaps the
+ * kernels of chunk k); records come back with buffer-global line indices.
+ * text may be pageable or pinned (sqbHostAlloc); pinned is faster. */
+int sqbScanHost (sqb_engine_t * e, const char * text, size_t nbytes,
+                 int options, sqb_stats_t * stats);
+const sqb_rec_t * sqbHostRecords    (sqb_engine_t * e, uint64_t * count);
+/* byte offset of every counted line of the last sqbScanHost (on request) */
+int               sqbHostLineStarts (sqb_engine_t * e, const uint64_t ** starts, uint64_t * count);
+
+void * sqbHostAlloc (size_t nbytes);      /* pinned host memory               */
+void   sqbHostFree  (void * p);
+void * sqbDeviceAlloc (size_t nbytes);    /* plain device memory (benchmarks) */
+void   sqbDeviceFree  (void * p);
+int    sqbMemcpyH2D (void * dst, const void * src, size_t nbytes);
+
+/* ---- seeq_t level batch entry (the batched analogue of seeqStringMatch) ---- */
+struct seeq_t;
+/* Matches every line of a host buffer against the pattern of `sq` in one GPU
+ * pass.  match_opt: SQ_FIRST/SQ_BEST/SQ_ALL | SQ_FAIL/SQ_CONVERT/SQ_IGNORE
+ * [| SQB_FASTA].  file_opt: SQ_ANY (0) returns the number of records and points
+ * *recs at them (file order, 0-based line indices, valid until the next call
+ * on `sq`); SQ_COUNTLINES (3) / SQ_COUNTMATCH (4) return the counts only.
+ * Returns -1 on error with seeqerr / errno set as for seeqStringMatch. */
+long seeqBatchMatch (struct seeq_t * sq, const char * text, size_t nbytes,
+                     int match_opt, int file_opt, const sqb_rec_t ** recs,
+                     sqb_stats_t * stats);
+/* the engine behind a seeq_t (created on first use); NULL if no device */
+sqb_engine_t * seeqEngine (struct seeq_t * sq);
+
+/* ---- multi-GPU helper ------------------------------------------------------ */
+/* Newline-aligned byte range of shard `rank` of `world` over a buffer: the
+ * boundary k*nbytes/world is moved forward to just after the next '\n'. */
+void sqbShardRange (const char * text, size_t nbytes, int rank, int world,
+                    size_t * begin, size_t * end);
+
+/* ---- synthetic reads (tests and benchmarks; same bytes on host and device) - */
+typedef struct {
+   uint64_t seed;
+   uint32_t line_len;      /* bases per line (without '\n')                  */
+   uint32_t plant_per_1024;/* lines that receive a mutated copy, per 1024    */
+   uint32_t max_edits;     /* 0..max_edits random edits per planted copy     */
+   uint32_t n_per_1024;    /* bases replaced by 'N', per 1024                */
+   uint32_t junk_per_1024; /* bases replaced by a byte of "RYKMSW.-"         */
+   uint32_t fastq;         /* 1: 4-line records (@id, seq, +, quality)       */
+   uint32_t plant_len;     /* length of plant[]                              */
+   char     plant[256];    /* sequence to plant (plain ACGT)                 */
+} sqb_gen_t;
+
+/* bytes produced for `nreads` reads starting at read index `first` */
+size_t sqbGenBytes  (const sqb_gen_t * g, uint64_t first, uint64_t nreads);
+int    sqbGenHost   (const sqb_gen_t * g, uint64_t first, uint64_t nreads, char * dst);
+int    sqbGenDevice (const sqb_gen_t * g, uint64_t first, uint64_t nreads, void * d_dst, void * stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,108 @@
+"""Builds the in-tree native artefacts (nvcc for sm_100a + gcc).
+
+  seeq_b200/libseeq_b200.so   the product: CUDA kernels + C-ABI (sqb*), the
+                              libseeq API (seeq*), the file driver and seeq()
+  seeq_b200/_relink/seeq      the reference CLI (seeq-main.c, compiled from the
+                              read-only mount, not copied) linked against it
+  seeq_b200/_relink/seeq*.so  the reference CPython module (seeqmodule.c)
+                              linked against it
+
+The last two exist only where /root/reference is mounted; they travel to the
+GPU box as prebuilt files.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import sysconfig
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+INC = os.path.join(ROOT, "include")
+LIB = os.path.join(HERE, "libseeq_b200.so")
+RELINK = os.path.join(HERE, "_relink")
+REFERENCE_DIR = os.environ.get("SEEQ_REFERENCE_DIR", "/root/reference")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+CU_SOURCES = ["sqb_engine.cu"]
+C_SOURCES = ["seeq_api.c", "seeq_file.c"]
+HEADERS = [os.path.join(CSRC, h) for h in
+           ("sqb_device.cuh", "sqb_kernels.cuh", "sqb_gen.h", "sqb_private.h")] + \
+          [os.path.join(INC, h) for h in ("libseeq.h", "seeq.h", "seeq_b200.h")]
+
+
+def _newer(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def _run(cmd) -> None:
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout)
+        raise RuntimeError("build step failed: " + cmd[0])
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    for src in CU_SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(objdir, src + ".o")
+        if force or _newer(o, [s] + HEADERS):
+            _run([NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp",
+                  "-I" + INC, "-I" + CSRC, "-c", s, "-o", o] + (["-Xptxas", "-v"] if verbose else []))
+        objs.append(o)
+    for src in C_SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(objdir, src + ".o")
+        if force or _newer(o, [s] + HEADERS):
+            _run(["gcc", "-std=c99", "-O2", "-fPIC", "-Wall", "-Wextra", "-I" + INC, "-I" + CSRC,
+                  "-c", s, "-o", o])
+        objs.append(o)
+    if force or _newer(LIB, objs):
+        _run([NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fopenmp", "-lgomp"])
+    return LIB
+
+
+def build_relinks(force: bool = False) -> dict:
+    """Re-link the reference front-ends against our library (no source copied)."""
+    out = {}
+    src = os.path.join(REFERENCE_DIR, "src")
+    if not os.path.isdir(src):
+        return out
+    os.makedirs(RELINK, exist_ok=True)
+    rpath = "-Wl,-rpath,$ORIGIN/.."
+    cli = os.path.join(RELINK, "seeq")
+    main_c = os.path.join(src, "seeq-main.c")
+    if force or _newer(cli, [main_c, LIB]):
+        # -ftrivial-auto-var-init=zero: seeq-main.c never assigns args.split
+        _run(["gcc", "-std=gnu99", "-O2", "-w", "-ftrivial-auto-var-init=zero", "-I" + INC,
+              main_c, "-o", cli, "-L" + HERE, "-lseeq_b200", rpath])
+    out["cli"] = cli
+    mod_c = os.path.join(src, "seeqmodule.c")
+    ext = sysconfig.get_config_var("EXT_SUFFIX") or ".so"
+    mod = os.path.join(RELINK, "seeq" + ext)
+    if force or _newer(mod, [mod_c, LIB]):
+        _run(["gcc", "-std=gnu99", "-O2", "-w", "-fPIC", "-shared", "-DMAJOR_VERSION=1", "-DMINOR_VERSION=2",
+              "-I" + INC, "-I" + sysconfig.get_paths()["include"], mod_c, "-o", mod,
+              "-L" + HERE, "-lseeq_b200", rpath])
+    out["module"] = mod
+    return out
+
+
+def build_all(force: bool = False, verbose: bool = False) -> None:
+    build_library(force, verbose)
+    build_relinks(force)
+
+
+if __name__ == "__main__":
+    build_all(force="-B" in sys.argv, verbose="-v" in sys.argv)
+    print(LIB)

@@ -1,0 +1,549 @@
+/*
+ * seeq_file.c -- file driver and CLI formatter on top of the batch engine
+ * (host side, C99, written from scratch).
+ *
+ * Mirrors, for the same names / arguments / return values / error codes:
+ *
+ *   seeqOpen       /root/reference/src/seeq.c:201-256
+ *   seeqClose      :258-291
+ *   seeqFileMatch  :293-392   line iterator: getline, '\n' strip, FASTA header
+ *                             rule, 1-based line counter, SQ_ANY / SQ_MATCH /
+ *                             SQ_NOMATCH / SQ_COUNTLINES / SQ_COUNTMATCH
+ *   seeq           :32-199    output formatter of the CLI
+ *
+ * The reference matches one line per getline().  Here the stream is read in
+ * large chunks that end on a line boundary; each chunk is matched on the GPU
+ * in ONE batch (K1..K4) and seeqFileMatch then hands its lines out one call at
+ * a time from the ordered record list, so callers see the same iterator.
+ */
+#define _GNU_SOURCE
+#include "sqb_private.h"
+
+#include <errno.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+
+/* ------------------------------------------------------------------------ */
+/* open / close                                                              */
+/* ------------------------------------------------------------------------ */
+seeqfile_t *seeqOpen(const char *file)
+{
+   seeqerr = 0;
+   sqb_file_t *f = calloc(1, sizeof *f);
+   if (f == NULL) { seeqerr = errno; return NULL; }
+
+   FILE *in = file ? fopen(file, "r") : stdin;
+   if (in == NULL) {
+      seeqerr = errno;          /* the raw errno, as the reference does (seeq.c:234) */
+      free(f);
+      return NULL;
+   }
+   f->magic = SQB_FILE_MAGIC;
+   f->pub.line = 0;
+   f->pub.fdi = in;
+
+   /* FASTA iff the very first byte of the stream is '>' (seeq.c:243-253) */
+   const int first = getc(in);
+   if (first == '>') {
+      f->pub.flags = 1;
+      f->pub.info = calloc(32, 1);
+      if (f->pub.info == NULL) { seeqerr = errno; free(f); return NULL; }
+   }
+   if (first != EOF) ungetc(first, in);
+   return &f->pub;
+}
+
+static void release_buffers(sqb_file_t *f)
+{
+   if (f->buf) {
+      if (f->pinned) sqbHostFree(f->buf);
+      else free(f->buf);
+   }
+   free(f->recs);
+   free(f->lines);
+   free(f->last_header);
+   f->buf = NULL;
+   f->recs = NULL;
+   f->lines = NULL;
+   f->last_header = NULL;
+}
+
+int seeqClose(seeqfile_t *sqfile)
+{
+   seeqerr = 0;
+   sqb_file_t *f = (sqb_file_t *)sqfile;
+   FILE *in = sqfile->fdi;
+   free(sqfile->info);
+   sqfile->info = NULL;
+   if (f->magic == SQB_FILE_MAGIC) release_buffers(f);
+   f->magic = 0;
+   free(f);
+   if (in != NULL && in != stdin) {
+      if (fclose(in) != 0) { seeqerr = errno; return -1; }
+   }
+   return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* chunk reader                                                              */
+/* ------------------------------------------------------------------------ */
+static size_t chunk_target(FILE *in)
+{
+   const char *env = getenv("SEEQ_B200_FILE_CHUNK_MB");
+   size_t mb = env ? (size_t)atol(env) : 64;
+   if (mb < 1) mb = 1;
+   if (mb > 1024) mb = 1024;
+   size_t target = mb << 20;
+   /* do not pin 64 MiB for a tiny regular file */
+   struct stat st;
+   if (fstat(fileno(in), &st) == 0 && S_ISREG(st.st_mode)) {
+      const long at = ftell(in);
+      size_t left = (size_t)st.st_size > (size_t)(at > 0 ? at : 0) ? (size_t)st.st_size - (size_t)(at > 0 ? at : 0) : 0;
+      left += 4096;
+      if (left < target) target = left;
+   }
+   return target;
+}
+
+static int buffer_reserve(sqb_file_t *f, size_t need)
+{
+   if (need <= f->cap) return 0;
+   size_t cap = f->cap ? f->cap : 4096;
+   while (cap < need) cap *= 2;
+   char *nb = sqbHostAlloc(cap);
+   if (nb == NULL) {
+      fprintf(stderr, "seeq-b200: %s\n", sqbLastError());
+      errno = ENODEV;
+      return -1;
+   }
+   if (f->fill) memcpy(nb, f->buf, f->fill);
+   if (f->buf) sqbHostFree(f->buf);
+   f->buf = nb;
+   f->cap = cap;
+   f->pinned = 1;
+   return 0;
+}
+
+/* start of the line that ends just before position `end` (end > 0) */
+static size_t line_start_before(const char *buf, size_t end)
+{
+   if (end == 0) return 0;
+   const char *nl = memrchr(buf, '\n', end - 1);
+   return nl ? (size_t)(nl - buf) + 1 : 0;
+}
+
+/* FASTA: remember the last header of the chunk that is about to be dropped */
+static int remember_last_header(sqb_file_t *f)
+{
+   size_t end = f->len;
+   while (end > 0) {
+      const size_t s = line_start_before(f->buf, end);
+      if (f->buf[s] == '>') {
+         size_t n = end - s;
+         if (n && f->buf[s + n - 1] == '\n') n--;
+         char *h = malloc(n + 1);
+         if (h == NULL) { seeqerr = 666; return -1; }    /* seeq.c:370 */
+         memcpy(h, f->buf + s, n);
+         h[n] = 0;
+         free(f->last_header);
+         f->last_header = h;
+         return 0;
+      }
+      end = s;
+   }
+   return 0;
+}
+
+/* Makes the next chunk resident.  1 = a chunk is resident, 0 = end of input. */
+static int chunk_load(sqb_file_t *f)
+{
+   FILE *in = f->pub.fdi;
+   if (f->started) {
+      if ((f->pub.flags & 1) && remember_last_header(f)) return -1;
+      f->line_base += f->nlines;
+   } else {
+      f->target = chunk_target(in);
+      f->started = 1;
+   }
+   /* carry the partial line to the front */
+   const size_t carry = f->fill - f->len;
+   if (carry && f->len) memmove(f->buf, f->buf + f->len, carry);
+   f->fill = carry;
+   f->len = 0;
+   f->cur_line = f->cur_rec = 0;
+   f->nlines = f->nrecs = 0;
+   f->res_valid = 0;
+   if (f->eof && carry == 0) return 0;
+
+   size_t want = f->target;
+   while (!f->eof) {
+      if (buffer_reserve(f, f->fill + want + 16)) return -1;
+      const size_t got = fread(f->buf + f->fill, 1, want, in);
+      f->fill += got;
+      if (got < want) {
+         if (ferror(in)) { seeqerr = 0; return -1; }      /* errno tells */
+         f->eof = 1;
+         break;
+      }
+      if (memrchr(f->buf, '\n', f->fill) != NULL) break;
+      /* a line longer than the chunk: keep reading */
+   }
+   if (f->eof) {
+      f->len = f->fill;                                   /* last line may lack '\n' */
+   } else {
+      const char *nl = memrchr(f->buf, '\n', f->fill);
+      f->len = (size_t)(nl - f->buf) + 1;
+   }
+   return f->len > 0 ? 1 : 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* batch results of the resident chunk                                       */
+/* ------------------------------------------------------------------------ */
+static int ensure_results(sqb_file_t *f, seeq_t *sq, int opt)
+{
+   const sqb_seeq_t *p = (const sqb_seeq_t *)sq;
+   if (f->res_valid && f->res_uid == p->uid && f->res_opt == opt) return 0;
+   sqb_engine_t *eng = seeqEngine(sq);
+   if (eng == NULL) return -1;
+   const int flags = opt | SQB_KEEP_LINES | ((f->pub.flags & 1) ? SQB_FASTA : 0);
+   sqb_stats_t st;
+   if (sqbScanHost(eng, f->buf, f->len, flags, &st)) {
+      fprintf(stderr, "seeq-b200: %s\n", sqbLastError());
+      errno = EIO;
+      return -1;
+   }
+   uint64_t nr = 0, nl = 0;
+   const sqb_rec_t *recs = sqbHostRecords(eng, &nr);
+   const uint64_t *lines = NULL;
+   sqbHostLineStarts(eng, &lines, &nl);
+   if (nr > f->rec_cap) {
+      free(f->recs);
+      f->rec_cap = (size_t)nr + (size_t)nr / 4 + 16;
+      f->recs = malloc(f->rec_cap * sizeof(sqb_rec_t));
+      if (f->recs == NULL) { f->rec_cap = 0; return -1; }
+   }
+   if (nl > f->line_cap) {
+      free(f->lines);
+      f->line_cap = (size_t)nl + (size_t)nl / 4 + 16;
+      f->lines = malloc(f->line_cap * sizeof(uint64_t));
+      if (f->lines == NULL) { f->line_cap = 0; return -1; }
+   }
+   if (nr) memcpy(f->recs, recs, (size_t)nr * sizeof(sqb_rec_t));
+   if (nl) memcpy(f->lines, lines, (size_t)nl * sizeof(uint64_t));
+   f->nrecs = (size_t)nr;
+   f->nlines = (size_t)nl;
+   f->res_uid = p->uid;
+   f->res_opt = opt;
+   f->res_valid = 1;
+   /* first record at or after the line to hand out next */
+   size_t lo = 0, hi = f->nrecs;
+   while (lo < hi) {
+      const size_t mid = (lo + hi) / 2;
+      if (f->recs[mid].line < f->cur_line) lo = mid + 1;
+      else hi = mid;
+   }
+   f->cur_rec = lo;
+   return 0;
+}
+
+/* copy bytes [off, end of line) of the chunk into sq->string (getline's buffer) */
+static int set_string(seeq_t *sq, const char *src, size_t n)
+{
+   if (sq->string == NULL || sq->bufsz < n + 1) {
+      size_t cap = sq->bufsz ? sq->bufsz : 128;
+      while (cap < n + 1) cap *= 2;
+      char *s = realloc(sq->string, cap);
+      if (s == NULL) return -1;
+      sq->string = s;
+      sq->bufsz = cap;
+   }
+   memcpy(sq->string, src, n);
+   sq->string[n] = 0;
+   return 0;
+}
+
+static size_t line_length(const sqb_file_t *f, size_t off)
+{
+   const char *nl = memchr(f->buf + off, '\n', f->len - off);
+   return nl ? (size_t)(nl - (f->buf + off)) : f->len - off;
+}
+
+/* FASTA: sqfile->info = last header line before chunk offset `off` */
+static int update_info(sqb_file_t *f, size_t off)
+{
+   size_t end = off;
+   while (end > 0) {
+      const size_t s = line_start_before(f->buf, end);
+      if (f->buf[s] == '>') {
+         size_t n = end - s;
+         if (n && f->buf[s + n - 1] == '\n') n--;
+         char *h = malloc(n + 1);
+         if (h == NULL) { seeqerr = 666; return -1; }
+         memcpy(h, f->buf + s, n);
+         h[n] = 0;
+         free(f->pub.info);
+         f->pub.info = h;
+         return 0;
+      }
+      end = s;
+   }
+   if (f->last_header) {
+      char *h = strdup(f->last_header);
+      if (h == NULL) { seeqerr = 666; return -1; }
+      free(f->pub.info);
+      f->pub.info = h;
+   }
+   return 0;
+}
+
+/* hand out counted line k of the chunk with its matches */
+static int serve_line(sqb_file_t *f, seeq_t *sq, size_t k, size_t rec0, size_t nrec)
+{
+   const size_t off = (size_t)f->lines[k];
+   if (set_string(sq, f->buf + off, line_length(f, off))) return -1;
+   if (sqb_store_matches(sq, f->recs + rec0, nrec)) return -1;
+   f->pub.line = f->line_base + k + 1;
+   if ((f->pub.flags & 1) && update_info(f, off)) return -1;
+   return 0;
+}
+
+/* the reference leaves the LAST line read in sq->string when it runs into the
+ * end of the input (getline buffer); do the same */
+static int leave_last_line(sqb_file_t *f, seeq_t *sq)
+{
+   if (f->len == 0) return 0;
+   size_t end = f->len;
+   if (f->buf[end - 1] == '\n') end--;                 /* getline's '\n' is stripped */
+   const char *nl = end ? memrchr(f->buf, '\n', end) : NULL;
+   const size_t start = nl ? (size_t)(nl - f->buf) + 1 : 0;
+   return set_string(sq, f->buf + start, end - start);
+}
+
+/* ------------------------------------------------------------------------ */
+/* seeqFileMatch                                                             */
+/* ------------------------------------------------------------------------ */
+long seeqFileMatch(seeqfile_t *sqfile, seeq_t *sq, int match_opt, int file_opt)
+{
+   seeqerr = 0;
+   sqb_file_t *f = (sqb_file_t *)sqfile;
+
+   if (file_opt == SQ_COUNTMATCH) match_opt = (match_opt & ~MASK_MATCH) | SQ_ALL;
+   else if (file_opt == SQ_COUNTLINES) match_opt = (match_opt & ~MASK_MATCH) | SQ_FIRST;
+
+   if (sqfile->fdi == NULL) { seeqerr = 10; return -1; }
+   if (f->magic != SQB_FILE_MAGIC) { errno = EINVAL; return -1; }
+
+   const int opt = match_opt & (MASK_MATCH | MASK_NONDNA);
+   const size_t startline = sqfile->line;
+   long count = 0;
+
+   /* ---- whole-input counts: one count-only batch per chunk ---------------- */
+   if (file_opt == SQ_COUNTLINES || file_opt == SQ_COUNTMATCH) {
+      sqb_engine_t *eng = seeqEngine(sq);
+      if (eng == NULL) return -1;
+      const int flags = opt | SQB_COUNT_ONLY | ((sqfile->flags & 1) ? SQB_FASTA : 0);
+      sq->hits = 0;
+      for (;;) {
+         /* rest of the resident chunk, from the next line to hand out */
+         size_t off = f->len;
+         if (f->started && f->len > 0) {
+            if (f->cur_line == 0) off = 0;
+            else if (f->res_valid && f->cur_line < f->nlines) off = (size_t)f->lines[f->cur_line];
+         }
+         if (off < f->len) {
+            sqb_stats_t st;
+            if (sqbScanHost(eng, f->buf + off, f->len - off, flags, &st)) {
+               fprintf(stderr, "seeq-b200: %s\n", sqbLastError());
+               errno = EIO;
+               return -1;
+            }
+            count += (long)(file_opt == SQ_COUNTLINES ? st.nmatched : st.nrecs);
+            sqfile->line += (size_t)st.nlines;
+            if (leave_last_line(f, sq)) return -1;
+            /* mark the chunk as consumed */
+            if (!f->res_valid) f->nlines = f->cur_line + (size_t)st.nlines;
+            f->cur_line = f->nlines;
+            f->cur_rec = f->nrecs;
+         }
+         const int more = chunk_load(f);
+         if (more < 0) return -1;
+         if (more == 0) break;
+      }
+      return sqfile->line == startline ? 0 : count;
+   }
+
+   /* ---- line iterator ----------------------------------------------------- */
+   for (;;) {
+      if (!f->started || f->len == 0 || (f->res_valid && f->cur_line >= f->nlines)) {
+         /* the resident chunk (if any) is used up */
+         if (f->started && f->len > 0 && sqfile->line != startline) {
+            if (leave_last_line(f, sq)) return -1;
+         }
+         const int more = chunk_load(f);
+         if (more < 0) return -1;
+         if (more == 0) return sqfile->line == startline ? 0 : count;
+      }
+      if (ensure_results(f, sq, opt)) return -1;
+      if (f->cur_line >= f->nlines) continue;              /* chunk without counted lines */
+
+      if (file_opt == SQ_MATCH) {
+         /* jump to the next line that owns a record */
+         if (f->cur_rec >= f->nrecs) {
+            sqfile->line = f->line_base + f->nlines;
+            f->cur_line = f->nlines;
+            sq->hits = 0;
+            continue;
+         }
+         const size_t k = f->recs[f->cur_rec].line;
+         size_t r1 = f->cur_rec;
+         while (r1 < f->nrecs && f->recs[r1].line == k) r1++;
+         if (serve_line(f, sq, k, f->cur_rec, r1 - f->cur_rec)) return -1;
+         f->cur_rec = r1;
+         f->cur_line = k + 1;
+         return 1;
+      }
+
+      /* SQ_ANY and SQ_NOMATCH walk line by line */
+      while (f->cur_line < f->nlines) {
+         const size_t k = f->cur_line;
+         size_t r1 = f->cur_rec;
+         while (r1 < f->nrecs && f->recs[r1].line == k) r1++;
+         const size_t nrec = r1 - f->cur_rec;
+         if (file_opt == SQ_NOMATCH && nrec > 0) {
+            /* a matching line is consumed silently; its hits add to the count
+             * returned if the input ends here (seeq.c:382-391) */
+            count += (long)nrec;
+            sqfile->line = f->line_base + k + 1;
+            sq->hits = nrec;          /* refreshed below if this was the last line */
+            if (k + 1 == f->nlines) {
+               if (serve_line(f, sq, k, f->cur_rec, nrec)) return -1;
+            }
+            f->cur_rec = r1;
+            f->cur_line = k + 1;
+            continue;
+         }
+         if (serve_line(f, sq, k, f->cur_rec, nrec)) return -1;
+         f->cur_rec = r1;
+         f->cur_line = k + 1;
+         return 1;
+      }
+   }
+}
+
+/* ------------------------------------------------------------------------ */
+/* seeq(): the CLI's formatter                                               */
+/* ------------------------------------------------------------------------ */
+static void put_range(const char *s, size_t from, size_t to)
+{
+   if (to > from) fwrite(s + from, 1, to - from, stdout);
+}
+
+int seeq(char *expression, char *input, struct seeqarg_t args)
+{
+   seeq_t *sq = seeqNew(expression, args.dist, args.memory);
+   if (sq == NULL) {
+      fprintf(stderr, "error in 'seeqNew()'; %s\n:", seeqPrintError());
+      return EXIT_FAILURE;
+   }
+   if (args.verbose) fprintf(stderr, "opening input file... ");
+   seeqfile_t *in = seeqOpen(input);
+   if (in == NULL) {
+      fprintf(stderr, "error in 'seeqOpen()': %s\n", seeqPrintError());
+      seeqFree(sq);
+      return EXIT_FAILURE;
+   }
+   const int fasta = in->flags & 1;
+   clock_t t0 = 0;
+   if (args.verbose) {
+      fprintf(stderr, "\nmatching...\n");
+      t0 = clock();
+   }
+
+   int opt = 0;
+   if (args.non_dna == 1) opt |= SQ_CONVERT;
+   else if (args.non_dna == 2) opt |= SQ_IGNORE;
+
+   if (args.count) {
+      const long n = seeqFileMatch(in, sq, opt, SQ_COUNTLINES);
+      if (n < 0) fprintf(stderr, "error in 'seeqFileMatch()': %s\n", seeqPrintError());
+      else fprintf(stdout, "%ld\n", n);
+   } else {
+      if (args.all) {                 /* -a wins over -b and implies match-only */
+         opt |= SQ_ALL;
+         args.matchonly = 1;
+      } else if (args.best) {
+         opt |= SQ_BEST;
+      }
+      /* the FASTA header is echoed only when nothing is printed in front of
+       * the sequence (seeq.c:117-121) */
+      const int echo_header = fasta && !args.split && !args.showline && !args.showpos && !args.showdist;
+      const int colour = COLOR_TERMINAL && isatty(fileno(stdout));
+      long rv;
+      if (args.invert) {
+         while ((rv = seeqFileMatch(in, sq, opt, SQ_NOMATCH)) > 0) {
+            if (args.showline) fprintf(stdout, "%ld ", (long)in->line);
+            if (echo_header) fprintf(stdout, "%s\n", in->info);
+            fprintf(stdout, "%s\n", sq->string);
+         }
+      } else {
+         while ((rv = seeqFileMatch(in, sq, opt, SQ_MATCH)) > 0) {
+            const char *s = sq->string;
+            match_t *mt;
+            while ((mt = seeqMatchIter(sq)) != NULL) {
+               if (args.compact) {
+                  fprintf(stdout, "%ld:%ld-%ld:%ld", (long)in->line, (long)mt->start, (long)mt->end - 1, (long)mt->dist);
+               } else {
+                  if (args.showline) fprintf(stdout, "%ld ", (long)in->line);
+                  if (args.showpos) fprintf(stdout, "%ld-%ld ", (long)mt->start, (long)mt->end - 1);
+                  if (args.showdist) fprintf(stdout, "%ld ", (long)mt->dist);
+                  if (echo_header) fprintf(stdout, "%s\n", in->info);
+                  /* strings are printed up to their first NUL, like "%s" */
+                  const size_t slen = strlen(s);
+                  const size_t a = mt->start < slen ? mt->start : slen;
+                  const size_t b = mt->end < slen ? mt->end : slen;
+                  if (args.matchonly) {
+                     put_range(s, a, b);
+                  } else if (args.prefix) {
+                     put_range(s, 0, a);
+                     /* the reference cuts the line here for good (seeq.c:148) */
+                     sq->string[a] = 0;
+                  } else if (args.endline) {
+                     put_range(s, b, slen);
+                  } else if (args.split) {
+                     put_range(s, 0, a);
+                     fputc('\t', stdout);
+                     put_range(s, a, b);
+                     fputc('\t', stdout);
+                     put_range(s, b, slen);
+                  } else if (args.printline) {
+                     if (colour) {
+                        put_range(s, 0, a);
+                        fputs(mt->dist ? BOLDRED : BOLDGREEN, stdout);
+                        put_range(s, a, b);
+                        fputs(RESET, stdout);
+                        put_range(s, b, slen);
+                     } else {
+                        put_range(s, 0, slen);
+                     }
+                  }
+               }
+               fputc('\n', stdout);
+            }
+         }
+      }
+      if (rv == -1) fprintf(stderr, "error in 'seeqFileMatch()': %s\n", seeqPrintError());
+   }
+
+   if (args.verbose) {
+      fprintf(stderr, "memory: %.2f MB (DFA: %.2f MB, trie: %.2f MB)\n", 0.0, 0.0, 0.0);
+      fprintf(stderr, "done in %.3fs\n", (double)(clock() - t0) / CLOCKS_PER_SEC);
+   }
+   seeqFree(sq);
+   seeqClose(in);
+   return EXIT_SUCCESS;
+}

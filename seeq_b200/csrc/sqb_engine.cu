@@ -1,0 +1,732 @@
+// sqb_engine.cu -- host side of the GPU matcher and its C-ABI (seeq_b200.h).
+//
+// One engine = one pattern on one device.  A scan runs K1 -> K2 -> (scan) ->
+// K3/K4 on one stream without any host round trip in between: kernels size
+// themselves from device-resident counters, the host only reads the final
+// counters.  Capacities that cannot be known up front (lines per byte, events
+// per byte in SQ_ALL) are guessed generously, detected exactly by the kernels
+// (which keep counting past the capacity) and, if ever exceeded, the scan is
+// repeated once with exact sizes (stats->reruns).
+#include <cerrno>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "seeq_b200.h"
+#include "sqb_gen.h"
+#include "sqb_kernels.cuh"
+
+using namespace sqb;
+
+// option bits of libseeq.h (kept numeric here: this file does not include it)
+enum { OPT_MATCH = 0x03, OPT_BEST = 0x01, OPT_ALL = 0x02, OPT_CONVERT = 0x04, OPT_IGNORE = 0x08,
+       OPT_NONDNA = 0x0C, OPT_STREAM = 0x10 };
+#define SQB_KEEP_LINES_INTERNAL SQB_KEEP_LINES
+
+static thread_local char g_err[512] = "";
+
+static void set_err(const char *fmt, ...)
+{
+   va_list ap;
+   va_start(ap, fmt);
+   vsnprintf(g_err, sizeof g_err, fmt, ap);
+   va_end(ap);
+}
+
+#define CU(call)                                                                       \
+   do {                                                                                \
+      cudaError_t e_ = (call);                                                         \
+      if (e_ != cudaSuccess) {                                                         \
+         set_err("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__,      \
+                 __LINE__, #call);                                                     \
+         return -1;                                                                    \
+      }                                                                                \
+   } while (0)
+
+// ---------------------------------------------------------------------------
+struct Slot {
+   cudaStream_t stream = nullptr;
+   // device
+   uint8_t *d_text = nullptr;   size_t text_cap = 0;      // host path only
+   uint32_t *d_ls = nullptr;    size_t line_cap = 0;      // entries (incl. sentinel)
+   unsigned long long *d_res = nullptr; size_t res_cap = 0;
+   uint32_t *d_cnt = nullptr;   size_t cnt_cap = 0;
+   uint32_t *d_offs = nullptr;  size_t offs_cap = 0;
+   Event *d_ev = nullptr;       size_t ev_cap = 0;
+   Rec *d_recs = nullptr;       size_t rec_cap = 0;
+   unsigned long long *d_ctl = nullptr; size_t ctl_cap = 0;   // counters + look-back words
+   // pinned host
+   unsigned long long *h_ctr = nullptr;
+   Rec *h_recs = nullptr;       size_t h_rec_cap = 0;
+   uint32_t *h_ls = nullptr;    size_t h_ls_cap = 0;
+   uint32_t *h_init = nullptr;                              // single-line ls init
+   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+   // description of the scan in flight
+   const uint8_t *cur_text = nullptr;
+   uint32_t cur_n = 0;
+   int cur_options = 0;
+   cudaStream_t cur_stream = nullptr;
+   uint32_t launches = 0;
+   bool busy = false;
+   // host-path bookkeeping
+   size_t chunk_off = 0;
+};
+
+struct sqb_engine {
+   int device = 0;
+   int sms = 148;
+   int m = 0, tau = 0;
+   int words = 1;                 // automaton words: 1, 2, 4, 8, 16 or 32
+   unsigned char keys[kMaxWords * 32];
+   Slot slot[2];
+   // lines / events per byte seen so far (capacity guesses)
+   double lines_per_byte = 1.0 / 24.0;
+   double events_per_byte = 1.0 / 64.0;
+   // results of the last sqbScanHost
+   std::vector<sqb_rec_t> host_recs;
+   std::vector<uint64_t> host_lines;
+   int last_slot = 0;
+   sqb_stats_t last_stats;
+};
+
+// ---------------------------------------------------------------------------
+// pattern tables
+// ---------------------------------------------------------------------------
+static int base_code(int ch)
+{
+   switch (ch) {
+   case 'A': case 'a': return 0;
+   case 'C': case 'c': return 1;
+   case 'G': case 'g': return 2;
+   case 'T': case 't': case 'U': case 'u': return 3;
+   case 'N': case 'n': return 4;
+   default: return -1;
+   }
+}
+
+// Forward tables follow seeqcore.h:89-111 + libseeq.c:255-270; in the reverse
+// pass every non-base byte is skipped (libseeq.c:297-311).
+static void build_pattern(const sqb_engine *e, int options, bool reverse, Pattern *p)
+{
+   memset(p, 0, sizeof *p);
+   p->m = e->m;
+   p->tau = e->tau;
+   const int W = e->words;
+   const int pad = W * 32 - e->m;
+   for (int c = 0; c < 5; c++) {
+      for (int b = 0; b < pad; b++) p->eq[c][b >> 5] |= 1u << (b & 31);      // wildcard rows
+      for (int j = 0; j < e->m; j++) {
+         const unsigned char k = reverse ? e->keys[e->m - 1 - j] : e->keys[j];
+         if (k & (1u << c)) p->eq[c][(pad + j) >> 5] |= 1u << ((pad + j) & 31);
+      }
+   }
+   const int nondna = options & OPT_NONDNA;
+   for (int b = 0; b < 256; b++) {
+      const int code = b < 128 ? base_code(b) : -1;
+      uint8_t cls;
+      if (code >= 0) cls = kKindBase | (uint8_t)code;
+      else if (reverse) cls = (nondna == OPT_CONVERT && b != 0 && b != '\n') ? (kKindBase | 4) : kKindSkip;
+      else if (b == 0) cls = kKindStop;
+      else if (b == '\n') cls = (options & OPT_STREAM) ? kKindSkip : kKindStop;
+      else if (nondna == OPT_CONVERT) cls = kKindBase | 4;
+      else if (nondna == OPT_IGNORE) cls = kKindSkip;
+      else cls = kKindStop;
+      p->cls[b] = cls;
+   }
+}
+
+// ---------------------------------------------------------------------------
+// memory helpers
+// ---------------------------------------------------------------------------
+template <class T> static int dev_reserve(T **p, size_t *cap, size_t need, size_t slack_div = 8)
+{
+   if (need <= *cap) return 0;
+   if (*p) CU(cudaFree(*p));
+   *p = nullptr;
+   *cap = 0;
+   const size_t want = need + need / slack_div + 256;
+   CU(cudaMalloc((void **)p, want * sizeof(T)));
+   *cap = want;
+   return 0;
+}
+
+template <class T> static int pin_reserve(T **p, size_t *cap, size_t need)
+{
+   if (need <= *cap) return 0;
+   if (*p) CU(cudaFreeHost(*p));
+   *p = nullptr;
+   *cap = 0;
+   const size_t want = need + need / 4 + 1024;
+   CU(cudaMallocHost((void **)p, want * sizeof(T)));
+   *cap = want;
+   return 0;
+}
+
+static void slot_free(Slot &s)
+{
+   cudaFree(s.d_text); cudaFree(s.d_ls); cudaFree(s.d_res); cudaFree(s.d_cnt); cudaFree(s.d_offs);
+   cudaFree(s.d_ev); cudaFree(s.d_recs); cudaFree(s.d_ctl);
+   cudaFreeHost(s.h_ctr); cudaFreeHost(s.h_recs); cudaFreeHost(s.h_ls); cudaFreeHost(s.h_init);
+   for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
+   if (s.stream) cudaStreamDestroy(s.stream);
+   s = Slot();
+}
+
+static int slot_init(Slot &s)
+{
+   if (s.stream) return 0;
+   CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+   CU(cudaMallocHost((void **)&s.h_ctr, C_COUNT * sizeof(unsigned long long)));
+   CU(cudaMallocHost((void **)&s.h_init, 4 * sizeof(uint32_t)));
+   for (auto &ev : s.ev) CU(cudaEventCreate(&ev));
+   return 0;
+}
+
+// ---------------------------------------------------------------------------
+// kernel dispatch
+// ---------------------------------------------------------------------------
+static int mode_of(int options)
+{
+   const int match = options & OPT_MATCH;
+   const bool count = options & SQB_COUNT_ONLY;
+   if (match == OPT_ALL) return count ? M_COUNTALL : M_ALL;
+   if (match == OPT_BEST) return count ? M_COUNT : M_BEST;
+   return count ? M_COUNT : M_FIRST;         // SQ_FIRST and SQ_COUNT (libseeq.c:219-221)
+}
+
+template <int W> static int launch_k2_thread(int mode, int grid, cudaStream_t st, const K2Args &a, const Pattern &p)
+{
+#define SQB_CASE(M)                                                                              \
+   case M: {                                                                                     \
+      static bool attr = false;                                                                  \
+      if (!attr) {                                                                               \
+         CU(cudaFuncSetAttribute(k2_forward_thread<W, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)kK2Stage));                                                \
+         attr = true;                                                                            \
+      }                                                                                          \
+      k2_forward_thread<W, M><<<grid, kThreads, kK2Stage, st>>>(a, p);                            \
+      break;                                                                                     \
+   }
+   switch (mode) {
+      SQB_CASE(M_COUNT)
+      SQB_CASE(M_FIRST)
+      SQB_CASE(M_BEST)
+      SQB_CASE(M_ALL)
+      SQB_CASE(M_COUNTALL)
+   }
+#undef SQB_CASE
+   CU(cudaGetLastError());
+   return 0;
+}
+
+template <int G> static int launch_k2_lanes(int mode, int grid, cudaStream_t st, const K2Args &a, const Pattern &p)
+{
+   switch (mode) {
+   case M_COUNT: k2_forward_lanes<G, M_COUNT><<<grid, kThreads, 0, st>>>(a, p); break;
+   case M_FIRST: k2_forward_lanes<G, M_FIRST><<<grid, kThreads, 0, st>>>(a, p); break;
+   case M_BEST: k2_forward_lanes<G, M_BEST><<<grid, kThreads, 0, st>>>(a, p); break;
+   case M_ALL: k2_forward_lanes<G, M_ALL><<<grid, kThreads, 0, st>>>(a, p); break;
+   case M_COUNTALL: k2_forward_lanes<G, M_COUNTALL><<<grid, kThreads, 0, st>>>(a, p); break;
+   }
+   CU(cudaGetLastError());
+   return 0;
+}
+
+static int launch_k2(const sqb_engine *e, int mode, int grid, cudaStream_t st, const K2Args &a, const Pattern &p)
+{
+   switch (e->words) {
+   case 1: return launch_k2_thread<1>(mode, grid, st, a, p);
+   case 2: return launch_k2_thread<2>(mode, grid, st, a, p);
+   case 4: return launch_k2_lanes<4>(mode, grid, st, a, p);
+   case 8: return launch_k2_lanes<8>(mode, grid, st, a, p);
+   case 16: return launch_k2_lanes<16>(mode, grid, st, a, p);
+   default: return launch_k2_lanes<32>(mode, grid, st, a, p);
+   }
+}
+
+static int launch_finish(const sqb_engine *e, bool all, int grid, cudaStream_t st, const FinArgs &a, const Pattern &rp)
+{
+#define SQB_FIN(W)                                                                  \
+   case W:                                                                          \
+      if (all) k34_finish_events<W><<<grid, kThreads, 0, st>>>(a, rp);              \
+      else k34_finish_lines<W><<<grid, kThreads, 0, st>>>(a, rp);                   \
+      break;
+   switch (e->words) {
+      SQB_FIN(1) SQB_FIN(2) SQB_FIN(4) SQB_FIN(8) SQB_FIN(16)
+   default:
+      if (all) k34_finish_events<32><<<grid, kThreads, 0, st>>>(a, rp);
+      else k34_finish_lines<32><<<grid, kThreads, 0, st>>>(a, rp);
+   }
+#undef SQB_FIN
+   CU(cudaGetLastError());
+   return 0;
+}
+
+// ---------------------------------------------------------------------------
+// one scan: issue (asynchronous) and finish (synchronise, verify capacities)
+// ---------------------------------------------------------------------------
+static size_t div_up(size_t a, size_t b) { return (a + b - 1) / b; }
+
+static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n, int options, cudaStream_t st)
+{
+   const int mode = mode_of(options);
+   const bool single = options & SQB_SINGLE_LINE;
+   const bool timing = options & SQB_TIMING;
+   s.cur_text = d_text;
+   s.cur_n = n;
+   s.cur_options = options;
+   s.cur_stream = st;
+   s.launches = 0;
+   s.busy = true;
+
+   // ---- capacities ----------------------------------------------------------
+   size_t want_lines = single ? 2 : (size_t)((double)n * e->lines_per_byte) + 1024;
+   if (want_lines > (size_t)n + 2) want_lines = (size_t)n + 2;
+   if (dev_reserve(&s.d_ls, &s.line_cap, want_lines)) return -1;
+   const size_t lines_cap = s.line_cap - 1;                 // one entry is the sentinel
+   if (mode == M_FIRST || mode == M_BEST) {
+      if (dev_reserve(&s.d_res, &s.res_cap, lines_cap, 64)) return -1;
+      if (dev_reserve(&s.d_recs, &s.rec_cap, lines_cap, 64)) return -1;
+   }
+   if (mode == M_ALL) {
+      if (dev_reserve(&s.d_cnt, &s.cnt_cap, lines_cap, 64)) return -1;
+      if (dev_reserve(&s.d_offs, &s.offs_cap, lines_cap, 64)) return -1;
+      size_t want_ev = (size_t)((double)n * e->events_per_byte) + 4096;
+      if (dev_reserve(&s.d_ev, &s.ev_cap, want_ev)) return -1;
+      if (dev_reserve(&s.d_recs, &s.rec_cap, s.ev_cap, 64)) return -1;
+   }
+   // control block: counters, then look-back words of K1, scan, finish
+   const size_t k1_tiles = div_up(n, kK1Tile) + 1;
+   const size_t scan_tiles = div_up(lines_cap, (size_t)kThreads * kScanItems) + 1;
+   const size_t fin_tiles = div_up(lines_cap, kThreads) + 1;
+   const size_t ctl_words = C_COUNT + k1_tiles + scan_tiles + fin_tiles;
+   if (dev_reserve(&s.d_ctl, &s.ctl_cap, ctl_words)) return -1;
+   unsigned long long *ctr = s.d_ctl;
+   unsigned long long *st_k1 = ctr + C_COUNT;
+   unsigned long long *st_scan = st_k1 + k1_tiles;
+   unsigned long long *st_fin = st_scan + scan_tiles;
+
+   if (timing) CU(cudaEventRecord(s.ev[0], st));
+   CU(cudaMemsetAsync(s.d_ctl, 0, ctl_words * sizeof(unsigned long long), st));
+
+   // ---- K1 ------------------------------------------------------------------
+   if (single) {
+      s.h_init[0] = 0;
+      s.h_init[1] = n;
+      CU(cudaMemcpyAsync(s.d_ls, s.h_init, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+      s.h_ctr[C_NLINES] = 1;      // reuse pinned word as the source of the line count
+      CU(cudaMemcpyAsync(ctr + C_NLINES, s.h_ctr + C_NLINES, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+   } else {
+      K1Args k1{d_text, n, s.d_ls, (uint32_t)s.line_cap, ctr, st_k1, (options & SQB_FASTA) ? 1 : 0};
+      static bool attr = false;
+      if (!attr) {
+         CU(cudaFuncSetAttribute(k1_line_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kK1Stage)));
+         attr = true;
+      }
+      const int grid = (int)std::min<size_t>(div_up(n, kK1Tile), (size_t)e->sms * 4);
+      k1_line_scan<<<grid, kThreads, 2 * kK1Stage, st>>>(k1);
+      CU(cudaGetLastError());
+      s.launches++;
+   }
+   if (timing) CU(cudaEventRecord(s.ev[1], st));
+
+   // ---- K2 ------------------------------------------------------------------
+   Pattern fwd, rev;
+   build_pattern(e, options, false, &fwd);
+   build_pattern(e, options, true, &rev);
+   const size_t max_lines = single ? 1 : std::min<size_t>(lines_cap, n);
+   const int lines_per_cta = e->words <= 2 ? kThreads : kThreads / e->words;
+   K2Args k2{d_text, n, s.d_ls, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_ev,
+             (uint32_t)std::min<size_t>(s.ev_cap, 0xffffffffu)};
+   {
+      const int grid = (int)std::min<size_t>(div_up(max_lines, lines_per_cta), (size_t)e->sms * 8);
+      if (launch_k2(e, mode, grid, st, k2, fwd)) return -1;
+      s.launches++;
+   }
+   if (timing) CU(cudaEventRecord(s.ev[2], st));
+
+   // ---- scan + K3/K4 --------------------------------------------------------
+   FinArgs fa{d_text, s.d_ls, (uint32_t)lines_cap, s.d_res, s.d_offs, s.d_ev, k2.ev_cap, s.d_recs,
+              (uint32_t)std::min<size_t>(s.rec_cap, 0xffffffffu), ctr, st_fin};
+   if (mode == M_FIRST || mode == M_BEST) {
+      const int grid = (int)std::min<size_t>(div_up(max_lines, kThreads), (size_t)e->sms * 8);
+      if (launch_finish(e, false, grid, st, fa, rev)) return -1;
+      s.launches++;
+   } else if (mode == M_ALL) {
+      ScanArgs sa{s.d_cnt, s.d_offs, (uint32_t)lines_cap, ctr, st_scan};
+      const int grid = (int)std::min<size_t>(div_up(max_lines, (size_t)kThreads * kScanItems), (size_t)e->sms * 8);
+      k_scan_counts<<<grid, kThreads, 0, st>>>(sa);
+      CU(cudaGetLastError());
+      const int grid2 = (int)std::min<size_t>(div_up(std::max<size_t>(s.ev_cap, 1), kThreads), (size_t)e->sms * 8);
+      if (launch_finish(e, true, single ? 1 : grid2, st, fa, rev)) return -1;
+      s.launches += 2;
+   }
+   if (timing) CU(cudaEventRecord(s.ev[3], st));
+   CU(cudaMemcpyAsync(s.h_ctr, ctr, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+   CU(cudaEventRecord(s.ev[4], st));
+   return 0;
+}
+
+// waits for the scan in `s`; repeats it if a capacity was exceeded
+static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
+{
+   uint32_t reruns = 0;
+   for (;;) {
+      CU(cudaEventSynchronize(s.ev[4]));
+      const int mode = mode_of(s.cur_options);
+      const unsigned long long nlines = s.h_ctr[C_NLINES];
+      const unsigned long long nev = s.h_ctr[C_EVENTS];
+      bool again = false;
+      if (nlines + 1 > s.line_cap) {
+         e->lines_per_byte = (double)(nlines + 2) / (double)std::max<uint32_t>(s.cur_n, 1) * 1.05;
+         again = true;
+      }
+      if (mode == M_ALL && nev > s.ev_cap) {
+         e->events_per_byte = (double)(nev + 1) / (double)std::max<uint32_t>(s.cur_n, 1) * 1.05;
+         again = true;
+      }
+      if (!again) break;
+      if (++reruns > 3) { set_err("capacity re-run did not converge"); return -1; }
+      if (slot_issue(e, s, s.cur_text, s.cur_n, s.cur_options, s.cur_stream)) return -1;
+   }
+   s.busy = false;
+   if (stats) {
+      memset(stats, 0, sizeof *stats);
+      stats->nbytes = s.cur_n;
+      stats->nlines = s.h_ctr[C_NLINES];
+      stats->nmatched = s.h_ctr[C_NMATCHED];
+      stats->nrecs = s.h_ctr[C_NRECS];
+      stats->launches = s.launches;
+      stats->reruns = reruns;
+      if (s.cur_options & SQB_TIMING) {
+         float ms = 0;
+         CU(cudaEventElapsedTime(&ms, s.ev[0], s.ev[3]));
+         stats->device_ms = ms;
+         for (int k = 0; k < 3; k++) {
+            CU(cudaEventElapsedTime(&ms, s.ev[k], s.ev[k + 1]));
+            stats->kernel_ms[k] = ms;
+         }
+      }
+   }
+   return 0;
+}
+
+// ---------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char *sqbLastError(void) { return g_err; }
+
+int sqbDeviceCount(void)
+{
+   int n = 0;
+   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+   return n;
+}
+
+int sqbMaxPatternLength(void) { return kMaxWords * 32; }
+
+sqb_engine_t *sqbEngineNew(const unsigned char *keys, int m, int tau, int device)
+{
+   if (keys == NULL || m < 1 || tau < 0 || tau >= m) {
+      set_err("invalid pattern (m=%d, tau=%d)", m, tau);
+      return NULL;
+   }
+   if (m > kMaxWords * 32) {
+      set_err("pattern of %d positions exceeds the %d supported by the blocked automaton", m, kMaxWords * 32);
+      return NULL;
+   }
+   int ndev = 0;
+   cudaError_t ce = cudaGetDeviceCount(&ndev);
+   if (ce != cudaSuccess || ndev == 0) {
+      set_err("no CUDA device available (%s); this library has no CPU fallback",
+              ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0");
+      cudaGetLastError();
+      return NULL;
+   }
+   if (device < 0) {
+      const char *env = getenv("SEEQ_B200_DEVICE");
+      if (env == NULL) env = getenv("LOCAL_RANK");
+      device = env ? atoi(env) % ndev : 0;
+   }
+   if (device >= ndev) { set_err("device %d out of range (%d devices)", device, ndev); return NULL; }
+   if (cudaSetDevice(device) != cudaSuccess) { set_err("cudaSetDevice(%d) failed", device); return NULL; }
+   sqb_engine *e = new sqb_engine();
+   e->device = device;
+   cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, device);
+   e->m = m;
+   e->tau = tau;
+   memcpy(e->keys, keys, (size_t)m);
+   const int words = (m + 31) / 32;
+   e->words = 1;
+   while (e->words < words) e->words *= 2;
+   if (e->words > 2 && e->words < 4) e->words = 4;
+   memset(&e->last_stats, 0, sizeof e->last_stats);
+   return e;
+}
+
+void sqbEngineFree(sqb_engine_t *e)
+{
+   if (e == NULL) return;
+   cudaSetDevice(e->device);
+   for (auto &s : e->slot) slot_free(s);
+   delete e;
+}
+
+int sqbScanDevice(sqb_engine_t *e, const void *d_text, size_t nbytes, int options, void *stream,
+                  sqb_stats_t *stats)
+{
+   if (nbytes >= 0xfffffff0ull) { set_err("sqbScanDevice: %zu bytes exceed the 4 GiB batch limit", nbytes); return -1; }
+   if (((uintptr_t)d_text & 15) != 0) { set_err("sqbScanDevice: text pointer must be 16-byte aligned"); return -1; }
+   CU(cudaSetDevice(e->device));
+   Slot &s = e->slot[0];
+   if (slot_init(s)) return -1;
+   e->last_slot = 0;
+   if (nbytes == 0 && !(options & SQB_SINGLE_LINE)) {
+      memset(&e->last_stats, 0, sizeof e->last_stats);
+      if (stats) memset(stats, 0, sizeof *stats);
+      memset(s.h_ctr, 0, C_COUNT * sizeof(unsigned long long));
+      return 0;
+   }
+   cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+   if (slot_issue(e, s, (const uint8_t *)d_text, (uint32_t)nbytes, options, st)) return -1;
+   if (slot_finish(e, s, &e->last_stats)) return -1;
+   if (stats) *stats = e->last_stats;
+   return 0;
+}
+
+const sqb_rec_t *sqbDeviceRecords(sqb_engine_t *e) { return (const sqb_rec_t *)e->slot[e->last_slot].d_recs; }
+const uint32_t *sqbDeviceLineStarts(sqb_engine_t *e) { return e->slot[e->last_slot].d_ls; }
+
+int sqbFetchRecords(sqb_engine_t *e, sqb_rec_t *dst, uint64_t first, uint64_t count)
+{
+   Slot &s = e->slot[e->last_slot];
+   if (first + count > s.h_ctr[C_NRECS]) { set_err("sqbFetchRecords: range beyond %llu records", s.h_ctr[C_NRECS]); return -1; }
+   if (count == 0) return 0;
+   CU(cudaMemcpy(dst, s.d_recs + first, count * sizeof(Rec), cudaMemcpyDeviceToHost));
+   return 0;
+}
+
+int sqbFetchLineStarts(sqb_engine_t *e, uint32_t *dst, uint64_t first, uint64_t count)
+{
+   Slot &s = e->slot[e->last_slot];
+   if (first + count > s.h_ctr[C_NLINES] + 1) { set_err("sqbFetchLineStarts: range beyond %llu lines", s.h_ctr[C_NLINES]); return -1; }
+   if (count == 0) return 0;
+   CU(cudaMemcpy(dst, s.d_ls + first, count * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+   return 0;
+}
+
+// ---- host path ----------------------------------------------------------------
+static size_t host_chunk_bytes(void)
+{
+   const char *env = getenv("SEEQ_B200_CHUNK_MB");
+   size_t mb = env ? (size_t)atol(env) : 64;
+   if (mb < 1) mb = 1;
+   if (mb > 2048) mb = 2048;
+   return mb << 20;
+}
+
+// collect the results of the chunk in flight in slot s (in chunk order)
+static int host_collect(sqb_engine *e, Slot &s, int options, uint64_t *line_base, sqb_stats_t *acc)
+{
+   sqb_stats_t st;
+   if (slot_finish(e, s, &st)) return -1;
+   const bool count_only = options & SQB_COUNT_ONLY;
+   if (!count_only && st.nrecs > 0) {
+      if (pin_reserve(&s.h_recs, &s.h_rec_cap, (size_t)st.nrecs)) return -1;
+      CU(cudaMemcpyAsync(s.h_recs, s.d_recs, st.nrecs * sizeof(Rec), cudaMemcpyDeviceToHost, s.stream));
+   }
+   if ((options & SQB_KEEP_LINES_INTERNAL) && st.nlines > 0) {
+      if (pin_reserve(&s.h_ls, &s.h_ls_cap, (size_t)st.nlines)) return -1;
+      CU(cudaMemcpyAsync(s.h_ls, s.d_ls, st.nlines * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+   }
+   CU(cudaStreamSynchronize(s.stream));
+   if (!count_only && st.nrecs > 0) {
+      const size_t old = e->host_recs.size();
+      e->host_recs.resize(old + st.nrecs);
+      const uint32_t lb = (uint32_t)*line_base;
+      sqb_rec_t *dst = e->host_recs.data() + old;
+      for (uint64_t k = 0; k < st.nrecs; k++) {
+         dst[k].line = s.h_recs[k].line + lb;
+         dst[k].start = s.h_recs[k].start;
+         dst[k].end = s.h_recs[k].end;
+         dst[k].dist = s.h_recs[k].dist;
+      }
+   }
+   if ((options & SQB_KEEP_LINES_INTERNAL) && st.nlines > 0) {
+      const size_t old = e->host_lines.size();
+      e->host_lines.resize(old + st.nlines);
+      for (uint64_t k = 0; k < st.nlines; k++) e->host_lines[old + k] = (uint64_t)s.chunk_off + s.h_ls[k];
+   }
+   *line_base += st.nlines;
+   acc->nbytes += st.nbytes;
+   acc->nlines += st.nlines;
+   acc->nmatched += st.nmatched;
+   acc->nrecs += st.nrecs;
+   acc->launches += st.launches;
+   acc->reruns += st.reruns;
+   acc->device_ms += st.device_ms;
+   for (int k = 0; k < 4; k++) acc->kernel_ms[k] += st.kernel_ms[k];
+   return 0;
+}
+
+int sqbScanHost(sqb_engine_t *e, const char *text, size_t nbytes, int options, sqb_stats_t *stats)
+{
+   CU(cudaSetDevice(e->device));
+   for (auto &s : e->slot) if (slot_init(s)) return -1;
+   e->host_recs.clear();
+   e->host_lines.clear();
+   sqb_stats_t acc;
+   memset(&acc, 0, sizeof acc);
+   const bool single = options & SQB_SINGLE_LINE;
+   const size_t chunk = host_chunk_bytes();
+   uint64_t line_base = 0;
+   size_t pos = 0;
+   int c = 0;
+   int pending[2] = {0, 0};
+   // FASTA is a property of the whole stream (seeq.c:243-253), not of a chunk
+   if (!single && !(options & SQB_FASTA)) {
+      /* caller decides; nothing to do */
+   }
+   while (pos < nbytes || (single && c == 0)) {
+      size_t len;
+      if (single) {
+         len = nbytes;
+      } else {
+         len = nbytes - pos;
+         if (len > chunk) {
+            // cut after the last newline inside the window, else extend to the next one
+            const char *nl = (const char *)memrchr(text + pos, '\n', chunk);
+            if (nl == NULL) nl = (const char *)memchr(text + pos + chunk, '\n', nbytes - pos - chunk);
+            len = nl ? (size_t)(nl - (text + pos)) + 1 : nbytes - pos;
+         }
+      }
+      if (len >= 0xfffffff0ull) { set_err("a single line of %zu bytes exceeds the 4 GiB batch limit", len); return -1; }
+      Slot &s = e->slot[c & 1];
+      if (pending[c & 1]) {
+         if (host_collect(e, s, options, &line_base, &acc)) return -1;
+         pending[c & 1] = 0;
+      }
+      if (dev_reserve(&s.d_text, &s.text_cap, len + 64)) return -1;
+      s.chunk_off = pos;
+      if (len) CU(cudaMemcpyAsync(s.d_text, text + pos, len, cudaMemcpyHostToDevice, s.stream));
+      if (len || single) {
+         if (slot_issue(e, s, s.d_text, (uint32_t)len, options, s.stream)) return -1;
+         pending[c & 1] = 1;
+      }
+      pos += len;
+      c++;
+      if (single) break;
+   }
+   // drain in chunk order
+   for (int k = 0; k < 2; k++) {
+      const int idx = (c + k) & 1;
+      if (pending[idx]) {
+         if (host_collect(e, e->slot[idx], options, &line_base, &acc)) return -1;
+         pending[idx] = 0;
+      }
+   }
+   e->last_stats = acc;
+   if (stats) *stats = acc;
+   return 0;
+}
+
+const sqb_rec_t *sqbHostRecords(sqb_engine_t *e, uint64_t *count)
+{
+   if (count) *count = e->host_recs.size();
+   return e->host_recs.data();
+}
+
+int sqbHostLineStarts(sqb_engine_t *e, const uint64_t **starts, uint64_t *count)
+{
+   if (starts) *starts = e->host_lines.data();
+   if (count) *count = e->host_lines.size();
+   return 0;
+}
+
+void *sqbHostAlloc(size_t nbytes)
+{
+   void *p = NULL;
+   if (cudaMallocHost(&p, nbytes ? nbytes : 1) != cudaSuccess) {
+      set_err("cudaMallocHost(%zu) failed", nbytes);
+      cudaGetLastError();
+      return NULL;
+   }
+   return p;
+}
+void sqbHostFree(void *p) { if (p) cudaFreeHost(p); }
+
+void *sqbDeviceAlloc(size_t nbytes)
+{
+   void *p = NULL;
+   if (cudaMalloc(&p, nbytes + 64) != cudaSuccess) {
+      set_err("cudaMalloc(%zu) failed", nbytes);
+      cudaGetLastError();
+      return NULL;
+   }
+   return p;
+}
+void sqbDeviceFree(void *p) { if (p) cudaFree(p); }
+
+int sqbMemcpyH2D(void *dst, const void *src, size_t nbytes)
+{
+   CU(cudaMemcpy(dst, src, nbytes, cudaMemcpyHostToDevice));
+   return 0;
+}
+
+void sqbShardRange(const char *text, size_t nbytes, int rank, int world, size_t *begin, size_t *end)
+{
+   size_t cut[2];
+   for (int k = 0; k < 2; k++) {
+      const int r = rank + k;
+      size_t p = r >= world ? nbytes : (size_t)((unsigned __int128)nbytes * (unsigned)r / (unsigned)world);
+      if (r > 0 && r < world && p > 0) {
+         // move forward to just after the next newline (a boundary that already
+         // follows a newline stays)
+         if (text[p - 1] != '\n') {
+            const char *nl = (const char *)memchr(text + p, '\n', nbytes - p);
+            p = nl ? (size_t)(nl - text) + 1 : nbytes;
+         }
+      }
+      cut[k] = p;
+   }
+   *begin = cut[0];
+   *end = cut[1];
+}
+
+// ---- synthetic reads --------------------------------------------------------
+size_t sqbGenBytes(const sqb_gen_t *g, uint64_t first, uint64_t nreads)
+{
+   (void)first;
+   return sqb_gen_record_bytes(g) * (size_t)nreads;
+}
+
+int sqbGenHost(const sqb_gen_t *g, uint64_t first, uint64_t nreads, char *dst)
+{
+   const size_t rb = sqb_gen_record_bytes(g);
+#pragma omp parallel for schedule(static)
+   for (long long r = 0; r < (long long)nreads; r++) sqb_gen_record(g, first + (uint64_t)r, dst + (size_t)r * rb);
+   return 0;
+}
+
+}  // extern "C"
+
+__global__ void k_gen_reads(const __grid_constant__ sqb_gen_t g, uint64_t first, uint64_t nreads, char *dst)
+{
+   const size_t rb = sqb_gen_record_bytes(&g);
+   for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nreads; r += (uint64_t)gridDim.x * blockDim.x)
+      sqb_gen_record(&g, first + r, dst + (size_t)r * rb);
+}
+
+extern "C" int sqbGenDevice(const sqb_gen_t *g, uint64_t first, uint64_t nreads, void *d_dst, void *stream)
+{
+   if (nreads == 0) return 0;
+   const int grid = (int)std::min<uint64_t>((nreads + 127) / 128, 148 * 16);
+   k_gen_reads<<<grid, 128, 0, (cudaStream_t)stream>>>(*g, first, nreads, (char *)d_dst);
+   CU(cudaGetLastError());
+   CU(cudaStreamSynchronize((cudaStream_t)stream));
+   return 0;
+}

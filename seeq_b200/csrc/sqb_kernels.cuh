@@ -1,0 +1,733 @@
+// sqb_kernels.cuh -- the hand-written sm_100a kernels of the matching path.
+//
+//   k1_line_scan          K1  newline / line-offset scan (TMA-staged tiles,
+//                             16-byte loads, warp-aggregated prefix, look-back)
+//   k2_forward_thread     K2  Myers/Hyyro forward matcher, one read per thread
+//                             (pattern <= 64 positions: 1 or 2 words)
+//   k2_forward_lanes      K2  blocked multi-word automaton across warp lanes
+//                             (pattern > 64 positions; carries via ballot)
+//   k_scan_counts             exclusive scan of per-line event counts (SQ_ALL)
+//   k34_finish_lines      K3+K4 for SQ_FIRST / SQ_BEST: reverse pass + ordered
+//                             ballot/popc compaction of one record per line
+//   k34_finish_events     K3+K4 for SQ_ALL: reverse pass per event + ordered
+//                             scatter to offs[line] + rank
+//
+// Semantics restated from /root/reference/src/libseeq.c:171-352.
+#pragma once
+
+#include "sqb_device.cuh"
+
+namespace sqb {
+
+// ---------------------------------------------------------------------------
+// parameters shared by host and device
+// ---------------------------------------------------------------------------
+constexpr int kMaxWords = 32;                 // pattern words per automaton (m <= 1024)
+
+// byte classes: low 3 bits = base code 0..4 (A C G T N), bits 5:4 = kind
+constexpr uint8_t kKindBase = 0x00;           // feeds the automaton
+constexpr uint8_t kKindSkip = 0x10;           // invisible (SQ_IGNORE, '\n' in SQ_STREAM)
+constexpr uint8_t kKindStop = 0x20;           // ends the line (NUL, '\n', SQ_FAIL)
+
+struct Pattern {
+   uint32_t eq[5][kMaxWords];                 // left-aligned match masks per base code
+   uint8_t  cls[256];                         // byte -> class
+   int      m;
+   int      tau;
+};
+
+enum Mode { M_COUNT = 0, M_FIRST = 1, M_BEST = 2, M_ALL = 3, M_COUNTALL = 4 };
+
+enum Counter {
+   C_NLINES = 0,     // counted lines (K1)
+   C_NMATCHED = 1,   // lines with >= 1 match
+   C_NRECS = 2,      // records / events in total
+   C_EVENTS = 3,     // events appended by K2 in SQ_ALL (may exceed the capacity)
+   C_TICKET_K1 = 4,
+   C_TICKET_SCAN = 5,
+   C_TICKET_FIN = 6,
+   C_COUNT = 8
+};
+
+struct Event {        // SQ_ALL: one forward event, unordered
+   uint32_t line;
+   uint32_t rank;     // index among the events of its line
+   uint32_t end;
+   uint32_t dist;
+};
+
+struct Rec {          // == sqb_rec_t
+   uint32_t line, start, end, dist;
+};
+
+constexpr unsigned long long kNoMatch = ~0ull;
+
+// ===========================================================================
+// K1: newline / line-offset scan
+// ===========================================================================
+constexpr int      kK1Vec  = 4;                              // 16-byte vectors per thread
+constexpr uint32_t kK1Tile = kThreads * kK1Vec * 16;         // 16 KiB of text per tile
+constexpr uint32_t kK1Stage = kK1Tile + 16;                  // + look-ahead for the FASTA test
+
+struct K1Args {
+   const uint8_t *text;
+   uint32_t n;
+   uint32_t *ls;                  // out: start offset of every counted line (+ sentinel n)
+   uint32_t ls_cap;               // capacity of ls (entries); counting continues beyond it
+   unsigned long long *ctr;
+   unsigned long long *status;    // look-back words, one per tile, zeroed
+   int fasta;
+};
+
+// exact per-byte equality mask: bit 8k+7 set iff byte k of w equals '\n'
+__device__ __forceinline__ uint32_t newline_bits(uint32_t w)
+{
+   const uint32_t x = w ^ 0x0A0A0A0Au;
+   return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+}
+
+__global__ void __launch_bounds__(kThreads) k1_line_scan(const K1Args a)
+{
+   extern __shared__ __align__(128) uint8_t dyn[];            // 2 x kK1Stage
+   __shared__ uint64_t bar[2];
+   __shared__ uint32_t s_tile[2];
+   __shared__ uint32_t s_wsum[kK1Vec][kWarps];
+   __shared__ unsigned long long s_base;
+
+   const uint32_t n = a.n;
+   const uint32_t ntiles = (n + kK1Tile - 1) / kK1Tile;
+   const uint32_t n16 = (n + 15u) & ~15u;
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+   auto issue = [&](int stage, uint32_t tile) {
+      const uint32_t start = tile * kK1Tile;
+      uint32_t bytes = n16 - start;
+      if (bytes > kK1Stage) bytes = kK1Stage;
+      mbar_expect_tx(&bar[stage], bytes);
+      bulk_g2s(dyn + stage * kK1Stage, a.text + start, bytes, &bar[stage]);
+   };
+
+   if (tid == 0) {
+      mbar_init(&bar[0], 1);
+      mbar_init(&bar[1], 1);
+      mbar_fence_init();
+      const uint32_t t = (uint32_t)atomicAdd(&a.ctr[C_TICKET_K1], 1ull);
+      s_tile[0] = t;
+      if (t < ntiles) issue(0, t);
+   }
+   __syncthreads();
+
+   uint32_t phase[2] = {0, 0};
+   for (int stage = 0;; stage ^= 1) {
+      const uint32_t tile = s_tile[stage];
+      if (tile >= ntiles) break;
+      if (tid == 0) {                       // prefetch the next ticket into the other stage
+         const uint32_t t = (uint32_t)atomicAdd(&a.ctr[C_TICKET_K1], 1ull);
+         s_tile[stage ^ 1] = t;
+         if (t < ntiles) issue(stage ^ 1, t);
+      }
+      mbar_wait(&bar[stage], phase[stage]);
+      phase[stage] ^= 1;
+
+      const uint8_t *buf = dyn + stage * kK1Stage;
+      const uint32_t tile_start = tile * kK1Tile;
+
+      // ---- per-thread masks of line starts ---------------------------------
+      uint32_t z[kK1Vec][4];
+      uint32_t c[kK1Vec];
+#pragma unroll
+      for (int k = 0; k < kK1Vec; k++) {
+         const uint32_t voff = (uint32_t)(k * kThreads + tid) * 16u;
+         const uint4 v = *reinterpret_cast<const uint4 *>(buf + voff);
+         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+         c[k] = 0;
+#pragma unroll
+         for (int q = 0; q < 4; q++) {
+            uint32_t bits = newline_bits(w[q]);
+            // a newline at p opens a line at p+1 only if p+1 < n, and in FASTA
+            // mode only if that line is not a header
+            uint32_t keep = 0;
+            while (bits) {
+               const int b = __ffs(bits) - 1;
+               bits &= bits - 1;
+               const uint32_t off = voff + (uint32_t)(q * 4 + (b >> 3));   // in tile
+               const uint32_t s = tile_start + off + 1u;
+               if (s < n && !(a.fasta && buf[off + 1u] == '>')) keep |= 1u << b;
+            }
+            z[k][q] = keep;
+            c[k] += __popc(keep);
+         }
+      }
+      // the first line of the buffer has no newline in front of it
+      uint32_t first = 0;
+      if (tile == 0 && tid == 0 && n > 0 && !(a.fasta && buf[0] == '>')) first = 1;
+      c[0] += first;
+
+      // ---- block prefix in (vector k, thread) order -------------------------
+      uint32_t inc[kK1Vec];
+#pragma unroll
+      for (int k = 0; k < kK1Vec; k++) {
+         uint32_t x = c[k];
+#pragma unroll
+         for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, x, d);
+            if (lane >= d) x += t;
+         }
+         inc[k] = x;
+         if (lane == 31) s_wsum[k][warp] = x;
+      }
+      __syncthreads();
+      uint32_t excl[kK1Vec];
+      uint32_t run = 0;
+#pragma unroll
+      for (int k = 0; k < kK1Vec; k++) {
+         uint32_t before = 0, tot = 0;
+#pragma unroll
+         for (int w = 0; w < kWarps; w++) {
+            const uint32_t x = s_wsum[k][w];
+            if (w < warp) before += x;
+            tot += x;
+         }
+         excl[k] = run + before + inc[k] - c[k];
+         run += tot;
+      }
+      const uint32_t tile_total = run;
+
+      const unsigned long long base = tile_lookback(a.status, tile, tile_total, &s_base);
+
+      // ---- emit -------------------------------------------------------------
+#pragma unroll
+      for (int k = 0; k < kK1Vec; k++) {
+         unsigned long long idx = base + excl[k];
+         if (k == 0 && first) {
+            if (idx < a.ls_cap) a.ls[idx] = 0;
+            idx++;
+         }
+         const uint32_t voff = (uint32_t)(k * kThreads + tid) * 16u;
+#pragma unroll
+         for (int q = 0; q < 4; q++) {
+            uint32_t bits = z[k][q];
+            while (bits) {
+               const int b = __ffs(bits) - 1;
+               bits &= bits - 1;
+               if (idx < a.ls_cap) a.ls[idx] = tile_start + voff + (uint32_t)(q * 4 + (b >> 3)) + 1u;
+               idx++;
+            }
+         }
+      }
+      if (tile == ntiles - 1 && tid == 0) {
+         const unsigned long long total = base + tile_total;
+         a.ctr[C_NLINES] = total;
+         if (total < a.ls_cap) a.ls[total] = n;         // sentinel
+      }
+      __syncthreads();       // stage buffer and s_tile[stage] may now be reused
+   }
+}
+
+// ===========================================================================
+// K2 (one read per thread)
+// ===========================================================================
+constexpr uint32_t kK2Stage = 48 * 1024;       // staged text per tile of kThreads lines
+
+struct K2Args {
+   const uint8_t *text;
+   uint32_t n;
+   const uint32_t *ls;
+   uint32_t max_lines;          // capacity of the per-line arrays (line count is clamped to it)
+   unsigned long long *ctr;
+   unsigned long long *res;     // M_FIRST / M_BEST: per-line (dist << 32 | end) or kNoMatch
+   uint32_t *cnt;               // M_ALL: per-line event count
+   Event *ev;                   // M_ALL: unordered events
+   uint32_t ev_cap;
+};
+
+template <int W> struct LutEntry;
+template <> struct __align__(8) LutEntry<1> {
+   uint32_t eq[1];
+   uint32_t kind;
+};
+template <> struct __align__(16) LutEntry<2> {
+   uint32_t eq[2];
+   uint32_t kind;
+   uint32_t pad;
+};
+
+// per-line state machine shared by the thread kernel; `rd(p)` returns text[p]
+template <int W, int MODE, class Reader>
+__device__ __forceinline__ void scan_line(const Reader &rd, const uint32_t line, const uint32_t begin,
+                                          const uint32_t limit, const LutEntry<W> *lut, const int m,
+                                          const int tau, const K2Args &a, uint32_t &matched,
+                                          uint32_t &nevents)
+{
+   BitVec<W> bv;
+   bv_reset(bv, m);
+   int score = m;                       // uncapped search distance; see DESIGN.md "capping"
+   bool flag = false;                   // the reference's `match` suppress flag
+   int best_d = tau + 1;
+   uint32_t best_end = 0;
+   uint32_t nev = 0;
+   bool hit = false;
+   uint32_t p = begin;
+
+   auto emit = [&](uint32_t end, int dist) {
+      if (MODE == M_ALL) {
+         const unsigned long long idx = atomicAdd(&a.ctr[C_EVENTS], 1ull);
+         if (idx < a.ev_cap) a.ev[idx] = Event{line, nev, end, (uint32_t)dist};
+      }
+      best_d = dist;
+      best_end = end;
+      hit = true;
+      nev++;
+   };
+
+   bool done = false;
+   while (p < limit) {
+      const uint8_t b = rd(p);
+      const LutEntry<W> e = lut[b];
+      if (e.kind != kKindBase) {
+         if (e.kind == kKindSkip) { p++; continue; }
+         break;
+      }
+      uint32_t rise, fall;
+      bv_step<W>(bv, e.eq, rise, fall);
+      const int streak = score;
+      score += (int)rise - (int)fall;
+      if (MODE == M_COUNT) {
+         if (score <= tau) { hit = true; done = true; break; }
+      } else {
+         if (!rise) flag = false;                                   // libseeq.c:278
+         bool evt = streak <= tau && !flag && (rise || streak == 0); // libseeq.c:286-288
+         if (MODE == M_BEST) evt = evt && streak < best_d;
+         if (evt) {
+            flag = true;
+            emit(p - begin, streak);
+            if (MODE == M_FIRST) { done = true; break; }
+         }
+      }
+      p++;
+   }
+   if (!done && MODE != M_COUNT) {
+      // terminal step (NUL / '\n' / illegal byte / end of buffer): the distance
+      // becomes tau+1, so any pending streak <= tau rises (libseeq.c:267-288)
+      const int streak = score;
+      bool evt = streak <= tau && !flag;
+      if (MODE == M_BEST) evt = evt && streak < best_d;
+      if (evt) emit(p - begin, streak);
+   }
+   if (MODE == M_FIRST || MODE == M_BEST)
+      a.res[line] = hit ? (((unsigned long long)(uint32_t)best_d << 32) | best_end) : kNoMatch;
+   if (MODE == M_ALL) a.cnt[line] = nev;
+   matched = hit ? 1u : 0u;
+   nevents = nev;
+}
+
+struct SmemReader {
+   const uint8_t *base;          // stage - aligned tile start
+   __device__ __forceinline__ uint8_t operator()(uint32_t p) const { return base[p]; }
+};
+struct GlobalReader {
+   const uint8_t *base;
+   __device__ __forceinline__ uint8_t operator()(uint32_t p) const { return __ldg(base + p); }
+};
+
+template <int W, int MODE>
+__global__ void __launch_bounds__(kThreads) k2_forward_thread(const K2Args a, const __grid_constant__ Pattern pat)
+{
+   extern __shared__ __align__(128) uint8_t stage[];          // kK2Stage
+   __shared__ LutEntry<W> lut[256];
+   __shared__ uint64_t bar;
+   __shared__ uint32_t s_red[2][kWarps];
+
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   {  // byte -> (match mask words, kind)
+      const uint8_t c = pat.cls[tid];
+      LutEntry<W> e;
+      e.kind = c & 0x30;
+#pragma unroll
+      for (int w = 0; w < W; w++) e.eq[w] = (c & 0x30) == kKindBase ? pat.eq[c & 7][w] : 0u;
+      lut[tid] = e;
+   }
+   if (tid == 0) {
+      mbar_init(&bar, 1);
+      mbar_fence_init();
+   }
+   __syncthreads();
+
+   const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
+   const uint32_t n = a.n;
+   const uint32_t ntiles = (nlines + kThreads - 1) / kThreads;
+   uint32_t phase = 0;
+   uint32_t my_matched = 0, my_events = 0;
+
+   for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const uint32_t l0 = tile * kThreads;
+      const uint32_t l1 = min(l0 + kThreads, nlines);
+      const uint32_t t_begin = a.ls[l0];
+      const uint32_t t_end = a.ls[l1];                 // sentinel ls[nlines] == n
+      const uint32_t a0 = t_begin & ~15u;
+      const uint32_t bytes = ((t_end + 15u) & ~15u) - a0;
+      const bool staged = bytes > 0 && bytes <= kK2Stage;
+      if (staged) {
+         if (tid == 0) {
+            mbar_expect_tx(&bar, bytes);
+            bulk_g2s(stage, a.text + a0, bytes, &bar);
+         }
+      }
+      const uint32_t line = l0 + tid;
+      uint32_t begin = 0;
+      if (line < l1) begin = a.ls[line];
+      if (staged) {
+         mbar_wait(&bar, phase);
+         phase ^= 1;
+      }
+      if (line < l1) {
+         uint32_t mt, ne;
+         const uint32_t limit = min(t_end, n);
+         if (staged)
+            scan_line<W, MODE>(SmemReader{stage - a0}, line, begin, limit, lut, pat.m, pat.tau, a, mt, ne);
+         else
+            scan_line<W, MODE>(GlobalReader{a.text}, line, begin, n, lut, pat.m, pat.tau, a, mt, ne);
+         my_matched += mt;
+         my_events += ne;
+      }
+      __syncthreads();      // everyone is done with the stage before it is refilled
+   }
+
+   if (MODE == M_COUNT || MODE == M_COUNTALL) {
+      // block reduction, one atomic per CTA and counter
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+         my_matched += __shfl_xor_sync(kFull, my_matched, d);
+         my_events += __shfl_xor_sync(kFull, my_events, d);
+      }
+      if (lane == 0) {
+         s_red[0][warp] = my_matched;
+         s_red[1][warp] = my_events;
+      }
+      __syncthreads();
+      if (tid == 0) {
+         unsigned long long sm = 0, se = 0;
+         for (int w = 0; w < kWarps; w++) {
+            sm += s_red[0][w];
+            se += s_red[1][w];
+         }
+         if (sm) atomicAdd(&a.ctr[C_NMATCHED], sm);
+         if (MODE == M_COUNTALL && se) atomicAdd(&a.ctr[C_NRECS], se);
+      }
+   }
+}
+
+// ===========================================================================
+// K2 (blocked multi-word automaton across G lanes of a warp; m > 64)
+// ===========================================================================
+template <int G, int MODE>
+__global__ void __launch_bounds__(kThreads) k2_forward_lanes(const K2Args a, const __grid_constant__ Pattern pat)
+{
+   __shared__ uint32_t s_eq[8][G];
+   __shared__ uint8_t s_cls[256];
+   __shared__ uint32_t s_red[2][kWarps];
+
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const int gl = lane & (G - 1);            // lane inside its group = word index
+   const int top = (lane | (G - 1));         // lane holding the most significant word
+   // bit l set <=> lane l is the top lane of its group
+   uint32_t topmask = 0;
+#pragma unroll
+   for (int l = G - 1; l < 32; l += G) topmask |= 1u << l;
+
+   s_cls[tid] = pat.cls[tid];
+   if (tid < 5 * G) s_eq[tid / G][tid % G] = pat.eq[tid / G][tid % G];
+   __syncthreads();
+
+   const int m = pat.m, tau = pat.tau;
+   const int pad = G * 32 - m;
+   const int lo = gl * 32;
+   const uint32_t pv0 = pad <= lo ? ~0u : (pad >= lo + 32 ? 0u : (~0u << (pad - lo)));
+
+   constexpr int kLinesPerBlock = kThreads / G;
+   const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
+   const uint32_t n = a.n;
+   const uint32_t ntiles = (nlines + kLinesPerBlock - 1) / kLinesPerBlock;
+   uint32_t my_matched = 0, my_events = 0;
+
+   for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const uint32_t line = tile * kLinesPerBlock + (uint32_t)(tid / G);
+      bool done = line >= nlines;
+      const uint32_t begin = done ? 0u : a.ls[line];
+      uint32_t p = begin;
+      uint32_t pv = pv0, mv = 0;
+      int score = m;
+      bool flag = false, hit = false;
+      int best_d = tau + 1;
+      uint32_t best_end = 0, nev = 0;
+
+      auto emit = [&](uint32_t end, int dist) {
+         if (MODE == M_ALL && gl == 0) {
+            const unsigned long long idx = atomicAdd(&a.ctr[C_EVENTS], 1ull);
+            if (idx < a.ev_cap) a.ev[idx] = Event{line, nev, end, (uint32_t)dist};
+         }
+         best_d = dist;
+         best_end = end;
+         hit = true;
+         nev++;
+      };
+
+      while (__any_sync(kFull, !done)) {
+         uint32_t kind = kKindStop;
+         uint32_t code = 0;
+         if (!done && p < n) {
+            const uint8_t c = s_cls[__ldg(a.text + p)];
+            kind = c & 0x30;
+            code = c & 7;
+         }
+         const bool stepping = !done && kind == kKindBase;
+         const uint32_t e = s_eq[code][gl];
+         // ---- one column of the blocked automaton (all lanes, uniformly) ----
+         const uint32_t xv = e | mv;
+         const uint32_t x = e & pv;
+         const uint32_t s0 = x + pv;
+         // carry look-ahead over the lanes of each group: generate / propagate
+         const uint32_t gen = __ballot_sync(kFull, s0 < x) & ~topmask;
+         const uint32_t prop = __ballot_sync(kFull, s0 == ~0u) & ~topmask;
+         const uint32_t carries = (((gen | prop) + gen) ^ prop);      // bit l = carry INTO lane l
+         const uint32_t sum = s0 + ((carries >> lane) & 1u);
+         const uint32_t xh = (sum ^ pv) | e;
+         uint32_t ph = mv | ~(xh | pv);
+         uint32_t mh = pv & xh;
+         const uint32_t phm = __ballot_sync(kFull, ph >> 31);
+         const uint32_t mhm = __ballot_sync(kFull, mh >> 31);
+         const uint32_t ph_in = gl ? ((phm >> (lane - 1)) & 1u) : 0u;
+         const uint32_t mh_in = gl ? ((mhm >> (lane - 1)) & 1u) : 0u;
+         ph = (ph << 1) | ph_in;
+         mh = (mh << 1) | mh_in;
+         const uint32_t rise = (phm >> top) & 1u, fall = (mhm >> top) & 1u;
+         if (stepping) {
+            pv = mh | ~(xv | ph);
+            mv = ph & xv;
+            const int streak = score;
+            score += (int)rise - (int)fall;
+            if (MODE == M_COUNT) {
+               if (score <= tau) { hit = true; done = true; }
+            } else {
+               if (!rise) flag = false;
+               bool evt = streak <= tau && !flag && (rise || streak == 0);
+               if (MODE == M_BEST) evt = evt && streak < best_d;
+               if (evt) {
+                  flag = true;
+                  emit(p - begin, streak);
+                  if (MODE == M_FIRST) done = true;
+               }
+            }
+            p++;
+         } else if (!done) {
+            if (kind == kKindSkip) {
+               p++;
+            } else {
+               if (MODE != M_COUNT) {
+                  const int streak = score;
+                  bool evt = streak <= tau && !flag;
+                  if (MODE == M_BEST) evt = evt && streak < best_d;
+                  if (evt) emit(p - begin, streak);
+               }
+               done = true;
+            }
+         }
+      }
+      if (line < nlines && gl == 0) {
+         if (MODE == M_FIRST || MODE == M_BEST)
+            a.res[line] = hit ? (((unsigned long long)(uint32_t)best_d << 32) | best_end) : kNoMatch;
+         if (MODE == M_ALL) a.cnt[line] = nev;
+         my_matched += hit ? 1u : 0u;
+         my_events += nev;
+      }
+   }
+
+   if (MODE == M_COUNT || MODE == M_COUNTALL) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+         my_matched += __shfl_xor_sync(kFull, my_matched, d);
+         my_events += __shfl_xor_sync(kFull, my_events, d);
+      }
+      if (lane == 0) {
+         s_red[0][warp] = my_matched;
+         s_red[1][warp] = my_events;
+      }
+      __syncthreads();
+      if (tid == 0) {
+         unsigned long long sm = 0, se = 0;
+         for (int w = 0; w < kWarps; w++) {
+            sm += s_red[0][w];
+            se += s_red[1][w];
+         }
+         if (sm) atomicAdd(&a.ctr[C_NMATCHED], sm);
+         if (MODE == M_COUNTALL && se) atomicAdd(&a.ctr[C_NRECS], se);
+      }
+   }
+}
+
+// ===========================================================================
+// K3: reverse start recovery (libseeq.c:290-316), W words per thread
+// ===========================================================================
+// rpat holds the masks of the REVERSED pattern and a class table in which
+// every non-base byte is kKindSkip (the reference skips them all here).
+template <int W>
+__device__ __forceinline__ uint32_t reverse_start(const uint8_t *__restrict__ text, const uint32_t line_begin,
+                                                  const uint32_t end, const int dist, const Pattern &rpat)
+{
+   const int tau = rpat.tau;
+   BitVec<W> bv;
+   bv_reset(bv, rpat.m);
+   int score = rpat.m;
+   int d = tau + 1, last_d;
+   uint32_t j = 0, skipped = 0;
+   do {
+      j++;
+      const uint8_t c = rpat.cls[__ldg(text + line_begin + end - j)];
+      last_d = d;
+      if ((c & 0x30) == kKindBase) {
+         skipped = 0;
+         uint32_t eq[W];
+#pragma unroll
+         for (int w = 0; w < W; w++) eq[w] = rpat.eq[c & 7][w];
+         uint32_t rise, fall;
+         bv_step<W>(bv, eq, rise, fall);
+         score += (int)rise - (int)fall;
+         d = min(score, tau + 1);
+      } else {
+         skipped++;
+      }
+   } while (d > dist && j < end);
+   j = (last_d < d ? j - 1 : j) - skipped;
+   return end - j;
+}
+
+// ===========================================================================
+// exclusive scan of per-line counts (SQ_ALL): cnt[] -> offs[], totals -> ctr
+// ===========================================================================
+constexpr int kScanItems = 4;
+
+struct ScanArgs {
+   const uint32_t *cnt;
+   uint32_t *offs;
+   uint32_t max_lines;
+   unsigned long long *ctr;
+   unsigned long long *status;
+};
+
+__global__ void __launch_bounds__(kThreads) k_scan_counts(const ScanArgs a)
+{
+   __shared__ BlockScanSmem sc;
+   __shared__ unsigned long long s_base;
+   __shared__ uint32_t s_tile;
+   const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
+   constexpr uint32_t kTile = kThreads * kScanItems;
+   const uint32_t ntiles = (nlines + kTile - 1) / kTile;
+   const int tid = threadIdx.x;
+   while (true) {
+      if (tid == 0) s_tile = (uint32_t)atomicAdd(&a.ctr[C_TICKET_SCAN], 1ull);
+      __syncthreads();
+      const uint32_t tile = s_tile;
+      if (tile >= ntiles) break;
+      const uint32_t i0 = tile * kTile + (uint32_t)tid * kScanItems;
+      uint32_t v[kScanItems];
+      uint32_t sum = 0, nz = 0;
+#pragma unroll
+      for (int k = 0; k < kScanItems; k++) {
+         v[k] = i0 + k < nlines ? a.cnt[i0 + k] : 0u;
+         sum += v[k];
+         nz += v[k] != 0;
+      }
+      uint32_t total;
+      const uint32_t excl = block_exclusive_scan(sum, sc, &total);
+      const unsigned long long base = tile_lookback(a.status, tile, total, &s_base);
+      unsigned long long run = base + excl;
+#pragma unroll
+      for (int k = 0; k < kScanItems; k++) {
+         if (i0 + k < nlines) a.offs[i0 + k] = (uint32_t)run;
+         run += v[k];
+      }
+      // matched lines: plain block reduction
+      uint32_t tnz;
+      (void)block_exclusive_scan(nz, sc, &tnz);
+      if (tid == 0) {
+         if (tnz) atomicAdd(&a.ctr[C_NMATCHED], (unsigned long long)tnz);
+         if (tile == ntiles - 1) a.ctr[C_NRECS] = base + total;
+      }
+   }
+}
+
+// ===========================================================================
+// K3 + K4 for SQ_FIRST / SQ_BEST: one candidate per line
+// ===========================================================================
+struct FinArgs {
+   const uint8_t *text;
+   const uint32_t *ls;
+   uint32_t max_lines;
+   const unsigned long long *res;
+   const uint32_t *offs;          // SQ_ALL only
+   const Event *ev;               // SQ_ALL only
+   uint32_t ev_cap;
+   Rec *recs;
+   uint32_t rec_cap;
+   unsigned long long *ctr;
+   unsigned long long *status;
+};
+
+template <int W>
+__global__ void __launch_bounds__(kThreads) k34_finish_lines(const FinArgs a, const __grid_constant__ Pattern rpat)
+{
+   __shared__ BlockScanSmem sc;
+   __shared__ unsigned long long s_base;
+   __shared__ uint32_t s_tile;
+   const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
+   const uint32_t ntiles = (nlines + kThreads - 1) / kThreads;
+   const int tid = threadIdx.x;
+   while (true) {
+      if (tid == 0) s_tile = (uint32_t)atomicAdd(&a.ctr[C_TICKET_FIN], 1ull);
+      __syncthreads();
+      const uint32_t tile = s_tile;
+      if (tile >= ntiles) break;
+      const uint32_t line = tile * kThreads + tid;
+      unsigned long long key = kNoMatch;
+      if (line < nlines) key = a.res[line];
+      const bool valid = key != kNoMatch;
+      Rec r{};
+      if (valid) {
+         r.line = line;
+         r.end = (uint32_t)key;
+         r.dist = (uint32_t)(key >> 32);
+         r.start = reverse_start<W>(a.text, a.ls[line], r.end, (int)r.dist, rpat);
+      }
+      // ordered compaction: ballot/popc inside the warp, scan across warps,
+      // look-back across tiles
+      uint32_t total;
+      const uint32_t excl = block_exclusive_scan(valid ? 1u : 0u, sc, &total);
+      const unsigned long long base = tile_lookback(a.status, tile, total, &s_base);
+      if (valid && base + excl < a.rec_cap) a.recs[base + excl] = r;
+      if (tile == ntiles - 1 && tid == 0) {
+         a.ctr[C_NMATCHED] = base + total;
+         a.ctr[C_NRECS] = base + total;
+      }
+   }
+}
+
+// K3 + K4 for SQ_ALL: one thread per event, destination offs[line] + rank
+template <int W>
+__global__ void __launch_bounds__(kThreads) k34_finish_events(const FinArgs a, const __grid_constant__ Pattern rpat)
+{
+   unsigned long long nev = a.ctr[C_EVENTS];
+   if (nev > a.ev_cap) nev = a.ev_cap;
+   for (unsigned long long i = (unsigned long long)blockIdx.x * kThreads + threadIdx.x; i < nev;
+        i += (unsigned long long)gridDim.x * kThreads) {
+      const Event e = a.ev[i];
+      Rec r;
+      r.line = e.line;
+      r.end = e.end;
+      r.dist = e.dist;
+      r.start = reverse_start<W>(a.text, a.ls[e.line], e.end, (int)e.dist, rpat);
+      const unsigned long long dst = (unsigned long long)a.offs[e.line] + e.rank;
+      if (dst < a.rec_cap) a.recs[dst] = r;
+   }
+}
+
+}  // namespace sqb

@@ -1,0 +1,61 @@
+/* sqb_private.h -- private layouts behind the public seeq_t / seeqfile_t.
+ *
+ * Both public structs are the FIRST member of a larger object allocated by
+ * seeqNew / seeqOpen, so the ABI seen by callers (field offsets of libseeq.h /
+ * seeq.h) is unchanged while the library keeps its own state behind them.
+ */
+#ifndef SQB_PRIVATE_H_
+#define SQB_PRIVATE_H_
+
+#include "seeq.h"
+#include "seeq_b200.h"
+
+#define SQB_SEEQ_MAGIC 0x5351423230305351ull   /* "SQB200SQ" */
+#define SQB_FILE_MAGIC 0x5351423230304649ull   /* "SQB200FI" */
+
+/* what seeq_t.dfa / .rdfa point to: mimics the head of the reference's dfa_t
+ * {pos, size, maxmemory, state_size, trie*} and trie_t {pos, size, height}
+ * (seeqcore.h:63-84) for callers that peek at it; carries no matcher state */
+typedef struct {
+   size_t  pos, size, maxmemory, state_size;
+   void  * trie;
+   size_t  trie_head[3];
+} sqb_shadow_t;
+
+typedef struct {
+   seeq_t         pub;          /* must be first */
+   unsigned long long magic;
+   sqb_engine_t * engine;       /* created on first use */
+   unsigned long long uid;      /* distinguishes seeq_t objects reusing an address */
+   size_t         maxmemory;
+   sqb_shadow_t   shadow[2];
+} sqb_seeq_t;
+
+/* one resident chunk of the input file and its batch results */
+typedef struct {
+   seeqfile_t     pub;          /* must be first */
+   unsigned long long magic;
+   /* chunk text: buf[0..len) holds whole lines (the last one may lack '\n'
+    * only at end of input); buf[len..fill) is the partial line carried over */
+   char         * buf;
+   size_t         cap, len, fill;
+   int            pinned;
+   int            eof;
+   int            started;      /* at least one chunk was loaded */
+   /* batch results for (res_sq, res_opt) over the resident chunk */
+   unsigned long long res_uid;
+   int            res_opt;
+   int            res_valid;
+   sqb_rec_t    * recs;         size_t nrecs, rec_cap;
+   uint64_t     * lines;        size_t nlines, line_cap;   /* offsets of counted lines */
+   size_t         cur_line;     /* next counted line of the chunk to hand out */
+   size_t         cur_rec;      /* first record with line >= cur_line         */
+   size_t         line_base;    /* counted lines before the resident chunk    */
+   size_t         target;       /* bytes to read per chunk                    */
+   char         * last_header;  /* FASTA: last header seen before the chunk   */
+} sqb_file_t;
+
+int  sqb_parse_pattern (const char * text, char * keys);
+int  sqb_store_matches (seeq_t * sq, const sqb_rec_t * recs, size_t n);
+
+#endif

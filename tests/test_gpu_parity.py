@@ -1,0 +1,163 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the oracle.
+
+Bit-exact comparison of records (line, start, end, dist) and counts on seeded
+inputs for every match mode x non-DNA mode, single- and multi-word patterns,
+plus the known-answer vectors of the reference test-suite through the real
+libseeq entry points.
+"""
+import random
+
+import numpy as np
+import pytest
+
+from oracle.pyoracle import (SQ_ALL, SQ_BEST, SQ_CONVERT, SQ_COUNTLINES, SQ_COUNTMATCH, SQ_FAIL,
+                             SQ_FIRST, SQ_IGNORE, SQ_STREAM)
+
+pytestmark = pytest.mark.gpu
+
+MATCH = [SQ_FIRST, SQ_BEST, SQ_ALL]
+NONDNA = [SQ_FAIL, SQ_CONVERT, SQ_IGNORE]
+
+
+@pytest.fixture(scope="module")
+def B():
+    from seeq_b200 import binding
+    binding.lib()
+    return binding
+
+
+def rand_pattern(rng, mmin, mmax):
+    m = rng.randint(mmin, mmax)
+    out = []
+    for _ in range(m):
+        r = rng.random()
+        if r < 0.08:
+            out.append("N")
+        elif r < 0.2:
+            out.append("[" + "".join(rng.sample("ACGT", rng.randint(1, 3))) + "]")
+        else:
+            out.append(rng.choice("ACGTacgu"))
+    return "".join(out)
+
+
+def plant(rng, pattern_keys, tau):
+    core = []
+    for k in pattern_keys:
+        opts = [c for b, c in ((1, "A"), (2, "C"), (4, "G"), (8, "T")) if k & b]
+        core.append(rng.choice(opts) if opts else "A")
+    for _ in range(rng.randint(0, tau + 1)):
+        if not core:
+            break
+        p = rng.randrange(len(core))
+        op = rng.random()
+        if op < 0.4:
+            core[p] = rng.choice("ACGT")
+        elif op < 0.7:
+            del core[p]
+        else:
+            core.insert(p, rng.choice("ACGT"))
+    return "".join(core)
+
+
+def make_buffer(rng, keys, tau, nlines, maxlen, alphabet, final_newline=True):
+    lines = []
+    for _ in range(nlines):
+        n = rng.randint(0, maxlen)
+        s = "".join(rng.choice(alphabet) for _ in range(n))
+        if rng.random() < 0.4 and n > 0:
+            at = rng.randrange(n)
+            s = s[:at] + plant(rng, keys, tau) + s[at:]
+        lines.append(s)
+    buf = "\n".join(lines)
+    if final_newline and nlines:
+        buf += "\n"
+    return buf.encode()
+
+
+def as_tuples(recs):
+    return [(int(r["line"]) + 1, int(r["start"]), int(r["end"]), int(r["dist"])) for r in recs]
+
+
+def check_buffer(B, oracle, pattern, tau, buf, opt):
+    sq = B.Seeq(pattern, tau)
+    keys = sq.keys
+    okeys, _ = oracle.parse(pattern)
+    assert keys == okeys
+    exp, nl, nm = oracle.buffer_scan(buf, keys, tau, opt)
+    exp = [tuple(int(x) for x in row) for row in exp]
+    st = B.StatsT()
+    flags = B.SQB_FASTA if buf[:1] == b">" else 0
+    got = as_tuples(sq.batch(buf, opt | flags, B.SQ_ANY, st))
+    assert (st.nlines, st.nmatched) == (nl, nm), (pattern, tau, opt)
+    assert got == exp, (pattern, tau, opt, buf[:200])
+    sq.close()
+
+
+@pytest.mark.parametrize("mrange", [(1, 12), (20, 32), (33, 64), (65, 128), (129, 200)])
+def test_buffers_all_modes(B, oracle, mrange):
+    rng = random.Random(mrange[0] * 7919)
+    for it in range(12):
+        pattern = rand_pattern(rng, *mrange)
+        keys, _ = oracle.parse(pattern)
+        tau = rng.randint(0, min(len(keys) - 1, 3 + len(keys) // 12))
+        alphabet = ["ACGT", "ACGTN", "ACGTNXacgu-"][it % 3]
+        buf = make_buffer(rng, keys, tau, rng.randint(1, 700), 90 + 4 * len(keys), alphabet,
+                          final_newline=it % 2 == 0)
+        for mo in MATCH:
+            for nd in NONDNA:
+                check_buffer(B, oracle, pattern, tau, buf, mo | nd)
+
+
+def test_counts(B, oracle):
+    rng = random.Random(4)
+    for it in range(10):
+        pattern = rand_pattern(rng, 4, 40)
+        keys, _ = oracle.parse(pattern)
+        tau = rng.randint(0, min(len(keys) - 1, 4))
+        buf = make_buffer(rng, keys, tau, 900, 160, "ACGTN")
+        sq = B.Seeq(pattern, tau)
+        r_all, _, _ = oracle.buffer_scan(buf, keys, tau, SQ_ALL)
+        _, _, nm = oracle.buffer_scan(buf, keys, tau, SQ_FIRST)
+        assert sq.batch(buf, 0, SQ_COUNTMATCH) == len(r_all)
+        assert sq.batch(buf, 0, SQ_COUNTLINES) == nm
+        sq.close()
+
+
+def test_string_api_fuzz(B, oracle):
+    rng = random.Random(17)
+    for it in range(60):
+        pattern = rand_pattern(rng, 1, 10)
+        keys, _ = oracle.parse(pattern)
+        tau = rng.randint(0, min(3, len(keys) - 1))
+        sq = B.Seeq(pattern, tau)
+        for _ in range(8):
+            text = "".join(rng.choice("ACGTNX\n") for _ in range(rng.randint(0, 70)))
+            for mo in MATCH:
+                for nd in NONDNA:
+                    for stream in (0, SQ_STREAM):
+                        opt = mo | nd | stream
+                        exp = [tuple(int(x) for x in r[1:]) for r in oracle.string_match(text, keys, tau, opt)]
+                        assert sq.string_match(text, opt) == exp, (pattern, tau, text, opt)
+        sq.close()
+
+
+def test_reference_string_vectors(B):
+    # /root/reference/test/testset.c:941-1030 through seeqNew/seeqStringMatch/seeqMatchIter
+    sq = B.Seeq("GATC", 1)
+    text = "TGACTGATGACGTAGTCTACGATCGATCAGTCA"
+    assert sq.string_match(text, SQ_FIRST) == [(1, 4, 1)]
+    assert sq.string_match(text, SQ_BEST) == [(20, 24, 0)]
+    assert sq.string_match(text, SQ_ALL) == [(1, 4, 1), (5, 9, 1), (8, 11, 1), (14, 17, 1),
+                                              (20, 24, 0), (24, 28, 0), (29, 32, 1)]
+    # stored right-to-left: match[0] is the last one (testset.c:961-987)
+    n = sq.L.seeqStringMatch(text.encode(), sq.sq, SQ_ALL)
+    assert n == 7 and sq.sq.contents.hits == 7
+    m = sq.sq.contents.match
+    assert (m[6].start, m[6].end, m[6].dist) == (1, 4, 1)
+    assert (m[0].start, m[0].end, m[0].dist) == (29, 32, 1)
+    sq.close()
+    for tau, text, exp in [(0, "GAAGAAG", [(0, 4, 0), (3, 7, 0)]), (1, "GAAGAAG", [(0, 4, 0), (3, 7, 0)]),
+                           (1, "GAAGACG", [(0, 4, 0), (3, 7, 1)])]:
+        sq = B.Seeq("GAAG", tau)
+        assert sq.string_match(text, SQ_ALL) == exp
+        sq.close()
