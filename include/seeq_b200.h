@@ -104,6 +104,7 @@ void   sqbHostFree  (void * p);
 void * sqbDeviceAlloc (size_t nbytes);    /* plain device memory (benchmarks) */
 void   sqbDeviceFree  (void * p);
 int    sqbMemcpyH2D (void * dst, const void * src, size_t nbytes);
+int    sqbMemcpyD2H (void * dst, const void * src, size_t nbytes);
 
 /* ---- seeq_t level batch entry (the batched analogue of seeqStringMatch) ---- */
 struct seeq_t;

@@ -99,6 +99,7 @@ SYMBOLS = {
     "sqbDeviceAlloc": (C.c_void_p, [C.c_size_t]),
     "sqbDeviceFree": (None, [C.c_void_p]),
     "sqbMemcpyH2D": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "sqbMemcpyD2H": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "seeqBatchMatch": (C.c_long, [_SEEQ, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                   C.POINTER(C.c_void_p), C.POINTER(StatsT)]),
     "seeqEngine": (C.c_void_p, [_SEEQ]),

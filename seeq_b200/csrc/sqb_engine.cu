@@ -677,6 +677,12 @@ int sqbMemcpyH2D(void *dst, const void *src, size_t nbytes)
    return 0;
 }
 
+int sqbMemcpyD2H(void *dst, const void *src, size_t nbytes)
+{
+   CU(cudaMemcpy(dst, src, nbytes, cudaMemcpyDeviceToHost));
+   return 0;
+}
+
 void sqbShardRange(const char *text, size_t nbytes, int rank, int world, size_t *begin, size_t *end)
 {
    size_t cut[2];
