@@ -239,10 +239,7 @@ def main():
     nbytes = rec_bytes * reads
 
     sq = B.Seeq(w["pattern"], w["tau"])
-    eng_ptr = sq.engine()
-    eng = B.Engine.__new__(B.Engine)
-    eng.L, eng.e = L, eng_ptr
-    eng.close = lambda: None
+    eng = B.Engine.borrowed(sq.engine())
 
     # this rank's slice of the global read stream, generated on the device
     stream = torch.cuda.current_stream()

@@ -214,14 +214,22 @@ class Engine:
 
     def __init__(self, keys: bytes, tau: int, device: int = -1):
         self.L = lib()
+        self.owned = True
         self.e = self.L.sqbEngineNew(keys, len(keys), tau, device)
         if not self.e:
             raise RuntimeError("sqbEngineNew failed: " + last_error())
 
+    @classmethod
+    def borrowed(cls, ptr: int) -> "Engine":
+        """View of an engine owned by someone else (a seeq_t: seeqEngine())."""
+        self = cls.__new__(cls)
+        self.L, self.e, self.owned = lib(), ptr, False
+        return self
+
     def close(self):
-        if self.e:
+        if getattr(self, "e", None) and self.owned:
             self.L.sqbEngineFree(self.e)
-            self.e = None
+        self.e = None
 
     __del__ = close
 
