@@ -1,0 +1,201 @@
+// sqb_bitslice.h -- the line-bit-sliced Levenshtein automaton (core of K2).
+//
+// One 32-bit word holds ONE BIT OF STATE FOR 32 DIFFERENT LINES.  The automaton
+// of a line is the column of vertical deltas of the search-type edit-distance
+// matrix (Myers 1999): row j of the pattern contributes two bit-planes, Pv[j]
+// (delta +1) and Mv[j] (delta -1).  Feeding one text column (one byte of each
+// of the 32 lines) walks the rows bottom-up, carrying the horizontal delta:
+//
+//    Xh = Eq | Mh_in          Ph_out = Mv | ~(Xh | Pv)     Mh_out = Pv & Xh
+//    Xv = Eq | Mv             Pv'    = Mh_in | ~(Xv | Ph_in)   Mv' = Ph_in & Xv
+//
+// = 6 three-input logic ops (LOP3) per row for 32 text bytes.  Eq is the class
+// mask of the row: which of the 32 lines carry a byte matching pattern row j.
+// The distance D = value of the last row is kept as a bit-sliced counter and
+// updated with the last row's horizontal delta; the report state machine of
+// the reference (libseeq.c:278-330: streak / match flag / best distance) is
+// evaluated with bitwise logic on those planes, for 32 lines at once.
+//
+// The R >= m rows of a kernel instance are padded AT THE BOTTOM with R-m rows
+// whose Eq is all-ones and whose deltas start at 0: they stay 0 and hand a 0
+// horizontal delta to the first pattern row, which is the free-start boundary
+// of the search recurrence.  The last row is therefore always row R-1.
+//
+// This header compiles for host and device: tests/host_bitslice.cpp runs the
+// same code on the CPU against the oracle.
+#ifndef SQB_BITSLICE_H_
+#define SQB_BITSLICE_H_
+
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define SQB_BS_HD __host__ __device__ __forceinline__
+#else
+#define SQB_BS_HD static inline
+#endif
+
+namespace sqb {
+
+// class codes of the tokenizer (K1), three bit-planes p2 p1 p0
+//   0 A   1 C   2 G   3 T/U   4 N   5 STOP   6 SKIP   7 NULL
+// Eq slots of one text column
+enum BsSlot { BS_A = 0, BS_C, BS_G, BS_T, BS_N, BS_ANY, BS_CUSTOM0, BS_CUSTOM1, BS_ONES, BS_SLOTS };
+
+enum BsMode { BS_FIRST = 0, BS_BEST = 1, BS_ALL = 2 };
+
+constexpr int kBsMaxRows = 32;
+constexpr int kBsBestBits = 4;          // best distance planes: tau + 1 <= 15
+
+struct BsPattern {
+   int32_t  m, tau, rows;               // rows = R of the kernel instance (>= m)
+   uint8_t  slot[kBsMaxRows];           // Eq slot of every row (pad rows: BS_ONES)
+   uint32_t custom[2][5];               // custom classes: all-ones where A,C,G,T,N belongs to the class
+   uint32_t tau_plane[8];               // bit k of tau, replicated: 0 or ~0
+   uint32_t m_plane[8];                 // bit k of m
+   uint32_t best_plane[kBsBestBits];    // bit k of tau + 1
+};
+
+constexpr int bs_score_bits(int R) { return R < 16 ? 4 : (R < 32 ? 5 : 6); }
+
+template <int R> struct BsState {
+   static constexpr int B = bs_score_bits(R);
+   uint32_t pv[R], mv[R];
+   uint32_t s[B];                       // distance of the last row, bit-sliced
+   uint32_t bd[kBsBestBits];            // best distance so far (BS_BEST)
+   uint32_t alive;                      // lines still being scanned
+   uint32_t flag;                       // the reference's `match` suppress flag
+   uint32_t hit;                        // lines with at least one event
+};
+
+template <int R> SQB_BS_HD void bs_reset(BsState<R> &st, const BsPattern &p, uint32_t valid)
+{
+   const int pad = R - p.m;
+#pragma unroll
+   for (int j = 0; j < R; j++) {
+      st.pv[j] = j >= pad ? ~0u : 0u;
+      st.mv[j] = 0u;
+   }
+#pragma unroll
+   for (int k = 0; k < BsState<R>::B; k++) st.s[k] = p.m_plane[k];
+#pragma unroll
+   for (int k = 0; k < kBsBestBits; k++) st.bd[k] = p.best_plane[k];
+   st.alive = valid;
+   st.flag = 0u;
+   st.hit = 0u;
+}
+
+// Eq slots and the class masks of one column from the three code planes
+SQB_BS_HD void bs_classes(uint32_t p0, uint32_t p1, uint32_t p2, const BsPattern &p, uint32_t *slots,
+                          uint32_t &anybase, uint32_t &stop, uint32_t &skip)
+{
+   const uint32_t a = ~p2 & ~p1 & ~p0, c = ~p2 & ~p1 & p0, g = ~p2 & p1 & ~p0, t = ~p2 & p1 & p0;
+   const uint32_t n = p2 & ~p1 & ~p0;
+   slots[BS_A] = a;
+   slots[BS_C] = c;
+   slots[BS_G] = g;
+   slots[BS_T] = t;
+   slots[BS_N] = n;
+   anybase = ~p2 | n;
+   slots[BS_ANY] = anybase;
+   slots[BS_CUSTOM0] = (a & p.custom[0][0]) | (c & p.custom[0][1]) | (g & p.custom[0][2]) | (t & p.custom[0][3]) |
+                       (n & p.custom[0][4]);
+   slots[BS_CUSTOM1] = (a & p.custom[1][0]) | (c & p.custom[1][1]) | (g & p.custom[1][2]) | (t & p.custom[1][3]) |
+                       (n & p.custom[1][4]);
+   slots[BS_ONES] = ~0u;
+   stop = p2 & ~p1 & p0;
+   skip = p2 & p1 & ~p0;
+}
+
+// One text column.  eq(j) returns the Eq mask of row j.  Returns the event mask:
+// bit r set <=> line r reports a match ending at this column with distance
+// `streak` = the value held by st.s BEFORE the call (returned in streak[]).
+template <int R, int MODE, bool SKIP, class EqOf>
+SQB_BS_HD uint32_t bs_step(BsState<R> &st, const BsPattern &p, const EqOf &eq, uint32_t anybase, uint32_t stopc,
+                           uint32_t skipc, uint32_t *streak)
+{
+   constexpr int B = BsState<R>::B;
+   const uint32_t base = anybase & st.alive;      // lines that feed a base to the automaton
+   const uint32_t stop = stopc & st.alive;        // lines that end here
+   (void)skipc;
+
+   // ---- the rows ------------------------------------------------------------
+   uint32_t ph = 0u, mh = 0u;
+#pragma unroll
+   for (int j = 0; j < R; j++) {
+      const uint32_t e = eq(j);
+      const uint32_t pv = st.pv[j], mv = st.mv[j];
+      const uint32_t xh = e | mh;
+      const uint32_t xv = e | mv;
+      const uint32_t ph_out = mv | ~(xh | pv);
+      const uint32_t mh_out = pv & xh;
+      uint32_t pv_new = mh | ~(xv | ph);
+      uint32_t mv_new = ph & xv;
+      if (SKIP) {                                 // an ignored byte leaves the automaton untouched
+         pv_new = (pv & skipc) | (pv_new & ~skipc);
+         mv_new = (mv & skipc) | (mv_new & ~skipc);
+      }
+      st.pv[j] = pv_new;
+      st.mv[j] = mv_new;
+      ph = ph_out;
+      mh = mh_out;
+   }
+
+   // ---- streak = distance before this column: <= tau ?  == 0 ? ---------------
+   uint32_t gt = 0u, nz = 0u;
+#pragma unroll
+   for (int k = 0; k < B; k++) {
+      const uint32_t s = st.s[k], t = p.tau_plane[k];
+      gt = (s & ~t) | (~(s ^ t) & gt);
+      nz |= s;
+      streak[k] = s;
+   }
+   const uint32_t le = ~gt, zero = ~nz;
+
+   // ---- report state machine (libseeq.c:267-330) ------------------------------
+   const uint32_t rise = (ph & base) | stop;      // the capped distance goes up (a terminal byte is tau+1)
+   const uint32_t fall = mh & base;
+   const uint32_t active = base | stop;
+   st.flag &= rise | ~active;                     // :278  any non-rise clears the flag
+   uint32_t evt = active & le & (zero | rise) & ~st.flag;      // :286-288
+   if (MODE == BS_BEST) {
+      uint32_t lt = 0u;                           // streak < best distance (4 low bits decide: streak <= tau)
+#pragma unroll
+      for (int k = 0; k < kBsBestBits; k++) {
+         const uint32_t s = k < B ? st.s[k] : 0u, d = st.bd[k];
+         lt = (~s & d) | (~(s ^ d) & lt);
+      }
+      evt &= lt;
+#pragma unroll
+      for (int k = 0; k < kBsBestBits; k++) {
+         const uint32_t s = k < B ? st.s[k] : 0u;
+         st.bd[k] = (evt & s) | (~evt & st.bd[k]);
+      }
+   }
+   st.flag |= evt;
+   st.hit |= evt;
+   st.alive &= ~stop;
+   if (MODE == BS_FIRST) st.alive &= ~evt;        // :330  the first match ends the scan of the line
+
+   // ---- distance += rise - fall (ripple over the bit-planes) -----------------
+   const uint32_t inc = ph & base;
+   uint32_t carry = inc | fall;
+#pragma unroll
+   for (int k = 0; k < B; k++) {
+      const uint32_t s = st.s[k];
+      st.s[k] = s ^ carry;
+      carry &= s ^ fall;
+   }
+   return evt;
+}
+
+// distance of line r from bit-planes
+template <int B> SQB_BS_HD uint32_t bs_value(const uint32_t *planes, int r)
+{
+   uint32_t v = 0;
+#pragma unroll
+   for (int k = 0; k < B; k++) v |= ((planes[k] >> r) & 1u) << k;
+   return v;
+}
+
+}  // namespace sqb
+#endif

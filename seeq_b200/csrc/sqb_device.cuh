@@ -159,6 +159,44 @@ __device__ __forceinline__ unsigned long long tile_lookback(unsigned long long *
    return r;
 }
 
+// Same, with ONE barrier: the caller provides a broadcast slot that is not
+// reused before the CTA has passed another barrier (e.g. one slot per stage).
+__device__ __forceinline__ unsigned long long tile_lookback1(unsigned long long *status, uint32_t tile,
+                                                             unsigned long long aggregate,
+                                                             unsigned long long *s_base)
+{
+   if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      if (lane == 0)
+         st_status(status + tile, (tile == 0 ? kStPrefix : kStAggregate) | aggregate);
+      unsigned long long excl = 0;
+      if (tile > 0) {
+         long long look = (long long)tile - 1;
+         while (true) {
+            const long long idx = look - lane;
+            unsigned long long w = kStPrefix;
+            if (idx >= 0) {
+               do {
+                  w = ld_status(status + idx);
+               } while ((w >> 62) == 0);
+            }
+            const uint32_t is_prefix = __ballot_sync(kFull, (w >> 62) == 2);
+            const int stop = is_prefix ? __ffs(is_prefix) - 1 : 31;
+            unsigned long long val = lane <= stop ? (w & kStValue) : 0ull;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(kFull, val, d);
+            excl += val;
+            if (is_prefix) break;
+            look -= 32;
+         }
+         if (lane == 0) st_status(status + tile, kStPrefix | (excl + aggregate));
+      }
+      if (lane == 0) *s_base = excl;
+   }
+   __syncthreads();
+   return *s_base;
+}
+
 // ---------------------------------------------------------------------------
 // Myers/Hyyro bit-vector automaton over W 32-bit words held by one thread.
 //

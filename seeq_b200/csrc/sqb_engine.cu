@@ -26,6 +26,7 @@ enum { OPT_MATCH = 0x03, OPT_BEST = 0x01, OPT_ALL = 0x02, OPT_CONVERT = 0x04, OP
 #define SQB_KEEP_LINES_INTERNAL SQB_KEEP_LINES
 
 static thread_local char g_err[512] = "";
+static const unsigned long long kMaxBatch = 0xfff00000ull;     // bytes per device batch (offsets are u32)
 
 static void set_err(const char *fmt, ...)
 {
@@ -51,6 +52,9 @@ struct Slot {
    // device
    uint8_t *d_text = nullptr;   size_t text_cap = 0;      // host path only
    uint32_t *d_ls = nullptr;    size_t line_cap = 0;      // entries (incl. sentinel)
+   uint8_t *d_codes = nullptr;  size_t codes_cap = 0;     // class nibbles (K1 -> bit-sliced K2)
+   uint32_t *d_ls_raw = nullptr; size_t ls_raw_cap = 0;   // line starts in tile-allocation order
+   uint32_t *d_tiles = nullptr; size_t tiles_cap = 0;     // per K1 tile: count, offset, base
    unsigned long long *d_res = nullptr; size_t res_cap = 0;
    uint32_t *d_cnt = nullptr;   size_t cnt_cap = 0;
    uint32_t *d_offs = nullptr;  size_t offs_cap = 0;
@@ -137,6 +141,23 @@ static void build_pattern(const sqb_engine *e, int options, bool reverse, Patter
    }
 }
 
+// byte -> class nibble of the tokenizer (K1); '\n' carries the newline marker (bit 3)
+static void build_class_table(int options, ClassTable *t)
+{
+   const int nondna = options & OPT_NONDNA;
+   for (int b = 0; b < 256; b++) {
+      const int code = b < 128 ? base_code(b) : -1;
+      uint8_t c;
+      if (code >= 0) c = (uint8_t)code;
+      else if (b == 0) c = kClsStop;
+      else if (b == '\n') c = kClsStop | 8;
+      else if (nondna == OPT_CONVERT) c = kClsN;
+      else if (nondna == OPT_IGNORE) c = kClsSkip;
+      else c = kClsStop;
+      t->code[b] = c;
+   }
+}
+
 // ---------------------------------------------------------------------------
 // memory helpers
 // ---------------------------------------------------------------------------
@@ -166,7 +187,7 @@ template <class T> static int pin_reserve(T **p, size_t *cap, size_t need)
 
 static void slot_free(Slot &s)
 {
-   cudaFree(s.d_text); cudaFree(s.d_ls); cudaFree(s.d_res); cudaFree(s.d_cnt); cudaFree(s.d_offs);
+   cudaFree(s.d_text); cudaFree(s.d_ls); cudaFree(s.d_codes); cudaFree(s.d_ls_raw); cudaFree(s.d_tiles); cudaFree(s.d_res); cudaFree(s.d_cnt); cudaFree(s.d_offs);
    cudaFree(s.d_ev); cudaFree(s.d_recs); cudaFree(s.d_ctl);
    cudaFreeHost(s.h_ctr); cudaFreeHost(s.h_recs); cudaFreeHost(s.h_ls); cudaFreeHost(s.h_init);
    for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
@@ -269,6 +290,14 @@ static int launch_finish(const sqb_engine *e, bool all, int grid, cudaStream_t s
 // ---------------------------------------------------------------------------
 static size_t div_up(size_t a, size_t b) { return (a + b - 1) / b; }
 
+// the line-bit-sliced matcher covers short patterns over many lines; everything
+// else (one string, long patterns) runs the thread-per-line / lane-blocked kernels
+static bool use_bitslice(const sqb_engine *e, int options)
+{
+   (void)e; (void)options;
+   return false;
+}
+
 static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n, int options, cudaStream_t st)
 {
    const int mode = mode_of(options);
@@ -285,6 +314,7 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
    size_t want_lines = single ? 2 : (size_t)((double)n * e->lines_per_byte) + 1024;
    if (want_lines > (size_t)n + 2) want_lines = (size_t)n + 2;
    if (dev_reserve(&s.d_ls, &s.line_cap, want_lines)) return -1;
+   if (!single && dev_reserve(&s.d_ls_raw, &s.ls_raw_cap, s.line_cap, 64)) return -1;
    const size_t lines_cap = s.line_cap - 1;                 // one entry is the sentinel
    if (mode == M_FIRST || mode == M_BEST) {
       if (dev_reserve(&s.d_res, &s.res_cap, lines_cap, 64)) return -1;
@@ -319,16 +349,34 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
       s.h_ctr[C_NLINES] = 1;      // reuse pinned word as the source of the line count
       CU(cudaMemcpyAsync(ctr + C_NLINES, s.h_ctr + C_NLINES, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
    } else {
-      K1Args k1{d_text, n, s.d_ls, (uint32_t)s.line_cap, ctr, st_k1, (options & SQB_FASTA) ? 1 : 0};
+      const bool want_codes = use_bitslice(e, options);
+      if (want_codes) {
+         const size_t need = k1_tiles * (kK1Tile / 2) + 256;
+         if (dev_reserve(&s.d_codes, &s.codes_cap, need)) return -1;
+      }
+      if (dev_reserve(&s.d_tiles, &s.tiles_cap, 3 * k1_tiles)) return -1;
+      uint32_t *tile_cnt = s.d_tiles, *tile_off = tile_cnt + k1_tiles, *tile_base = tile_off + k1_tiles;
+      const uint32_t ntiles = (uint32_t)div_up(n, kK1Tile);
+      K1Args k1{d_text, n, s.d_ls_raw, (uint32_t)s.line_cap, want_codes ? (uint2 *)s.d_codes : nullptr, ctr,
+                tile_cnt, tile_off, (options & SQB_FASTA) ? 1 : 0};
+      ClassTable ct;
+      build_class_table(options, &ct);
       static bool attr = false;
       if (!attr) {
-         CU(cudaFuncSetAttribute(k1_line_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kK1Stage)));
+         CU(cudaFuncSetAttribute(k1_scan_classify<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
+         CU(cudaFuncSetAttribute(k1_scan_classify<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
          attr = true;
       }
-      const int grid = (int)std::min<size_t>(div_up(n, kK1Tile), (size_t)e->sms * 4);
-      k1_line_scan<<<grid, kThreads, 2 * kK1Stage, st>>>(k1);
+      const int grid = (int)std::min<size_t>(div_up(n, kK1Tile), (size_t)e->sms * 3);
+      if (want_codes) k1_scan_classify<true><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
+      else k1_scan_classify<false><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
       CU(cudaGetLastError());
-      s.launches++;
+      K1ScanArgs ks{tile_cnt, tile_base, ntiles, ctr};
+      k1_scan_tiles<<<1, 1024, 0, st>>>(ks);
+      K1GatherArgs kg{s.d_ls_raw, s.d_ls, (uint32_t)s.line_cap, tile_cnt, tile_off, tile_base, ntiles, n, ctr};
+      k1_gather<<<(int)std::min<size_t>(div_up(ntiles, kWarps), (size_t)e->sms * 8), kThreads, 0, st>>>(kg);
+      CU(cudaGetLastError());
+      s.launches += 3;
    }
    if (timing) CU(cudaEventRecord(s.ev[1], st));
 
@@ -479,7 +527,7 @@ void sqbEngineFree(sqb_engine_t *e)
 int sqbScanDevice(sqb_engine_t *e, const void *d_text, size_t nbytes, int options, void *stream,
                   sqb_stats_t *stats)
 {
-   if (nbytes >= 0xfffffff0ull) { set_err("sqbScanDevice: %zu bytes exceed the 4 GiB batch limit", nbytes); return -1; }
+   if (nbytes >= kMaxBatch) { set_err("sqbScanDevice: %zu bytes exceed the batch limit of %zu", nbytes, (size_t)kMaxBatch); return -1; }
    if (((uintptr_t)d_text & 15) != 0) { set_err("sqbScanDevice: text pointer must be 16-byte aligned"); return -1; }
    CU(cudaSetDevice(e->device));
    Slot &s = e->slot[0];
@@ -604,7 +652,7 @@ int sqbScanHost(sqb_engine_t *e, const char *text, size_t nbytes, int options, s
             len = nl ? (size_t)(nl - (text + pos)) + 1 : nbytes - pos;
          }
       }
-      if (len >= 0xfffffff0ull) { set_err("a single line of %zu bytes exceeds the 4 GiB batch limit", len); return -1; }
+      if (len >= kMaxBatch) { set_err("a single line of %zu bytes exceeds the batch limit of %zu", len, (size_t)kMaxBatch); return -1; }
       Slot &s = e->slot[c & 1];
       if (pending[c & 1]) {
          if (host_collect(e, s, options, &line_base, &acc)) return -1;

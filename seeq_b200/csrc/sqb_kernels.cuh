@@ -46,6 +46,7 @@ enum Counter {
    C_TICKET_K1 = 4,
    C_TICKET_SCAN = 5,
    C_TICKET_FIN = 6,
+   C_LS_CURSOR = 7,  // K1: allocation cursor into the unordered line-start array
    C_COUNT = 8
 };
 
@@ -63,41 +64,65 @@ struct Rec {          // == sqb_rec_t
 constexpr unsigned long long kNoMatch = ~0ull;
 
 // ===========================================================================
-// K1: newline / line-offset scan
+// K1: line-offset scan + class coding ("tokenizer")
 // ===========================================================================
-constexpr int      kK1Vec  = 4;                              // 16-byte vectors per thread
-constexpr uint32_t kK1Tile = kThreads * kK1Vec * 16;         // 16 KiB of text per tile
-constexpr uint32_t kK1Stage = kK1Tile + 16;                  // + look-ahead for the FASTA test
+// One pass over the text (HBM-bound).  Tiles of 32 KiB are staged into shared
+// memory by TMA bulk copies (two stages, mbarrier), tiles are handed out in
+// ticket order.  Inside a tile warp w owns the 4 KiB [w*4096, (w+1)*4096) and
+// lane l the 16-byte vectors (k*512 + l*16), k = 0..7, so that text order is
+// (warp, k, lane).  Every byte goes through a 256-entry class table held in
+// shared memory, pre-shifted per byte position so that the 16 look-ups of a
+// vector OR together into 16 class nibbles (8 bytes of `codes`).  Bit 3 of a
+// nibble marks '\n', which is all the line scan needs: per-vector newline masks
+// -> popc -> packed warp-shuffle scan -> block totals.  A tile then allocates
+// room for its line starts with ONE atomicAdd on a cursor (no tile waits for
+// another: a decoupled look-back here was measured to stall 58 % of the time)
+// and writes them, ordered inside the tile, into `ls_raw`.  Two tiny kernels
+// finish the job: k1_scan_tiles (exclusive scan of the per-tile counts = first
+// line number of every tile) and k1_gather (moves the tile segments into line
+// order, `ls`).
+//
+// Class nibble (bits 2:0): 0 A, 1 C, 2 G, 3 T/U, 4 N (or any other byte with
+// SQ_CONVERT), 5 STOP (NUL, '\n', other bytes with SQ_FAIL), 6 SKIP (other
+// bytes with SQ_IGNORE), 7 NULL (padding in front of a line; K2 only).
+constexpr int      kK1Vec       = 8;                          // 16-byte vectors per lane and tile
+constexpr uint32_t kK1WarpBytes = kK1Vec * 512;               // 4 KiB of text per warp
+constexpr uint32_t kK1Tile      = kWarps * kK1WarpBytes;      // 32 KiB of text per tile
+constexpr uint32_t kK1Stage     = kK1Tile + 16;               // + look-ahead for the FASTA test
+constexpr uint32_t kK1Smem      = 2 * kK1Stage + 8 * 256 * 4; // stages + pre-shifted class tables
+
+constexpr uint8_t kClsN = 4, kClsStop = 5, kClsSkip = 6, kClsNull = 7;
+
+struct ClassTable {
+   uint8_t code[256];              // class nibble per byte value ('\n' has bit 3 set)
+};
 
 struct K1Args {
    const uint8_t *text;
    uint32_t n;
-   uint32_t *ls;                  // out: start offset of every counted line (+ sentinel n)
-   uint32_t ls_cap;               // capacity of ls (entries); counting continues beyond it
+   uint32_t *ls_raw;              // out: line starts, tile segments in allocation order
+   uint32_t ls_cap;               // capacity of ls_raw / ls (entries); counting continues beyond it
+   uint2 *codes;                  // out: 16 class nibbles per 16 text bytes (nullptr: not wanted)
    unsigned long long *ctr;
-   unsigned long long *status;    // look-back words, one per tile, zeroed
+   uint32_t *tile_cnt;            // out: counted lines starting in each tile
+   uint32_t *tile_off;            // out: where the tile's segment starts in ls_raw
    int fasta;
 };
 
-// exact per-byte equality mask: bit 8k+7 set iff byte k of w equals '\n'
-__device__ __forceinline__ uint32_t newline_bits(uint32_t w)
+template <bool CODES>
+__global__ void __launch_bounds__(kThreads) k1_scan_classify(const K1Args a, const __grid_constant__ ClassTable ct)
 {
-   const uint32_t x = w ^ 0x0A0A0A0Au;
-   return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
-}
-
-__global__ void __launch_bounds__(kThreads) k1_line_scan(const K1Args a)
-{
-   extern __shared__ __align__(128) uint8_t dyn[];            // 2 x kK1Stage
+   extern __shared__ __align__(128) uint8_t dyn[];            // 2 x kK1Stage, then the tables
    __shared__ uint64_t bar[2];
    __shared__ uint32_t s_tile[2];
-   __shared__ uint32_t s_wsum[kK1Vec][kWarps];
-   __shared__ unsigned long long s_base;
+   __shared__ uint32_t s_wsum[kWarps];
+   __shared__ uint32_t s_base[2];
 
    const uint32_t n = a.n;
    const uint32_t ntiles = (n + kK1Tile - 1) / kK1Tile;
    const uint32_t n16 = (n + 15u) & ~15u;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   uint32_t *lut = reinterpret_cast<uint32_t *>(dyn + 2 * kK1Stage);     // [8][256]
 
    auto issue = [&](int stage, uint32_t tile) {
       const uint32_t start = tile * kK1Tile;
@@ -107,6 +132,11 @@ __global__ void __launch_bounds__(kThreads) k1_line_scan(const K1Args a)
       bulk_g2s(dyn + stage * kK1Stage, a.text + start, bytes, &bar[stage]);
    };
 
+   {  // table j holds the class nibble shifted to nibble j of a word
+      const uint32_t c = ct.code[tid];
+#pragma unroll
+      for (int j = 0; j < 8; j++) lut[j * 256 + tid] = c << (4 * j);
+   }
    if (tid == 0) {
       mbar_init(&bar[0], 1);
       mbar_init(&bar[1], 1);
@@ -131,96 +161,189 @@ __global__ void __launch_bounds__(kThreads) k1_line_scan(const K1Args a)
 
       const uint8_t *buf = dyn + stage * kK1Stage;
       const uint32_t tile_start = tile * kK1Tile;
+      const uint32_t woff = (uint32_t)warp * kK1WarpBytes + (uint32_t)lane * 16u;
 
-      // ---- per-thread masks of line starts ---------------------------------
-      uint32_t z[kK1Vec][4];
-      uint32_t c[kK1Vec];
+      // ---- classify, collect newline masks ----------------------------------
+      // nl[k]: bit 4b set <=> byte b (0..7) is '\n', bit 4b+1 <=> byte 8+b is
+      uint32_t nl[kK1Vec];
 #pragma unroll
       for (int k = 0; k < kK1Vec; k++) {
-         const uint32_t voff = (uint32_t)(k * kThreads + tid) * 16u;
-         const uint4 v = *reinterpret_cast<const uint4 *>(buf + voff);
+         const uint32_t off = woff + (uint32_t)k * 512u;
+         const uint4 v = *reinterpret_cast<const uint4 *>(buf + off);
          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-         c[k] = 0;
+         uint32_t lo = 0, hi = 0;
 #pragma unroll
-         for (int q = 0; q < 4; q++) {
-            uint32_t bits = newline_bits(w[q]);
-            // a newline at p opens a line at p+1 only if p+1 < n, and in FASTA
-            // mode only if that line is not a header
-            uint32_t keep = 0;
+         for (int j = 0; j < 8; j++) {
+            const uint32_t x = w[j >> 2], y = w[2 + (j >> 2)];
+            const int r = j & 3;
+            const uint32_t ix = r == 0 ? (x << 2) & 0x3FCu : (x >> (8 * r - 2)) & 0x3FCu;
+            const uint32_t iy = r == 0 ? (y << 2) & 0x3FCu : (y >> (8 * r - 2)) & 0x3FCu;
+            lo |= *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(lut) + j * 1024 + ix);
+            hi |= *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(lut) + j * 1024 + iy);
+         }
+         const uint32_t pos = tile_start + off;
+         if (pos + 16u > n) {               // bytes at or beyond n are STOP and never newlines
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+               if (pos + (uint32_t)j >= n) lo = (lo & ~(0xFu << (4 * j))) | ((uint32_t)kClsStop << (4 * j));
+               if (pos + 8u + (uint32_t)j >= n) hi = (hi & ~(0xFu << (4 * j))) | ((uint32_t)kClsStop << (4 * j));
+            }
+         }
+         if (CODES) a.codes[pos >> 4] = make_uint2(lo, hi);
+         uint32_t m = ((lo >> 3) & 0x11111111u) | ((hi >> 2) & 0x22222222u);
+         // a newline at p opens a line at p+1 only if p+1 < n, and in FASTA mode
+         // only if that line is not a header
+         if (m != 0 && (a.fasta || pos + 17u > n)) {
+            uint32_t bits = m;
             while (bits) {
                const int b = __ffs(bits) - 1;
                bits &= bits - 1;
-               const uint32_t off = voff + (uint32_t)(q * 4 + (b >> 3));   // in tile
-               const uint32_t s = tile_start + off + 1u;
-               if (s < n && !(a.fasta && buf[off + 1u] == '>')) keep |= 1u << b;
+               const uint32_t byte = (uint32_t)(b >> 2) + ((uint32_t)(b & 1) << 3);
+               const uint32_t s = pos + byte + 1u;
+               if (s >= n || (a.fasta && buf[off + byte + 1u] == '>')) m &= ~(1u << b);
             }
-            z[k][q] = keep;
-            c[k] += __popc(keep);
          }
+         nl[k] = m;
       }
       // the first line of the buffer has no newline in front of it
-      uint32_t first = 0;
-      if (tile == 0 && tid == 0 && n > 0 && !(a.fasta && buf[0] == '>')) first = 1;
-      c[0] += first;
+      const uint32_t first = (tile == 0 && tid == 0 && n > 0 && !(a.fasta && buf[0] == '>')) ? 1u : 0u;
 
-      // ---- block prefix in (vector k, thread) order -------------------------
-      uint32_t inc[kK1Vec];
+      // ---- prefix over (warp, k, lane): two 16-bit counts per shuffle ---------
+      uint32_t cnt[kK1Vec / 2];
 #pragma unroll
-      for (int k = 0; k < kK1Vec; k++) {
-         uint32_t x = c[k];
+      for (int h = 0; h < kK1Vec / 2; h++)
+         cnt[h] = (uint32_t)__popc(nl[2 * h]) + ((uint32_t)__popc(nl[2 * h + 1]) << 16);
+      cnt[0] += first;
+      uint32_t inc[kK1Vec / 2];
+#pragma unroll
+      for (int h = 0; h < kK1Vec / 2; h++) {
+         uint32_t x = cnt[h];
 #pragma unroll
          for (int d = 1; d < 32; d <<= 1) {
             const uint32_t t = __shfl_up_sync(kFull, x, d);
             if (lane >= d) x += t;
          }
-         inc[k] = x;
-         if (lane == 31) s_wsum[k][warp] = x;
+         inc[h] = x;
       }
-      __syncthreads();
+      // exclusive offset of vector k of this lane inside the warp
       uint32_t excl[kK1Vec];
       uint32_t run = 0;
 #pragma unroll
-      for (int k = 0; k < kK1Vec; k++) {
-         uint32_t before = 0, tot = 0;
-#pragma unroll
-         for (int w = 0; w < kWarps; w++) {
-            const uint32_t x = s_wsum[k][w];
-            if (w < warp) before += x;
-            tot += x;
-         }
-         excl[k] = run + before + inc[k] - c[k];
-         run += tot;
+      for (int h = 0; h < kK1Vec / 2; h++) {
+         const uint32_t tot = __shfl_sync(kFull, inc[h], 31);
+         const uint32_t e = inc[h] - cnt[h];
+         excl[2 * h] = run + (e & 0xFFFFu);
+         run += tot & 0xFFFFu;
+         excl[2 * h + 1] = run + (e >> 16);
+         run += tot >> 16;
       }
-      const uint32_t tile_total = run;
+      if (lane == 0) s_wsum[warp] = run;
+      __syncthreads();
+      uint32_t before = 0, tile_total = 0;
+#pragma unroll
+      for (int w2 = 0; w2 < kWarps; w2++) {
+         const uint32_t x = s_wsum[w2];
+         if (w2 < warp) before += x;
+         tile_total += x;
+      }
+      if (tid == 0) {
+         const uint32_t at = (uint32_t)atomicAdd(&a.ctr[C_LS_CURSOR], (unsigned long long)tile_total);
+         a.tile_cnt[tile] = tile_total;
+         a.tile_off[tile] = at;
+         s_base[stage] = at;
+      }
+      __syncthreads();
+      const uint32_t base = s_base[stage] + before;
 
-      const unsigned long long base = tile_lookback(a.status, tile, tile_total, &s_base);
-
-      // ---- emit -------------------------------------------------------------
+      // ---- emit (ordered inside the tile) -------------------------------------
 #pragma unroll
       for (int k = 0; k < kK1Vec; k++) {
-         unsigned long long idx = base + excl[k];
+         uint32_t idx = base + excl[k];
          if (k == 0 && first) {
-            if (idx < a.ls_cap) a.ls[idx] = 0;
+            if (idx < a.ls_cap) a.ls_raw[idx] = 0;
             idx++;
          }
-         const uint32_t voff = (uint32_t)(k * kThreads + tid) * 16u;
+         const uint32_t pos = tile_start + woff + (uint32_t)k * 512u;
 #pragma unroll
-         for (int q = 0; q < 4; q++) {
-            uint32_t bits = z[k][q];
+         for (int half = 0; half < 2; half++) {
+            uint32_t bits = nl[k] & (half ? 0x22222222u : 0x11111111u);
             while (bits) {
                const int b = __ffs(bits) - 1;
                bits &= bits - 1;
-               if (idx < a.ls_cap) a.ls[idx] = tile_start + voff + (uint32_t)(q * 4 + (b >> 3)) + 1u;
+               if (idx < a.ls_cap) a.ls_raw[idx] = pos + (uint32_t)(b >> 2) + (uint32_t)(half << 3) + 1u;
                idx++;
             }
          }
       }
-      if (tile == ntiles - 1 && tid == 0) {
-         const unsigned long long total = base + tile_total;
-         a.ctr[C_NLINES] = total;
-         if (total < a.ls_cap) a.ls[total] = n;         // sentinel
+   }
+}
+
+// exclusive scan of the per-tile line counts (one CTA of 1024 threads):
+// tile_base[t] = number of the first line of tile t; total -> ctr[C_NLINES]
+struct K1ScanArgs {
+   const uint32_t *tile_cnt;
+   uint32_t *tile_base;
+   uint32_t ntiles;
+   unsigned long long *ctr;
+};
+
+__global__ void __launch_bounds__(1024) k1_scan_tiles(const K1ScanArgs a)
+{
+   __shared__ unsigned long long s_warp[32];
+   __shared__ unsigned long long s_carry;
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   if (tid == 0) s_carry = 0;
+   __syncthreads();
+   for (uint32_t t0 = 0; t0 < a.ntiles; t0 += 1024) {
+      const uint32_t t = t0 + tid;
+      const unsigned long long v = t < a.ntiles ? a.tile_cnt[t] : 0u;
+      unsigned long long x = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+         const unsigned long long y = __shfl_up_sync(kFull, x, d);
+         if (lane >= d) x += y;
       }
-      __syncthreads();       // stage buffer and s_tile[stage] may now be reused
+      if (lane == 31) s_warp[warp] = x;
+      __syncthreads();
+      unsigned long long before = s_carry, tot = 0;
+      for (int w = 0; w < 32; w++) {
+         const unsigned long long y = s_warp[w];
+         if (w < warp) before += y;
+         tot += y;
+      }
+      // line numbers are u32 (a batch is < 4 GiB of text)
+      if (t < a.ntiles) a.tile_base[t] = (uint32_t)(before + x - v);
+      __syncthreads();
+      if (tid == 0) s_carry += tot;
+      __syncthreads();
+   }
+   if (tid == 0) a.ctr[C_NLINES] = s_carry;
+}
+
+// tile segments of ls_raw -> ls in line order (one warp per tile) + sentinel
+struct K1GatherArgs {
+   const uint32_t *ls_raw;
+   uint32_t *ls;
+   uint32_t ls_cap;
+   const uint32_t *tile_cnt, *tile_off, *tile_base;
+   uint32_t ntiles;
+   uint32_t n;
+   const unsigned long long *ctr;
+};
+
+__global__ void __launch_bounds__(kThreads) k1_gather(const K1GatherArgs a)
+{
+   const int lane = threadIdx.x & 31;
+   const uint32_t wid = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+   const uint32_t nwarps = (gridDim.x * kThreads) >> 5;
+   for (uint32_t t = wid; t < a.ntiles; t += nwarps) {
+      const uint32_t cnt = a.tile_cnt[t], src = a.tile_off[t], dst = a.tile_base[t];
+      for (uint32_t j = lane; j < cnt; j += 32)
+         if (dst + j < a.ls_cap && src + j < a.ls_cap) a.ls[dst + j] = a.ls_raw[src + j];
+   }
+   if (blockIdx.x == 0 && threadIdx.x == 0) {
+      const unsigned long long total = a.ctr[C_NLINES];
+      if (total < a.ls_cap) a.ls[total] = a.n;         // sentinel
    }
 }
 

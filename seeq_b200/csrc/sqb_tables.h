@@ -1,0 +1,110 @@
+// sqb_tables.h -- host-side construction of the tables the kernels consume:
+// the byte -> class nibble table of the tokenizer (K1) and the row / slot
+// description of the bit-sliced matcher (K2).  Plain C++, no CUDA: shared by
+// sqb_engine.cu and the host test harness tests/host_bitslice.cpp.
+#ifndef SQB_TABLES_H_
+#define SQB_TABLES_H_
+
+#include <stdint.h>
+#include <string.h>
+
+#include "sqb_bitslice.h"
+
+namespace sqb {
+
+// option bits of libseeq.h
+enum { OPT_MATCH = 0x03, OPT_BEST = 0x01, OPT_ALL = 0x02, OPT_CONVERT = 0x04, OPT_IGNORE = 0x08,
+       OPT_NONDNA = 0x0C, OPT_STREAM = 0x10 };
+
+constexpr uint8_t kClsN = 4, kClsStop = 5, kClsSkip = 6, kClsNull = 7, kClsNewline = 8;
+
+struct ClassTable {
+   uint8_t code[256];              // class nibble per byte value ('\n' has bit 3 set)
+};
+
+static inline int base_code(int ch)
+{
+   switch (ch) {
+   case 'A': case 'a': return 0;
+   case 'C': case 'c': return 1;
+   case 'G': case 'g': return 2;
+   case 'T': case 't': case 'U': case 'u': return 3;
+   case 'N': case 'n': return 4;
+   default: return -1;
+   }
+}
+
+// Follows seeqcore.h:89-111 + libseeq.c:255-270: NUL and '\n' end the line,
+// any other non-base byte ends it (SQ_FAIL), is a text N (SQ_CONVERT) or is
+// invisible (SQ_IGNORE).  Bytes >= 0x80 are "other" (the reference indexes its
+// table with a signed char there: undefined).
+static inline void build_class_table(int options, ClassTable *t)
+{
+   const int nondna = options & OPT_NONDNA;
+   for (int b = 0; b < 256; b++) {
+      const int code = b < 128 ? base_code(b) : -1;
+      uint8_t c;
+      if (code >= 0) c = (uint8_t)code;
+      else if (b == 0) c = kClsStop;
+      else if (b == '\n') c = kClsStop | kClsNewline;
+      else if (nondna == OPT_CONVERT) c = kClsN;
+      else if (nondna == OPT_IGNORE) c = kClsSkip;
+      else c = kClsStop;
+      t->code[b] = c;
+   }
+}
+
+// rows of the kernel instance that serves a pattern of m positions (0: none)
+static inline int bs_rows_for(int m)
+{
+   static const int buckets[] = {8, 12, 16, 24, 32};
+   for (int b : buckets) if (m <= b) return b;
+   return 0;
+}
+
+// keys: one class byte per pattern position (bit0 A .. bit3 T, 0x1F = N).
+// Returns false if the pattern needs more than two custom classes or does not
+// fit (the caller then uses the word-parallel kernels).
+static inline bool build_bs_pattern(const unsigned char *keys, int m, int tau, BsPattern *p)
+{
+   memset(p, 0, sizeof *p);
+   const int R = bs_rows_for(m);
+   if (R == 0 || tau + 1 > 15) return false;
+   p->m = m;
+   p->tau = tau;
+   p->rows = R;
+   const int pad = R - m;
+   int ncustom = 0;
+   unsigned char custom_key[2] = {0, 0};
+   for (int j = 0; j < R; j++) {
+      if (j < pad) { p->slot[j] = BS_ONES; continue; }
+      const unsigned char k = keys[j - pad] & 0x1F;
+      int slot = -1;
+      switch (k) {
+      case 0x01: slot = BS_A; break;
+      case 0x02: slot = BS_C; break;
+      case 0x04: slot = BS_G; break;
+      case 0x08: slot = BS_T; break;
+      case 0x10: slot = BS_N; break;
+      case 0x1F: slot = BS_ANY; break;
+      default:
+         for (int c = 0; c < ncustom; c++) if (custom_key[c] == k) slot = BS_CUSTOM0 + c;
+         if (slot < 0) {
+            if (ncustom == 2) return false;
+            custom_key[ncustom] = k;
+            for (int b = 0; b < 5; b++) p->custom[ncustom][b] = (k >> b) & 1 ? ~0u : 0u;
+            slot = BS_CUSTOM0 + ncustom++;
+         }
+      }
+      p->slot[j] = (uint8_t)slot;
+   }
+   for (int k = 0; k < 8; k++) {
+      p->tau_plane[k] = (tau >> k) & 1 ? ~0u : 0u;
+      p->m_plane[k] = (m >> k) & 1 ? ~0u : 0u;
+   }
+   for (int k = 0; k < kBsBestBits; k++) p->best_plane[k] = ((tau + 1) >> k) & 1 ? ~0u : 0u;
+   return true;
+}
+
+}  // namespace sqb
+#endif

@@ -1,0 +1,92 @@
+"""CPU: the bit-sliced automaton (seeq_b200/csrc/sqb_bitslice.h, the core of the CUDA
+matcher K2) compiled for the host and driven exactly like the kernel drives it, against
+the oracle: same events (line, end, dist) in every match mode x non-DNA mode."""
+import ctypes as C
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle.pyoracle import SQ_ALL, SQ_BEST, SQ_CONVERT, SQ_FAIL, SQ_FIRST, SQ_IGNORE
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(ROOT, "seeq_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("bs") / "host_bitslice.so")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-I" + CSRC,
+                    os.path.join(HERE, "host_bitslice.cpp"), "-o", so], check=True)
+    L = C.CDLL(so)
+    L.bs_host_scan.restype = C.c_long
+    L.bs_host_scan.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int, C.c_int, C.c_int,
+                               C.POINTER(C.c_uint64), C.c_long]
+    return L
+
+
+def rand_pattern(rng, mmin, mmax, custom=True):
+    m = rng.randint(mmin, mmax)
+    brackets = [rng.sample("ACGT", rng.randint(2, 3)) for _ in range(2)]
+    out = []
+    for _ in range(m):
+        r = rng.random()
+        if r < 0.08:
+            out.append("N")
+        elif r < 0.2 and custom:
+            out.append("[" + "".join(rng.choice(brackets)) + "]")
+        else:
+            out.append(rng.choice("ACGTacgu"))
+    return "".join(out)
+
+
+def make_buffer(rng, nlines, maxlen, alphabet, plant, final_newline):
+    lines = []
+    for _ in range(nlines):
+        n = rng.randint(0, maxlen)
+        s = [rng.choice(alphabet) for _ in range(n)]
+        if rng.random() < 0.5 and n > 0:
+            at = rng.randrange(n)
+            q = list(plant)
+            for _ in range(rng.randint(0, 3)):
+                if q:
+                    k = rng.randrange(len(q))
+                    q[k:k + 1] = rng.choice([[], [rng.choice("ACGT")], [q[k], rng.choice("ACGT")]])
+            s[at:at] = q
+        lines.append("".join(s))
+    buf = "\n".join(lines)
+    if final_newline and nlines:
+        buf += "\n"
+    return buf.encode()
+
+
+@pytest.mark.parametrize("mrange", [(1, 8), (9, 12), (13, 16), (17, 24), (25, 32)])
+def test_bitsliced_events_equal_oracle(harness, oracle, mrange):
+    rng = random.Random(mrange[1] * 31)
+    checked = 0
+    for it in range(30):
+        pattern = rand_pattern(rng, *mrange)
+        keys, _ = oracle.parse(pattern)
+        if not keys:
+            continue
+        tau = rng.randint(0, min(len(keys) - 1, 3 + len(keys) // 8))
+        plant = "".join(rng.choice([c for b, c in ((1, "A"), (2, "C"), (4, "G"), (8, "T")) if k & b] or ["A"])
+                        for k in keys)
+        alphabet = ["ACGT", "ACGTN", "ACGTNXacgu-"][it % 3]
+        buf = make_buffer(rng, rng.randint(1, 150), 60 + 3 * len(keys), alphabet, plant, it % 2 == 0)
+        out = np.zeros((len(buf) + 64, 3), dtype=np.uint64)
+        for mo in (SQ_FIRST, SQ_BEST, SQ_ALL):
+            for nd in (SQ_FAIL, SQ_CONVERT, SQ_IGNORE):
+                n = harness.bs_host_scan(buf, len(buf), keys, len(keys), tau, mo | nd,
+                                         out.ctypes.data_as(C.POINTER(C.c_uint64)), out.shape[0])
+                if n == -1:
+                    continue              # more than two custom classes: not a bit-sliced pattern
+                assert n >= 0
+                exp, _, _ = oracle.buffer_scan(buf, keys, tau, mo | nd)
+                exp = exp[:, [0, 2, 3]]
+                assert np.array_equal(out[:n], exp), (pattern, tau, mo, nd, buf[:120])
+                checked += 1
+    assert checked > 100
