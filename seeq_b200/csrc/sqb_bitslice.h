@@ -48,7 +48,9 @@ constexpr int kBsBestBits = 4;          // best distance planes: tau + 1 <= 15
 
 struct BsPattern {
    int32_t  m, tau, rows;               // rows = R of the kernel instance (>= m)
+   int32_t  ncustom;                    // custom classes in use (0..2)
    uint8_t  slot[kBsMaxRows];           // Eq slot of every row (pad rows: BS_ONES)
+   uint32_t slot_off[kBsMaxRows];       // the same as byte offset slot * 32 lanes * 4 (kernel smem layout)
    uint32_t custom[2][5];               // custom classes: all-ones where A,C,G,T,N belongs to the class
    uint32_t tau_plane[8];               // bit k of tau, replicated: 0 or ~0
    uint32_t m_plane[8];                 // bit k of m

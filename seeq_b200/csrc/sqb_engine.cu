@@ -17,12 +17,10 @@
 #include "seeq_b200.h"
 #include "sqb_gen.h"
 #include "sqb_kernels.cuh"
+#include "sqb_k2_bitslice.cuh"
 
 using namespace sqb;
 
-// option bits of libseeq.h (kept numeric here: this file does not include it)
-enum { OPT_MATCH = 0x03, OPT_BEST = 0x01, OPT_ALL = 0x02, OPT_CONVERT = 0x04, OPT_IGNORE = 0x08,
-       OPT_NONDNA = 0x0C, OPT_STREAM = 0x10 };
 #define SQB_KEEP_LINES_INTERNAL SQB_KEEP_LINES
 
 static thread_local char g_err[512] = "";
@@ -84,6 +82,10 @@ struct sqb_engine {
    int m = 0, tau = 0;
    int words = 1;                 // automaton words: 1, 2, 4, 8, 16 or 32
    unsigned char keys[kMaxWords * 32];
+   bool bs_ok = false;            // the pattern fits the bit-sliced matcher
+   BsGate bs_gate{65536u, 2048u};
+   uint32_t bs_min_bytes = 1u << 20;
+   BsPattern bs_pat;
    Slot slot[2];
    // lines / events per byte seen so far (capacity guesses)
    double lines_per_byte = 1.0 / 24.0;
@@ -98,18 +100,6 @@ struct sqb_engine {
 // ---------------------------------------------------------------------------
 // pattern tables
 // ---------------------------------------------------------------------------
-static int base_code(int ch)
-{
-   switch (ch) {
-   case 'A': case 'a': return 0;
-   case 'C': case 'c': return 1;
-   case 'G': case 'g': return 2;
-   case 'T': case 't': case 'U': case 'u': return 3;
-   case 'N': case 'n': return 4;
-   default: return -1;
-   }
-}
-
 // Forward tables follow seeqcore.h:89-111 + libseeq.c:255-270; in the reverse
 // pass every non-base byte is skipped (libseeq.c:297-311).
 static void build_pattern(const sqb_engine *e, int options, bool reverse, Pattern *p)
@@ -138,23 +128,6 @@ static void build_pattern(const sqb_engine *e, int options, bool reverse, Patter
       else if (nondna == OPT_IGNORE) cls = kKindSkip;
       else cls = kKindStop;
       p->cls[b] = cls;
-   }
-}
-
-// byte -> class nibble of the tokenizer (K1); '\n' carries the newline marker (bit 3)
-static void build_class_table(int options, ClassTable *t)
-{
-   const int nondna = options & OPT_NONDNA;
-   for (int b = 0; b < 256; b++) {
-      const int code = b < 128 ? base_code(b) : -1;
-      uint8_t c;
-      if (code >= 0) c = (uint8_t)code;
-      else if (b == 0) c = kClsStop;
-      else if (b == '\n') c = kClsStop | 8;
-      else if (nondna == OPT_CONVERT) c = kClsN;
-      else if (nondna == OPT_IGNORE) c = kClsSkip;
-      else c = kClsStop;
-      t->code[b] = c;
    }
 }
 
@@ -292,10 +265,50 @@ static size_t div_up(size_t a, size_t b) { return (a + b - 1) / b; }
 
 // the line-bit-sliced matcher covers short patterns over many lines; everything
 // else (one string, long patterns) runs the thread-per-line / lane-blocked kernels
-static bool use_bitslice(const sqb_engine *e, int options)
+static bool use_bitslice(const sqb_engine *e, int options, uint32_t n)
 {
-   (void)e; (void)options;
-   return false;
+   return e->bs_ok && !(options & (SQB_SINGLE_LINE | OPT_STREAM)) && n >= e->bs_min_bytes;
+}
+
+template <int R, int MODE> static int launch_bs2(bool skip, int grid, cudaStream_t st, const K2BsArgs &a, const BsPattern &p)
+{
+   const size_t smem = (MODE == BS_ALL ? sizeof(BsWarpSmemAll) : sizeof(BsWarpSmem)) * kBsWarps;
+   static bool attr = false;
+   if (!attr) {
+      CU(cudaFuncSetAttribute(k2_bitslice<R, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU(cudaFuncSetAttribute(k2_bitslice<R, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+   }
+   if (skip) k2_bitslice<R, MODE, true><<<grid, kBsThreads, smem, st>>>(a, p);
+   else k2_bitslice<R, MODE, false><<<grid, kBsThreads, smem, st>>>(a, p);
+   CU(cudaGetLastError());
+   return 0;
+}
+
+template <int R> static int launch_bs1(int bsmode, bool skip, int grid, cudaStream_t st, const K2BsArgs &a, const BsPattern &p)
+{
+   switch (bsmode) {
+   case BS_FIRST: return launch_bs2<R, BS_FIRST>(skip, grid, st, a, p);
+   case BS_BEST: return launch_bs2<R, BS_BEST>(skip, grid, st, a, p);
+   default: return launch_bs2<R, BS_ALL>(skip, grid, st, a, p);
+   }
+}
+
+static int launch_bitslice(const sqb_engine *e, int mode, int options, size_t max_lines, cudaStream_t st, const K2BsArgs &a)
+{
+   const int bsmode = (mode == M_ALL || mode == M_COUNTALL) ? BS_ALL : (mode == M_BEST ? BS_BEST : BS_FIRST);
+   const bool skip = (options & OPT_NONDNA) == OPT_IGNORE;
+   const int R = e->bs_pat.rows;
+   const int per_sm = R <= 16 ? 4 : 3;
+   const int grid = (int)std::max<size_t>(1, std::min<size_t>(div_up(div_up(max_lines, kBsTileLines), kBsWarps),
+                                                               (size_t)e->sms * per_sm));
+   switch (R) {
+   case 8: return launch_bs1<8>(bsmode, skip, grid, st, a, e->bs_pat);
+   case 12: return launch_bs1<12>(bsmode, skip, grid, st, a, e->bs_pat);
+   case 16: return launch_bs1<16>(bsmode, skip, grid, st, a, e->bs_pat);
+   case 24: return launch_bs1<24>(bsmode, skip, grid, st, a, e->bs_pat);
+   default: return launch_bs1<32>(bsmode, skip, grid, st, a, e->bs_pat);
+   }
 }
 
 static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n, int options, cudaStream_t st)
@@ -349,7 +362,7 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
       s.h_ctr[C_NLINES] = 1;      // reuse pinned word as the source of the line count
       CU(cudaMemcpyAsync(ctr + C_NLINES, s.h_ctr + C_NLINES, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
    } else {
-      const bool want_codes = use_bitslice(e, options);
+      const bool want_codes = use_bitslice(e, options, n);
       if (want_codes) {
          const size_t need = k1_tiles * (kK1Tile / 2) + 256;
          if (dev_reserve(&s.d_codes, &s.codes_cap, need)) return -1;
@@ -386,8 +399,19 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
    build_pattern(e, options, true, &rev);
    const size_t max_lines = single ? 1 : std::min<size_t>(lines_cap, n);
    const int lines_per_cta = e->words <= 2 ? kThreads : kThreads / e->words;
+   const bool bitslice = !single && use_bitslice(e, options, n);
    K2Args k2{d_text, n, s.d_ls, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_ev,
-             (uint32_t)std::min<size_t>(s.ev_cap, 0xffffffffu)};
+             (uint32_t)std::min<size_t>(s.ev_cap, 0xffffffffu), bitslice ? 1 : 0, e->bs_gate};
+   if (bitslice) {
+      // the bit-sliced kernel stores only the lines that match
+      if (mode == M_FIRST || mode == M_BEST)
+         CU(cudaMemsetAsync(s.d_res, 0xFF, std::min<size_t>(lines_cap, (size_t)n + 1) * sizeof(unsigned long long), st));
+      K2BsArgs kb{(const uint2 *)s.d_codes, (uint32_t)(div_up(n, kK1Tile) * (kK1Tile / 16)), n, s.d_ls,
+                  (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_ev, k2.ev_cap,
+                  (mode == M_COUNT || mode == M_COUNTALL) ? 1 : 0, e->bs_gate};
+      if (launch_bitslice(e, mode, options, max_lines, st, kb)) return -1;
+      s.launches++;
+   }
    {
       const int grid = (int)std::min<size_t>(div_up(max_lines, lines_per_cta), (size_t)e->sms * 8);
       if (launch_k2(e, mode, grid, st, k2, fwd)) return -1;
@@ -513,6 +537,13 @@ sqb_engine_t *sqbEngineNew(const unsigned char *keys, int m, int tau, int device
    while (e->words < words) e->words *= 2;
    if (e->words > 2 && e->words < 4) e->words = 4;
    memset(&e->last_stats, 0, sizeof e->last_stats);
+   e->bs_ok = build_bs_pattern(e->keys, m, tau, &e->bs_pat);
+   // test / tuning knobs: SEEQ_B200_MATCHER=word forces the word-parallel kernels,
+   // =bitslice lifts the size thresholds of the bit-sliced one
+   if (const char *mk = getenv("SEEQ_B200_MATCHER")) {
+      if (!strcmp(mk, "word")) e->bs_ok = false;
+      if (!strcmp(mk, "bitslice")) { e->bs_gate = BsGate{1u, 1u << 30}; e->bs_min_bytes = 0; }
+   }
    return e;
 }
 

@@ -16,6 +16,7 @@
 #pragma once
 
 #include "sqb_device.cuh"
+#include "sqb_tables.h"
 
 namespace sqb {
 
@@ -63,6 +64,18 @@ struct Rec {          // == sqb_rec_t
 
 constexpr unsigned long long kNoMatch = ~0ull;
 
+// device-side choice between the bit-sliced matcher (sqb_k2_bitslice.cuh) and the
+// word-parallel ones below: both are launched, exactly one of them does the scan
+struct BsGate {
+   uint32_t min_lines;          // fewer lines do not fill the bit-sliced warps (default 65536)
+   uint32_t max_avg_line;       // bytes; longer lines run thread-per-line (default 2048)
+};
+
+__device__ __forceinline__ bool bs_selected(const BsGate &g, unsigned long long nlines, uint32_t nbytes)
+{
+   return nlines >= g.min_lines && (unsigned long long)nbytes <= nlines * g.max_avg_line;
+}
+
 // ===========================================================================
 // K1: line-offset scan + class coding ("tokenizer")
 // ===========================================================================
@@ -90,12 +103,6 @@ constexpr uint32_t kK1WarpBytes = kK1Vec * 512;               // 4 KiB of text p
 constexpr uint32_t kK1Tile      = kWarps * kK1WarpBytes;      // 32 KiB of text per tile
 constexpr uint32_t kK1Stage     = kK1Tile + 16;               // + look-ahead for the FASTA test
 constexpr uint32_t kK1Smem      = 2 * kK1Stage + 8 * 256 * 4; // stages + pre-shifted class tables
-
-constexpr uint8_t kClsN = 4, kClsStop = 5, kClsSkip = 6, kClsNull = 7;
-
-struct ClassTable {
-   uint8_t code[256];              // class nibble per byte value ('\n' has bit 3 set)
-};
 
 struct K1Args {
    const uint8_t *text;
@@ -362,6 +369,8 @@ struct K2Args {
    uint32_t *cnt;               // M_ALL: per-line event count
    Event *ev;                   // M_ALL: unordered events
    uint32_t ev_cap;
+   int gate;                    // 1: leave the scan to the bit-sliced kernel when it is selected
+   BsGate bs;
 };
 
 template <int W> struct LutEntry;
@@ -461,6 +470,7 @@ __global__ void __launch_bounds__(kThreads) k2_forward_thread(const K2Args a, co
    __shared__ uint64_t bar;
    __shared__ uint32_t s_red[2][kWarps];
 
+   if (a.gate && bs_selected(a.bs, a.ctr[C_NLINES], a.n)) return;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    {  // byte -> (match mask words, kind)
       const uint8_t c = pat.cls[tid];
@@ -550,6 +560,7 @@ __global__ void __launch_bounds__(kThreads) k2_forward_lanes(const K2Args a, con
    __shared__ uint8_t s_cls[256];
    __shared__ uint32_t s_red[2][kWarps];
 
+   if (a.gate && bs_selected(a.bs, a.ctr[C_NLINES], a.n)) return;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const int gl = lane & (G - 1);            // lane inside its group = word index
    const int top = (lane | (G - 1));         // lane holding the most significant word

@@ -77,7 +77,7 @@ static inline bool build_bs_pattern(const unsigned char *keys, int m, int tau, B
    int ncustom = 0;
    unsigned char custom_key[2] = {0, 0};
    for (int j = 0; j < R; j++) {
-      if (j < pad) { p->slot[j] = BS_ONES; continue; }
+      if (j < pad) { p->slot[j] = BS_ONES; continue; }     // rows beyond R stay 0 (unused)
       const unsigned char k = keys[j - pad] & 0x1F;
       int slot = -1;
       switch (k) {
@@ -98,6 +98,8 @@ static inline bool build_bs_pattern(const unsigned char *keys, int m, int tau, B
       }
       p->slot[j] = (uint8_t)slot;
    }
+   p->ncustom = ncustom;
+   for (int j = 0; j < kBsMaxRows; j++) p->slot_off[j] = (uint32_t)p->slot[j] * 32u * 4u;
    for (int k = 0; k < 8; k++) {
       p->tau_plane[k] = (tau >> k) & 1 ? ~0u : 0u;
       p->m_plane[k] = (m >> k) & 1 ? ~0u : 0u;

@@ -27,3 +27,14 @@ def reference():
     if not pyoracle.have_reference():
         pytest.skip("oracle/_ref not built (reference tree absent)")
     return pyoracle.Reference()
+
+
+@pytest.fixture(params=["auto", "bitslice", "word"])
+def matcher(request, monkeypatch):
+    """Which K2 serves the scan: the engine's own choice, the bit-sliced kernel forced
+    (size thresholds lifted) or the word-parallel kernels forced.  Read by sqbEngineNew."""
+    if request.param == "auto":
+        monkeypatch.delenv("SEEQ_B200_MATCHER", raising=False)
+    else:
+        monkeypatch.setenv("SEEQ_B200_MATCHER", request.param)
+    return request.param

@@ -52,7 +52,7 @@ def test_oracle_matches_reference_fixture(B, oracle, name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_cuda_matches_reference_fixture(B, name):
+def test_cuda_matches_reference_fixture(B, name, matcher):
     buf, gold = case_input(B, name)
     case = CASES[name]
     sq = B.Seeq(case["pattern"], case["tau"])

@@ -172,7 +172,7 @@ def test_seeq_cli_errors(testdata):
     assert run_seeq("CACAGAT", testdata, dist=-1)[1:] == (1, 1)
 
 
-def test_iterator_over_many_chunks(B, oracle, tmp_path, monkeypatch):
+def test_iterator_over_many_chunks(B, oracle, tmp_path, monkeypatch, matcher):
     """seeqFileMatch hands out lines one call at a time although the file is matched
     in batches: force tiny chunks so that the walk crosses many chunk boundaries."""
     monkeypatch.setenv("SEEQ_B200_FILE_CHUNK_MB", "1")
@@ -205,7 +205,7 @@ def test_iterator_over_many_chunks(B, oracle, tmp_path, monkeypatch):
         sq.close()
 
 
-def test_sharded_scan_equals_unsharded(B, oracle):
+def test_sharded_scan_equals_unsharded(B, oracle, matcher):
     """Newline-aligned byte ranges scanned independently (one per GPU on the box; here
     one after another on cuda:0) + line-base prefix == the unsharded scan."""
     from seeq_b200 import shard

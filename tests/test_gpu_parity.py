@@ -94,7 +94,7 @@ def check_buffer(B, oracle, pattern, tau, buf, opt):
 
 
 @pytest.mark.parametrize("mrange", [(1, 12), (20, 32), (33, 64), (65, 128), (129, 200)])
-def test_buffers_all_modes(B, oracle, mrange):
+def test_buffers_all_modes(B, oracle, mrange, matcher):
     rng = random.Random(mrange[0] * 7919)
     for it in range(12):
         pattern = rand_pattern(rng, *mrange)
@@ -108,7 +108,7 @@ def test_buffers_all_modes(B, oracle, mrange):
                 check_buffer(B, oracle, pattern, tau, buf, mo | nd)
 
 
-def test_counts(B, oracle):
+def test_counts(B, oracle, matcher):
     rng = random.Random(4)
     for it in range(10):
         pattern = rand_pattern(rng, 4, 40)
