@@ -53,6 +53,8 @@ struct Slot {
    uint8_t *d_codes = nullptr;  size_t codes_cap = 0;     // class nibbles (K1 -> bit-sliced K2)
    uint32_t *d_ls_raw = nullptr; size_t ls_raw_cap = 0;   // line starts in tile-allocation order
    uint32_t *d_tiles = nullptr; size_t tiles_cap = 0;     // per K1 tile: count, offset, base
+   uint4 *d_planes = nullptr;   size_t planes_cap = 0;    // bit-planes, 32 uint4 per tile column
+   uint32_t *d_bstiles = nullptr; size_t bstiles_cap = 0; // per match tile: columns, offset
    unsigned long long *d_res = nullptr; size_t res_cap = 0;
    uint32_t *d_cnt = nullptr;   size_t cnt_cap = 0;
    uint32_t *d_offs = nullptr;  size_t offs_cap = 0;
@@ -83,8 +85,9 @@ struct sqb_engine {
    int words = 1;                 // automaton words: 1, 2, 4, 8, 16 or 32
    unsigned char keys[kMaxWords * 32];
    bool bs_ok = false;            // the pattern fits the bit-sliced matcher
-   BsGate bs_gate{65536u, 2048u};
+   BsGate bs_gate{65536u, 4096u};
    uint32_t bs_min_bytes = 1u << 20;
+   double cols_per_byte = 1.3 / 1024.0;   // tile columns per text byte (plane buffer guess)
    BsPattern bs_pat;
    Slot slot[2];
    // lines / events per byte seen so far (capacity guesses)
@@ -160,7 +163,7 @@ template <class T> static int pin_reserve(T **p, size_t *cap, size_t need)
 
 static void slot_free(Slot &s)
 {
-   cudaFree(s.d_text); cudaFree(s.d_ls); cudaFree(s.d_codes); cudaFree(s.d_ls_raw); cudaFree(s.d_tiles); cudaFree(s.d_res); cudaFree(s.d_cnt); cudaFree(s.d_offs);
+   cudaFree(s.d_text); cudaFree(s.d_ls); cudaFree(s.d_codes); cudaFree(s.d_ls_raw); cudaFree(s.d_tiles); cudaFree(s.d_planes); cudaFree(s.d_bstiles); cudaFree(s.d_res); cudaFree(s.d_cnt); cudaFree(s.d_offs);
    cudaFree(s.d_ev); cudaFree(s.d_recs); cudaFree(s.d_ctl);
    cudaFreeHost(s.h_ctr); cudaFreeHost(s.h_recs); cudaFreeHost(s.h_ls); cudaFreeHost(s.h_init);
    for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
@@ -299,9 +302,10 @@ static int launch_bitslice(const sqb_engine *e, int mode, int options, size_t ma
    const int bsmode = (mode == M_ALL || mode == M_COUNTALL) ? BS_ALL : (mode == M_BEST ? BS_BEST : BS_FIRST);
    const bool skip = (options & OPT_NONDNA) == OPT_IGNORE;
    const int R = e->bs_pat.rows;
-   const int per_sm = R <= 16 ? 4 : 3;
+   int per_sm = R <= 16 ? 4 : 3;
+   if (const char *c = getenv("SEEQ_B200_BS_CTAS")) per_sm = std::max(1, atoi(c));
    const int grid = (int)std::max<size_t>(1, std::min<size_t>(div_up(div_up(max_lines, kBsTileLines), kBsWarps),
-                                                               (size_t)e->sms * per_sm));
+                                                               (size_t)e->sms * per_sm * 2));
    switch (R) {
    case 8: return launch_bs1<8>(bsmode, skip, grid, st, a, e->bs_pat);
    case 12: return launch_bs1<12>(bsmode, skip, grid, st, a, e->bs_pat);
@@ -401,14 +405,28 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
    const int lines_per_cta = e->words <= 2 ? kThreads : kThreads / e->words;
    const bool bitslice = !single && use_bitslice(e, options, n);
    K2Args k2{d_text, n, s.d_ls, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_ev,
-             (uint32_t)std::min<size_t>(s.ev_cap, 0xffffffffu), bitslice ? 1 : 0, e->bs_gate};
+             (uint32_t)std::min<size_t>(s.ev_cap, 0xffffffffu), bitslice ? 1 : 0};
    if (bitslice) {
       // the bit-sliced kernel stores only the lines that match
       if (mode == M_FIRST || mode == M_BEST)
          CU(cudaMemsetAsync(s.d_res, 0xFF, std::min<size_t>(lines_cap, (size_t)n + 1) * sizeof(unsigned long long), st));
-      K2BsArgs kb{(const uint2 *)s.d_codes, (uint32_t)(div_up(n, kK1Tile) * (kK1Tile / 16)), n, s.d_ls,
-                  (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_ev, k2.ev_cap,
-                  (mode == M_COUNT || mode == M_COUNTALL) ? 1 : 0, e->bs_gate};
+      const size_t max_tiles = div_up(lines_cap, kBsTileLines) + 1;
+      if (dev_reserve(&s.d_bstiles, &s.bstiles_cap, 2 * max_tiles)) return -1;
+      const size_t want_cols = (size_t)((double)n * e->cols_per_byte) + 4096;
+      if (dev_reserve(&s.d_planes, &s.planes_cap, want_cols * 32, 16)) return -1;
+      uint32_t *tile_cols = s.d_bstiles, *tile_off = tile_cols + max_tiles;
+      BsPrepArgs bp{s.d_ls, (uint32_t)lines_cap, n, ctr, tile_cols, tile_off, (uint32_t)max_tiles,
+                    (unsigned long long)(s.planes_cap / 32), e->bs_gate};
+      k15_tile_cols<<<(int)std::min<size_t>(div_up(max_tiles, kWarps), (size_t)e->sms * 8), kThreads, 0, st>>>(bp);
+      k15_scan<<<1, 1024, 0, st>>>(bp);
+      BsPackArgs pk{(const uint4 *)s.d_codes, (uint32_t)(div_up(n, kK1Tile) * (kK1Tile / 32)), s.d_ls,
+                    (uint32_t)lines_cap, ctr, tile_cols, tile_off, s.d_planes};
+      k15_pack<<<(int)std::max<size_t>(1, std::min<size_t>(div_up(div_up(max_lines, 64), kWarps), (size_t)e->sms * 16)),
+                 kThreads, 0, st>>>(pk);
+      CU(cudaGetLastError());
+      s.launches += 3;
+      K2BsArgs kb{s.d_planes, tile_cols, tile_off, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_ev, k2.ev_cap,
+                  (mode == M_COUNT || mode == M_COUNTALL) ? 1 : 0};
       if (launch_bitslice(e, mode, options, max_lines, st, kb)) return -1;
       s.launches++;
    }
@@ -453,6 +471,10 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
       bool again = false;
       if (nlines + 1 > s.line_cap) {
          e->lines_per_byte = (double)(nlines + 2) / (double)std::max<uint32_t>(s.cur_n, 1) * 1.05;
+         again = true;
+      }
+      if (s.h_ctr[C_BS_SELECTED] == 2ull) {          // plane buffer too small for the bit-sliced scan
+         e->cols_per_byte = (double)(s.h_ctr[C_BS_COLS] + 64) / (double)std::max<uint32_t>(s.cur_n, 1) * 1.05;
          again = true;
       }
       if (mode == M_ALL && nev > s.ev_cap) {
@@ -542,7 +564,7 @@ sqb_engine_t *sqbEngineNew(const unsigned char *keys, int m, int tau, int device
    // =bitslice lifts the size thresholds of the bit-sliced one
    if (const char *mk = getenv("SEEQ_B200_MATCHER")) {
       if (!strcmp(mk, "word")) e->bs_ok = false;
-      if (!strcmp(mk, "bitslice")) { e->bs_gate = BsGate{1u, 1u << 30}; e->bs_min_bytes = 0; }
+      if (!strcmp(mk, "bitslice")) { e->bs_gate = BsGate{1u, 1u << 30}; e->bs_min_bytes = 1; }
    }
    return e;
 }

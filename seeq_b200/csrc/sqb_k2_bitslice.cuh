@@ -1,24 +1,32 @@
 // sqb_k2_bitslice.cuh -- K2, line-bit-sliced forward matcher (patterns <= 32
 // positions over many short lines; the integer-pipe-lean path).
 //
-// A warp owns a tile of 1024 consecutive lines; in the automaton phase LANE g
-// owns the 32 lines [g*32, g*32+32) of the tile, one bit each (sqb_bitslice.h).
-// The text is consumed as the class nibbles written by K1 (`codes`, 4 bits per
-// text byte).  Work alternates between two phases of 16 text columns:
+// Lines are handled in TILES of 1024 consecutive lines = one warp of the match
+// kernel, in which LANE g owns the 32 lines [g*32, g*32+32) of the tile, one bit
+// each (sqb_bitslice.h).  The text reaches it as bit-planes:
 //
-//   pack   32 rounds; in round i lane L loads the 8 code bytes (16 columns) of
-//          line i*32+L at its 16-byte-aligned position, the warp transposes
-//          the 32x32 bit matrix with a 5-stage shuffle butterfly (twice: two
-//          words), and lane j stores "bit j of all 32 lines" = plane (j&3) of
-//          column (j>>2) of group i to shared memory;
-//   match  lane g reads the three class planes of its group column by column
-//          (conflict-free: row stride 33), derives the Eq slots, and runs one
-//          bs_step per column = 6 LOP3 per pattern row for 32 text bytes.
+//   k15_tile_cols / k15_scan   columns per tile (longest line + 1) and their
+//                              exclusive prefix = where the tile's planes live;
+//                              also the device-side decision whether this scan
+//                              is bit-sliced at all (enough lines, no long line)
+//   k15_pack    a warp takes 64 consecutive lines (2 groups).  Lane L streams
+//               the class nibbles (K1's `codes`) of lines L and 32+L with
+//               16-byte loads, realigns them to the line start with funnel
+//               shifts, and the warp transposes each 32x32 bit block with a
+//               5-stage shuffle butterfly: lane j then holds plane (j&3) of
+//               column (j>>2) for 32 lines.  Stored as planes[tile][column][g]
+//               = {p0,p1,p2,-} (uint4), 32 B per store and column.
+//   k2_bitslice lane g loads ONE uint4 per column (the warp: 512 contiguous
+//               bytes), derives the Eq slots and runs bs_step = 6 LOP3 per
+//               pattern row for 32 text bytes.  Events (rare) leave the
+//               bit-sliced world through a per-lane slow path.
 //
-// Lines do not start 16-byte aligned: the nibbles in front of a line start are
-// forced to the NULL class (no pattern row matches it), which leaves the initial
-// automaton untouched, and the reported end is corrected by (begin & 15).
-// Events (rare) leave the bit-sliced world through a per-lane slow path.
+// A first version fused the pack step into the match kernel (32 lines x 32
+// lanes per warp, 16-column windows through shared memory): parity was green,
+// but every window touched a different 64-byte block of 1024 lines, the
+// working set of the resident warps (155 MB) exceeded L2 and ncu showed 8.5 GB
+// of DRAM reads for 0.75 GB of codes.  Packing line-major in its own kernel
+// keeps the working set at 64 lines per warp and reads every byte once.
 #pragma once
 
 #include <type_traits>
@@ -28,33 +36,101 @@
 
 namespace sqb {
 
-constexpr int kBsWarps   = 4;                       // warps per CTA
+constexpr int kBsWarps   = 4;                       // warps per CTA of the match kernel
 constexpr int kBsThreads = kBsWarps * 32;
-constexpr int kBsCols    = 16;                      // text columns per phase
-constexpr int kBsStride  = 33;                      // padded row of the plane buffer (words)
 constexpr int kBsTileLines = 1024;                  // lines per warp tile
 
-struct K2BsArgs {
-   const uint2 *codes;            // 16 class nibbles per 16 text bytes
-   uint32_t ncode8;               // entries of codes[]
-   uint32_t n;                    // text bytes
+struct BsPrepArgs {
    const uint32_t *ls;
    uint32_t max_lines;
+   uint32_t n;                    // text bytes
    unsigned long long *ctr;
-   unsigned long long *res;       // BS_FIRST / BS_BEST: per-line (dist << 32 | end); preset to kNoMatch
-   uint32_t *cnt;                 // BS_ALL: per-line event count
-   Event *ev;                     // BS_ALL: unordered events
-   uint32_t ev_cap;
-   int count_only;                // counts only: no res / event stores
-   BsGate bs;
+   uint32_t *tile_cols;           // columns of every tile
+   uint32_t *tile_off;            // exclusive prefix of tile_cols
+   uint32_t max_tiles;
+   unsigned long long planes_cap; // columns the plane buffer can hold
+   BsGate gate;
 };
 
-struct BsWarpSmem {
-   uint32_t planes[2][32 * kBsStride];
-   uint32_t slots[BS_SLOTS][32];
-};
-struct BsWarpSmemAll : BsWarpSmem {
-   uint32_t cnt[32 * 32];         // events per line of the tile (BS_ALL)
+// columns of every tile = longest line (with its terminator) + 1; one warp per tile
+__global__ void __launch_bounds__(kThreads) k15_tile_cols(const BsPrepArgs a)
+{
+   const int lane = threadIdx.x & 31;
+   const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
+   const uint32_t ntiles = (nlines + kBsTileLines - 1) / kBsTileLines;
+   const uint32_t wid = (blockIdx.x * kThreads + threadIdx.x) >> 5, nw = (gridDim.x * kThreads) >> 5;
+   for (uint32_t t = wid; t < ntiles; t += nw) {
+      uint32_t mx = 0;
+      const uint32_t l0 = t * kBsTileLines;
+#pragma unroll 4
+      for (int k = 0; k < 32; k++) {
+         const uint32_t l = l0 + (uint32_t)k * 32u + (uint32_t)lane;
+         if (l < nlines) mx = max(mx, a.ls[l + 1] - a.ls[l]);
+      }
+      mx = __reduce_max_sync(kFull, mx);
+      if (lane == 0) a.tile_cols[t] = mx + 1u;
+   }
+}
+
+// exclusive scan of tile_cols (one CTA) and the decision: 1 = bit-sliced scan,
+// 0 = word-parallel kernels, 2 = bit-sliced but the plane buffer is too small
+// (the host repeats the scan with the exact size, ctr[C_BS_COLS])
+__global__ void __launch_bounds__(1024) k15_scan(const BsPrepArgs a)
+{
+   __shared__ unsigned long long s_warp[32];
+   __shared__ uint32_t s_max[32];
+   __shared__ unsigned long long s_carry;
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const unsigned long long nl_dev = a.ctr[C_NLINES];
+   const uint32_t nlines = (uint32_t)min(nl_dev, (unsigned long long)a.max_lines);
+   const uint32_t ntiles = (nlines + kBsTileLines - 1) / kBsTileLines;
+   if (tid == 0) s_carry = 0;
+   __syncthreads();
+   uint32_t mymax = 0;
+   for (uint32_t t0 = 0; t0 < ntiles; t0 += 1024) {
+      const uint32_t t = t0 + tid;
+      const unsigned long long v = t < ntiles ? a.tile_cols[t] : 0u;
+      mymax = max(mymax, (uint32_t)v);
+      unsigned long long x = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+         const unsigned long long y = __shfl_up_sync(kFull, x, d);
+         if (lane >= d) x += y;
+      }
+      if (lane == 31) s_warp[warp] = x;
+      __syncthreads();
+      unsigned long long before = s_carry, tot = 0;
+      for (int w = 0; w < 32; w++) {
+         const unsigned long long y = s_warp[w];
+         if (w < warp) before += y;
+         tot += y;
+      }
+      if (t < ntiles) a.tile_off[t] = (uint32_t)(before + x - v);      // total <= text bytes < 2^32
+      __syncthreads();
+      if (tid == 0) s_carry += tot;
+      __syncthreads();
+   }
+   mymax = __reduce_max_sync(kFull, mymax);
+   if (lane == 0) s_max[warp] = mymax;
+   __syncthreads();
+   if (tid == 0) {
+      uint32_t mx = 0;
+      for (int w = 0; w < 32; w++) mx = max(mx, s_max[w]);
+      const unsigned long long cols = s_carry;
+      const bool want = nl_dev <= a.max_lines && nl_dev >= a.gate.min_lines && mx <= a.gate.max_line + 1u;
+      a.ctr[C_BS_COLS] = cols;
+      a.ctr[C_BS_SELECTED] = !want ? 0ull : (cols <= a.planes_cap ? 1ull : 2ull);
+   }
+}
+
+struct BsPackArgs {
+   const uint4 *codes;            // 32 class nibbles per 16 bytes
+   uint32_t ncode16;              // entries of codes[]
+   const uint32_t *ls;
+   uint32_t max_lines;
+   const unsigned long long *ctr;
+   const uint32_t *tile_cols, *tile_off;
+   uint4 *planes;                 // [tile_off + column][32 groups] {p0, p1, p2, -}
 };
 
 // 32x32 bit transpose across the warp: on return lane j holds, in bit i, bit j
@@ -69,23 +145,51 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, const uint32_t 
    return x;
 }
 
-template <int R, int MODE, bool SKIP>
-__global__ void __launch_bounds__(kBsThreads, R <= 16 ? 4 : 3)
-k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
+// nibble stream of one line, realigned: every call returns the next 32 nibbles
+// (128 bits) starting at the line start
+struct NibbleStream {
+   const uint4 *codes;
+   uint32_t chunk, last;          // next 16-byte chunk to load, last valid chunk
+   uint32_t ws, bs;               // word and bit shift of the line start inside its first chunk
+   uint4 prev;
+   bool valid;
+
+   __device__ __forceinline__ void open(const uint4 *c, uint32_t ncode16, uint32_t begin, bool ok)
+   {
+      codes = c;
+      last = ncode16 - 1u;
+      valid = ok;
+      chunk = min(begin >> 5, last);
+      ws = (begin & 31u) >> 3;
+      bs = (begin & 7u) * 4u;
+      prev = valid ? codes[chunk] : make_uint4(0x55555555u, 0x55555555u, 0x55555555u, 0x55555555u);
+      chunk = min(chunk + 1u, last);
+   }
+   __device__ __forceinline__ void next(uint32_t (&out)[4])
+   {
+      uint4 cur = prev;
+      if (valid) cur = codes[chunk];
+      chunk = min(chunk + 1u, last);
+      const uint32_t w[8] = {prev.x, prev.y, prev.z, prev.w, cur.x, cur.y, cur.z, cur.w};
+      uint32_t u[5];
+#pragma unroll
+      for (int i = 0; i < 5; i++) {
+         const uint32_t lo = (ws & 1u) ? w[i + 1] : w[i];
+         const uint32_t hi = (ws & 1u) ? w[i + 3] : w[i + 2];
+         u[i] = (ws & 2u) ? hi : lo;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) out[i] = __funnelshift_r(u[i], u[i + 1], bs);
+      prev = cur;
+   }
+};
+
+__global__ void __launch_bounds__(kThreads) k15_pack(const BsPackArgs a)
 {
-   using Smem = typename std::conditional<MODE == BS_ALL, BsWarpSmemAll, BsWarpSmem>::type;
-   extern __shared__ __align__(16) uint8_t dyn[];
-   __shared__ uint32_t s_red[2][kBsWarps];
-
-   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-   Smem &sm = reinterpret_cast<Smem *>(dyn)[warp];
-
-   const unsigned long long nl_dev = a.ctr[C_NLINES];
-   if (!bs_selected(a.bs, nl_dev, a.n)) return;                 // the word-parallel kernel takes this scan
-   const uint32_t nlines = (uint32_t)min(nl_dev, (unsigned long long)a.max_lines);
-   const uint32_t ntiles = (nlines + kBsTileLines - 1) / kBsTileLines;
-
-   // per-lane constants of the transpose butterfly
+   if (a.ctr[C_BS_SELECTED] != 1ull) return;
+   const int lane = threadIdx.x & 31;
+   const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
+   const uint32_t npairs = (nlines + 63u) / 64u;
    uint32_t keep[5], rot[5];
    {
       const uint32_t m[5] = {0x0000FFFFu, 0x00FF00FFu, 0x0F0F0F0Fu, 0x33333333u, 0x55555555u};
@@ -96,6 +200,72 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
          rot[s] = (lane & d) ? 32u - d : d;
       }
    }
+   const uint32_t wid = (blockIdx.x * kThreads + threadIdx.x) >> 5, nw = (gridDim.x * kThreads) >> 5;
+   for (uint32_t pair = wid; pair < npairs; pair += nw) {
+      const uint32_t tile = pair >> 4;                          // 16 pairs of groups per tile
+      const uint32_t g0 = (pair & 15u) * 2u;                    // even group of the pair inside the tile
+      const uint32_t ncols = a.tile_cols[tile];
+      uint4 *out = a.planes + (size_t)a.tile_off[tile] * 32u;
+      const uint32_t la = pair * 64u + (uint32_t)lane, lb = la + 32u;
+      NibbleStream sa, sb;
+      sa.open(a.codes, a.ncode16, la < nlines ? a.ls[la] : 0u, la < nlines);
+      sb.open(a.codes, a.ncode16, lb < nlines ? a.ls[lb] : 0u, lb < nlines);
+      // what this lane stores per 8-column block: 8 bytes = two planes of one group
+      //   even lanes: group g0,     planes (j&2), (j&2)+1 of column j>>2
+      //   odd  lanes: group g0 + 1, the same planes
+      const uint32_t slot16 = (g0 + (uint32_t)(lane & 1)) * 2u + (uint32_t)((lane >> 1) & 1);   // in 8-byte units
+      for (uint32_t c0 = 0; c0 < ncols; c0 += 32) {
+         uint32_t wa[4], wb[4];
+         sa.next(wa);
+         sb.next(wb);
+#pragma unroll
+         for (int k = 0; k < 4; k++) {
+            const uint32_t ta = warp_transpose32(wa[k], keep, rot);
+            const uint32_t tb = warp_transpose32(wb[k], keep, rot);
+            // lane j holds plane (j&3) of column (j>>2): pair up planes 0|1 and 2|3
+            const uint32_t give = (lane & 1) ? ta : tb;
+            const uint32_t got = __shfl_xor_sync(kFull, give, 1);
+            const uint2 v = (lane & 1) ? make_uint2(got, tb) : make_uint2(ta, got);
+            const uint32_t col = c0 + 8u * (uint32_t)k + (uint32_t)(lane >> 2);
+            if (col < ncols) reinterpret_cast<uint2 *>(out + (size_t)col * 32u)[slot16] = v;
+         }
+      }
+   }
+}
+
+struct K2BsArgs {
+   const uint4 *planes;
+   const uint32_t *tile_cols, *tile_off;
+   uint32_t max_lines;
+   unsigned long long *ctr;
+   unsigned long long *res;       // BS_FIRST / BS_BEST: per-line (dist << 32 | end); preset to kNoMatch
+   uint32_t *cnt;                 // BS_ALL: per-line event count
+   Event *ev;                     // BS_ALL: unordered events
+   uint32_t ev_cap;
+   int count_only;                // counts only: no res / event stores
+};
+
+struct BsWarpSmem {
+   uint32_t slots[BS_SLOTS][32];
+};
+struct BsWarpSmemAll : BsWarpSmem {
+   uint32_t cnt[32 * 32];         // events per line of the tile (BS_ALL)
+};
+
+template <int R, int MODE, bool SKIP>
+__global__ void __launch_bounds__(kBsThreads, R <= 16 ? 4 : 3)
+k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
+{
+   using Smem = typename std::conditional<MODE == BS_ALL, BsWarpSmemAll, BsWarpSmem>::type;
+   extern __shared__ __align__(128) uint8_t dyn[];
+   __shared__ uint32_t s_red[2][kBsWarps];
+
+   if (a.ctr[C_BS_SELECTED] != 1ull) return;              // the word-parallel kernel takes this scan
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   Smem &sm = reinterpret_cast<Smem *>(dyn)[warp];
+   const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
+   const uint32_t ntiles = (nlines + kBsTileLines - 1) / kBsTileLines;
+
    sm.slots[BS_ONES][lane] = ~0u;
    const uint32_t *slot_base = &sm.slots[0][lane];
    constexpr int B = BsState<R>::B;
@@ -113,105 +283,81 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
          for (int i = 0; i < 32; i++) static_cast<BsWarpSmemAll &>(sm).cnt[i * 32 + lane] = 0u;
       }
       uint32_t lane_events = 0;
+      const uint32_t ncols = a.tile_cols[tile];
+      const uint4 *col = a.planes + (size_t)a.tile_off[tile] * 32u + lane;
 
-      for (uint32_t col0 = 0; __any_sync(kFull, st.alive != 0u); col0 += kBsCols) {
-         // ---- pack: 32 rounds, lane = line of the round --------------------------
-         __syncwarp();
-#pragma unroll 4
-         for (int i = 0; i < 32; i++) {
-            const uint32_t line = line0 + (uint32_t)i * 32u + (uint32_t)lane;
-            uint2 v = make_uint2(0x55555555u, 0x55555555u);            // STOP
-            if (line < nlines) {
-               const uint32_t begin = a.ls[line];
-               const uint32_t at = min((begin >> 4) + (col0 >> 4), a.ncode8 - 1u);
-               v = a.codes[at];
-               if (col0 == 0) {                   // NULL class in front of the line start
-                  const uint32_t o = begin & 15u;
-                  const uint32_t lo = o >= 8u ? ~0u : ((1u << (4u * o)) - 1u);
-                  const uint32_t hi = o > 8u ? ((1u << (4u * (o - 8u))) - 1u) : 0u;
-                  v.x |= 0x77777777u & lo;
-                  v.y |= 0x77777777u & hi;
-               }
-            }
-            sm.planes[0][i * kBsStride + lane] = warp_transpose32(v.x, keep, rot);
-            sm.planes[1][i * kBsStride + lane] = warp_transpose32(v.y, keep, rot);
-         }
-         __syncwarp();
-
-         // ---- match: lane = group of 32 lines -------------------------------------
+      uint4 nxt = col[0];                                         // ncols >= 1
 #pragma unroll 1
-         for (int c = 0; c < kBsCols; c++) {
-            if (c && !__any_sync(kFull, st.alive != 0u)) break;
-            const uint32_t *pl = &sm.planes[c >> 3][lane * kBsStride + 4 * (c & 7)];
-            const uint32_t p0 = pl[0], p1 = pl[1], p2 = pl[2];
-            uint32_t anybase, stop, skip;
-            {
-               const uint32_t na = ~p2 & ~p1 & ~p0, nc = ~p2 & ~p1 & p0, ng = ~p2 & p1 & ~p0, nt = ~p2 & p1 & p0;
-               const uint32_t nn = p2 & ~p1 & ~p0;
-               anybase = ~p2 | nn;
-               stop = p2 & ~p1 & p0;
-               skip = p2 & p1 & ~p0;
-               sm.slots[BS_A][lane] = na;
-               sm.slots[BS_C][lane] = nc;
-               sm.slots[BS_G][lane] = ng;
-               sm.slots[BS_T][lane] = nt;
-               sm.slots[BS_N][lane] = nn;
-               sm.slots[BS_ANY][lane] = anybase;
-               if (pat.ncustom > 0)
-                  sm.slots[BS_CUSTOM0][lane] = (na & pat.custom[0][0]) | (nc & pat.custom[0][1]) |
-                                               (ng & pat.custom[0][2]) | (nt & pat.custom[0][3]) |
-                                               (nn & pat.custom[0][4]);
-               if (pat.ncustom > 1)
-                  sm.slots[BS_CUSTOM1][lane] = (na & pat.custom[1][0]) | (nc & pat.custom[1][1]) |
-                                               (ng & pat.custom[1][2]) | (nt & pat.custom[1][3]) |
-                                               (nn & pat.custom[1][4]);
-            }
-            uint32_t streak[B];
-            auto eq = [&](int j) -> uint32_t {
-               return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(slot_base) + pat.slot_off[j]);
-            };
-            const uint32_t evt = bs_step<R, MODE, SKIP>(st, pat, eq, anybase, stop, skip, streak);
+      for (uint32_t c = 0; c < ncols; c++) {
+         if (!__any_sync(kFull, st.alive != 0u)) break;
+         const uint4 cur = nxt;
+         if (c + 1 < ncols) nxt = col[(size_t)(c + 1) * 32u];
+         const uint32_t p0 = cur.x, p1 = cur.y, p2 = cur.z;
+         uint32_t anybase, stop, skip;
+         {
+            const uint32_t na = ~p2 & ~p1 & ~p0, nc = ~p2 & ~p1 & p0, ng = ~p2 & p1 & ~p0, nt = ~p2 & p1 & p0;
+            const uint32_t nn = p2 & ~p1 & ~p0;
+            anybase = ~p2 | nn;
+            stop = p2 & ~p1 & p0;
+            skip = p2 & p1 & ~p0;
+            sm.slots[BS_A][lane] = na;
+            sm.slots[BS_C][lane] = nc;
+            sm.slots[BS_G][lane] = ng;
+            sm.slots[BS_T][lane] = nt;
+            sm.slots[BS_N][lane] = nn;
+            sm.slots[BS_ANY][lane] = anybase;
+            if (pat.ncustom > 0)
+               sm.slots[BS_CUSTOM0][lane] = (na & pat.custom[0][0]) | (nc & pat.custom[0][1]) |
+                                            (ng & pat.custom[0][2]) | (nt & pat.custom[0][3]) |
+                                            (nn & pat.custom[0][4]);
+            if (pat.ncustom > 1)
+               sm.slots[BS_CUSTOM1][lane] = (na & pat.custom[1][0]) | (nc & pat.custom[1][1]) |
+                                            (ng & pat.custom[1][2]) | (nt & pat.custom[1][3]) |
+                                            (nn & pat.custom[1][4]);
+         }
+         uint32_t streak[B];
+         auto eq = [&](int j) -> uint32_t {
+            return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(slot_base) + pat.slot_off[j]);
+         };
+         const uint32_t evt = bs_step<R, MODE, SKIP>(st, pat, eq, anybase, stop, skip, streak);
 
-            // ---- events leave the bit-sliced world here (rare) ---------------------
-            if (MODE == BS_ALL) {
-               if (__any_sync(kFull, evt != 0u)) {
-                  // warp-aggregated room for the events of this column
-                  const uint32_t ne = (uint32_t)__popc(evt);
-                  uint32_t inc = ne;
+         // ---- events leave the bit-sliced world here (rare) ---------------------
+         if (MODE == BS_ALL) {
+            if (__any_sync(kFull, evt != 0u)) {
+               // warp-aggregated room for the events of this column
+               const uint32_t ne = (uint32_t)__popc(evt);
+               uint32_t inc = ne;
 #pragma unroll
-                  for (int d = 1; d < 32; d <<= 1) {
-                     const uint32_t t = __shfl_up_sync(kFull, inc, d);
-                     if (lane >= d) inc += t;
-                  }
-                  unsigned long long base = 0;
-                  if (!a.count_only) {
-                     if (lane == 31) base = atomicAdd(&a.ctr[C_EVENTS], (unsigned long long)inc);
-                     base = __shfl_sync(kFull, base, 31);
-                  }
-                  unsigned long long idx = base + inc - ne;
-                  uint32_t e = evt;
-                  while (e) {
-                     const int r = __ffs(e) - 1;
-                     e &= e - 1;
-                     const uint32_t line = line0 + (uint32_t)lane * 32u + (uint32_t)r;
-                     const uint32_t rank = static_cast<BsWarpSmemAll &>(sm).cnt[lane * 32 + r]++;
-                     if (!a.count_only) {
-                        const uint32_t end = col0 + (uint32_t)c - (a.ls[line] & 15u);
-                        if (idx < a.ev_cap) a.ev[idx] = Event{line, rank, end, bs_value<B>(streak, r)};
-                        idx++;
-                     }
-                  }
-                  lane_events += ne;
+               for (int d = 1; d < 32; d <<= 1) {
+                  const uint32_t t = __shfl_up_sync(kFull, inc, d);
+                  if (lane >= d) inc += t;
                }
-            } else if (evt != 0u && !a.count_only) {
+               unsigned long long base = 0;
+               if (!a.count_only) {
+                  if (lane == 31) base = atomicAdd(&a.ctr[C_EVENTS], (unsigned long long)inc);
+                  base = __shfl_sync(kFull, base, 31);
+               }
+               unsigned long long idx = base + inc - ne;
                uint32_t e = evt;
                while (e) {
                   const int r = __ffs(e) - 1;
                   e &= e - 1;
                   const uint32_t line = line0 + (uint32_t)lane * 32u + (uint32_t)r;
-                  const uint32_t end = col0 + (uint32_t)c - (a.ls[line] & 15u);
-                  a.res[line] = ((unsigned long long)bs_value<B>(streak, r) << 32) | end;
+                  const uint32_t rank = static_cast<BsWarpSmemAll &>(sm).cnt[lane * 32 + r]++;
+                  if (!a.count_only) {
+                     if (idx < a.ev_cap) a.ev[idx] = Event{line, rank, c, bs_value<B>(streak, r)};
+                     idx++;
+                  }
                }
+               lane_events += ne;
+            }
+         } else if (evt != 0u && !a.count_only) {
+            uint32_t e = evt;
+            while (e) {
+               const int r = __ffs(e) - 1;
+               e &= e - 1;
+               const uint32_t line = line0 + (uint32_t)lane * 32u + (uint32_t)r;
+               a.res[line] = ((unsigned long long)bs_value<B>(streak, r) << 32) | c;
             }
          }
       }

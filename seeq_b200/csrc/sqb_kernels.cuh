@@ -48,7 +48,9 @@ enum Counter {
    C_TICKET_SCAN = 5,
    C_TICKET_FIN = 6,
    C_LS_CURSOR = 7,  // K1: allocation cursor into the unordered line-start array
-   C_COUNT = 8
+   C_BS_SELECTED = 8,// 1: the bit-sliced matcher serves this scan, 0: the word-parallel one, 2: planes too small
+   C_BS_COLS = 9,    // tile columns the plane buffer must hold
+   C_COUNT = 12
 };
 
 struct Event {        // SQ_ALL: one forward event, unordered
@@ -68,13 +70,8 @@ constexpr unsigned long long kNoMatch = ~0ull;
 // word-parallel ones below: both are launched, exactly one of them does the scan
 struct BsGate {
    uint32_t min_lines;          // fewer lines do not fill the bit-sliced warps (default 65536)
-   uint32_t max_avg_line;       // bytes; longer lines run thread-per-line (default 2048)
+   uint32_t max_line;           // bytes; inputs with a longer line run thread-per-line (default 4096)
 };
-
-__device__ __forceinline__ bool bs_selected(const BsGate &g, unsigned long long nlines, uint32_t nbytes)
-{
-   return nlines >= g.min_lines && (unsigned long long)nbytes <= nlines * g.max_avg_line;
-}
 
 // ===========================================================================
 // K1: line-offset scan + class coding ("tokenizer")
@@ -370,7 +367,6 @@ struct K2Args {
    Event *ev;                   // M_ALL: unordered events
    uint32_t ev_cap;
    int gate;                    // 1: leave the scan to the bit-sliced kernel when it is selected
-   BsGate bs;
 };
 
 template <int W> struct LutEntry;
@@ -470,7 +466,7 @@ __global__ void __launch_bounds__(kThreads) k2_forward_thread(const K2Args a, co
    __shared__ uint64_t bar;
    __shared__ uint32_t s_red[2][kWarps];
 
-   if (a.gate && bs_selected(a.bs, a.ctr[C_NLINES], a.n)) return;
+   if (a.gate && a.ctr[C_BS_SELECTED] != 0ull) return;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    {  // byte -> (match mask words, kind)
       const uint8_t c = pat.cls[tid];
@@ -560,7 +556,7 @@ __global__ void __launch_bounds__(kThreads) k2_forward_lanes(const K2Args a, con
    __shared__ uint8_t s_cls[256];
    __shared__ uint32_t s_red[2][kWarps];
 
-   if (a.gate && bs_selected(a.bs, a.ctr[C_NLINES], a.n)) return;
+   if (a.gate && a.ctr[C_BS_SELECTED] != 0ull) return;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const int gl = lane & (G - 1);            // lane inside its group = word index
    const int top = (lane | (G - 1));         // lane holding the most significant word
