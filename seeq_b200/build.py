@@ -30,8 +30,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 CU_SOURCES = ["sqb_engine.cu"]
 C_SOURCES = ["seeq_api.c", "seeq_file.c"]
-HEADERS = [os.path.join(CSRC, h) for h in
-           ("sqb_device.cuh", "sqb_kernels.cuh", "sqb_gen.h", "sqb_private.h")] + \
+HEADERS = sorted(os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".h", ".cuh"))) + \
           [os.path.join(INC, h) for h in ("libseeq.h", "seeq.h", "seeq_b200.h")]
 
 

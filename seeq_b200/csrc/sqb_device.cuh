@@ -15,6 +15,14 @@ constexpr int kThreads   = 256;          // threads per CTA in every kernel
 constexpr int kWarps     = kThreads / 32;
 constexpr uint32_t kFull = 0xffffffffu;
 
+// a * b + c on the FMA pipe (IMAD), leaving the ALU pipe to the logic ops
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+   uint32_t d;
+   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+   return d;
+}
+
 // ---------------------------------------------------------------------------
 // mbarrier + bulk async copy (SASS: SYNCS.*, UBLKCP)
 // ---------------------------------------------------------------------------

@@ -39,6 +39,7 @@ namespace sqb {
 constexpr int kBsWarps   = 4;                       // warps per CTA of the match kernel
 constexpr int kBsThreads = kBsWarps * 32;
 constexpr int kBsTileLines = 1024;                  // lines per warp tile
+constexpr int kBsBlock   = 4;                       // columns per prefetch block of the match kernel
 
 struct BsPrepArgs {
    const uint32_t *ls;
@@ -286,12 +287,25 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
       const uint32_t ncols = a.tile_cols[tile];
       const uint4 *col = a.planes + (size_t)a.tile_off[tile] * 32u + lane;
 
-      uint4 nxt = col[0];                                         // ncols >= 1
+      // columns are consumed in blocks of kBsBlock; the next block is in flight while
+      // this one is matched (global latency >> one column of work)
+      auto fetch = [&](uint32_t c) { return col[(size_t)min(c, ncols - 1u) * 32u]; };     // ncols >= 1
+      uint4 nxt[kBsBlock];
+#pragma unroll
+      for (int k = 0; k < kBsBlock; k++) nxt[k] = fetch((uint32_t)k);
 #pragma unroll 1
-      for (uint32_t c = 0; c < ncols; c++) {
+      for (uint32_t c0 = 0; c0 < ncols; c0 += kBsBlock) {
          if (!__any_sync(kFull, st.alive != 0u)) break;
-         const uint4 cur = nxt;
-         if (c + 1 < ncols) nxt = col[(size_t)(c + 1) * 32u];
+         uint4 blk[kBsBlock];
+#pragma unroll
+         for (int k = 0; k < kBsBlock; k++) {
+            blk[k] = nxt[k];
+            nxt[k] = fetch(c0 + kBsBlock + (uint32_t)k);
+         }
+#pragma unroll
+         for (int k = 0; k < kBsBlock; k++) {
+         const uint32_t c = c0 + (uint32_t)k;       // columns >= ncols: every line is dead, nothing happens
+         const uint4 cur = blk[k];
          const uint32_t p0 = cur.x, p1 = cur.y, p2 = cur.z;
          uint32_t anybase, stop, skip;
          {
@@ -359,6 +373,7 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
                const uint32_t line = line0 + (uint32_t)lane * 32u + (uint32_t)r;
                a.res[line] = ((unsigned long long)bs_value<B>(streak, r) << 32) | c;
             }
+         }
          }
       }
       my_matched += (uint32_t)__popc(st.hit);

@@ -81,8 +81,8 @@ struct BsGate {
 // ticket order.  Inside a tile warp w owns the 4 KiB [w*4096, (w+1)*4096) and
 // lane l the 16-byte vectors (k*512 + l*16), k = 0..7, so that text order is
 // (warp, k, lane).  Every byte goes through a 256-entry class table held in
-// shared memory, pre-shifted per byte position so that the 16 look-ups of a
-// vector OR together into 16 class nibbles (8 bytes of `codes`).  Bit 3 of a
+// shared memory; the 16 look-ups of a vector are packed into 16 class nibbles
+// (8 bytes of `codes`).  Bit 3 of a
 // nibble marks '\n', which is all the line scan needs: per-vector newline masks
 // -> popc -> packed warp-shuffle scan -> block totals.  A tile then allocates
 // room for its line starts with ONE atomicAdd on a cursor (no tile waits for
@@ -99,7 +99,7 @@ constexpr int      kK1Vec       = 8;                          // 16-byte vectors
 constexpr uint32_t kK1WarpBytes = kK1Vec * 512;               // 4 KiB of text per warp
 constexpr uint32_t kK1Tile      = kWarps * kK1WarpBytes;      // 32 KiB of text per tile
 constexpr uint32_t kK1Stage     = kK1Tile + 16;               // + look-ahead for the FASTA test
-constexpr uint32_t kK1Smem      = 2 * kK1Stage + 8 * 256 * 4; // stages + pre-shifted class tables
+constexpr uint32_t kK1Smem      = 2 * kK1Stage + 256;         // stages + class table
 
 struct K1Args {
    const uint8_t *text;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kThreads) k1_scan_classify(const K1Args a, con
    const uint32_t ntiles = (n + kK1Tile - 1) / kK1Tile;
    const uint32_t n16 = (n + 15u) & ~15u;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-   uint32_t *lut = reinterpret_cast<uint32_t *>(dyn + 2 * kK1Stage);     // [8][256]
+   uint8_t *lut = dyn + 2 * kK1Stage;                                    // [256] class nibbles
 
    auto issue = [&](int stage, uint32_t tile) {
       const uint32_t start = tile * kK1Tile;
@@ -136,11 +136,7 @@ __global__ void __launch_bounds__(kThreads) k1_scan_classify(const K1Args a, con
       bulk_g2s(dyn + stage * kK1Stage, a.text + start, bytes, &bar[stage]);
    };
 
-   {  // table j holds the class nibble shifted to nibble j of a word
-      const uint32_t c = ct.code[tid];
-#pragma unroll
-      for (int j = 0; j < 8; j++) lut[j * 256 + tid] = c << (4 * j);
-   }
+   lut[tid] = ct.code[tid];
    if (tid == 0) {
       mbar_init(&bar[0], 1);
       mbar_init(&bar[1], 1);
@@ -175,15 +171,15 @@ __global__ void __launch_bounds__(kThreads) k1_scan_classify(const K1Args a, con
          const uint32_t off = woff + (uint32_t)k * 512u;
          const uint4 v = *reinterpret_cast<const uint4 *>(buf + off);
          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+         // per byte: PRMT (ALU pipe) extracts it, LDS.U8 looks its nibble up, IMAD (FMA
+         // pipe) drops it into place -- the two math pipes and the LSU share the work
          uint32_t lo = 0, hi = 0;
 #pragma unroll
          for (int j = 0; j < 8; j++) {
-            const uint32_t x = w[j >> 2], y = w[2 + (j >> 2)];
-            const int r = j & 3;
-            const uint32_t ix = r == 0 ? (x << 2) & 0x3FCu : (x >> (8 * r - 2)) & 0x3FCu;
-            const uint32_t iy = r == 0 ? (y << 2) & 0x3FCu : (y >> (8 * r - 2)) & 0x3FCu;
-            lo |= *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(lut) + j * 1024 + ix);
-            hi |= *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(lut) + j * 1024 + iy);
+            const uint32_t bx = __byte_perm(w[j >> 2], 0u, 0x4440u + (uint32_t)(j & 3));
+            const uint32_t by = __byte_perm(w[2 + (j >> 2)], 0u, 0x4440u + (uint32_t)(j & 3));
+            lo = mad_u32((uint32_t)lut[bx], 1u << (4 * j), lo);
+            hi = mad_u32((uint32_t)lut[by], 1u << (4 * j), hi);
          }
          const uint32_t pos = tile_start + off;
          if (pos + 16u > n) {               // bytes at or beyond n are STOP and never newlines
@@ -294,34 +290,33 @@ struct K1ScanArgs {
 __global__ void __launch_bounds__(1024) k1_scan_tiles(const K1ScanArgs a)
 {
    __shared__ unsigned long long s_warp[32];
-   __shared__ unsigned long long s_carry;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-   if (tid == 0) s_carry = 0;
-   __syncthreads();
-   for (uint32_t t0 = 0; t0 < a.ntiles; t0 += 1024) {
-      const uint32_t t = t0 + tid;
-      const unsigned long long v = t < a.ntiles ? a.tile_cnt[t] : 0u;
-      unsigned long long x = v;
+   // thread t owns the contiguous run [t*per, (t+1)*per): serial sum, one block scan, serial write
+   const uint32_t per = (a.ntiles + 1023u) / 1024u;
+   const uint32_t t0 = min((uint32_t)tid * per, a.ntiles), t1 = min(t0 + per, a.ntiles);
+   unsigned long long sum = 0;
+   for (uint32_t t = t0; t < t1; t++) sum += a.tile_cnt[t];
+   unsigned long long x = sum;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-         const unsigned long long y = __shfl_up_sync(kFull, x, d);
-         if (lane >= d) x += y;
-      }
-      if (lane == 31) s_warp[warp] = x;
-      __syncthreads();
-      unsigned long long before = s_carry, tot = 0;
-      for (int w = 0; w < 32; w++) {
-         const unsigned long long y = s_warp[w];
-         if (w < warp) before += y;
-         tot += y;
-      }
-      // line numbers are u32 (a batch is < 4 GiB of text)
-      if (t < a.ntiles) a.tile_base[t] = (uint32_t)(before + x - v);
-      __syncthreads();
-      if (tid == 0) s_carry += tot;
-      __syncthreads();
+   for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long y = __shfl_up_sync(kFull, x, d);
+      if (lane >= d) x += y;
    }
-   if (tid == 0) a.ctr[C_NLINES] = s_carry;
+   if (lane == 31) s_warp[warp] = x;
+   __syncthreads();
+   unsigned long long before = 0, tot = 0;
+   for (int w = 0; w < 32; w++) {
+      const unsigned long long y = s_warp[w];
+      if (w < warp) before += y;
+      tot += y;
+   }
+   unsigned long long run = before + x - sum;
+   // line numbers are u32 (a batch is < 4 GiB of text)
+   for (uint32_t t = t0; t < t1; t++) {
+      a.tile_base[t] = (uint32_t)run;
+      run += a.tile_cnt[t];
+   }
+   if (tid == 0) a.ctr[C_NLINES] = tot;
 }
 
 // tile segments of ls_raw -> ls in line order (one warp per tile) + sentinel
