@@ -55,6 +55,7 @@ struct Slot {
    uint32_t *d_tiles = nullptr; size_t tiles_cap = 0;     // per K1 tile: count, offset, base
    uint4 *d_planes = nullptr;   size_t planes_cap = 0;    // bit-planes, 32 uint4 per tile column
    uint32_t *d_bstiles = nullptr; size_t bstiles_cap = 0; // per match tile: columns, offset
+   uint32_t *d_fintiles = nullptr; size_t fintiles_cap = 0; // per 1024-line tile: records, matched lines, first record
    unsigned long long *d_res = nullptr; size_t res_cap = 0;
    uint32_t *d_cnt = nullptr;   size_t cnt_cap = 0;
    uint32_t *d_offs = nullptr;  size_t offs_cap = 0;
@@ -163,7 +164,7 @@ template <class T> static int pin_reserve(T **p, size_t *cap, size_t need)
 
 static void slot_free(Slot &s)
 {
-   cudaFree(s.d_text); cudaFree(s.d_ls); cudaFree(s.d_codes); cudaFree(s.d_ls_raw); cudaFree(s.d_tiles); cudaFree(s.d_planes); cudaFree(s.d_bstiles); cudaFree(s.d_res); cudaFree(s.d_cnt); cudaFree(s.d_offs);
+   cudaFree(s.d_text); cudaFree(s.d_ls); cudaFree(s.d_codes); cudaFree(s.d_ls_raw); cudaFree(s.d_tiles); cudaFree(s.d_planes); cudaFree(s.d_bstiles); cudaFree(s.d_fintiles); cudaFree(s.d_res); cudaFree(s.d_cnt); cudaFree(s.d_offs);
    cudaFree(s.d_ev); cudaFree(s.d_recs); cudaFree(s.d_ctl);
    cudaFreeHost(s.h_ctr); cudaFreeHost(s.h_recs); cudaFreeHost(s.h_ls); cudaFreeHost(s.h_init);
    for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
@@ -344,16 +345,13 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
       if (dev_reserve(&s.d_ev, &s.ev_cap, want_ev)) return -1;
       if (dev_reserve(&s.d_recs, &s.rec_cap, s.ev_cap, 64)) return -1;
    }
-   // control block: counters, then look-back words of K1, scan, finish
+   // control block: the counters; per-tile arrays of K1 and of the compaction
    const size_t k1_tiles = div_up(n, kK1Tile) + 1;
-   const size_t scan_tiles = div_up(lines_cap, (size_t)kThreads * kScanItems) + 1;
-   const size_t fin_tiles = div_up(lines_cap, kThreads) + 1;
-   const size_t ctl_words = C_COUNT + k1_tiles + scan_tiles + fin_tiles;
+   const size_t fin_tiles = div_up(lines_cap, kFinTile) + 1;
+   const size_t ctl_words = C_COUNT;
    if (dev_reserve(&s.d_ctl, &s.ctl_cap, ctl_words)) return -1;
+   if (dev_reserve(&s.d_fintiles, &s.fintiles_cap, 3 * fin_tiles)) return -1;
    unsigned long long *ctr = s.d_ctl;
-   unsigned long long *st_k1 = ctr + C_COUNT;
-   unsigned long long *st_scan = st_k1 + k1_tiles;
-   unsigned long long *st_fin = st_scan + scan_tiles;
 
    if (timing) CU(cudaEventRecord(s.ev[0], st));
    CU(cudaMemsetAsync(s.d_ctl, 0, ctl_words * sizeof(unsigned long long), st));
@@ -438,20 +436,28 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
    if (timing) CU(cudaEventRecord(s.ev[2], st));
 
    // ---- scan + K3/K4 --------------------------------------------------------
+   uint32_t *tile_sum = s.d_fintiles, *tile_nz = tile_sum + fin_tiles, *tile_recbase = tile_nz + fin_tiles;
    FinArgs fa{d_text, s.d_ls, (uint32_t)lines_cap, s.d_res, s.d_offs, s.d_ev, k2.ev_cap, s.d_recs,
-              (uint32_t)std::min<size_t>(s.rec_cap, 0xffffffffu), ctr, st_fin};
-   if (mode == M_FIRST || mode == M_BEST) {
-      const int grid = (int)std::min<size_t>(div_up(max_lines, kThreads), (size_t)e->sms * 8);
-      if (launch_finish(e, false, grid, st, fa, rev)) return -1;
-      s.launches++;
-   } else if (mode == M_ALL) {
-      ScanArgs sa{s.d_cnt, s.d_offs, (uint32_t)lines_cap, ctr, st_scan};
-      const int grid = (int)std::min<size_t>(div_up(max_lines, (size_t)kThreads * kScanItems), (size_t)e->sms * 8);
-      k_scan_counts<<<grid, kThreads, 0, st>>>(sa);
-      CU(cudaGetLastError());
-      const int grid2 = (int)std::min<size_t>(div_up(std::max<size_t>(s.ev_cap, 1), kThreads), (size_t)e->sms * 8);
-      if (launch_finish(e, true, single ? 1 : grid2, st, fa, rev)) return -1;
-      s.launches += 2;
+              (uint32_t)std::min<size_t>(s.rec_cap, 0xffffffffu), ctr, tile_recbase};
+   if (mode == M_FIRST || mode == M_BEST || mode == M_ALL) {
+      const bool all = mode == M_ALL;
+      TileSumArgs ts{all ? nullptr : s.d_res, all ? s.d_cnt : nullptr, (uint32_t)lines_cap, ctr, tile_sum, tile_nz,
+                     tile_recbase};
+      const int gsum = (int)std::max<size_t>(1, std::min<size_t>(div_up(div_up(max_lines, kFinTile), kWarps), (size_t)e->sms * 8));
+      k_tile_sums<<<gsum, kThreads, 0, st>>>(ts);
+      k_tile_scan<<<1, 1024, 0, st>>>(ts);
+      const int gtile = (int)std::max<size_t>(1, std::min<size_t>(div_up(max_lines, kFinTile), (size_t)e->sms * 8));
+      if (!all) {
+         if (launch_finish(e, false, gtile, st, fa, rev)) return -1;
+         s.launches += 3;
+      } else {
+         OffsArgs oa{s.d_cnt, s.d_offs, (uint32_t)lines_cap, ctr, tile_recbase};
+         k_offsets<<<gtile, kThreads, 0, st>>>(oa);
+         CU(cudaGetLastError());
+         const int grid2 = (int)std::min<size_t>(div_up(std::max<size_t>(s.ev_cap, 1), kThreads), (size_t)e->sms * 8);
+         if (launch_finish(e, true, single ? 1 : grid2, st, fa, rev)) return -1;
+         s.launches += 4;
+      }
    }
    if (timing) CU(cudaEventRecord(s.ev[3], st));
    CU(cudaMemcpyAsync(s.h_ctr, ctr, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));

@@ -695,25 +695,40 @@ __global__ void __launch_bounds__(kThreads) k2_forward_lanes(const K2Args a, con
 // ===========================================================================
 // rpat holds the masks of the REVERSED pattern and a class table in which
 // every non-base byte is kKindSkip (the reference skips them all here).
+// The byte-class and match-mask tables are staged in shared memory by the
+// caller (rev_tables_load): indexed per thread, they would serialise in the
+// constant bank.
+template <int W> struct RevTables {
+   uint8_t cls[256];
+   uint32_t eq[8][W];
+};
+
+template <int W> __device__ __forceinline__ void rev_tables_load(RevTables<W> &t, const Pattern &rpat)
+{
+   for (int i = threadIdx.x; i < 256; i += blockDim.x) t.cls[i] = rpat.cls[i];
+   for (int i = threadIdx.x; i < 8 * W; i += blockDim.x) t.eq[i / W][i % W] = (i / W) < 5 ? rpat.eq[i / W][i % W] : 0u;
+   __syncthreads();
+}
+
 template <int W>
 __device__ __forceinline__ uint32_t reverse_start(const uint8_t *__restrict__ text, const uint32_t line_begin,
-                                                  const uint32_t end, const int dist, const Pattern &rpat)
+                                                  const uint32_t end, const int dist, const int m, const int tau,
+                                                  const RevTables<W> &tab)
 {
-   const int tau = rpat.tau;
    BitVec<W> bv;
-   bv_reset(bv, rpat.m);
-   int score = rpat.m;
+   bv_reset(bv, m);
+   int score = m;
    int d = tau + 1, last_d;
    uint32_t j = 0, skipped = 0;
    do {
       j++;
-      const uint8_t c = rpat.cls[__ldg(text + line_begin + end - j)];
+      const uint8_t c = tab.cls[__ldg(text + line_begin + end - j)];
       last_d = d;
       if ((c & 0x30) == kKindBase) {
          skipped = 0;
          uint32_t eq[W];
 #pragma unroll
-         for (int w = 0; w < W; w++) eq[w] = rpat.eq[c & 7][w];
+         for (int w = 0; w < W; w++) eq[w] = tab.eq[c & 7][w];
          uint32_t rise, fall;
          bv_step<W>(bv, eq, rise, fall);
          score += (int)rise - (int)fall;
@@ -727,56 +742,117 @@ __device__ __forceinline__ uint32_t reverse_start(const uint8_t *__restrict__ te
 }
 
 // ===========================================================================
-// exclusive scan of per-line counts (SQ_ALL): cnt[] -> offs[], totals -> ctr
+// K4: ordered compaction without inter-CTA waiting
 // ===========================================================================
-constexpr int kScanItems = 4;
+// Records must come out in line order.  Instead of a decoupled look-back (which
+// was measured to leave the CTAs stalled on barriers most of the time), the
+// lines are cut into tiles of 1024: k_tile_sums counts the records of every
+// tile, k_tile_scan (one CTA) turns the counts into the first record index of
+// every tile and the totals, and the finishing kernels then work tile by tile
+// with nothing but a block-wide scan.
+constexpr uint32_t kFinTile = 1024;
 
-struct ScanArgs {
+struct TileSumArgs {
+   const unsigned long long *res;     // SQ_FIRST / SQ_BEST candidates (or nullptr)
+   const uint32_t *cnt;               // SQ_ALL per-line event counts (or nullptr)
+   uint32_t max_lines;
+   unsigned long long *ctr;
+   uint32_t *tile_sum;                // records per tile
+   uint32_t *tile_nz;                 // lines with >= 1 record per tile
+   uint32_t *tile_base;               // out of k_tile_scan
+};
+
+__global__ void __launch_bounds__(kThreads) k_tile_sums(const TileSumArgs a)
+{
+   const int lane = threadIdx.x & 31;
+   const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
+   const uint32_t ntiles = (nlines + kFinTile - 1) / kFinTile;
+   const uint32_t wid = (blockIdx.x * kThreads + threadIdx.x) >> 5, nw = (gridDim.x * kThreads) >> 5;
+   for (uint32_t t = wid; t < ntiles; t += nw) {
+      uint32_t sum = 0, nz = 0;
+#pragma unroll 4
+      for (int k = 0; k < 32; k++) {
+         const uint32_t l = t * kFinTile + (uint32_t)k * 32u + (uint32_t)lane;
+         if (l < nlines) {
+            const uint32_t v = a.cnt ? a.cnt[l] : (a.res[l] != kNoMatch ? 1u : 0u);
+            sum += v;
+            nz += v != 0u;
+         }
+      }
+      sum = __reduce_add_sync(kFull, sum);
+      nz = __reduce_add_sync(kFull, nz);
+      if (lane == 0) {
+         a.tile_sum[t] = sum;
+         a.tile_nz[t] = nz;
+      }
+   }
+}
+
+__global__ void __launch_bounds__(1024) k_tile_scan(const TileSumArgs a)
+{
+   __shared__ unsigned long long s_warp[32], s_nz[32];
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
+   const uint32_t ntiles = (nlines + kFinTile - 1) / kFinTile;
+   const uint32_t per = (ntiles + 1023u) / 1024u;
+   const uint32_t t0 = min((uint32_t)tid * per, ntiles), t1 = min(t0 + per, ntiles);
+   unsigned long long sum = 0, nz = 0;
+   for (uint32_t t = t0; t < t1; t++) {
+      sum += a.tile_sum[t];
+      nz += a.tile_nz[t];
+   }
+   unsigned long long x = sum;
+#pragma unroll
+   for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long y = __shfl_up_sync(kFull, x, d);
+      if (lane >= d) x += y;
+   }
+   nz = __reduce_add_sync(kFull, (uint32_t)nz);          // a tile has <= 1024 lines, a warp <= 2^20
+   if (lane == 31) s_warp[warp] = x;
+   if (lane == 0) s_nz[warp] = nz;
+   __syncthreads();
+   unsigned long long before = 0, tot = 0, tnz = 0;
+   for (int w = 0; w < 32; w++) {
+      const unsigned long long y = s_warp[w];
+      if (w < warp) before += y;
+      tot += y;
+      tnz += s_nz[w];
+   }
+   unsigned long long run = before + x - sum;
+   for (uint32_t t = t0; t < t1; t++) {
+      a.tile_base[t] = (uint32_t)run;                    // records of a batch fit 32 bits (checked by the host)
+      run += a.tile_sum[t];
+   }
+   if (tid == 0) {
+      a.ctr[C_NRECS] = tot;
+      a.ctr[C_NMATCHED] = tnz;
+   }
+}
+
+// SQ_ALL: offs[line] = first record of the line (tile base + scan inside the tile)
+struct OffsArgs {
    const uint32_t *cnt;
    uint32_t *offs;
    uint32_t max_lines;
-   unsigned long long *ctr;
-   unsigned long long *status;
+   const unsigned long long *ctr;
+   const uint32_t *tile_base;
 };
 
-__global__ void __launch_bounds__(kThreads) k_scan_counts(const ScanArgs a)
+__global__ void __launch_bounds__(kThreads) k_offsets(const OffsArgs a)
 {
    __shared__ BlockScanSmem sc;
-   __shared__ unsigned long long s_base;
-   __shared__ uint32_t s_tile;
    const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
-   constexpr uint32_t kTile = kThreads * kScanItems;
-   const uint32_t ntiles = (nlines + kTile - 1) / kTile;
-   const int tid = threadIdx.x;
-   while (true) {
-      if (tid == 0) s_tile = (uint32_t)atomicAdd(&a.ctr[C_TICKET_SCAN], 1ull);
-      __syncthreads();
-      const uint32_t tile = s_tile;
-      if (tile >= ntiles) break;
-      const uint32_t i0 = tile * kTile + (uint32_t)tid * kScanItems;
-      uint32_t v[kScanItems];
-      uint32_t sum = 0, nz = 0;
-#pragma unroll
-      for (int k = 0; k < kScanItems; k++) {
-         v[k] = i0 + k < nlines ? a.cnt[i0 + k] : 0u;
-         sum += v[k];
-         nz += v[k] != 0;
-      }
-      uint32_t total;
-      const uint32_t excl = block_exclusive_scan(sum, sc, &total);
-      const unsigned long long base = tile_lookback(a.status, tile, total, &s_base);
-      unsigned long long run = base + excl;
-#pragma unroll
-      for (int k = 0; k < kScanItems; k++) {
-         if (i0 + k < nlines) a.offs[i0 + k] = (uint32_t)run;
-         run += v[k];
-      }
-      // matched lines: plain block reduction
-      uint32_t tnz;
-      (void)block_exclusive_scan(nz, sc, &tnz);
-      if (tid == 0) {
-         if (tnz) atomicAdd(&a.ctr[C_NMATCHED], (unsigned long long)tnz);
-         if (tile == ntiles - 1) a.ctr[C_NRECS] = base + total;
+   const uint32_t ntiles = (nlines + kFinTile - 1) / kFinTile;
+   for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      uint32_t run = a.tile_base[tile];
+#pragma unroll 1
+      for (int k = 0; k < (int)(kFinTile / kThreads); k++) {
+         const uint32_t line = tile * kFinTile + (uint32_t)k * kThreads + threadIdx.x;
+         const uint32_t v = line < nlines ? a.cnt[line] : 0u;
+         uint32_t total;
+         const uint32_t excl = block_exclusive_scan(v, sc, &total);
+         if (line < nlines) a.offs[line] = run + excl;
+         run += total;
       }
    }
 }
@@ -795,43 +871,38 @@ struct FinArgs {
    Rec *recs;
    uint32_t rec_cap;
    unsigned long long *ctr;
-   unsigned long long *status;
+   const uint32_t *tile_base;     // first record of every 1024-line tile
 };
 
 template <int W>
 __global__ void __launch_bounds__(kThreads) k34_finish_lines(const FinArgs a, const __grid_constant__ Pattern rpat)
 {
    __shared__ BlockScanSmem sc;
-   __shared__ unsigned long long s_base;
-   __shared__ uint32_t s_tile;
+   __shared__ RevTables<W> tab;
+   rev_tables_load(tab, rpat);
    const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
-   const uint32_t ntiles = (nlines + kThreads - 1) / kThreads;
+   const uint32_t ntiles = (nlines + kFinTile - 1) / kFinTile;
    const int tid = threadIdx.x;
-   while (true) {
-      if (tid == 0) s_tile = (uint32_t)atomicAdd(&a.ctr[C_TICKET_FIN], 1ull);
-      __syncthreads();
-      const uint32_t tile = s_tile;
-      if (tile >= ntiles) break;
-      const uint32_t line = tile * kThreads + tid;
-      unsigned long long key = kNoMatch;
-      if (line < nlines) key = a.res[line];
-      const bool valid = key != kNoMatch;
-      Rec r{};
-      if (valid) {
-         r.line = line;
-         r.end = (uint32_t)key;
-         r.dist = (uint32_t)(key >> 32);
-         r.start = reverse_start<W>(a.text, a.ls[line], r.end, (int)r.dist, rpat);
-      }
-      // ordered compaction: ballot/popc inside the warp, scan across warps,
-      // look-back across tiles
-      uint32_t total;
-      const uint32_t excl = block_exclusive_scan(valid ? 1u : 0u, sc, &total);
-      const unsigned long long base = tile_lookback(a.status, tile, total, &s_base);
-      if (valid && base + excl < a.rec_cap) a.recs[base + excl] = r;
-      if (tile == ntiles - 1 && tid == 0) {
-         a.ctr[C_NMATCHED] = base + total;
-         a.ctr[C_NRECS] = base + total;
+   for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      uint32_t run = a.tile_base[tile];
+#pragma unroll 1
+      for (int k = 0; k < (int)(kFinTile / kThreads); k++) {
+         const uint32_t line = tile * kFinTile + (uint32_t)k * kThreads + (uint32_t)tid;
+         unsigned long long key = kNoMatch;
+         if (line < nlines) key = a.res[line];
+         const bool valid = key != kNoMatch;
+         Rec r{};
+         if (valid) {
+            r.line = line;
+            r.end = (uint32_t)key;
+            r.dist = (uint32_t)(key >> 32);
+            r.start = reverse_start<W>(a.text, a.ls[line], r.end, (int)r.dist, rpat.m, rpat.tau, tab);
+         }
+         // ordered compaction: ballot/popc inside the warp, scan across the warps
+         uint32_t total;
+         const uint32_t excl = block_exclusive_scan(valid ? 1u : 0u, sc, &total);
+         if (valid && run + excl < a.rec_cap) a.recs[run + excl] = r;
+         run += total;
       }
    }
 }
@@ -840,6 +911,8 @@ __global__ void __launch_bounds__(kThreads) k34_finish_lines(const FinArgs a, co
 template <int W>
 __global__ void __launch_bounds__(kThreads) k34_finish_events(const FinArgs a, const __grid_constant__ Pattern rpat)
 {
+   __shared__ RevTables<W> tab;
+   rev_tables_load(tab, rpat);
    unsigned long long nev = a.ctr[C_EVENTS];
    if (nev > a.ev_cap) nev = a.ev_cap;
    for (unsigned long long i = (unsigned long long)blockIdx.x * kThreads + threadIdx.x; i < nev;
@@ -849,7 +922,7 @@ __global__ void __launch_bounds__(kThreads) k34_finish_events(const FinArgs a, c
       r.line = e.line;
       r.end = e.end;
       r.dist = e.dist;
-      r.start = reverse_start<W>(a.text, a.ls[e.line], e.end, (int)e.dist, rpat);
+      r.start = reverse_start<W>(a.text, a.ls[e.line], e.end, (int)e.dist, rpat.m, rpat.tau, tab);
       const unsigned long long dst = (unsigned long long)a.offs[e.line] + e.rank;
       if (dst < a.rec_cap) a.recs[dst] = r;
    }
