@@ -43,11 +43,19 @@ enum BsSlot { BS_A = 0, BS_C, BS_G, BS_T, BS_N, BS_ANY, BS_CUSTOM0, BS_CUSTOM1, 
 
 enum BsMode { BS_FIRST = 0, BS_BEST = 1, BS_ALL = 2 };
 
-constexpr int kBsMaxRows = 32;
+constexpr int kBsMaxRows = 128;         // rows of the longest pattern: 4 parts of 32 rows
 constexpr int kBsBestBits = 4;          // best distance planes: tau + 1 <= 15
 
+// Patterns of more than 32 positions are cut into G PARTS of R rows each, part p
+// = rows [p*R, (p+1)*R).  Rows only depend on the rows below them (the horizontal
+// delta flows upwards), so the parts form a pipeline: part p works on text column
+// c - p while part p-1 works on column c - p + 1 and hands over the horizontal
+// delta (ph, mh) of its top row.  In the CUDA kernel the parts of a group of 32
+// lines sit in G lanes of one warp and the hand-over is one pair of shuffles.
 struct BsPattern {
-   int32_t  m, tau, rows;               // rows = R of the kernel instance (>= m)
+   int32_t  m, tau;
+   int32_t  rows;                       // R: rows per part of the kernel instance
+   int32_t  parts;                      // G: 1, 2 or 4;  R * G >= m
    int32_t  ncustom;                    // custom classes in use (0..2)
    uint8_t  slot[kBsMaxRows];           // Eq slot of every row (pad rows: BS_ONES)
    uint32_t slot_off[kBsMaxRows];       // the same as byte offset slot * 32 lanes * 4 (kernel smem layout)
@@ -57,11 +65,12 @@ struct BsPattern {
    uint32_t best_plane[kBsBestBits];    // bit k of tau + 1
 };
 
-constexpr int bs_score_bits(int R) { return R < 16 ? 4 : (R < 32 ? 5 : 6); }
+// planes of the distance counter: it runs from 0 to the number of rows
+constexpr int bs_score_bits(int rows) { return rows < 16 ? 4 : (rows < 32 ? 5 : (rows < 64 ? 6 : (rows < 128 ? 7 : 8))); }
 
-template <int R> struct BsState {
-   static constexpr int B = bs_score_bits(R);
-   uint32_t pv[R], mv[R];
+template <int R, int G = 1> struct BsState {
+   static constexpr int B = bs_score_bits(R * G);
+   uint32_t pv[R], mv[R];               // the rows of ONE part
    uint32_t s[B];                       // distance of the last row, bit-sliced
    uint32_t bd[kBsBestBits];            // best distance so far (BS_BEST)
    uint32_t alive;                      // lines still being scanned
@@ -69,19 +78,23 @@ template <int R> struct BsState {
    uint32_t hit;                        // lines with at least one event
 };
 
-template <int R> SQB_BS_HD void bs_reset(BsState<R> &st, const BsPattern &p, uint32_t valid)
+// part: which part of the pattern this state holds (0 .. G-1); `valid` = lines in
+// use.  Only the LAST part tracks the distance and reports, the others keep
+// alive == 0 and never produce an event.
+template <int R, int G>
+SQB_BS_HD void bs_reset(BsState<R, G> &st, const BsPattern &p, uint32_t valid, int part = 0)
 {
-   const int pad = R - p.m;
+   const int pad = R * G - p.m;                   // wildcard rows at the bottom (all inside part 0)
 #pragma unroll
    for (int j = 0; j < R; j++) {
-      st.pv[j] = j >= pad ? ~0u : 0u;
+      st.pv[j] = (part * R + j) >= pad ? ~0u : 0u;
       st.mv[j] = 0u;
    }
 #pragma unroll
-   for (int k = 0; k < BsState<R>::B; k++) st.s[k] = p.m_plane[k];
+   for (int k = 0; k < BsState<R, G>::B; k++) st.s[k] = p.m_plane[k];
 #pragma unroll
    for (int k = 0; k < kBsBestBits; k++) st.bd[k] = p.best_plane[k];
-   st.alive = valid;
+   st.alive = part == G - 1 ? valid : 0u;
    st.flag = 0u;
    st.hit = 0u;
 }
@@ -108,39 +121,67 @@ SQB_BS_HD void bs_classes(uint32_t p0, uint32_t p1, uint32_t p2, const BsPattern
    skip = p2 & p1 & ~p0;
 }
 
-// One text column.  eq(j) returns the Eq mask of row j.  Returns the event mask:
-// bit r set <=> line r reports a match ending at this column with distance
-// `streak` = the value held by st.s BEFORE the call (returned in streak[]).
-template <int R, int MODE, bool SKIP, class EqOf>
-SQB_BS_HD uint32_t bs_step(BsState<R> &st, const BsPattern &p, const EqOf &eq, uint32_t anybase, uint32_t stopc,
-                           uint32_t skipc, uint32_t *streak)
+// The rows of one part for one text column.  eq(j) returns the Eq mask of row j
+// of this part.  ph / mh: on entry the horizontal delta handed over by the part
+// below (0 for part 0), on return the delta of this part's top row.  Rows below
+// `first` are skipped (wildcard rows of part 0: their deltas are 0 forever).
+//
+// A NULL column (class 7: no base, no stop, no skip) leaves a state that is
+// still at its reset value unchanged and hands 0 upwards: a mismatch against
+// the initial column [0, 1, .., m] reproduces it.  The kernel feeds NULL columns
+// to the upper parts while the pipeline fills.
+#define SQB_BS_ROW(j)                                                            \
+   case j:                                                                       \
+      if (j < R) {                                                               \
+         const uint32_t e = eq(j);                                               \
+         const uint32_t pv = st.pv[j < R ? j : 0], mv = st.mv[j < R ? j : 0];    \
+         const uint32_t xh = e | mh;                                             \
+         const uint32_t xv = e | mv;                                             \
+         const uint32_t ph_out = mv | ~(xh | pv);                                \
+         const uint32_t mh_out = pv & xh;                                        \
+         uint32_t pv_new = mh | ~(xv | ph);                                      \
+         uint32_t mv_new = ph & xv;                                              \
+         if (SKIP) { /* an ignored byte leaves the automaton untouched */        \
+            pv_new = (pv & skipc) | (pv_new & ~skipc);                           \
+            mv_new = (mv & skipc) | (mv_new & ~skipc);                           \
+         }                                                                       \
+         st.pv[j < R ? j : 0] = pv_new;                                          \
+         st.mv[j < R ? j : 0] = mv_new;                                          \
+         ph = ph_out;                                                            \
+         mh = mh_out;                                                            \
+      }                                                                          \
+      /* fall through */
+
+template <int R, int G, bool SKIP, class EqOf>
+SQB_BS_HD void bs_rows(BsState<R, G> &st, const EqOf &eq, uint32_t skipc, uint32_t &ph, uint32_t &mh, int first = 0)
 {
-   constexpr int B = BsState<R>::B;
+   static_assert(R <= 32, "at most 32 rows per part");
+   (void)skipc;
+   switch (first) {
+   default:
+      SQB_BS_ROW(0) SQB_BS_ROW(1) SQB_BS_ROW(2) SQB_BS_ROW(3) SQB_BS_ROW(4) SQB_BS_ROW(5) SQB_BS_ROW(6) SQB_BS_ROW(7)
+      SQB_BS_ROW(8) SQB_BS_ROW(9) SQB_BS_ROW(10) SQB_BS_ROW(11) SQB_BS_ROW(12) SQB_BS_ROW(13) SQB_BS_ROW(14)
+      SQB_BS_ROW(15) SQB_BS_ROW(16) SQB_BS_ROW(17) SQB_BS_ROW(18) SQB_BS_ROW(19) SQB_BS_ROW(20) SQB_BS_ROW(21)
+      SQB_BS_ROW(22) SQB_BS_ROW(23) SQB_BS_ROW(24) SQB_BS_ROW(25) SQB_BS_ROW(26) SQB_BS_ROW(27) SQB_BS_ROW(28)
+      SQB_BS_ROW(29) SQB_BS_ROW(30) SQB_BS_ROW(31)
+      break;
+   }
+}
+#undef SQB_BS_ROW
+
+// The report state machine of the LAST part for one text column.  ph / mh = the
+// horizontal delta of the top row (the last pattern position).  Returns the
+// event mask: bit r set <=> line r reports a match ending at this column with
+// distance `streak` = the value held by st.s BEFORE the call (returned in
+// streak[]).  `quiet` = lines whose events update the suppress flag but are not
+// reported (the warm-up of a line segment); pass 0 otherwise.
+template <int R, int G, int MODE>
+SQB_BS_HD uint32_t bs_report(BsState<R, G> &st, const BsPattern &p, uint32_t ph, uint32_t mh, uint32_t anybase,
+                             uint32_t stopc, uint32_t *streak, uint32_t quiet = 0u)
+{
+   constexpr int B = BsState<R, G>::B;
    const uint32_t base = anybase & st.alive;      // lines that feed a base to the automaton
    const uint32_t stop = stopc & st.alive;        // lines that end here
-   (void)skipc;
-
-   // ---- the rows ------------------------------------------------------------
-   uint32_t ph = 0u, mh = 0u;
-#pragma unroll
-   for (int j = 0; j < R; j++) {
-      const uint32_t e = eq(j);
-      const uint32_t pv = st.pv[j], mv = st.mv[j];
-      const uint32_t xh = e | mh;
-      const uint32_t xv = e | mv;
-      const uint32_t ph_out = mv | ~(xh | pv);
-      const uint32_t mh_out = pv & xh;
-      uint32_t pv_new = mh | ~(xv | ph);
-      uint32_t mv_new = ph & xv;
-      if (SKIP) {                                 // an ignored byte leaves the automaton untouched
-         pv_new = (pv & skipc) | (pv_new & ~skipc);
-         mv_new = (mv & skipc) | (mv_new & ~skipc);
-      }
-      st.pv[j] = pv_new;
-      st.mv[j] = mv_new;
-      ph = ph_out;
-      mh = mh_out;
-   }
 
    // ---- streak = distance before this column: <= tau ?  == 0 ? ---------------
    uint32_t gt = 0u, nz = 0u;
@@ -159,6 +200,8 @@ SQB_BS_HD uint32_t bs_step(BsState<R> &st, const BsPattern &p, const EqOf &eq, u
    const uint32_t active = base | stop;
    st.flag &= rise | ~active;                     // :278  any non-rise clears the flag
    uint32_t evt = active & le & (zero | rise) & ~st.flag;      // :286-288
+   st.flag |= evt;                                // also during a warm-up
+   evt &= ~quiet;
    if (MODE == BS_BEST) {
       uint32_t lt = 0u;                           // streak < best distance (4 low bits decide: streak <= tau)
 #pragma unroll
@@ -166,6 +209,10 @@ SQB_BS_HD uint32_t bs_step(BsState<R> &st, const BsPattern &p, const EqOf &eq, u
          const uint32_t s = k < B ? st.s[k] : 0u, d = st.bd[k];
          lt = (~s & d) | (~(s ^ d) & lt);
       }
+      // libseeq.c:286-288 leaves the flag alone when `streak < best_d` fails; setting it
+      // anyway is unobservable: until the flag is cleared the distance only rises, so
+      // no later candidate of the run can beat best_d either (BEST = strict running
+      // minimum over the SQ_ALL events)
       evt &= lt;
 #pragma unroll
       for (int k = 0; k < kBsBestBits; k++) {
@@ -173,7 +220,6 @@ SQB_BS_HD uint32_t bs_step(BsState<R> &st, const BsPattern &p, const EqOf &eq, u
          st.bd[k] = (evt & s) | (~evt & st.bd[k]);
       }
    }
-   st.flag |= evt;
    st.hit |= evt;
    st.alive &= ~stop;
    if (MODE == BS_FIRST) st.alive &= ~evt;        // :330  the first match ends the scan of the line
@@ -188,6 +234,16 @@ SQB_BS_HD uint32_t bs_step(BsState<R> &st, const BsPattern &p, const EqOf &eq, u
       carry &= s ^ fall;
    }
    return evt;
+}
+
+// One text column of a single-part automaton (G == 1): rows + report.
+template <int R, int MODE, bool SKIP, class EqOf>
+SQB_BS_HD uint32_t bs_step(BsState<R, 1> &st, const BsPattern &p, const EqOf &eq, uint32_t anybase, uint32_t stopc,
+                           uint32_t skipc, uint32_t *streak, uint32_t quiet = 0u)
+{
+   uint32_t ph = 0u, mh = 0u;
+   bs_rows<R, 1, SKIP>(st, eq, skipc, ph, mh, R - p.m);
+   return bs_report<R, 1, MODE>(st, p, ph, mh, anybase, stopc, streak, quiet);
 }
 
 // distance of line r from bit-planes

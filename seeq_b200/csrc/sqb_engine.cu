@@ -274,27 +274,27 @@ static bool use_bitslice(const sqb_engine *e, int options, uint32_t n)
    return e->bs_ok && !(options & (SQB_SINGLE_LINE | OPT_STREAM)) && n >= e->bs_min_bytes;
 }
 
-template <int R, int MODE> static int launch_bs2(bool skip, int grid, cudaStream_t st, const K2BsArgs &a, const BsPattern &p)
+template <int R, int G, int MODE> static int launch_bs2(bool skip, int grid, cudaStream_t st, const K2BsArgs &a, const BsPattern &p)
 {
    const size_t smem = (MODE == BS_ALL ? sizeof(BsWarpSmemAll) : sizeof(BsWarpSmem)) * kBsWarps;
    static bool attr = false;
    if (!attr) {
-      CU(cudaFuncSetAttribute(k2_bitslice<R, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CU(cudaFuncSetAttribute(k2_bitslice<R, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU(cudaFuncSetAttribute(k2_bitslice<R, G, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU(cudaFuncSetAttribute(k2_bitslice<R, G, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr = true;
    }
-   if (skip) k2_bitslice<R, MODE, true><<<grid, kBsThreads, smem, st>>>(a, p);
-   else k2_bitslice<R, MODE, false><<<grid, kBsThreads, smem, st>>>(a, p);
+   if (skip) k2_bitslice<R, G, MODE, true><<<grid, kBsThreads, smem, st>>>(a, p);
+   else k2_bitslice<R, G, MODE, false><<<grid, kBsThreads, smem, st>>>(a, p);
    CU(cudaGetLastError());
    return 0;
 }
 
-template <int R> static int launch_bs1(int bsmode, bool skip, int grid, cudaStream_t st, const K2BsArgs &a, const BsPattern &p)
+template <int R, int G> static int launch_bs1(int bsmode, bool skip, int grid, cudaStream_t st, const K2BsArgs &a, const BsPattern &p)
 {
    switch (bsmode) {
-   case BS_FIRST: return launch_bs2<R, BS_FIRST>(skip, grid, st, a, p);
-   case BS_BEST: return launch_bs2<R, BS_BEST>(skip, grid, st, a, p);
-   default: return launch_bs2<R, BS_ALL>(skip, grid, st, a, p);
+   case BS_FIRST: return launch_bs2<R, G, BS_FIRST>(skip, grid, st, a, p);
+   case BS_BEST: return launch_bs2<R, G, BS_BEST>(skip, grid, st, a, p);
+   default: return launch_bs2<R, G, BS_ALL>(skip, grid, st, a, p);
    }
 }
 
@@ -302,18 +302,19 @@ static int launch_bitslice(const sqb_engine *e, int mode, int options, size_t ma
 {
    const int bsmode = (mode == M_ALL || mode == M_COUNTALL) ? BS_ALL : (mode == M_BEST ? BS_BEST : BS_FIRST);
    const bool skip = (options & OPT_NONDNA) == OPT_IGNORE;
-   const int R = e->bs_pat.rows;
-   int per_sm = R <= 16 ? 4 : 3;
+   const int R = e->bs_pat.rows, G = e->bs_pat.parts;
+   int per_sm = G > 1 ? 2 : (R <= 16 ? 4 : 3);
    if (const char *c = getenv("SEEQ_B200_BS_CTAS")) per_sm = std::max(1, atoi(c));
-   const int grid = (int)std::max<size_t>(1, std::min<size_t>(div_up(div_up(max_lines, kBsTileLines), kBsWarps),
+   // work items = (tile, 1/G of its groups), one warp each
+   const int grid = (int)std::max<size_t>(1, std::min<size_t>(div_up(div_up(max_lines, kBsTileLines) * G, kBsWarps),
                                                                (size_t)e->sms * per_sm * 2));
-   switch (R) {
-   case 8: return launch_bs1<8>(bsmode, skip, grid, st, a, e->bs_pat);
-   case 12: return launch_bs1<12>(bsmode, skip, grid, st, a, e->bs_pat);
-   case 16: return launch_bs1<16>(bsmode, skip, grid, st, a, e->bs_pat);
-   case 24: return launch_bs1<24>(bsmode, skip, grid, st, a, e->bs_pat);
-   default: return launch_bs1<32>(bsmode, skip, grid, st, a, e->bs_pat);
-   }
+#define SQB_SHAPE(RR, GG) if (R == RR && G == GG) return launch_bs1<RR, GG>(bsmode, skip, grid, st, a, e->bs_pat);
+   SQB_SHAPE(8, 1) SQB_SHAPE(12, 1) SQB_SHAPE(16, 1) SQB_SHAPE(24, 1) SQB_SHAPE(32, 1)
+   SQB_SHAPE(20, 2) SQB_SHAPE(24, 2) SQB_SHAPE(32, 2)
+   SQB_SHAPE(20, 4) SQB_SHAPE(24, 4) SQB_SHAPE(28, 4) SQB_SHAPE(32, 4)
+#undef SQB_SHAPE
+   set_err("no bit-sliced kernel for %d rows x %d parts", R, G);
+   return -1;
 }
 
 static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n, int options, cudaStream_t st)

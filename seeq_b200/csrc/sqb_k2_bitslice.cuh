@@ -250,61 +250,102 @@ struct BsWarpSmem {
    uint32_t slots[BS_SLOTS][32];
 };
 struct BsWarpSmemAll : BsWarpSmem {
-   uint32_t cnt[32 * 32];         // events per line of the tile (BS_ALL)
+   uint32_t cnt[32 * 32];         // events per line of the warp's groups (BS_ALL)
 };
 
-template <int R, int MODE, bool SKIP>
-__global__ void __launch_bounds__(kBsThreads, R <= 16 ? 4 : 3)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+   uint32_t v;
+   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");     // ordered after the slot stores
+   return v;
+}
+
+// R rows per part, G parts per group of 32 lines (sqb_bitslice.h).  A warp serves
+// 32 / G groups of one tile: lane = part * (32 / G) + group, so that the lanes
+// of one part read neighbouring uint4 of one plane column.  Part p runs p
+// columns behind part 0 and receives the horizontal delta of the part below
+// with one pair of shuffles per column; only the last part reports.
+template <int R, int G, int MODE, bool SKIP>
+__global__ void __launch_bounds__(kBsThreads, G > 1 ? 2 : (R <= 16 ? 4 : 3))
 k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
 {
    using Smem = typename std::conditional<MODE == BS_ALL, BsWarpSmemAll, BsWarpSmem>::type;
+   using State = BsState<R, G>;
    extern __shared__ __align__(128) uint8_t dyn[];
    __shared__ uint32_t s_red[2][kBsWarps];
+   __shared__ uint32_t s_off[G > 1 ? R * G : 1];
 
    if (a.ctr[C_BS_SELECTED] != 1ull) return;              // the word-parallel kernel takes this scan
+   constexpr int NG = 32 / G;                             // groups per warp
+   constexpr int B = State::B;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const int part = lane / NG, gl = lane % NG;
    Smem &sm = reinterpret_cast<Smem *>(dyn)[warp];
    const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
    const uint32_t ntiles = (nlines + kBsTileLines - 1) / kBsTileLines;
+   const uint32_t nitems = ntiles * (uint32_t)G;          // (tile, quarter) pairs
 
    sm.slots[BS_ONES][lane] = ~0u;
    const uint32_t *slot_base = &sm.slots[0][lane];
-   constexpr int B = BsState<R>::B;
+   // shared-memory address of the Eq mask of every row of this lane's part: with
+   // G > 1 the slot of a row differs between the lanes of a warp, so the addresses
+   // live in registers (from a staged copy of the table: a per-lane index into the
+   // kernel parameters would serialise in the constant bank)
+   uint32_t raddr[G > 1 ? R : 1];
+   if (G > 1) {
+      for (int i = tid; i < R * G; i += kBsThreads) s_off[i] = pat.slot_off[i];
+      __syncthreads();
+      const uint32_t sb = smem_addr(slot_base);
+#pragma unroll
+      for (int j = 0; j < R; j++) raddr[j] = sb + s_off[part * R + j];
+   }
+   const int first_row = G == 1 ? R - pat.m : 0;          // wildcard rows are skipped
 
    uint32_t my_matched = 0, my_events = 0;
 
-   for (uint32_t tile = blockIdx.x * kBsWarps + warp; tile < ntiles; tile += gridDim.x * kBsWarps) {
+   for (uint32_t item = blockIdx.x * kBsWarps + warp; item < nitems; item += gridDim.x * kBsWarps) {
+      const uint32_t tile = item / (uint32_t)G, q = item % (uint32_t)G;
+      const uint32_t group = q * (uint32_t)NG + (uint32_t)gl;           // group of the tile served by this lane
       const uint32_t line0 = tile * kBsTileLines;
-      const uint32_t left = nlines - line0;                       // > 0
-      const uint32_t mine = left > (uint32_t)lane * 32u ? min(left - (uint32_t)lane * 32u, 32u) : 0u;
-      BsState<R> st;
-      bs_reset(st, pat, mine == 32u ? ~0u : ((1u << mine) - 1u));
+      const uint32_t left = nlines - line0;                              // > 0
+      const uint32_t mine = left > group * 32u ? min(left - group * 32u, 32u) : 0u;
+      State st;
+      bs_reset(st, pat, mine == 32u ? ~0u : ((1u << mine) - 1u), part);
       if (MODE == BS_ALL) {
 #pragma unroll
          for (int i = 0; i < 32; i++) static_cast<BsWarpSmemAll &>(sm).cnt[i * 32 + lane] = 0u;
       }
       uint32_t lane_events = 0;
       const uint32_t ncols = a.tile_cols[tile];
-      const uint4 *col = a.planes + (size_t)a.tile_off[tile] * 32u + lane;
+      const uint32_t niter = ncols + (uint32_t)(G - 1);
+      const uint4 *col = a.planes + (size_t)a.tile_off[tile] * 32u + group;
 
       // columns are consumed in blocks of kBsBlock; the next block is in flight while
-      // this one is matched (global latency >> one column of work)
-      auto fetch = [&](uint32_t c) { return col[(size_t)min(c, ncols - 1u) * 32u]; };     // ncols >= 1
+      // this one is matched (global latency >> one column of work).  Iteration t of
+      // part p is column t - p; before the line start that is a NULL column.
+      auto fetch = [&](uint32_t t) {
+         const int c = (int)t - part;
+         uint4 v = col[(size_t)min((uint32_t)max(c, 0), ncols - 1u) * 32u];          // ncols >= 1
+         if (G > 1 && c < 0) v = make_uint4(~0u, ~0u, ~0u, 0u);
+         return v;
+      };
       uint4 nxt[kBsBlock];
 #pragma unroll
       for (int k = 0; k < kBsBlock; k++) nxt[k] = fetch((uint32_t)k);
+      uint32_t ph_prev = 0u, mh_prev = 0u;               // what this part handed upwards one iteration ago
 #pragma unroll 1
-      for (uint32_t c0 = 0; c0 < ncols; c0 += kBsBlock) {
+      for (uint32_t t0 = 0; t0 < niter; t0 += kBsBlock) {
          if (!__any_sync(kFull, st.alive != 0u)) break;
          uint4 blk[kBsBlock];
 #pragma unroll
          for (int k = 0; k < kBsBlock; k++) {
             blk[k] = nxt[k];
-            nxt[k] = fetch(c0 + kBsBlock + (uint32_t)k);
+            nxt[k] = fetch(t0 + kBsBlock + (uint32_t)k);
          }
 #pragma unroll
          for (int k = 0; k < kBsBlock; k++) {
-         const uint32_t c = c0 + (uint32_t)k;       // columns >= ncols: every line is dead, nothing happens
+         // iterations >= niter: every line is dead, nothing happens
+         const uint32_t c = t0 + (uint32_t)k - (uint32_t)part;       // column of this lane (last part: >= 0 while alive)
          const uint4 cur = blk[k];
          const uint32_t p0 = cur.x, p1 = cur.y, p2 = cur.z;
          uint32_t anybase, stop, skip;
@@ -329,11 +370,21 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
                                             (ng & pat.custom[1][2]) | (nt & pat.custom[1][3]) |
                                             (nn & pat.custom[1][4]);
          }
-         uint32_t streak[B];
+         uint32_t ph = 0u, mh = 0u;
+         if (G > 1) {
+            ph = __shfl_up_sync(kFull, ph_prev, NG);
+            mh = __shfl_up_sync(kFull, mh_prev, NG);
+            if (part == 0) ph = mh = 0u;
+         }
          auto eq = [&](int j) -> uint32_t {
+            if (G > 1) return lds_u32(raddr[G > 1 ? j : 0]);
             return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(slot_base) + pat.slot_off[j]);
          };
-         const uint32_t evt = bs_step<R, MODE, SKIP>(st, pat, eq, anybase, stop, skip, streak);
+         bs_rows<R, G, SKIP>(st, eq, skip, ph, mh, first_row);
+         ph_prev = ph;
+         mh_prev = mh;
+         uint32_t streak[B];
+         const uint32_t evt = bs_report<R, G, MODE>(st, pat, ph, mh, anybase, stop, streak);
 
          // ---- events leave the bit-sliced world here (rare) ---------------------
          if (MODE == BS_ALL) {
@@ -356,8 +407,8 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
                while (e) {
                   const int r = __ffs(e) - 1;
                   e &= e - 1;
-                  const uint32_t line = line0 + (uint32_t)lane * 32u + (uint32_t)r;
-                  const uint32_t rank = static_cast<BsWarpSmemAll &>(sm).cnt[lane * 32 + r]++;
+                  const uint32_t line = line0 + group * 32u + (uint32_t)r;
+                  const uint32_t rank = static_cast<BsWarpSmemAll &>(sm).cnt[gl * 32 + r]++;
                   if (!a.count_only) {
                      if (idx < a.ev_cap) a.ev[idx] = Event{line, rank, c, bs_value<B>(streak, r)};
                      idx++;
@@ -370,7 +421,7 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
             while (e) {
                const int r = __ffs(e) - 1;
                e &= e - 1;
-               const uint32_t line = line0 + (uint32_t)lane * 32u + (uint32_t)r;
+               const uint32_t line = line0 + group * 32u + (uint32_t)r;
                a.res[line] = ((unsigned long long)bs_value<B>(streak, r) << 32) | c;
             }
          }
@@ -381,8 +432,8 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
       if (MODE == BS_ALL && !a.count_only) {
          __syncwarp();
 #pragma unroll 4
-         for (int i = 0; i < 32; i++) {
-            const uint32_t line = line0 + (uint32_t)i * 32u + (uint32_t)lane;
+         for (int i = 0; i < NG; i++) {
+            const uint32_t line = line0 + (q * (uint32_t)NG + (uint32_t)i) * 32u + (uint32_t)lane;
             if (line < nlines) a.cnt[line] = static_cast<BsWarpSmemAll &>(sm).cnt[i * 32 + lane];
          }
          __syncwarp();

@@ -76,27 +76,35 @@ struct BsGate {
 // ===========================================================================
 // K1: line-offset scan + class coding ("tokenizer")
 // ===========================================================================
-// One pass over the text (HBM-bound).  Tiles of 32 KiB are staged into shared
-// memory by TMA bulk copies (two stages, mbarrier), tiles are handed out in
-// ticket order.  Inside a tile warp w owns the 4 KiB [w*4096, (w+1)*4096) and
-// lane l the 16-byte vectors (k*512 + l*16), k = 0..7, so that text order is
-// (warp, k, lane).  Every byte goes through a 256-entry class table held in
-// shared memory; the 16 look-ups of a vector are packed into 16 class nibbles
-// (8 bytes of `codes`).  Bit 3 of a
-// nibble marks '\n', which is all the line scan needs: per-vector newline masks
-// -> popc -> packed warp-shuffle scan -> block totals.  A tile then allocates
-// room for its line starts with ONE atomicAdd on a cursor (no tile waits for
-// another: a decoupled look-back here was measured to stall 58 % of the time)
-// and writes them, ordered inside the tile, into `ls_raw`.  Two tiny kernels
-// finish the job: k1_scan_tiles (exclusive scan of the per-tile counts = first
-// line number of every tile) and k1_gather (moves the tile segments into line
-// order, `ls`).
+// One pass over the text (HBM-bound in principle, issue-bound in practice: one
+// table look-up per byte).  Tiles of 32 KiB are staged into shared memory by TMA
+// bulk copies (two stages, mbarrier) and handed out in ticket order.  Inside a
+// tile warp w owns the 4 KiB [w*4096, (w+1)*4096) and lane l the 128 CONTIGUOUS
+// bytes [l*128, (l+1)*128) of it, read as eight 16-byte vectors in the rotated
+// order (k + l) & 7 so that the quarter-warps hit distinct banks.
+//
+// Every byte goes through a 256-entry class table held in shared memory (PRMT
+// extracts it, LDS.U8 looks it up, IMAD drops the nibble into place: one
+// instruction on each of the ALU, LSU and FMA pipes).  Bit 3 of a nibble marks
+// '\n', which is all the line scan needs: the newline flags of a lane's 128
+// bytes are folded into four words (one per 32 text bytes), counted with popc,
+// and ONE warp-shuffle scan + the block totals give every lane its place.
+//
+// The class nibbles (64 B per lane) are written IN PLACE over the warp's own
+// text (all lanes hold their text in registers by then) and leave the SM as one
+// 2 KiB bulk (TMA) store per warp -- coalesced and asynchronous.  A tile
+// allocates room for its line starts with ONE atomicAdd on a cursor (no tile
+// waits for another: a decoupled look-back here was measured to stall 58 % of
+// the time) and writes them, ordered inside the tile, into `ls_raw`.  Two tiny
+// kernels finish the job: k1_scan_tiles (exclusive scan of the per-tile counts =
+// first line number of every tile) and k1_gather (moves the tile segments into
+// line order, `ls`).
 //
 // Class nibble (bits 2:0): 0 A, 1 C, 2 G, 3 T/U, 4 N (or any other byte with
 // SQ_CONVERT), 5 STOP (NUL, '\n', other bytes with SQ_FAIL), 6 SKIP (other
-// bytes with SQ_IGNORE), 7 NULL (padding in front of a line; K2 only).
-constexpr int      kK1Vec       = 8;                          // 16-byte vectors per lane and tile
-constexpr uint32_t kK1WarpBytes = kK1Vec * 512;               // 4 KiB of text per warp
+// bytes with SQ_IGNORE), 7 NULL (no byte: columns in front of a line; K2 only).
+constexpr uint32_t kK1LaneBytes = 128;                        // contiguous text bytes per lane and tile
+constexpr uint32_t kK1WarpBytes = 32 * kK1LaneBytes;          // 4 KiB of text per warp
 constexpr uint32_t kK1Tile      = kWarps * kK1WarpBytes;      // 32 KiB of text per tile
 constexpr uint32_t kK1Stage     = kK1Tile + 16;               // + look-ahead for the FASTA test
 constexpr uint32_t kK1Smem      = 2 * kK1Stage + 256;         // stages + class table
@@ -113,10 +121,22 @@ struct K1Args {
    int fasta;
 };
 
-template <bool CODES>
-__global__ void __launch_bounds__(kThreads) k1_scan_classify(const K1Args a, const __grid_constant__ ClassTable ct)
+// shared -> global bulk (TMA) store of the calling thread's bulk group
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes)
 {
-   extern __shared__ __align__(128) uint8_t dyn[];            // 2 x kK1Stage, then the tables
+   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src)),
+                "r"(bytes)
+                : "memory");
+   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <bool CODES>
+__global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, const __grid_constant__ ClassTable ct)
+{
+   extern __shared__ __align__(128) uint8_t dyn[];            // 2 x kK1Stage, then the class table
    __shared__ uint64_t bar[2];
    __shared__ uint32_t s_tile[2];
    __shared__ uint32_t s_wsum[kWarps];
@@ -127,6 +147,9 @@ __global__ void __launch_bounds__(kThreads) k1_scan_classify(const K1Args a, con
    const uint32_t n16 = (n + 15u) & ~15u;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    uint8_t *lut = dyn + 2 * kK1Stage;                                    // [256] class nibbles
+   const uint32_t rot = (uint32_t)lane & 7u;
+   const uint32_t lane_off = (uint32_t)warp * kK1WarpBytes + (uint32_t)lane * kK1LaneBytes;   // text of this lane
+   const uint32_t code_off = (uint32_t)warp * kK1WarpBytes + (uint32_t)lane * (kK1LaneBytes / 2);  // its nibbles, in place
 
    auto issue = [&](int stage, uint32_t tile) {
       const uint32_t start = tile * kK1Tile;
@@ -147,98 +170,96 @@ __global__ void __launch_bounds__(kThreads) k1_scan_classify(const K1Args a, con
    }
    __syncthreads();
 
-   uint32_t phase[2] = {0, 0};
+   uint32_t phases = 0;                   // bit s = parity to wait for on stage s
+   bool store_pending = false;            // lane 0 of every warp: a bulk store of the other stage may still read it
    for (int stage = 0;; stage ^= 1) {
       const uint32_t tile = s_tile[stage];
       if (tile >= ntiles) break;
-      if (tid == 0) {                       // prefetch the next ticket into the other stage
-         const uint32_t t = (uint32_t)atomicAdd(&a.ctr[C_TICKET_K1], 1ull);
-         s_tile[stage ^ 1] = t;
-         if (t < ntiles) issue(stage ^ 1, t);
-      }
-      mbar_wait(&bar[stage], phase[stage]);
-      phase[stage] ^= 1;
+      mbar_wait(&bar[stage], (phases >> stage) & 1u);
+      phases ^= 1u << stage;
 
-      const uint8_t *buf = dyn + stage * kK1Stage;
-      const uint32_t tile_start = tile * kK1Tile;
-      const uint32_t woff = (uint32_t)warp * kK1WarpBytes + (uint32_t)lane * 16u;
+      uint8_t *buf = dyn + stage * kK1Stage;
+      const uint32_t pos0 = tile * kK1Tile + lane_off;        // text position of this lane's first byte
 
-      // ---- classify, collect newline masks ----------------------------------
-      // nl[k]: bit 4b set <=> byte b (0..7) is '\n', bit 4b+1 <=> byte 8+b is
-      uint32_t nl[kK1Vec];
+      // ---- classify: vector slot k holds text vector (k + rot) & 7 of the lane ----
+      uint32_t lo[8], hi[8];
 #pragma unroll
-      for (int k = 0; k < kK1Vec; k++) {
-         const uint32_t off = woff + (uint32_t)k * 512u;
-         const uint4 v = *reinterpret_cast<const uint4 *>(buf + off);
+      for (int k = 0; k < 8; k++) {
+         const uint4 v = *reinterpret_cast<const uint4 *>(buf + lane_off + ((((uint32_t)k + rot) & 7u) << 4));
          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-         // per byte: PRMT (ALU pipe) extracts it, LDS.U8 looks its nibble up, IMAD (FMA
-         // pipe) drops it into place -- the two math pipes and the LSU share the work
-         uint32_t lo = 0, hi = 0;
+         uint32_t l = 0, h = 0;
 #pragma unroll
          for (int j = 0; j < 8; j++) {
             const uint32_t bx = __byte_perm(w[j >> 2], 0u, 0x4440u + (uint32_t)(j & 3));
             const uint32_t by = __byte_perm(w[2 + (j >> 2)], 0u, 0x4440u + (uint32_t)(j & 3));
-            lo = mad_u32((uint32_t)lut[bx], 1u << (4 * j), lo);
-            hi = mad_u32((uint32_t)lut[by], 1u << (4 * j), hi);
+            l = mad_u32((uint32_t)lut[bx], 1u << (4 * j), l);
+            h = mad_u32((uint32_t)lut[by], 1u << (4 * j), h);
          }
-         const uint32_t pos = tile_start + off;
-         if (pos + 16u > n) {               // bytes at or beyond n are STOP and never newlines
+         lo[k] = l;
+         hi[k] = h;
+      }
+      if (pos0 + kK1LaneBytes > n) {        // bytes at or beyond n are STOP and never newlines
+#pragma unroll
+         for (int k = 0; k < 8; k++) {
+            const uint32_t p = pos0 + ((((uint32_t)k + rot) & 7u) << 4);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-               if (pos + (uint32_t)j >= n) lo = (lo & ~(0xFu << (4 * j))) | ((uint32_t)kClsStop << (4 * j));
-               if (pos + 8u + (uint32_t)j >= n) hi = (hi & ~(0xFu << (4 * j))) | ((uint32_t)kClsStop << (4 * j));
+               if (p + (uint32_t)j >= n) lo[k] = (lo[k] & ~(0xFu << (4 * j))) | ((uint32_t)kClsStop << (4 * j));
+               if (p + 8u + (uint32_t)j >= n) hi[k] = (hi[k] & ~(0xFu << (4 * j))) | ((uint32_t)kClsStop << (4 * j));
             }
          }
-         if (CODES) a.codes[pos >> 4] = make_uint2(lo, hi);
-         uint32_t m = ((lo >> 3) & 0x11111111u) | ((hi >> 2) & 0x22222222u);
-         // a newline at p opens a line at p+1 only if p+1 < n, and in FASTA mode
-         // only if that line is not a header
-         if (m != 0 && (a.fasta || pos + 17u > n)) {
-            uint32_t bits = m;
+      }
+
+      // ---- newline flags: f[v] bit 4i+2 <=> byte i, bit 4i+3 <=> byte 8+i of vector v ----
+      uint32_t f[8];
+      {
+         uint32_t g[8], h2[8];
+#pragma unroll
+         for (int k = 0; k < 8; k++) g[k] = ((lo[k] & 0x88888888u) >> 1) | (hi[k] & 0x88888888u);
+         // slot k holds vector (k + rot) & 7: rotate the slots back into text order
+#pragma unroll
+         for (int v = 0; v < 8; v++) h2[v] = (rot & 1u) ? g[(v + 7) & 7] : g[v];
+#pragma unroll
+         for (int v = 0; v < 8; v++) g[v] = (rot & 2u) ? h2[(v + 6) & 7] : h2[v];
+#pragma unroll
+         for (int v = 0; v < 8; v++) f[v] = (rot & 4u) ? g[(v + 4) & 7] : g[v];
+      }
+      // c[q] bit 4i+e <=> byte 8e+i of the 32-byte chunk q of the lane
+      uint32_t c[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) c[q] = (f[2 * q] >> 2) | f[2 * q + 1];
+
+      // a newline at p opens a line at p+1 only if p+1 < n, and in FASTA mode only
+      // if that line is not a header (the text is still intact here)
+      if (a.fasta || pos0 + kK1LaneBytes + 1u > n) {
+#pragma unroll
+         for (int q = 0; q < 4; q++) {
+            uint32_t bits = c[q];
             while (bits) {
                const int b = __ffs(bits) - 1;
                bits &= bits - 1;
-               const uint32_t byte = (uint32_t)(b >> 2) + ((uint32_t)(b & 1) << 3);
-               const uint32_t s = pos + byte + 1u;
-               if (s >= n || (a.fasta && buf[off + byte + 1u] == '>')) m &= ~(1u << b);
+               const uint32_t byte = 32u * (uint32_t)q + 8u * (uint32_t)(b & 3) + (uint32_t)(b >> 2);
+               const uint32_t s = pos0 + byte + 1u;
+               if (s >= n || (a.fasta && buf[lane_off + byte + 1u] == '>')) c[q] &= ~(1u << b);
             }
          }
-         nl[k] = m;
       }
       // the first line of the buffer has no newline in front of it
       const uint32_t first = (tile == 0 && tid == 0 && n > 0 && !(a.fasta && buf[0] == '>')) ? 1u : 0u;
 
-      // ---- prefix over (warp, k, lane): two 16-bit counts per shuffle ---------
-      uint32_t cnt[kK1Vec / 2];
+      // ---- one prefix over the lanes of the warp, then over the warps ------------
+      const uint32_t cnt = (uint32_t)(__popc(c[0]) + __popc(c[1]) + __popc(c[2]) + __popc(c[3])) + first;
+      uint32_t inc = cnt;
 #pragma unroll
-      for (int h = 0; h < kK1Vec / 2; h++)
-         cnt[h] = (uint32_t)__popc(nl[2 * h]) + ((uint32_t)__popc(nl[2 * h + 1]) << 16);
-      cnt[0] += first;
-      uint32_t inc[kK1Vec / 2];
-#pragma unroll
-      for (int h = 0; h < kK1Vec / 2; h++) {
-         uint32_t x = cnt[h];
-#pragma unroll
-         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(kFull, x, d);
-            if (lane >= d) x += t;
-         }
-         inc[h] = x;
+      for (int d = 1; d < 32; d <<= 1) {
+         const uint32_t t = __shfl_up_sync(kFull, inc, d);
+         if (lane >= d) inc += t;
       }
-      // exclusive offset of vector k of this lane inside the warp
-      uint32_t excl[kK1Vec];
-      uint32_t run = 0;
-#pragma unroll
-      for (int h = 0; h < kK1Vec / 2; h++) {
-         const uint32_t tot = __shfl_sync(kFull, inc[h], 31);
-         const uint32_t e = inc[h] - cnt[h];
-         excl[2 * h] = run + (e & 0xFFFFu);
-         run += tot & 0xFFFFu;
-         excl[2 * h + 1] = run + (e >> 16);
-         run += tot >> 16;
-      }
-      if (lane == 0) s_wsum[warp] = run;
-      __syncthreads();
+      if (lane == 31) s_wsum[warp] = inc;
+      // the bulk store this warp issued one tile ago has long read its stage; make
+      // sure before the stage is refilled below
+      if (CODES && store_pending) bulk_wait_read();
+      __syncthreads();                       // A: every lane holds its text in registers, s_wsum is complete
       uint32_t before = 0, tile_total = 0;
 #pragma unroll
       for (int w2 = 0; w2 < kWarps; w2++) {
@@ -247,35 +268,62 @@ __global__ void __launch_bounds__(kThreads) k1_scan_classify(const K1Args a, con
          tile_total += x;
       }
       if (tid == 0) {
+         // prefetch the next ticket into the other stage (its last store has been waited for)
+         const uint32_t t = (uint32_t)atomicAdd(&a.ctr[C_TICKET_K1], 1ull);
+         s_tile[stage ^ 1] = t;
+         if (t < ntiles) issue(stage ^ 1, t);
          const uint32_t at = (uint32_t)atomicAdd(&a.ctr[C_LS_CURSOR], (unsigned long long)tile_total);
          a.tile_cnt[tile] = tile_total;
          a.tile_off[tile] = at;
          s_base[stage] = at;
       }
-      __syncthreads();
-      const uint32_t base = s_base[stage] + before;
+
+      // ---- class nibbles: in place over the warp's own text, one bulk store per warp ----
+      if (CODES) {
+#pragma unroll
+         for (int k = 0; k < 8; k++)
+            *reinterpret_cast<uint2 *>(buf + code_off + ((((uint32_t)k + rot) & 7u) << 3)) = make_uint2(lo[k], hi[k]);
+         fence_proxy_async();
+         __syncwarp();
+         if (lane == 0) {
+            const uint32_t wpos = tile * kK1Tile + (uint32_t)warp * kK1WarpBytes;
+            bulk_s2g(reinterpret_cast<uint8_t *>(a.codes) + (wpos >> 1), buf + (uint32_t)warp * kK1WarpBytes,
+                     kK1WarpBytes / 2);
+            store_pending = true;
+         }
+      }
+      __syncthreads();                       // B: s_base, s_tile
+      uint32_t idx = s_base[stage] + before + inc - cnt;
 
       // ---- emit (ordered inside the tile) -------------------------------------
+      if (first) {
+         if (idx < a.ls_cap) a.ls_raw[idx] = 0;
+         idx++;
+      }
 #pragma unroll
-      for (int k = 0; k < kK1Vec; k++) {
-         uint32_t idx = base + excl[k];
-         if (k == 0 && first) {
-            if (idx < a.ls_cap) a.ls_raw[idx] = 0;
+      for (int q = 0; q < 4; q++) {
+         const uint32_t bits = c[q];
+         if (bits == 0) continue;
+         const uint32_t p = pos0 + 32u * (uint32_t)q + 1u;
+         if ((bits & (bits - 1)) == 0) {           // one line start in these 32 bytes (the usual case)
+            const int b = __ffs(bits) - 1;
+            if (idx < a.ls_cap) a.ls_raw[idx] = p + 8u * (uint32_t)(b & 3) + (uint32_t)(b >> 2);
             idx++;
-         }
-         const uint32_t pos = tile_start + woff + (uint32_t)k * 512u;
-#pragma unroll
-         for (int half = 0; half < 2; half++) {
-            uint32_t bits = nl[k] & (half ? 0x22222222u : 0x11111111u);
-            while (bits) {
-               const int b = __ffs(bits) - 1;
-               bits &= bits - 1;
-               if (idx < a.ls_cap) a.ls_raw[idx] = pos + (uint32_t)(b >> 2) + (uint32_t)(half << 3) + 1u;
-               idx++;
+         } else {                                  // several: walk them in text order
+#pragma unroll 1
+            for (int e = 0; e < 4; e++) {
+               uint32_t be = bits & (0x11111111u << e);
+               while (be) {
+                  const int b = __ffs(be) - 1;
+                  be &= be - 1;
+                  if (idx < a.ls_cap) a.ls_raw[idx] = p + 8u * (uint32_t)e + (uint32_t)(b >> 2);
+                  idx++;
+               }
             }
          }
       }
    }
+   if (CODES && store_pending) bulk_wait_all();
 }
 
 // exclusive scan of the per-tile line counts (one CTA of 1024 threads):
@@ -291,30 +339,37 @@ __global__ void __launch_bounds__(1024) k1_scan_tiles(const K1ScanArgs a)
 {
    __shared__ unsigned long long s_warp[32];
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-   // thread t owns the contiguous run [t*per, (t+1)*per): serial sum, one block scan, serial write
-   const uint32_t per = (a.ntiles + 1023u) / 1024u;
-   const uint32_t t0 = min((uint32_t)tid * per, a.ntiles), t1 = min(t0 + per, a.ntiles);
+   // warp w owns the contiguous run [w*per, (w+1)*per) and walks it 32 tiles at a
+   // time (coalesced): first its total, then -- after the 32 totals are scanned --
+   // the exclusive prefix of every tile
+   const uint32_t per = ((a.ntiles + 1023u) / 1024u) * 32u;
+   const uint32_t t0 = min((uint32_t)warp * per, a.ntiles), t1 = min(t0 + per, a.ntiles);
    unsigned long long sum = 0;
-   for (uint32_t t = t0; t < t1; t++) sum += a.tile_cnt[t];
-   unsigned long long x = sum;
+#pragma unroll 4
+   for (uint32_t t = t0 + (uint32_t)lane; t < t1; t += 32) sum += a.tile_cnt[t];
 #pragma unroll
-   for (int d = 1; d < 32; d <<= 1) {
-      const unsigned long long y = __shfl_up_sync(kFull, x, d);
-      if (lane >= d) x += y;
-   }
-   if (lane == 31) s_warp[warp] = x;
+   for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(kFull, sum, d);
+   if (lane == 0) s_warp[warp] = sum;
    __syncthreads();
-   unsigned long long before = 0, tot = 0;
+   unsigned long long run = 0, tot = 0;
    for (int w = 0; w < 32; w++) {
       const unsigned long long y = s_warp[w];
-      if (w < warp) before += y;
+      if (w < warp) run += y;
       tot += y;
    }
-   unsigned long long run = before + x - sum;
    // line numbers are u32 (a batch is < 4 GiB of text)
-   for (uint32_t t = t0; t < t1; t++) {
-      a.tile_base[t] = (uint32_t)run;
-      run += a.tile_cnt[t];
+#pragma unroll 2
+   for (uint32_t tb = t0; tb < t1; tb += 32) {
+      const uint32_t t = tb + (uint32_t)lane;
+      const uint32_t v = t < t1 ? a.tile_cnt[t] : 0u;
+      uint32_t x = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+         const uint32_t y = __shfl_up_sync(kFull, x, d);
+         if (lane >= d) x += y;
+      }
+      if (t < t1) a.tile_base[t] = (uint32_t)run + x - v;
+      run += __shfl_sync(kFull, x, 31);
    }
    if (tid == 0) a.ctr[C_NLINES] = tot;
 }
@@ -874,36 +929,47 @@ struct FinArgs {
    const uint32_t *tile_base;     // first record of every 1024-line tile
 };
 
+// Per tile of 1024 lines: (1) the candidates are compacted, in line order, into
+// shared memory (ballot/popc inside the warp, scan across the warps); (2) the
+// threads then run the reverse pass over the DENSE candidate list -- half of the
+// lines of a typical input have no match, and a thread per line would leave those
+// lanes idle through the whole pass -- and write the records, already in order,
+// behind the tile's first record (k_tile_sums / k_tile_scan).
 template <int W>
 __global__ void __launch_bounds__(kThreads) k34_finish_lines(const FinArgs a, const __grid_constant__ Pattern rpat)
 {
    __shared__ BlockScanSmem sc;
    __shared__ RevTables<W> tab;
+   __shared__ uint4 cand[kFinTile];                       // line, line start, end, dist
    rev_tables_load(tab, rpat);
    const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
    const uint32_t ntiles = (nlines + kFinTile - 1) / kFinTile;
    const int tid = threadIdx.x;
    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      uint32_t run = a.tile_base[tile];
+      uint32_t run = 0;
 #pragma unroll 1
       for (int k = 0; k < (int)(kFinTile / kThreads); k++) {
          const uint32_t line = tile * kFinTile + (uint32_t)k * kThreads + (uint32_t)tid;
          unsigned long long key = kNoMatch;
          if (line < nlines) key = a.res[line];
          const bool valid = key != kNoMatch;
-         Rec r{};
-         if (valid) {
-            r.line = line;
-            r.end = (uint32_t)key;
-            r.dist = (uint32_t)(key >> 32);
-            r.start = reverse_start<W>(a.text, a.ls[line], r.end, (int)r.dist, rpat.m, rpat.tau, tab);
-         }
-         // ordered compaction: ballot/popc inside the warp, scan across the warps
          uint32_t total;
          const uint32_t excl = block_exclusive_scan(valid ? 1u : 0u, sc, &total);
-         if (valid && run + excl < a.rec_cap) a.recs[run + excl] = r;
+         if (valid) cand[run + excl] = make_uint4(line, a.ls[line], (uint32_t)key, (uint32_t)(key >> 32));
          run += total;
       }
+      __syncthreads();
+      const uint32_t base = a.tile_base[tile];
+      for (uint32_t i = (uint32_t)tid; i < run; i += kThreads) {
+         const uint4 c = cand[i];
+         Rec r;
+         r.line = c.x;
+         r.end = c.z;
+         r.dist = c.w;
+         r.start = reverse_start<W>(a.text, c.y, c.z, (int)c.w, rpat.m, rpat.tau, tab);
+         if (base + i < a.rec_cap) a.recs[base + i] = r;
+      }
+      __syncthreads();                                    // cand is reused by the next tile
    }
 }
 

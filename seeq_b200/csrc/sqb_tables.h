@@ -54,12 +54,17 @@ static inline void build_class_table(int options, ClassTable *t)
    }
 }
 
-// rows of the kernel instance that serves a pattern of m positions (0: none)
-static inline int bs_rows_for(int m)
+// the kernel instance (R rows per part, G parts) that serves a pattern of m
+// positions; false if there is none (m > 128)
+struct BsShape { int rows, parts; };
+static const BsShape kBsShapes[] = {{8, 1}, {12, 1}, {16, 1}, {24, 1}, {32, 1},      // m <= 32: one lane per group
+                                    {20, 2}, {24, 2}, {32, 2},                       // m <= 64: two lanes
+                                    {20, 4}, {24, 4}, {28, 4}, {32, 4}};             // m <= 128: four lanes
+static inline bool bs_shape_for(int m, BsShape *out)
 {
-   static const int buckets[] = {8, 12, 16, 24, 32};
-   for (int b : buckets) if (m <= b) return b;
-   return 0;
+   for (const BsShape &b : kBsShapes)
+      if (m <= b.rows * b.parts) { *out = b; return true; }
+   return false;
 }
 
 // keys: one class byte per pattern position (bit0 A .. bit3 T, 0x1F = N).
@@ -68,16 +73,18 @@ static inline int bs_rows_for(int m)
 static inline bool build_bs_pattern(const unsigned char *keys, int m, int tau, BsPattern *p)
 {
    memset(p, 0, sizeof *p);
-   const int R = bs_rows_for(m);
-   if (R == 0 || tau + 1 > 15) return false;
+   BsShape shape;
+   if (!bs_shape_for(m, &shape) || tau + 1 > 15) return false;
    p->m = m;
    p->tau = tau;
-   p->rows = R;
+   p->rows = shape.rows;
+   p->parts = shape.parts;
+   const int R = shape.rows * shape.parts;        // rows of the whole automaton
    const int pad = R - m;
    int ncustom = 0;
    unsigned char custom_key[2] = {0, 0};
    for (int j = 0; j < R; j++) {
-      if (j < pad) { p->slot[j] = BS_ONES; continue; }     // rows beyond R stay 0 (unused)
+      if (j < pad) { p->slot[j] = BS_ONES; continue; }     // entries beyond R stay 0 (unused)
       const unsigned char k = keys[j - pad] & 0x1F;
       int slot = -1;
       switch (k) {
