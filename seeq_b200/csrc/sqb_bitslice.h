@@ -75,7 +75,8 @@ template <int R, int G = 1> struct BsState {
    uint32_t bd[kBsBestBits];            // best distance so far (BS_BEST)
    uint32_t alive;                      // lines still being scanned
    uint32_t flag;                       // the reference's `match` suppress flag
-   uint32_t hit;                        // lines with at least one event
+   uint32_t hit;                        // lines with at least one (reported) event
+   uint32_t stopped;                    // lines that ran into a STOP byte
 };
 
 // part: which part of the pattern this state holds (0 .. G-1); `valid` = lines in
@@ -97,6 +98,7 @@ SQB_BS_HD void bs_reset(BsState<R, G> &st, const BsPattern &p, uint32_t valid, i
    st.alive = part == G - 1 ? valid : 0u;
    st.flag = 0u;
    st.hit = 0u;
+   st.stopped = 0u;
 }
 
 // Eq slots and the class masks of one column from the three code planes
@@ -123,51 +125,41 @@ SQB_BS_HD void bs_classes(uint32_t p0, uint32_t p1, uint32_t p2, const BsPattern
 
 // The rows of one part for one text column.  eq(j) returns the Eq mask of row j
 // of this part.  ph / mh: on entry the horizontal delta handed over by the part
-// below (0 for part 0), on return the delta of this part's top row.  Rows below
-// `first` are skipped (wildcard rows of part 0: their deltas are 0 forever).
+// below (0 for part 0), on return the delta of this part's top row.
+//
+// (Skipping the wildcard rows of part 0 with a computed jump into the unrolled
+// rows was tried: the basic-block boundaries stop the scheduler from hoisting
+// the Eq loads, k2_bitslice<12> went from 447 to 558 us on cfg2.)
 //
 // A NULL column (class 7: no base, no stop, no skip) leaves a state that is
 // still at its reset value unchanged and hands 0 upwards: a mismatch against
 // the initial column [0, 1, .., m] reproduces it.  The kernel feeds NULL columns
 // to the upper parts while the pipeline fills.
-#define SQB_BS_ROW(j)                                                            \
-   case j:                                                                       \
-      if (j < R) {                                                               \
-         const uint32_t e = eq(j);                                               \
-         const uint32_t pv = st.pv[j < R ? j : 0], mv = st.mv[j < R ? j : 0];    \
-         const uint32_t xh = e | mh;                                             \
-         const uint32_t xv = e | mv;                                             \
-         const uint32_t ph_out = mv | ~(xh | pv);                                \
-         const uint32_t mh_out = pv & xh;                                        \
-         uint32_t pv_new = mh | ~(xv | ph);                                      \
-         uint32_t mv_new = ph & xv;                                              \
-         if (SKIP) { /* an ignored byte leaves the automaton untouched */        \
-            pv_new = (pv & skipc) | (pv_new & ~skipc);                           \
-            mv_new = (mv & skipc) | (mv_new & ~skipc);                           \
-         }                                                                       \
-         st.pv[j < R ? j : 0] = pv_new;                                          \
-         st.mv[j < R ? j : 0] = mv_new;                                          \
-         ph = ph_out;                                                            \
-         mh = mh_out;                                                            \
-      }                                                                          \
-      /* fall through */
-
 template <int R, int G, bool SKIP, class EqOf>
-SQB_BS_HD void bs_rows(BsState<R, G> &st, const EqOf &eq, uint32_t skipc, uint32_t &ph, uint32_t &mh, int first = 0)
+SQB_BS_HD void bs_rows(BsState<R, G> &st, const EqOf &eq, uint32_t skipc, uint32_t &ph, uint32_t &mh)
 {
    static_assert(R <= 32, "at most 32 rows per part");
    (void)skipc;
-   switch (first) {
-   default:
-      SQB_BS_ROW(0) SQB_BS_ROW(1) SQB_BS_ROW(2) SQB_BS_ROW(3) SQB_BS_ROW(4) SQB_BS_ROW(5) SQB_BS_ROW(6) SQB_BS_ROW(7)
-      SQB_BS_ROW(8) SQB_BS_ROW(9) SQB_BS_ROW(10) SQB_BS_ROW(11) SQB_BS_ROW(12) SQB_BS_ROW(13) SQB_BS_ROW(14)
-      SQB_BS_ROW(15) SQB_BS_ROW(16) SQB_BS_ROW(17) SQB_BS_ROW(18) SQB_BS_ROW(19) SQB_BS_ROW(20) SQB_BS_ROW(21)
-      SQB_BS_ROW(22) SQB_BS_ROW(23) SQB_BS_ROW(24) SQB_BS_ROW(25) SQB_BS_ROW(26) SQB_BS_ROW(27) SQB_BS_ROW(28)
-      SQB_BS_ROW(29) SQB_BS_ROW(30) SQB_BS_ROW(31)
-      break;
+#pragma unroll
+   for (int j = 0; j < R; j++) {
+      const uint32_t e = eq(j);
+      const uint32_t pv = st.pv[j], mv = st.mv[j];
+      const uint32_t xh = e | mh;
+      const uint32_t xv = e | mv;
+      const uint32_t ph_out = mv | ~(xh | pv);
+      const uint32_t mh_out = pv & xh;
+      uint32_t pv_new = mh | ~(xv | ph);
+      uint32_t mv_new = ph & xv;
+      if (SKIP) {                                 // an ignored byte leaves the automaton untouched
+         pv_new = (pv & skipc) | (pv_new & ~skipc);
+         mv_new = (mv & skipc) | (mv_new & ~skipc);
+      }
+      st.pv[j] = pv_new;
+      st.mv[j] = mv_new;
+      ph = ph_out;
+      mh = mh_out;
    }
 }
-#undef SQB_BS_ROW
 
 // The report state machine of the LAST part for one text column.  ph / mh = the
 // horizontal delta of the top row (the last pattern position).  Returns the
@@ -221,6 +213,7 @@ SQB_BS_HD uint32_t bs_report(BsState<R, G> &st, const BsPattern &p, uint32_t ph,
       }
    }
    st.hit |= evt;
+   st.stopped |= stop;
    st.alive &= ~stop;
    if (MODE == BS_FIRST) st.alive &= ~evt;        // :330  the first match ends the scan of the line
 
@@ -242,7 +235,7 @@ SQB_BS_HD uint32_t bs_step(BsState<R, 1> &st, const BsPattern &p, const EqOf &eq
                            uint32_t skipc, uint32_t *streak, uint32_t quiet = 0u)
 {
    uint32_t ph = 0u, mh = 0u;
-   bs_rows<R, 1, SKIP>(st, eq, skipc, ph, mh, R - p.m);
+   bs_rows<R, 1, SKIP>(st, eq, skipc, ph, mh);
    return bs_report<R, 1, MODE>(st, p, ph, mh, anybase, stopc, streak, quiet);
 }
 

@@ -52,7 +52,11 @@ struct Slot {
    uint32_t *d_ls = nullptr;    size_t line_cap = 0;      // entries (incl. sentinel)
    uint8_t *d_codes = nullptr;  size_t codes_cap = 0;     // class nibbles (K1 -> bit-sliced K2)
    uint32_t *d_ls_raw = nullptr; size_t ls_raw_cap = 0;   // line starts in tile-allocation order
-   uint32_t *d_tiles = nullptr; size_t tiles_cap = 0;     // per K1 tile: count, offset, base
+   uint32_t *d_tiles = nullptr; size_t tiles_cap = 0;     // per K1 tile: count, offset, base (+ 4 arrays of the segment cuts)
+   uint32_t *d_lid = nullptr;   size_t lid_cap = 0;       // segment cuts: line of every ls entry
+   uint32_t *d_lbeg = nullptr;  size_t lbeg_cap = 0;      //               start of that line
+   uint32_t *d_gmask = nullptr; size_t gmask_cap = 0;     //               per group of 32 entries: continuations, followed
+   uint8_t *d_segflags = nullptr; size_t segflags_cap = 0; //              segstop[], deadseg[]
    uint4 *d_planes = nullptr;   size_t planes_cap = 0;    // bit-planes, 32 uint4 per tile column
    uint32_t *d_bstiles = nullptr; size_t bstiles_cap = 0; // per match tile: columns, offset
    uint32_t *d_fintiles = nullptr; size_t fintiles_cap = 0; // per 1024-line tile: records, matched lines, first record
@@ -86,6 +90,7 @@ struct sqb_engine {
    int words = 1;                 // automaton words: 1, 2, 4, 8, 16 or 32
    unsigned char keys[kMaxWords * 32];
    bool bs_ok = false;            // the pattern fits the bit-sliced matcher
+   bool cuts = true;              // long lines may be cut into segments (SEEQ_B200_CUTS=0 disables)
    BsGate bs_gate{65536u, 4096u};
    uint32_t bs_min_bytes = 1u << 20;
    double cols_per_byte = 1.3 / 1024.0;   // tile columns per text byte (plane buffer guess)
@@ -164,7 +169,7 @@ template <class T> static int pin_reserve(T **p, size_t *cap, size_t need)
 
 static void slot_free(Slot &s)
 {
-   cudaFree(s.d_text); cudaFree(s.d_ls); cudaFree(s.d_codes); cudaFree(s.d_ls_raw); cudaFree(s.d_tiles); cudaFree(s.d_planes); cudaFree(s.d_bstiles); cudaFree(s.d_fintiles); cudaFree(s.d_res); cudaFree(s.d_cnt); cudaFree(s.d_offs);
+   cudaFree(s.d_text); cudaFree(s.d_ls); cudaFree(s.d_codes); cudaFree(s.d_ls_raw); cudaFree(s.d_tiles); cudaFree(s.d_lid); cudaFree(s.d_lbeg); cudaFree(s.d_gmask); cudaFree(s.d_segflags); cudaFree(s.d_planes); cudaFree(s.d_bstiles); cudaFree(s.d_fintiles); cudaFree(s.d_res); cudaFree(s.d_cnt); cudaFree(s.d_offs);
    cudaFree(s.d_ev); cudaFree(s.d_recs); cudaFree(s.d_ctl);
    cudaFreeHost(s.h_ctr); cudaFreeHost(s.h_recs); cudaFreeHost(s.h_ls); cudaFreeHost(s.h_init);
    for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
@@ -274,6 +279,19 @@ static bool use_bitslice(const sqb_engine *e, int options, uint32_t n)
    return e->bs_ok && !(options & (SQB_SINGLE_LINE | OPT_STREAM)) && n >= e->bs_min_bytes;
 }
 
+// long lines are cut into segments (sqb_tables.h) when the scan is bit-sliced, returns
+// records and runs in a mode in which every byte in front of a STOP feeds the
+// automaton.  Not with SQ_IGNORE (a warm-up could hold too few automaton inputs),
+// not in FASTA mode (a cut inside a long header line would be scanned), not when
+// the caller wants the line starts back, not in the count-only modes.
+static bool use_cuts(const sqb_engine *e, int options, uint32_t n)
+{
+   if (!use_bitslice(e, options, n) || !e->cuts) return false;
+   if (options & (SQB_FASTA | SQB_COUNT_ONLY | SQB_KEEP_LINES_INTERNAL)) return false;
+   if ((options & OPT_NONDNA) == OPT_IGNORE) return false;
+   return bs_warmup(e->m, e->tau) <= kCutWindow;
+}
+
 template <int R, int G, int MODE> static int launch_bs2(bool skip, int grid, cudaStream_t st, const K2BsArgs &a, const BsPattern &p)
 {
    const size_t smem = (MODE == BS_ALL ? sizeof(BsWarpSmemAll) : sizeof(BsWarpSmem)) * kBsWarps;
@@ -356,6 +374,7 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
 
    if (timing) CU(cudaEventRecord(s.ev[0], st));
    CU(cudaMemsetAsync(s.d_ctl, 0, ctl_words * sizeof(unsigned long long), st));
+   const bool cut = !single && use_cuts(e, options, n);
 
    // ---- K1 ------------------------------------------------------------------
    if (single) {
@@ -364,32 +383,45 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
       CU(cudaMemcpyAsync(s.d_ls, s.h_init, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
       s.h_ctr[C_NLINES] = 1;      // reuse pinned word as the source of the line count
       CU(cudaMemcpyAsync(ctr + C_NLINES, s.h_ctr + C_NLINES, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(ctr + C_NPSEUDO, s.h_ctr + C_NLINES, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
    } else {
       const bool want_codes = use_bitslice(e, options, n);
       if (want_codes) {
          const size_t need = k1_tiles * (kK1Tile / 2) + 256;
          if (dev_reserve(&s.d_codes, &s.codes_cap, need)) return -1;
       }
-      if (dev_reserve(&s.d_tiles, &s.tiles_cap, 3 * k1_tiles)) return -1;
+      if (dev_reserve(&s.d_tiles, &s.tiles_cap, 7 * k1_tiles)) return -1;
       uint32_t *tile_cnt = s.d_tiles, *tile_off = tile_cnt + k1_tiles, *tile_base = tile_off + k1_tiles;
+      uint32_t *tile_real = tile_base + k1_tiles, *tile_rbase = tile_real + k1_tiles;
+      uint32_t *tile_last = tile_rbase + k1_tiles, *tile_lbeg = tile_last + k1_tiles;
+      if (cut) {
+         if (dev_reserve(&s.d_lid, &s.lid_cap, s.line_cap, 64)) return -1;
+         if (dev_reserve(&s.d_lbeg, &s.lbeg_cap, s.line_cap, 64)) return -1;
+         if (dev_reserve(&s.d_gmask, &s.gmask_cap, 2 * (div_up(s.line_cap, 64) * 2 + 64), 64)) return -1;
+         if (dev_reserve(&s.d_segflags, &s.segflags_cap, 2 * s.line_cap, 64)) return -1;
+         CU(cudaMemsetAsync(s.d_segflags, 0, 2 * s.line_cap, st));
+      }
       const uint32_t ntiles = (uint32_t)div_up(n, kK1Tile);
       K1Args k1{d_text, n, s.d_ls_raw, (uint32_t)s.line_cap, want_codes ? (uint2 *)s.d_codes : nullptr, ctr,
-                tile_cnt, tile_off, (options & SQB_FASTA) ? 1 : 0};
+                tile_cnt, tile_off, tile_real, tile_last, (options & SQB_FASTA) ? 1 : 0};
       ClassTable ct;
       build_class_table(options, &ct);
       static bool attr = false;
       if (!attr) {
-         CU(cudaFuncSetAttribute(k1_scan_classify<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
-         CU(cudaFuncSetAttribute(k1_scan_classify<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
+         CU(cudaFuncSetAttribute(k1_scan_classify<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
+         CU(cudaFuncSetAttribute(k1_scan_classify<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
+         CU(cudaFuncSetAttribute(k1_scan_classify<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
          attr = true;
       }
       const int grid = (int)std::min<size_t>(div_up(n, kK1Tile), (size_t)e->sms * 3);
-      if (want_codes) k1_scan_classify<true><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
-      else k1_scan_classify<false><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
+      if (cut) k1_scan_classify<true, true><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
+      else if (want_codes) k1_scan_classify<true, false><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
+      else k1_scan_classify<false, false><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
       CU(cudaGetLastError());
-      K1ScanArgs ks{tile_cnt, tile_base, ntiles, ctr};
+      K1ScanArgs ks{tile_cnt, tile_base, ntiles, ctr, cut ? tile_real : nullptr, tile_rbase, tile_last, tile_lbeg};
       k1_scan_tiles<<<1, 1024, 0, st>>>(ks);
-      K1GatherArgs kg{s.d_ls_raw, s.d_ls, (uint32_t)s.line_cap, tile_cnt, tile_off, tile_base, ntiles, n, ctr};
+      K1GatherArgs kg{s.d_ls_raw, s.d_ls, (uint32_t)s.line_cap, tile_cnt, tile_off, tile_base, ntiles, n, ctr,
+                      cut ? s.d_codes : nullptr, tile_rbase, tile_lbeg, s.d_lid, s.d_lbeg};
       k1_gather<<<(int)std::min<size_t>(div_up(ntiles, kWarps), (size_t)e->sms * 8), kThreads, 0, st>>>(kg);
       CU(cudaGetLastError());
       s.launches += 3;
@@ -414,20 +446,31 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
       const size_t want_cols = (size_t)((double)n * e->cols_per_byte) + 4096;
       if (dev_reserve(&s.d_planes, &s.planes_cap, want_cols * 32, 16)) return -1;
       uint32_t *tile_cols = s.d_bstiles, *tile_off = tile_cols + max_tiles;
+      const uint32_t wup = bs_warmup(e->m, e->tau);
+      uint32_t *gmask = s.d_gmask, *gfollow = cut ? s.d_gmask + s.gmask_cap / 2 : nullptr;
+      uint8_t *segstop = s.d_segflags, *deadseg = cut ? s.d_segflags + s.line_cap : nullptr;
       BsPrepArgs bp{s.d_ls, (uint32_t)lines_cap, n, ctr, tile_cols, tile_off, (uint32_t)max_tiles,
-                    (unsigned long long)(s.planes_cap / 32), e->bs_gate};
+                    (unsigned long long)(s.planes_cap / 32), e->bs_gate, cut ? s.d_lid : nullptr, wup};
       k15_tile_cols<<<(int)std::min<size_t>(div_up(max_tiles, kWarps), (size_t)e->sms * 8), kThreads, 0, st>>>(bp);
       k15_scan<<<1, 1024, 0, st>>>(bp);
       BsPackArgs pk{(const uint4 *)s.d_codes, (uint32_t)(div_up(n, kK1Tile) * (kK1Tile / 32)), s.d_ls,
-                    (uint32_t)lines_cap, ctr, tile_cols, tile_off, s.d_planes};
+                    (uint32_t)lines_cap, ctr, tile_cols, tile_off, s.d_planes, cut ? s.d_lid : nullptr, wup,
+                    gmask, gfollow};
       k15_pack<<<(int)std::max<size_t>(1, std::min<size_t>(div_up(div_up(max_lines, 64), kWarps), (size_t)e->sms * 16)),
                  kThreads, 0, st>>>(pk);
       CU(cudaGetLastError());
       s.launches += 3;
       K2BsArgs kb{s.d_planes, tile_cols, tile_off, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_ev, k2.ev_cap,
-                  (mode == M_COUNT || mode == M_COUNTALL) ? 1 : 0};
+                  (mode == M_COUNT || mode == M_COUNTALL) ? 1 : 0, cut ? gmask : nullptr, gfollow, segstop, wup};
       if (launch_bitslice(e, mode, options, max_lines, st, kb)) return -1;
       s.launches++;
+      if (cut) {
+         SegReduceArgs sr{s.d_lid, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, segstop, deadseg, mode};
+         k_seg_reduce<<<(int)std::max<size_t>(1, std::min<size_t>(div_up(max_lines, kThreads), (size_t)e->sms * 8)),
+                        kThreads, 0, st>>>(sr);
+         CU(cudaGetLastError());
+         s.launches++;
+      }
    }
    {
       const int grid = (int)std::min<size_t>(div_up(max_lines, lines_per_cta), (size_t)e->sms * 8);
@@ -439,7 +482,9 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
    // ---- scan + K3/K4 --------------------------------------------------------
    uint32_t *tile_sum = s.d_fintiles, *tile_nz = tile_sum + fin_tiles, *tile_recbase = tile_nz + fin_tiles;
    FinArgs fa{d_text, s.d_ls, (uint32_t)lines_cap, s.d_res, s.d_offs, s.d_ev, k2.ev_cap, s.d_recs,
-              (uint32_t)std::min<size_t>(s.rec_cap, 0xffffffffu), ctr, tile_recbase};
+              (uint32_t)std::min<size_t>(s.rec_cap, 0xffffffffu), ctr, tile_recbase,
+              cut ? s.d_lid : nullptr, cut ? s.d_lbeg : nullptr,
+              (cut && mode == M_ALL) ? s.d_segflags + s.line_cap : nullptr, bs_warmup(e->m, e->tau)};
    if (mode == M_FIRST || mode == M_BEST || mode == M_ALL) {
       const bool all = mode == M_ALL;
       TileSumArgs ts{all ? nullptr : s.d_res, all ? s.d_cnt : nullptr, (uint32_t)lines_cap, ctr, tile_sum, tile_nz,
@@ -473,7 +518,7 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
    for (;;) {
       CU(cudaEventSynchronize(s.ev[4]));
       const int mode = mode_of(s.cur_options);
-      const unsigned long long nlines = s.h_ctr[C_NLINES];
+      const unsigned long long nlines = std::max(s.h_ctr[C_NLINES], s.h_ctr[C_NPSEUDO]);   // entries of ls
       const unsigned long long nev = s.h_ctr[C_EVENTS];
       bool again = false;
       if (nlines + 1 > s.line_cap) {
@@ -573,6 +618,7 @@ sqb_engine_t *sqbEngineNew(const unsigned char *keys, int m, int tau, int device
       if (!strcmp(mk, "word")) e->bs_ok = false;
       if (!strcmp(mk, "bitslice")) { e->bs_gate = BsGate{1u, 1u << 30}; e->bs_min_bytes = 1; }
    }
+   if (const char *c = getenv("SEEQ_B200_CUTS")) e->cuts = atoi(c) != 0;
    return e;
 }
 

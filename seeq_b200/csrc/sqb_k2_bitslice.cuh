@@ -51,13 +51,38 @@ struct BsPrepArgs {
    uint32_t max_tiles;
    unsigned long long planes_cap; // columns the plane buffer can hold
    BsGate gate;
+   const uint32_t *lid;           // line of every ls entry (segment cuts), or nullptr
+   uint32_t wup;                  // warm-up bytes in front of a continuation segment
 };
+
+// With segment cuts an entry l of ls is a CONTINUATION if it belongs to the same
+// line as the entry before it, and is FOLLOWED if the next entry continues it.
+// A continuation scans from ls[l] - wup; a followed segment scans up to and
+// including the first byte of the next one and then falls silent (NULL columns).
+struct SegShape {
+   uint32_t begin;                // first text byte fed to the automaton
+   uint32_t limit;                // columns to feed (0xffffffff: until the STOP of the line)
+   bool cont, follow;
+};
+__device__ __forceinline__ SegShape seg_shape(const uint32_t *ls, const uint32_t *lid, uint32_t wup, uint32_t l,
+                                              uint32_t nlines)
+{
+   SegShape g{ls[l], 0xffffffffu, false, false};
+   if (lid) {
+      const uint32_t me = lid[l];
+      g.cont = l > 0u && lid[l - 1u] == me;
+      g.follow = l + 1u < nlines && lid[l + 1u] == me;
+      if (g.cont) g.begin -= wup;
+      if (g.follow) g.limit = ls[l + 1u] + 1u - g.begin;
+   }
+   return g;
+}
 
 // columns of every tile = longest line (with its terminator) + 1; one warp per tile
 __global__ void __launch_bounds__(kThreads) k15_tile_cols(const BsPrepArgs a)
 {
    const int lane = threadIdx.x & 31;
-   const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
+   const uint32_t nlines = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
    const uint32_t ntiles = (nlines + kBsTileLines - 1) / kBsTileLines;
    const uint32_t wid = (blockIdx.x * kThreads + threadIdx.x) >> 5, nw = (gridDim.x * kThreads) >> 5;
    for (uint32_t t = wid; t < ntiles; t += nw) {
@@ -66,7 +91,14 @@ __global__ void __launch_bounds__(kThreads) k15_tile_cols(const BsPrepArgs a)
 #pragma unroll 4
       for (int k = 0; k < 32; k++) {
          const uint32_t l = l0 + (uint32_t)k * 32u + (uint32_t)lane;
-         if (l < nlines) mx = max(mx, a.ls[l + 1] - a.ls[l]);
+         if (l < nlines) {
+            uint32_t len = a.ls[l + 1] - a.ls[l];
+            if (a.lid) {
+               const SegShape g = seg_shape(a.ls, a.lid, a.wup, l, nlines);
+               len = g.follow ? g.limit : a.ls[l + 1] - g.begin;
+            }
+            mx = max(mx, len);
+         }
       }
       mx = __reduce_max_sync(kFull, mx);
       if (lane == 0) a.tile_cols[t] = mx + 1u;
@@ -82,7 +114,7 @@ __global__ void __launch_bounds__(1024) k15_scan(const BsPrepArgs a)
    __shared__ uint32_t s_max[32];
    __shared__ unsigned long long s_carry;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-   const unsigned long long nl_dev = a.ctr[C_NLINES];
+   const unsigned long long nl_dev = a.ctr[C_NPSEUDO];
    const uint32_t nlines = (uint32_t)min(nl_dev, (unsigned long long)a.max_lines);
    const uint32_t ntiles = (nlines + kBsTileLines - 1) / kBsTileLines;
    if (tid == 0) s_carry = 0;
@@ -118,7 +150,9 @@ __global__ void __launch_bounds__(1024) k15_scan(const BsPrepArgs a)
       uint32_t mx = 0;
       for (int w = 0; w < 32; w++) mx = max(mx, s_max[w]);
       const unsigned long long cols = s_carry;
-      const bool want = nl_dev <= a.max_lines && nl_dev >= a.gate.min_lines && mx <= a.gate.max_line + 1u;
+      // with segment cuts the entries of ls are segments: only the bit-sliced kernel knows them
+      const bool want = nl_dev <= a.max_lines &&
+                        (a.lid != nullptr || (nl_dev >= a.gate.min_lines && mx <= a.gate.max_line + 1u));
       a.ctr[C_BS_COLS] = cols;
       a.ctr[C_BS_SELECTED] = !want ? 0ull : (cols <= a.planes_cap ? 1ull : 2ull);
    }
@@ -132,7 +166,23 @@ struct BsPackArgs {
    const unsigned long long *ctr;
    const uint32_t *tile_cols, *tile_off;
    uint4 *planes;                 // [tile_off + column][32 groups] {p0, p1, p2, -}
+   const uint32_t *lid;           // segment cuts (or nullptr)
+   uint32_t wup;
+   uint32_t *gmask, *gfollow;     // out, per group of 32 entries: continuations / followed segments
 };
+
+// class nibbles at columns >= limit of a followed segment become NULL (7): the
+// segment falls silent there (block = the 32 columns starting at c0)
+__device__ __forceinline__ void null_fill(uint32_t (&w)[4], uint32_t c0, uint32_t limit)
+{
+   if (limit >= c0 + 32u) return;
+   const uint32_t keep = limit > c0 ? limit - c0 : 0u;          // 0..31 nibbles stay
+#pragma unroll
+   for (int i = 0; i < 4; i++) {
+      const uint32_t k = keep > 8u * (uint32_t)i ? min(keep - 8u * (uint32_t)i, 8u) : 0u;
+      if (k < 8u) w[i] |= 0x77777777u << (4u * k);
+   }
+}
 
 // 32x32 bit transpose across the warp: on return lane j holds, in bit i, bit j
 // of lane i's input.  keep[s] / rot[s] are per-lane constants of stage s.
@@ -189,7 +239,7 @@ __global__ void __launch_bounds__(kThreads) k15_pack(const BsPackArgs a)
 {
    if (a.ctr[C_BS_SELECTED] != 1ull) return;
    const int lane = threadIdx.x & 31;
-   const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
+   const uint32_t nlines = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
    const uint32_t npairs = (nlines + 63u) / 64u;
    uint32_t keep[5], rot[5];
    {
@@ -209,8 +259,21 @@ __global__ void __launch_bounds__(kThreads) k15_pack(const BsPackArgs a)
       uint4 *out = a.planes + (size_t)a.tile_off[tile] * 32u;
       const uint32_t la = pair * 64u + (uint32_t)lane, lb = la + 32u;
       NibbleStream sa, sb;
-      sa.open(a.codes, a.ncode16, la < nlines ? a.ls[la] : 0u, la < nlines);
-      sb.open(a.codes, a.ncode16, lb < nlines ? a.ls[lb] : 0u, lb < nlines);
+      SegShape ga{0u, 0xffffffffu, false, false}, gb{0u, 0xffffffffu, false, false};
+      if (la < nlines) ga = seg_shape(a.ls, a.lid, a.wup, la, nlines);
+      if (lb < nlines) gb = seg_shape(a.ls, a.lid, a.wup, lb, nlines);
+      sa.open(a.codes, a.ncode16, ga.begin, la < nlines);
+      sb.open(a.codes, a.ncode16, gb.begin, lb < nlines);
+      if (a.lid) {
+         const uint32_t ca = __ballot_sync(kFull, ga.cont), cb = __ballot_sync(kFull, gb.cont);
+         const uint32_t fa = __ballot_sync(kFull, ga.follow), fb = __ballot_sync(kFull, gb.follow);
+         if (lane == 0) {
+            a.gmask[pair * 2u] = ca;
+            a.gmask[pair * 2u + 1u] = cb;
+            a.gfollow[pair * 2u] = fa;
+            a.gfollow[pair * 2u + 1u] = fb;
+         }
+      }
       // what this lane stores per 8-column block: 8 bytes = two planes of one group
       //   even lanes: group g0,     planes (j&2), (j&2)+1 of column j>>2
       //   odd  lanes: group g0 + 1, the same planes
@@ -219,6 +282,8 @@ __global__ void __launch_bounds__(kThreads) k15_pack(const BsPackArgs a)
          uint32_t wa[4], wb[4];
          sa.next(wa);
          sb.next(wb);
+         null_fill(wa, c0, ga.limit);
+         null_fill(wb, c0, gb.limit);
 #pragma unroll
          for (int k = 0; k < 4; k++) {
             const uint32_t ta = warp_transpose32(wa[k], keep, rot);
@@ -244,6 +309,9 @@ struct K2BsArgs {
    Event *ev;                     // BS_ALL: unordered events
    uint32_t ev_cap;
    int count_only;                // counts only: no res / event stores
+   const uint32_t *gmask, *gfollow;  // segment cuts: per group, continuations / followed segments (or nullptr)
+   uint8_t *segstop;              // out: followed segments that ran into a STOP (the rest of the line is dead)
+   uint32_t wup;                  // a continuation reports the events that end after its warm-up
 };
 
 struct BsWarpSmem {
@@ -281,7 +349,7 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const int part = lane / NG, gl = lane % NG;
    Smem &sm = reinterpret_cast<Smem *>(dyn)[warp];
-   const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
+   const uint32_t nlines = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
    const uint32_t ntiles = (nlines + kBsTileLines - 1) / kBsTileLines;
    const uint32_t nitems = ntiles * (uint32_t)G;          // (tile, quarter) pairs
 
@@ -299,7 +367,6 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
 #pragma unroll
       for (int j = 0; j < R; j++) raddr[j] = sb + s_off[part * R + j];
    }
-   const int first_row = G == 1 ? R - pat.m : 0;          // wildcard rows are skipped
 
    uint32_t my_matched = 0, my_events = 0;
 
@@ -316,6 +383,11 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
          for (int i = 0; i < 32; i++) static_cast<BsWarpSmemAll &>(sm).cnt[i * 32 + lane] = 0u;
       }
       uint32_t lane_events = 0;
+      uint32_t qmask = 0u, fmask = 0u;
+      if (a.gmask) {
+         qmask = a.gmask[tile * 32u + group];
+         fmask = a.gfollow[tile * 32u + group];
+      }
       const uint32_t ncols = a.tile_cols[tile];
       const uint32_t niter = ncols + (uint32_t)(G - 1);
       const uint4 *col = a.planes + (size_t)a.tile_off[tile] * 32u + group;
@@ -380,11 +452,11 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
             if (G > 1) return lds_u32(raddr[G > 1 ? j : 0]);
             return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(slot_base) + pat.slot_off[j]);
          };
-         bs_rows<R, G, SKIP>(st, eq, skip, ph, mh, first_row);
+         bs_rows<R, G, SKIP>(st, eq, skip, ph, mh);
          ph_prev = ph;
          mh_prev = mh;
          uint32_t streak[B];
-         const uint32_t evt = bs_report<R, G, MODE>(st, pat, ph, mh, anybase, stop, streak);
+         const uint32_t evt = bs_report<R, G, MODE>(st, pat, ph, mh, anybase, stop, streak, c <= a.wup ? qmask : 0u);
 
          // ---- events leave the bit-sliced world here (rare) ---------------------
          if (MODE == BS_ALL) {
@@ -429,6 +501,8 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
       }
       my_matched += (uint32_t)__popc(st.hit);
       my_events += lane_events;
+      for (uint32_t ss = st.stopped & fmask; ss; ss &= ss - 1u)
+         a.segstop[line0 + group * 32u + (uint32_t)(__ffs(ss) - 1)] = 1;
       if (MODE == BS_ALL && !a.count_only) {
          __syncwarp();
 #pragma unroll 4

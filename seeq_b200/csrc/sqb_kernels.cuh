@@ -50,7 +50,10 @@ enum Counter {
    C_LS_CURSOR = 7,  // K1: allocation cursor into the unordered line-start array
    C_BS_SELECTED = 8,// 1: the bit-sliced matcher serves this scan, 0: the word-parallel one, 2: planes too small
    C_BS_COLS = 9,    // tile columns the plane buffer must hold
-   C_COUNT = 12
+   C_NPSEUDO = 10,   // entries of ls: counted lines + segment cuts (== C_NLINES without cuts)
+   C_NCUTS = 11,     // segment cuts made by K1
+   C_NZ_CORR = 12,   // SQ_ALL with cuts: segments with events beyond the first of their line
+   C_COUNT = 16
 };
 
 struct Event {        // SQ_ALL: one forward event, unordered
@@ -116,8 +119,10 @@ struct K1Args {
    uint32_t ls_cap;               // capacity of ls_raw / ls (entries); counting continues beyond it
    uint2 *codes;                  // out: 16 class nibbles per 16 text bytes (nullptr: not wanted)
    unsigned long long *ctr;
-   uint32_t *tile_cnt;            // out: counted lines starting in each tile
+   uint32_t *tile_cnt;            // out: entries (line starts + cuts) of each tile
    uint32_t *tile_off;            // out: where the tile's segment starts in ls_raw
+   uint32_t *tile_real;           // out (CUT): counted lines starting in each tile
+   uint32_t *tile_last;           // out (CUT): 1 + the last line start inside the tile (0: none)
    int fasta;
 };
 
@@ -133,15 +138,22 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <bool CODES>
+// CUT: long lines are cut into segments (sqb_tables.h).  The candidates A = 1024
+// (mod 2048) are the first bytes of lanes 8 and 24 of every warp, and "the line
+// has been running for 1024 bytes" = the eight lanes in front hold no line start:
+// two shuffles of the warp scan decide it.
+template <bool CODES, bool CUT>
 __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, const __grid_constant__ ClassTable ct)
 {
    extern __shared__ __align__(128) uint8_t dyn[];            // 2 x kK1Stage, then the class table
    __shared__ uint64_t bar[2];
    __shared__ uint32_t s_tile[2];
    __shared__ uint32_t s_wsum[kWarps];
+   __shared__ uint32_t s_wcut[kWarps];
    __shared__ uint32_t s_base[2];
+   __shared__ uint32_t s_last[2];
 
+   static_assert(kCutWindow == 8 * kK1LaneBytes && kCutStride == 16 * kK1LaneBytes, "cut candidates = lanes 8 and 24");
    const uint32_t n = a.n;
    const uint32_t ntiles = (n + kK1Tile - 1) / kK1Tile;
    const uint32_t n16 = (n + 15u) & ~15u;
@@ -167,9 +179,11 @@ __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, 
       const uint32_t t = (uint32_t)atomicAdd(&a.ctr[C_TICKET_K1], 1ull);
       s_tile[0] = t;
       if (t < ntiles) issue(0, t);
+      s_last[0] = s_last[1] = 0u;
    }
    __syncthreads();
 
+   uint32_t prev_tile = 0xffffffffu;      // tid 0: the tile whose last line start is still to be published
    uint32_t phases = 0;                   // bit s = parity to wait for on stage s
    bool store_pending = false;            // lane 0 of every warp: a bulk store of the other stage may still read it
    for (int stage = 0;; stage ^= 1) {
@@ -256,16 +270,26 @@ __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, 
          if (lane >= d) inc += t;
       }
       if (lane == 31) s_wsum[warp] = inc;
+      uint32_t cut = 0, cutinc = 0;          // a cut at the first byte of this lane; cuts up to and including this lane
+      if (CUT) {
+         const uint32_t prev1 = __shfl_up_sync(kFull, inc, 1);
+         const uint32_t prev9 = __shfl_up_sync(kFull, inc, 9);
+         if ((lane == 8 || lane == 24) && pos0 < n) cut = (prev1 - (lane == 8 ? 0u : prev9)) == 0u ? 1u : 0u;
+         const uint32_t cut8 = __shfl_sync(kFull, cut, 8), cut24 = __shfl_sync(kFull, cut, 24);
+         cutinc = (lane >= 8 ? cut8 : 0u) + (lane >= 24 ? cut24 : 0u);
+         if (lane == 31) s_wcut[warp] = cut8 + cut24;
+      }
       // the bulk store this warp issued one tile ago has long read its stage; make
       // sure before the stage is refilled below
       if (CODES && store_pending) bulk_wait_read();
       __syncthreads();                       // A: every lane holds its text in registers, s_wsum is complete
-      uint32_t before = 0, tile_total = 0;
+      uint32_t before = 0, tile_total = 0, tile_cuts = 0;
 #pragma unroll
       for (int w2 = 0; w2 < kWarps; w2++) {
-         const uint32_t x = s_wsum[w2];
+         const uint32_t x = s_wsum[w2] + (CUT ? s_wcut[w2] : 0u);
          if (w2 < warp) before += x;
          tile_total += x;
+         if (CUT) tile_cuts += s_wcut[w2];
       }
       if (tid == 0) {
          // prefetch the next ticket into the other stage (its last store has been waited for)
@@ -276,6 +300,14 @@ __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, 
          a.tile_cnt[tile] = tile_total;
          a.tile_off[tile] = at;
          s_base[stage] = at;
+         if (CUT) {
+            a.tile_real[tile] = tile_total - tile_cuts;
+            if (tile_cuts) atomicAdd(&a.ctr[C_NCUTS], (unsigned long long)tile_cuts);
+            // every warp has passed A: the emit of the previous tile (other stage) is complete
+            if (prev_tile != 0xffffffffu) a.tile_last[prev_tile] = s_last[stage ^ 1];
+            s_last[stage ^ 1] = 0u;
+            prev_tile = tile;
+         }
       }
 
       // ---- class nibbles: in place over the warp's own text, one bulk store per warp ----
@@ -293,11 +325,17 @@ __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, 
          }
       }
       __syncthreads();                       // B: s_base, s_tile
-      uint32_t idx = s_base[stage] + before + inc - cnt;
+      uint32_t idx = s_base[stage] + before + (inc - cnt) + (cutinc - cut);
 
       // ---- emit (ordered inside the tile) -------------------------------------
+      uint32_t mylast = 0;                          // CUT: 1 + the last LINE start emitted by this lane
       if (first) {
          if (idx < a.ls_cap) a.ls_raw[idx] = 0;
+         idx++;
+         mylast = 1u;
+      }
+      if (CUT && cut) {                             // the segment start comes before the line starts of the lane
+         if (idx < a.ls_cap) a.ls_raw[idx] = pos0;
          idx++;
       }
 #pragma unroll
@@ -307,8 +345,10 @@ __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, 
          const uint32_t p = pos0 + 32u * (uint32_t)q + 1u;
          if ((bits & (bits - 1)) == 0) {           // one line start in these 32 bytes (the usual case)
             const int b = __ffs(bits) - 1;
-            if (idx < a.ls_cap) a.ls_raw[idx] = p + 8u * (uint32_t)(b & 3) + (uint32_t)(b >> 2);
+            const uint32_t s = p + 8u * (uint32_t)(b & 3) + (uint32_t)(b >> 2);
+            if (idx < a.ls_cap) a.ls_raw[idx] = s;
             idx++;
+            mylast = s + 1u;
          } else {                                  // several: walk them in text order
 #pragma unroll 1
             for (int e = 0; e < 4; e++) {
@@ -316,65 +356,133 @@ __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, 
                while (be) {
                   const int b = __ffs(be) - 1;
                   be &= be - 1;
-                  if (idx < a.ls_cap) a.ls_raw[idx] = p + 8u * (uint32_t)e + (uint32_t)(b >> 2);
+                  const uint32_t s = p + 8u * (uint32_t)e + (uint32_t)(b >> 2);
+                  if (idx < a.ls_cap) a.ls_raw[idx] = s;
                   idx++;
+                  mylast = s + 1u;
                }
             }
          }
       }
+      if (CUT) {
+         const uint32_t wl = __reduce_max_sync(kFull, mylast);
+         if (lane == 0 && wl) atomicMax(&s_last[stage], wl);
+      }
    }
    if (CODES && store_pending) bulk_wait_all();
+   if (CUT) {
+      __syncthreads();
+      if (tid == 0 && prev_tile != 0xffffffffu) a.tile_last[prev_tile] = s_last[0] | s_last[1];   // the other one is 0
+   }
 }
 
-// exclusive scan of the per-tile line counts (one CTA of 1024 threads):
-// tile_base[t] = number of the first line of tile t; total -> ctr[C_NLINES]
+// exclusive scans over the K1 tiles (one CTA of 1024 threads):
+//   tile_base[t]  = index in ls of the first entry of tile t;  total -> ctr[C_NPSEUDO]
+// and, when K1 made segment cuts (tile_real != nullptr),
+//   tile_rbase[t] = number of the first LINE of tile t;         total -> ctr[C_NLINES]
+//   tile_lbeg[t]  = 1 + the last line start before tile t (running maximum of tile_last)
 struct K1ScanArgs {
    const uint32_t *tile_cnt;
    uint32_t *tile_base;
    uint32_t ntiles;
    unsigned long long *ctr;
+   const uint32_t *tile_real;     // nullptr: no cuts, every entry is a line
+   uint32_t *tile_rbase;
+   const uint32_t *tile_last;
+   uint32_t *tile_lbeg;
 };
 
 __global__ void __launch_bounds__(1024) k1_scan_tiles(const K1ScanArgs a)
 {
-   __shared__ unsigned long long s_warp[32];
+   __shared__ unsigned long long s_warp[32], s_real[32];
+   __shared__ uint32_t s_max[32];
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const bool cut = a.tile_real != nullptr;
    // warp w owns the contiguous run [w*per, (w+1)*per) and walks it 32 tiles at a
-   // time (coalesced): first its total, then -- after the 32 totals are scanned --
+   // time (coalesced): first its totals, then -- after the 32 totals are scanned --
    // the exclusive prefix of every tile
    const uint32_t per = ((a.ntiles + 1023u) / 1024u) * 32u;
    const uint32_t t0 = min((uint32_t)warp * per, a.ntiles), t1 = min(t0 + per, a.ntiles);
-   unsigned long long sum = 0;
+   unsigned long long sum = 0, rsum = 0;
+   uint32_t mx = 0;
 #pragma unroll 4
-   for (uint32_t t = t0 + (uint32_t)lane; t < t1; t += 32) sum += a.tile_cnt[t];
+   for (uint32_t t = t0 + (uint32_t)lane; t < t1; t += 32) {
+      sum += a.tile_cnt[t];
+      if (cut) {
+         rsum += a.tile_real[t];
+         mx = max(mx, a.tile_last[t]);
+      }
+   }
 #pragma unroll
-   for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(kFull, sum, d);
-   if (lane == 0) s_warp[warp] = sum;
+   for (int d = 16; d > 0; d >>= 1) {
+      sum += __shfl_xor_sync(kFull, sum, d);
+      rsum += __shfl_xor_sync(kFull, rsum, d);
+   }
+   mx = __reduce_max_sync(kFull, mx);
+   if (lane == 0) {
+      s_warp[warp] = sum;
+      s_real[warp] = rsum;
+      s_max[warp] = mx;
+   }
    __syncthreads();
-   unsigned long long run = 0, tot = 0;
+   unsigned long long run = 0, tot = 0, rrun = 0, rtot = 0;
+   uint32_t mrun = 0;
    for (int w = 0; w < 32; w++) {
-      const unsigned long long y = s_warp[w];
-      if (w < warp) run += y;
+      const unsigned long long y = s_warp[w], z = s_real[w];
+      if (w < warp) {
+         run += y;
+         rrun += z;
+         mrun = max(mrun, s_max[w]);
+      }
       tot += y;
+      rtot += z;
    }
    // line numbers are u32 (a batch is < 4 GiB of text)
 #pragma unroll 2
    for (uint32_t tb = t0; tb < t1; tb += 32) {
       const uint32_t t = tb + (uint32_t)lane;
       const uint32_t v = t < t1 ? a.tile_cnt[t] : 0u;
-      uint32_t x = v;
+      const uint32_t rv = (cut && t < t1) ? a.tile_real[t] : 0u;
+      const uint32_t lv = (cut && t < t1) ? a.tile_last[t] : 0u;
+      uint32_t x = v, rx = rv, lx = lv;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
          const uint32_t y = __shfl_up_sync(kFull, x, d);
-         if (lane >= d) x += y;
+         const uint32_t ry = __shfl_up_sync(kFull, rx, d);
+         const uint32_t ly = __shfl_up_sync(kFull, lx, d);
+         if (lane >= d) {
+            x += y;
+            rx += ry;
+            lx = max(lx, ly);
+         }
       }
-      if (t < t1) a.tile_base[t] = (uint32_t)run + x - v;
+      // exclusive running maximum: the inclusive one of the lane in front
+      uint32_t lprev = __shfl_up_sync(kFull, lx, 1);
+      if (lane == 0) lprev = 0u;
+      if (t < t1) {
+         a.tile_base[t] = (uint32_t)run + x - v;
+         if (cut) {
+            a.tile_rbase[t] = (uint32_t)rrun + rx - rv;
+            a.tile_lbeg[t] = max(mrun, lprev);
+         }
+      }
       run += __shfl_sync(kFull, x, 31);
+      rrun += __shfl_sync(kFull, rx, 31);
+      mrun = max(mrun, __shfl_sync(kFull, lx, 31));
    }
-   if (tid == 0) a.ctr[C_NLINES] = tot;
+   if (tid == 0) {
+      a.ctr[C_NPSEUDO] = tot;
+      a.ctr[C_NLINES] = cut ? rtot : tot;
+   }
 }
 
-// tile segments of ls_raw -> ls in line order (one warp per tile) + sentinel
+// tile segments of ls_raw -> ls in order (one warp per tile) + sentinel.  With
+// segment cuts also, for every entry p of ls:
+//   lid[p]  = number of the line the entry belongs to
+//   lbeg[p] = start of that line
+// An entry is a line start iff it is 0 or follows a newline (bit 3 of the class
+// nibble in front of it); a cut never does (there is no line start in the 1024
+// bytes before it).
 struct K1GatherArgs {
    const uint32_t *ls_raw;
    uint32_t *ls;
@@ -383,6 +491,9 @@ struct K1GatherArgs {
    uint32_t ntiles;
    uint32_t n;
    const unsigned long long *ctr;
+   const uint8_t *codes;          // nullptr: no cuts
+   const uint32_t *tile_rbase, *tile_lbeg;
+   uint32_t *lid, *lbeg;
 };
 
 __global__ void __launch_bounds__(kThreads) k1_gather(const K1GatherArgs a)
@@ -390,13 +501,42 @@ __global__ void __launch_bounds__(kThreads) k1_gather(const K1GatherArgs a)
    const int lane = threadIdx.x & 31;
    const uint32_t wid = (blockIdx.x * kThreads + threadIdx.x) >> 5;
    const uint32_t nwarps = (gridDim.x * kThreads) >> 5;
+   const bool cut = a.codes != nullptr;
    for (uint32_t t = wid; t < a.ntiles; t += nwarps) {
       const uint32_t cnt = a.tile_cnt[t], src = a.tile_off[t], dst = a.tile_base[t];
-      for (uint32_t j = lane; j < cnt; j += 32)
-         if (dst + j < a.ls_cap && src + j < a.ls_cap) a.ls[dst + j] = a.ls_raw[src + j];
+      if (!cut) {
+         for (uint32_t j = lane; j < cnt; j += 32)
+            if (dst + j < a.ls_cap && src + j < a.ls_cap) a.ls[dst + j] = a.ls_raw[src + j];
+         continue;
+      }
+      uint32_t nreal = a.tile_rbase[t];                 // line starts before the current 32 entries
+      uint32_t lastp1 = a.tile_lbeg[t];                 // 1 + the last line start before them
+      for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+         const uint32_t j = j0 + (uint32_t)lane;
+         const bool ok = j < cnt && dst + j < a.ls_cap && src + j < a.ls_cap;
+         const uint32_t pos = ok ? a.ls_raw[src + j] : 0u;
+         bool real = false;
+         if (ok) real = pos == 0u || ((a.codes[(pos - 1u) >> 1] >> ((((pos - 1u) & 1u) << 2) + 3u)) & 1u);
+         const uint32_t bal = __ballot_sync(kFull, real);
+         const uint32_t rb = nreal + (uint32_t)__popc(bal & ((1u << lane) - 1u));     // line starts before this entry
+         uint32_t x = real ? pos + 1u : 0u;
+#pragma unroll
+         for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(kFull, x, d);
+            if (lane >= d) x = max(x, y);
+         }
+         x = max(x, lastp1);
+         if (ok) {
+            a.ls[dst + j] = pos;
+            a.lid[dst + j] = real ? rb : rb - 1u;
+            a.lbeg[dst + j] = x - 1u;
+         }
+         nreal += (uint32_t)__popc(bal);
+         lastp1 = __shfl_sync(kFull, x, 31);
+      }
    }
    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      const unsigned long long total = a.ctr[C_NLINES];
+      const unsigned long long total = a.ctr[C_NPSEUDO];
       if (total < a.ls_cap) a.ls[total] = a.n;         // sentinel
    }
 }
@@ -532,7 +672,7 @@ __global__ void __launch_bounds__(kThreads) k2_forward_thread(const K2Args a, co
    }
    __syncthreads();
 
-   const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
+   const uint32_t nlines = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
    const uint32_t n = a.n;
    const uint32_t ntiles = (nlines + kThreads - 1) / kThreads;
    uint32_t phase = 0;
@@ -625,7 +765,7 @@ __global__ void __launch_bounds__(kThreads) k2_forward_lanes(const K2Args a, con
    const uint32_t pv0 = pad <= lo ? ~0u : (pad >= lo + 32 ? 0u : (~0u << (pad - lo)));
 
    constexpr int kLinesPerBlock = kThreads / G;
-   const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
+   const uint32_t nlines = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
    const uint32_t n = a.n;
    const uint32_t ntiles = (nlines + kLinesPerBlock - 1) / kLinesPerBlock;
    uint32_t my_matched = 0, my_events = 0;
@@ -773,25 +913,41 @@ __device__ __forceinline__ uint32_t reverse_start(const uint8_t *__restrict__ te
    BitVec<W> bv;
    bv_reset(bv, m);
    int score = m;
-   int d = tau + 1, last_d;
+   int d = tau + 1, last_d = tau + 1;
    uint32_t j = 0, skipped = 0;
-   do {
-      j++;
-      const uint8_t c = tab.cls[__ldg(text + line_begin + end - j)];
-      last_d = d;
-      if ((c & 0x30) == kKindBase) {
-         skipped = 0;
-         uint32_t eq[W];
+   const uint8_t *p = text + line_begin + end;           // the pass reads p[-1], p[-2], ...
+   bool more = end > 0;
+   // the bytes are fetched eight at a time (independent loads) and then walked in
+   // registers: a load per step would put the global latency on the dependency
+   // chain of every step
+   constexpr int kChunk = 8;
+   while (more) {
+      const uint32_t left = end - j;                     // > 0
+      uint8_t b[kChunk];
 #pragma unroll
-         for (int w = 0; w < W; w++) eq[w] = tab.eq[c & 7][w];
-         uint32_t rise, fall;
-         bv_step<W>(bv, eq, rise, fall);
-         score += (int)rise - (int)fall;
-         d = min(score, tau + 1);
-      } else {
-         skipped++;
+      for (int i = 0; i < kChunk; i++) b[i] = (uint32_t)i < left ? __ldg(p - j - 1 - i) : (uint8_t)0;
+#pragma unroll
+      for (int i = 0; i < kChunk; i++) {
+         if (more) {
+            j++;
+            const uint8_t c = tab.cls[b[i]];
+            last_d = d;
+            if ((c & 0x30) == kKindBase) {
+               skipped = 0;
+               uint32_t eq[W];
+#pragma unroll
+               for (int w = 0; w < W; w++) eq[w] = tab.eq[c & 7][w];
+               uint32_t rise, fall;
+               bv_step<W>(bv, eq, rise, fall);
+               score += (int)rise - (int)fall;
+               d = min(score, tau + 1);
+            } else {
+               skipped++;
+            }
+            more = d > dist && j < end;
+         }
       }
-   } while (d > dist && j < end);
+   }
    j = (last_d < d ? j - 1 : j) - skipped;
    return end - j;
 }
@@ -820,7 +976,7 @@ struct TileSumArgs {
 __global__ void __launch_bounds__(kThreads) k_tile_sums(const TileSumArgs a)
 {
    const int lane = threadIdx.x & 31;
-   const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
+   const uint32_t nlines = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
    const uint32_t ntiles = (nlines + kFinTile - 1) / kFinTile;
    const uint32_t wid = (blockIdx.x * kThreads + threadIdx.x) >> 5, nw = (gridDim.x * kThreads) >> 5;
    for (uint32_t t = wid; t < ntiles; t += nw) {
@@ -847,7 +1003,7 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const TileSumArgs a)
 {
    __shared__ unsigned long long s_warp[32], s_nz[32];
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-   const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
+   const uint32_t nlines = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
    const uint32_t ntiles = (nlines + kFinTile - 1) / kFinTile;
    const uint32_t per = (ntiles + 1023u) / 1024u;
    const uint32_t t0 = min((uint32_t)tid * per, ntiles), t1 = min(t0 + per, ntiles);
@@ -880,7 +1036,77 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const TileSumArgs a)
    }
    if (tid == 0) {
       a.ctr[C_NRECS] = tot;
-      a.ctr[C_NMATCHED] = tnz;
+      a.ctr[C_NMATCHED] = tnz - a.ctr[C_NZ_CORR];        // SQ_ALL with cuts: lines, not segments, with records
+   }
+}
+
+// ===========================================================================
+// Segment cuts: one result per LINE
+// ===========================================================================
+// The matcher treats every segment of a cut line as a line of its own.  This
+// kernel restores the line semantics before the compaction: one thread per cut
+// line walks its segments in order.
+//   SQ_FIRST  only the first segment with a candidate keeps it
+//   SQ_BEST   the candidate with the smallest distance, the earliest on a tie
+//   SQ_ALL    nothing to merge; counts the segments with events beyond the first
+//             of their line (C_NZ_CORR: matched LINES = matched segments - that)
+// In every mode the segments behind one that ran into a STOP byte (segstop; an
+// illegal byte with SQ_FAIL, a NUL) are dead: the reference stops scanning the
+// line there (libseeq.c:267-270).
+struct SegReduceArgs {
+   const uint32_t *lid;
+   uint32_t max_lines;
+   unsigned long long *ctr;
+   unsigned long long *res;       // SQ_FIRST / SQ_BEST
+   uint32_t *cnt;                 // SQ_ALL
+   const uint8_t *segstop;
+   uint8_t *deadseg;              // out (SQ_ALL): segments whose events are to be dropped
+   int mode;
+};
+
+__global__ void __launch_bounds__(kThreads) k_seg_reduce(const SegReduceArgs a)
+{
+   if (a.ctr[C_NCUTS] == 0ull) return;
+   const uint32_t np = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
+   unsigned long long corr = 0;
+   for (uint32_t p = blockIdx.x * kThreads + threadIdx.x; p < np; p += gridDim.x * kThreads) {
+      const uint32_t me = a.lid[p];
+      if ((p > 0u && a.lid[p - 1u] == me) || p + 1u >= np || a.lid[p + 1u] != me) continue;   // heads of cut lines only
+      bool dead = false, have = false;
+      uint32_t best_q = 0, best_d = 0, with_events = 0;
+      for (uint32_t q = p; q < np && a.lid[q] == me; q++) {
+         if (a.mode == M_ALL) {
+            if (dead) {
+               a.cnt[q] = 0u;
+               a.deadseg[q] = 1;
+            } else if (a.cnt[q] != 0u) {
+               with_events++;
+            }
+         } else {
+            const unsigned long long key = a.res[q];
+            if (key != kNoMatch) {
+               const uint32_t d = (uint32_t)(key >> 32);
+               bool keep = !dead;
+               if (keep && have) {
+                  if (a.mode == M_BEST && d < best_d) a.res[best_q] = kNoMatch;     // a strictly better one further on
+                  else keep = false;
+               }
+               if (keep) {
+                  have = true;
+                  best_q = q;
+                  best_d = d;
+               } else {
+                  a.res[q] = kNoMatch;
+               }
+            }
+         }
+         if (a.segstop[q]) dead = true;
+      }
+      if (with_events > 1u) corr += with_events - 1u;
+   }
+   if (a.mode == M_ALL) {
+      corr = __reduce_add_sync(kFull, (uint32_t)corr);                  // < 2^32 per warp
+      if ((threadIdx.x & 31) == 0 && corr) atomicAdd(&a.ctr[C_NZ_CORR], corr);
    }
 }
 
@@ -896,7 +1122,7 @@ struct OffsArgs {
 __global__ void __launch_bounds__(kThreads) k_offsets(const OffsArgs a)
 {
    __shared__ BlockScanSmem sc;
-   const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
+   const uint32_t nlines = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
    const uint32_t ntiles = (nlines + kFinTile - 1) / kFinTile;
    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       uint32_t run = a.tile_base[tile];
@@ -927,7 +1153,24 @@ struct FinArgs {
    uint32_t rec_cap;
    unsigned long long *ctr;
    const uint32_t *tile_base;     // first record of every 1024-line tile
+   const uint32_t *lid, *lbeg;    // segment cuts: line and line start of every ls entry (or nullptr)
+   const uint8_t *deadseg;        // SQ_ALL with cuts: segments whose events are dropped
+   uint32_t wup;
 };
+
+// what K2 reports for entry p of ls (a line, or a segment of a cut line) in terms
+// of the line: its number, its start and the offset of column 0 inside it
+struct LineOf {
+   uint32_t line, begin, col0;
+};
+__device__ __forceinline__ LineOf line_of(const FinArgs &a, uint32_t p)
+{
+   const uint32_t lp = a.ls[p];
+   if (a.lid == nullptr) return LineOf{p, lp, 0u};
+   const uint32_t line = a.lid[p], lb = a.lbeg[p];
+   const bool cont = p > 0u && a.lid[p - 1u] == line;
+   return LineOf{line, lb, lp - (cont ? a.wup : 0u) - lb};
+}
 
 // Per tile of 1024 lines: (1) the candidates are compacted, in line order, into
 // shared memory (ballot/popc inside the warp, scan across the warps); (2) the
@@ -942,7 +1185,7 @@ __global__ void __launch_bounds__(kThreads) k34_finish_lines(const FinArgs a, co
    __shared__ RevTables<W> tab;
    __shared__ uint4 cand[kFinTile];                       // line, line start, end, dist
    rev_tables_load(tab, rpat);
-   const uint32_t nlines = (uint32_t)min(a.ctr[C_NLINES], (unsigned long long)a.max_lines);
+   const uint32_t nlines = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
    const uint32_t ntiles = (nlines + kFinTile - 1) / kFinTile;
    const int tid = threadIdx.x;
    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -955,7 +1198,10 @@ __global__ void __launch_bounds__(kThreads) k34_finish_lines(const FinArgs a, co
          const bool valid = key != kNoMatch;
          uint32_t total;
          const uint32_t excl = block_exclusive_scan(valid ? 1u : 0u, sc, &total);
-         if (valid) cand[run + excl] = make_uint4(line, a.ls[line], (uint32_t)key, (uint32_t)(key >> 32));
+         if (valid) {
+            const LineOf lo = line_of(a, line);
+            cand[run + excl] = make_uint4(lo.line, lo.begin, (uint32_t)key + lo.col0, (uint32_t)(key >> 32));
+         }
          run += total;
       }
       __syncthreads();
@@ -984,11 +1230,13 @@ __global__ void __launch_bounds__(kThreads) k34_finish_events(const FinArgs a, c
    for (unsigned long long i = (unsigned long long)blockIdx.x * kThreads + threadIdx.x; i < nev;
         i += (unsigned long long)gridDim.x * kThreads) {
       const Event e = a.ev[i];
+      if (a.deadseg && a.deadseg[e.line]) continue;        // behind a STOP of its line
+      const LineOf lo = line_of(a, e.line);
       Rec r;
-      r.line = e.line;
-      r.end = e.end;
+      r.line = lo.line;
+      r.end = e.end + lo.col0;
       r.dist = e.dist;
-      r.start = reverse_start<W>(a.text, a.ls[e.line], e.end, (int)e.dist, rpat.m, rpat.tau, tab);
+      r.start = reverse_start<W>(a.text, lo.begin, r.end, (int)e.dist, rpat.m, rpat.tau, tab);
       const unsigned long long dst = (unsigned long long)a.offs[e.line] + e.rank;
       if (dst < a.rec_cap) a.recs[dst] = r;
    }

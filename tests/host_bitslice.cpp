@@ -48,7 +48,7 @@ static void run_group(const std::vector<uint8_t> &cls, size_t n, const std::vect
          bs_classes(p0, p1, p2, p, slots, anybase, stop, skip);
          auto eq = [&](int j) { return slots[p.slot[g * R + j]]; };
          uint32_t ph = in_ph[g], mh = in_mh[g];
-         bs_rows<R, G, SKIP>(st[g], eq, skip, ph, mh, g == 0 ? R * G - p.m : 0);
+         bs_rows<R, G, SKIP>(st[g], eq, skip, ph, mh);
          out_ph[g] = ph;
          out_mh[g] = mh;
          if (g == G - 1) {
@@ -113,6 +113,180 @@ extern "C" long bs_host_scan(const char *buf, size_t n, const unsigned char *key
       out[3 * k + 1] = ev[i].end;
       out[3 * k + 2] = ev[i].dist;
       k++;
+   }
+   return k;
+}
+
+
+// ---------------------------------------------------------------------------
+// Long lines cut into segments (sqb_tables.h: kCutStride / kCutWindow), with the
+// stride and window as parameters so that short random lines exercise many cuts.
+// Mirrors the GPU pipeline: K1 (cut decision), pack (warm-up in front of a
+// continuation, NULL columns behind a segment that is followed by another one),
+// K2 (quiet warm-up, stopped lines), k_seg_reduce (one result per real line;
+// segments behind a STOP are dead).
+// ---------------------------------------------------------------------------
+struct Seg {
+   size_t start;        // first byte whose events this segment reports (A, or the line start)
+   size_t line;         // real line index
+   size_t lbeg;         // start of the real line
+   bool cont, follow;
+};
+
+template <int R, int G, int MODE>
+static void run_group_cut(const std::vector<uint8_t> &cls, size_t n, const std::vector<Seg> &segs, size_t l0, size_t l1,
+                          uint32_t wup, const BsPattern &p, std::vector<std::vector<Ev>> &per_seg,
+                          std::vector<uint8_t> &segstop)
+{
+   BsState<R, G> st[G];
+   const int nl = (int)(l1 - l0);
+   for (int g = 0; g < G; g++) bs_reset(st[g], p, nl == 32 ? ~0u : ((1u << nl) - 1u), g);
+   uint32_t contmask = 0, followmask = 0;
+   std::vector<size_t> s0(nl), len(nl);
+   for (int r = 0; r < nl; r++) {
+      const Seg &sg = segs[l0 + r];
+      if (sg.cont) contmask |= 1u << r;
+      if (sg.follow) followmask |= 1u << r;
+      s0[r] = sg.start - (sg.cont ? wup : 0);
+      const size_t next = l0 + r + 1 < segs.size() ? segs[l0 + r + 1].start : n;
+      len[r] = (next - sg.start) + (sg.cont ? wup : 0) + (sg.follow ? 1 : 0);
+   }
+   size_t ncols = 0;
+   for (int r = 0; r < nl; r++) ncols = std::max(ncols, len[r] + 1);
+   uint32_t out_ph[G] = {0}, out_mh[G] = {0};
+   uint32_t streak[8];
+   for (long t = 0; t < (long)ncols + G - 1 && st[G - 1].alive; t++) {
+      uint32_t in_ph[G], in_mh[G];
+      for (int g = 0; g < G; g++) {
+         in_ph[g] = g ? out_ph[g - 1] : 0u;
+         in_mh[g] = g ? out_mh[g - 1] : 0u;
+      }
+      for (int g = 0; g < G; g++) {
+         const long col = t - g;
+         uint32_t p0 = 0, p1 = 0, p2 = 0;
+         for (int r = 0; r < nl; r++) {
+            uint8_t c;
+            if (col < 0) c = kClsNull;
+            else if (segs[l0 + r].follow && (size_t)col >= len[r]) c = kClsNull;      // silent end of a segment
+            else {
+               const size_t pos = s0[r] + (size_t)col;
+               c = pos >= n ? kClsStop : (cls[pos] & 7);
+            }
+            p0 |= (uint32_t)(c & 1) << r;
+            p1 |= (uint32_t)((c >> 1) & 1) << r;
+            p2 |= (uint32_t)((c >> 2) & 1) << r;
+         }
+         for (int r = nl; r < 32; r++) { p0 |= 1u << r; p2 |= 1u << r; }     // STOP
+         uint32_t slots[BS_SLOTS], anybase, stop, skip;
+         bs_classes(p0, p1, p2, p, slots, anybase, stop, skip);
+         auto eq = [&](int j) { return slots[p.slot[g * R + j]]; };
+         uint32_t ph = in_ph[g], mh = in_mh[g];
+         bs_rows<R, G, false>(st[g], eq, skip, ph, mh);
+         out_ph[g] = ph;
+         out_mh[g] = mh;
+         if (g == G - 1) {
+            const uint32_t quiet = (col <= (long)wup) ? contmask : 0u;
+            const uint32_t evt = bs_report<R, G, MODE>(st[g], p, ph, mh, anybase, stop, streak, quiet);
+            for (int r = 0; r < nl; r++)
+               if ((evt >> r) & 1u) {
+                  const Seg &sg = segs[l0 + r];
+                  // column -> end offset inside the real line (what the finish kernels do)
+                  const uint64_t end = (uint64_t)(s0[r] + (size_t)col - sg.lbeg);
+                  per_seg[l0 + r].push_back(Ev{(uint64_t)sg.line, end, bs_value<BsState<R, G>::B>(streak, r)});
+               }
+         }
+      }
+   }
+   for (int r = 0; r < nl; r++)
+      if (((st[G - 1].stopped & followmask) >> r) & 1u) segstop[l0 + r] = 1;
+}
+
+extern "C" long bs_host_scan_cut(const char *buf, size_t n, const unsigned char *keys, int m, int tau, int options,
+                                 size_t stride, size_t window, uint64_t *out, long cap, long *ncuts)
+{
+   BsPattern p;
+   if (!build_bs_pattern(keys, m, tau, &p)) return -1;
+   if ((options & OPT_NONDNA) == OPT_IGNORE) return -1;      // no cuts with SQ_IGNORE
+   const uint32_t wup = bs_warmup(m, tau);
+   if (wup > window) return -1;
+   ClassTable ct;
+   build_class_table(options, &ct);
+   std::vector<uint8_t> cls(n);
+   for (size_t i = 0; i < n; i++) cls[i] = ct.code[(unsigned char)buf[i]];
+   // K1: line starts and cuts
+   std::vector<Seg> segs;
+   {
+      std::vector<uint8_t> is_start(n + 1, 0);
+      if (n > 0) is_start[0] = 1;
+      for (size_t i = 0; i + 1 < n; i++) if (buf[i] == '\n') is_start[i + 1] = 1;
+      std::vector<uint8_t> is_cut(n + 1, 0);
+      *ncuts = 0;
+      for (size_t a = window; a < n; a += stride) {
+         bool any = a - window == 0;                            // the first line start sits in the window of a == window
+         for (size_t q = a - window; q + 1 <= a && !any; q++) any = buf[q] == '\n';   // newline in [a - window, a - 1]
+         if (!any) { is_cut[a] = 1; (*ncuts)++; }
+      }
+      size_t line = 0, lbeg = 0;
+      bool have = false;
+      for (size_t i = 0; i < n; i++) {
+         if (is_start[i]) {
+            if (have) line++;
+            have = true;
+            lbeg = i;
+            segs.push_back(Seg{i, line, lbeg, false, false});
+         } else if (is_cut[i]) {
+            segs.push_back(Seg{i, line, lbeg, true, false});
+         }
+      }
+      for (size_t k = 0; k + 1 < segs.size(); k++) segs[k].follow = segs[k + 1].cont;
+   }
+   const int match = options & OPT_MATCH;
+   const int mode = match == OPT_ALL ? BS_ALL : (match == OPT_BEST ? BS_BEST : BS_FIRST);
+   std::vector<std::vector<Ev>> per_seg(segs.size());
+   std::vector<uint8_t> segstop(segs.size(), 0);
+   for (size_t l0 = 0; l0 < segs.size(); l0 += 32) {
+      const size_t l1 = std::min(segs.size(), l0 + 32);
+#define SHAPE(R, G)                                                                                          \
+   if (p.rows == R && p.parts == G) {                                                                        \
+      if (mode == BS_FIRST) run_group_cut<R, G, BS_FIRST>(cls, n, segs, l0, l1, wup, p, per_seg, segstop);   \
+      if (mode == BS_BEST) run_group_cut<R, G, BS_BEST>(cls, n, segs, l0, l1, wup, p, per_seg, segstop);     \
+      if (mode == BS_ALL) run_group_cut<R, G, BS_ALL>(cls, n, segs, l0, l1, wup, p, per_seg, segstop);       \
+   }
+      SHAPE(8, 1) SHAPE(12, 1) SHAPE(16, 1) SHAPE(24, 1) SHAPE(32, 1)
+      SHAPE(20, 2) SHAPE(24, 2) SHAPE(32, 2)
+      SHAPE(20, 4) SHAPE(24, 4) SHAPE(28, 4) SHAPE(32, 4)
+#undef SHAPE
+   }
+   // k_seg_reduce: one result per real line, segments behind a STOP are dead
+   long k = 0;
+   for (size_t s = 0; s < segs.size();) {
+      size_t e = s + 1;
+      while (e < segs.size() && segs[e].cont) e++;
+      bool dead = false, have = false;
+      Ev best{0, 0, 0};
+      for (size_t q = s; q < e; q++) {
+         if (!dead) {
+            for (size_t i = 0; i < per_seg[q].size(); i++) {
+               const Ev &ev = per_seg[q][i];
+               if (mode == BS_ALL) {
+                  if (k >= cap) return -2;
+                  out[3 * k] = ev.line + 1; out[3 * k + 1] = ev.end; out[3 * k + 2] = ev.dist; k++;
+               } else if (mode == BS_FIRST) {
+                  if (!have) { best = ev; have = true; }
+               } else {
+                  // inside a segment the last improvement wins; across segments a strictly smaller distance
+                  const bool last_of_seg = i + 1 == per_seg[q].size();
+                  if (last_of_seg && (!have || ev.dist < best.dist)) { best = ev; have = true; }
+               }
+            }
+         }
+         if (segstop[q]) dead = true;
+      }
+      if (mode != BS_ALL && have) {
+         if (k >= cap) return -2;
+         out[3 * k] = best.line + 1; out[3 * k + 1] = best.end; out[3 * k + 2] = best.dist; k++;
+      }
+      s = e;
    }
    return k;
 }

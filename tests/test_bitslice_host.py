@@ -25,6 +25,9 @@ def harness(tmp_path_factory):
     L.bs_host_scan.restype = C.c_long
     L.bs_host_scan.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int, C.c_int, C.c_int,
                                C.POINTER(C.c_uint64), C.c_long]
+    L.bs_host_scan_cut.restype = C.c_long
+    L.bs_host_scan_cut.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_size_t,
+                                   C.c_size_t, C.POINTER(C.c_uint64), C.c_long, C.POINTER(C.c_long)]
     return L
 
 
@@ -91,3 +94,52 @@ def test_bitsliced_events_equal_oracle(harness, oracle, mrange):
                 assert np.array_equal(out[:n], exp), (pattern, tau, mo, nd, buf[:120])
                 checked += 1
     assert checked > (100 if mrange[1] <= 32 else 40)
+
+
+@pytest.mark.parametrize("mrange,stride,window", [((1, 8), 64, 32), ((4, 16), 96, 48), ((12, 32), 256, 128),
+                                                   ((33, 48), 512, 256), ((65, 100), 1024, 512)])
+def test_cut_segments_equal_oracle(harness, oracle, mrange, stride, window):
+    """Long lines cut into segments with a warm-up of m + 2 tau + 2 bytes reproduce the
+    events of the uncut line (the rule the GPU pipeline uses with stride 2048 / window 1024)."""
+    rng = random.Random(mrange[1] * 77 + stride)
+    checked = cuts = 0
+    for it in range(40 if mrange[1] <= 32 else 12):
+        pattern = rand_pattern(rng, *mrange)
+        keys, _ = oracle.parse(pattern)
+        if not keys:
+            continue
+        tau = rng.randint(0, min(len(keys) - 1, 3 + len(keys) // 8, 14))
+        if len(keys) + 2 * tau + 2 > window:
+            continue
+        plant = "".join(rng.choice([c for b, c in ((1, "A"), (2, "C"), (4, "G"), (8, "T")) if k & b] or ["A"])
+                        for k in keys)
+        alphabet = ["ACGT", "ACGTN", "ACGTNNX"][it % 3]           # X: a STOP in the middle of a line (SQ_FAIL)
+        lines = []
+        for _ in range(rng.randint(1, 40)):
+            n = rng.choice([rng.randint(0, window), rng.randint(window, 6 * stride)])
+            s = [rng.choice(alphabet[:4] if rng.random() < 0.98 else alphabet) for _ in range(n)]
+            for _ in range(rng.randint(0, 1 + n // (3 * len(keys) + 20))):
+                at = rng.randrange(n + 1)
+                q = list(plant)
+                for _ in range(rng.randint(0, tau + 1)):
+                    if q:
+                        k = rng.randrange(len(q))
+                        q[k:k + 1] = rng.choice([[], [rng.choice("ACGT")], [q[k], rng.choice("ACGT")]])
+                s[at:at] = q
+            lines.append("".join(s))
+        buf = "\n".join(lines).encode() + (b"\n" if it % 2 == 0 else b"")
+        out = np.zeros((len(buf) + 64, 3), dtype=np.uint64)
+        ncuts = C.c_long(0)
+        for mo in (SQ_FIRST, SQ_BEST, SQ_ALL):
+            for nd in (SQ_FAIL, SQ_CONVERT):
+                n = harness.bs_host_scan_cut(buf, len(buf), keys, len(keys), tau, mo | nd, stride, window,
+                                             out.ctypes.data_as(C.POINTER(C.c_uint64)), out.shape[0], C.byref(ncuts))
+                if n == -1:
+                    continue
+                assert n >= 0
+                exp, _, _ = oracle.buffer_scan(buf, keys, tau, mo | nd)
+                exp = exp[:, [0, 2, 3]]
+                assert np.array_equal(out[:n], exp), (pattern, tau, mo, nd, len(buf))
+                checked += 1
+                cuts += ncuts.value
+    assert checked > 30 and cuts > 100

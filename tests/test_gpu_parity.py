@@ -108,6 +108,65 @@ def test_buffers_all_modes(B, oracle, mrange, matcher):
                 check_buffer(B, oracle, pattern, tau, buf, mo | nd)
 
 
+def long_line_buffer(rng, keys, tau, nlines, maxlen, junk):
+    """Ragged long lines (the matcher cuts them into segments at text offsets 1024 mod
+    2048), pattern instances planted at random and right across the cut offsets."""
+    lines = []
+    for _ in range(nlines):
+        n = rng.choice([rng.randint(0, 300), rng.randint(900, 3500), rng.randint(3000, maxlen)])
+        lines.append([rng.choice("ACGT") for _ in range(n)])
+    buf = bytearray("\n".join("".join(l) for l in lines).encode() + b"\n")
+    m = len(keys)
+    for a in range(1024, len(buf), 2048):
+        if rng.random() < 0.7:
+            inst = plant(rng, keys, tau).encode()
+            at = a - rng.randint(0, m + tau + 1) + rng.randint(0, 3)
+            if at >= 0 and at + len(inst) < len(buf) and b"\n" not in buf[at:at + len(inst)]:
+                buf[at:at + len(inst)] = inst
+    for _ in range(len(buf) // 700):
+        inst = plant(rng, keys, tau).encode()
+        at = rng.randrange(max(1, len(buf) - len(inst) - 1))
+        if b"\n" not in buf[at:at + len(inst)]:
+            buf[at:at + len(inst)] = inst
+    for _ in range(junk):                       # bytes that end a line (SQ_FAIL), are N (SQ_CONVERT) or invisible
+        at = rng.randrange(len(buf))
+        if buf[at] != 10:
+            buf[at] = rng.choice(b"XN-")
+    return bytes(buf)
+
+
+@pytest.mark.parametrize("mrange", [(4, 12), (20, 32), (36, 48), (90, 110)])
+def test_long_lines(B, oracle, mrange, matcher):
+    rng = random.Random(mrange[0] * 131)
+    for it in range(4):
+        pattern = rand_pattern(rng, *mrange)
+        keys, _ = oracle.parse(pattern)
+        tau = rng.randint(0, min(len(keys) - 1, 2 + len(keys) // 10))
+        buf = long_line_buffer(rng, keys, tau, rng.randint(3, 60), 12000, junk=(0, 6, 40)[it % 3])
+        for mo in MATCH:
+            for nd in NONDNA:
+                check_buffer(B, oracle, pattern, tau, buf, mo | nd)
+
+
+def test_long_lines_large(B, oracle):
+    """More than the 1 MB the engine wants before it goes bit-sliced on its own: 10-kb
+    reads (BASELINE config 3 shape) with the engine's default choices."""
+    rng = random.Random(99)
+    pattern = "".join(rng.choice("ACGT") for _ in range(40))
+    keys, _ = oracle.parse(pattern)
+    buf = long_line_buffer(rng, keys, 4, 520, 10000, junk=3)
+    assert len(buf) > (1 << 20)
+    for mo in MATCH:
+        for nd in (SQ_FAIL, SQ_CONVERT):
+            check_buffer(B, oracle, pattern, 4, buf, mo | nd)
+    sq = B.Seeq(pattern, 4)
+    r_all, _, _ = oracle.buffer_scan(buf, keys, 4, SQ_ALL)
+    _, _, nm = oracle.buffer_scan(buf, keys, 4, SQ_FIRST)
+    assert sq.batch(buf, 0, SQ_COUNTMATCH) == len(r_all)
+    assert sq.batch(buf, 0, SQ_COUNTLINES) == nm
+    sq.close()
+
+
 def test_counts(B, oracle, matcher):
     rng = random.Random(4)
     for it in range(10):

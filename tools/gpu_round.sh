@@ -23,3 +23,5 @@ PY
 done
 bash tools/gpu_profile.sh $TAG cfg2 11 > gpurun_out/${TAG}_profile.log 2>&1
 tail -3 gpurun_out/${TAG}_profile.log
+bash tools/gpu_profile.sh $TAG cfg3 0 >> gpurun_out/${TAG}_profile.log 2>&1
+bash tools/gpu_profile.sh $TAG cfg4 0 >> gpurun_out/${TAG}_profile.log 2>&1
