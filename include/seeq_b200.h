@@ -50,7 +50,11 @@ typedef struct {
    uint64_t nmatched;   /* lines with at least one match                     */
    uint64_t nrecs;      /* records (SQ_FIRST/SQ_BEST: == nmatched)           */
    double   device_ms;  /* CUDA-event time of the kernels of this scan       */
-   double   kernel_ms[4];/* K1, K2, scan+K3/K4, spare (only with SQB_TIMING) */
+   double   kernel_ms[8];/* only with SQB_TIMING.  Stages: [0] K1 (tokenizer, tile
+                         * scan, gather)  [1] K2 (bit-plane pack + matcher)  [2]
+                         * scan + K3/K4.  Single kernels: [3] the matcher
+                         * (k2_bitslice / k2_forward_*)  [4] k15_pack  [5]
+                         * k1_scan_classify                                    */
    uint32_t launches;   /* kernels launched by this scan                     */
    uint32_t reruns;     /* scans repeated because a capacity guess was low   */
 } sqb_stats_t;

@@ -49,7 +49,7 @@ class SeeqArgT(C.Structure):
 
 class StatsT(C.Structure):
     _fields_ = [("nbytes", C.c_uint64), ("nlines", C.c_uint64), ("nmatched", C.c_uint64),
-                ("nrecs", C.c_uint64), ("device_ms", C.c_double), ("kernel_ms", C.c_double * 4),
+                ("nrecs", C.c_uint64), ("device_ms", C.c_double), ("kernel_ms", C.c_double * 8),
                 ("launches", C.c_uint32), ("reruns", C.c_uint32)]
 
 

@@ -45,6 +45,9 @@ static void set_err(const char *fmt, ...)
    } while (0)
 
 // ---------------------------------------------------------------------------
+// CUDA events of a scan (SQB_TIMING records all of them, otherwise only E_DONE)
+enum { E_BEGIN = 0, E_K1C_END, E_K1_END, E_PACK_BEGIN, E_PACK_END, E_MATCH_END, E_K2_END, E_FIN_END, E_DONE, E_COUNT };
+
 struct Slot {
    cudaStream_t stream = nullptr;
    // device
@@ -71,7 +74,7 @@ struct Slot {
    Rec *h_recs = nullptr;       size_t h_rec_cap = 0;
    uint32_t *h_ls = nullptr;    size_t h_ls_cap = 0;
    uint32_t *h_init = nullptr;                              // single-line ls init
-   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+   cudaEvent_t ev[E_COUNT] = {};
    // description of the scan in flight
    const uint8_t *cur_text = nullptr;
    uint32_t cur_n = 0;
@@ -372,7 +375,7 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
    if (dev_reserve(&s.d_fintiles, &s.fintiles_cap, 3 * fin_tiles)) return -1;
    unsigned long long *ctr = s.d_ctl;
 
-   if (timing) CU(cudaEventRecord(s.ev[0], st));
+   if (timing) CU(cudaEventRecord(s.ev[E_BEGIN], st));
    CU(cudaMemsetAsync(s.d_ctl, 0, ctl_words * sizeof(unsigned long long), st));
    const bool cut = !single && use_cuts(e, options, n);
 
@@ -418,6 +421,7 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
       else if (want_codes) k1_scan_classify<true, false><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
       else k1_scan_classify<false, false><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
       CU(cudaGetLastError());
+      if (timing) CU(cudaEventRecord(s.ev[E_K1C_END], st));
       K1ScanArgs ks{tile_cnt, tile_base, ntiles, ctr, cut ? tile_real : nullptr, tile_rbase, tile_last, tile_lbeg};
       k1_scan_tiles<<<1, 1024, 0, st>>>(ks);
       K1GatherArgs kg{s.d_ls_raw, s.d_ls, (uint32_t)s.line_cap, tile_cnt, tile_off, tile_base, ntiles, n, ctr,
@@ -426,7 +430,8 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
       CU(cudaGetLastError());
       s.launches += 3;
    }
-   if (timing) CU(cudaEventRecord(s.ev[1], st));
+   if (timing && single) CU(cudaEventRecord(s.ev[E_K1C_END], st));
+   if (timing) CU(cudaEventRecord(s.ev[E_K1_END], st));
 
    // ---- K2 ------------------------------------------------------------------
    Pattern fwd, rev;
@@ -437,6 +442,10 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
    const bool bitslice = !single && use_bitslice(e, options, n);
    K2Args k2{d_text, n, s.d_ls, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_ev,
              (uint32_t)std::min<size_t>(s.ev_cap, 0xffffffffu), bitslice ? 1 : 0};
+   if (timing && !bitslice) {
+      CU(cudaEventRecord(s.ev[E_PACK_BEGIN], st));
+      CU(cudaEventRecord(s.ev[E_PACK_END], st));
+   }
    if (bitslice) {
       // the bit-sliced kernel stores only the lines that match
       if (mode == M_FIRST || mode == M_BEST)
@@ -448,36 +457,40 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
       uint32_t *tile_cols = s.d_bstiles, *tile_off = tile_cols + max_tiles;
       const uint32_t wup = bs_warmup(e->m, e->tau);
       uint32_t *gmask = s.d_gmask, *gfollow = cut ? s.d_gmask + s.gmask_cap / 2 : nullptr;
-      uint8_t *segstop = s.d_segflags, *deadseg = cut ? s.d_segflags + s.line_cap : nullptr;
+      uint8_t *segstop = s.d_segflags;
       BsPrepArgs bp{s.d_ls, (uint32_t)lines_cap, n, ctr, tile_cols, tile_off, (uint32_t)max_tiles,
                     (unsigned long long)(s.planes_cap / 32), e->bs_gate, cut ? s.d_lid : nullptr, wup};
       k15_tile_cols<<<(int)std::min<size_t>(div_up(max_tiles, kWarps), (size_t)e->sms * 8), kThreads, 0, st>>>(bp);
       k15_scan<<<1, 1024, 0, st>>>(bp);
+      if (timing) CU(cudaEventRecord(s.ev[E_PACK_BEGIN], st));
       BsPackArgs pk{(const uint4 *)s.d_codes, (uint32_t)(div_up(n, kK1Tile) * (kK1Tile / 32)), s.d_ls,
                     (uint32_t)lines_cap, ctr, tile_cols, tile_off, s.d_planes, cut ? s.d_lid : nullptr, wup,
                     gmask, gfollow};
       k15_pack<<<(int)std::max<size_t>(1, std::min<size_t>(div_up(div_up(max_lines, 64), kWarps), (size_t)e->sms * 16)),
                  kThreads, 0, st>>>(pk);
       CU(cudaGetLastError());
+      if (timing) CU(cudaEventRecord(s.ev[E_PACK_END], st));
       s.launches += 3;
       K2BsArgs kb{s.d_planes, tile_cols, tile_off, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_ev, k2.ev_cap,
                   (mode == M_COUNT || mode == M_COUNTALL) ? 1 : 0, cut ? gmask : nullptr, gfollow, segstop, wup};
       if (launch_bitslice(e, mode, options, max_lines, st, kb)) return -1;
       s.launches++;
-      if (cut) {
-         SegReduceArgs sr{s.d_lid, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, segstop, deadseg, mode};
-         k_seg_reduce<<<(int)std::max<size_t>(1, std::min<size_t>(div_up(max_lines, kThreads), (size_t)e->sms * 8)),
-                        kThreads, 0, st>>>(sr);
-         CU(cudaGetLastError());
-         s.launches++;
-      }
    }
    {
       const int grid = (int)std::min<size_t>(div_up(max_lines, lines_per_cta), (size_t)e->sms * 8);
       if (launch_k2(e, mode, grid, st, k2, fwd)) return -1;
       s.launches++;
    }
-   if (timing) CU(cudaEventRecord(s.ev[2], st));
+   if (timing) CU(cudaEventRecord(s.ev[E_MATCH_END], st));
+   if (cut) {
+      // one result per line out of the results per segment
+      SegReduceArgs sr{s.d_lid, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_segflags, s.d_segflags + s.line_cap, mode};
+      k_seg_reduce<<<(int)std::max<size_t>(1, std::min<size_t>(div_up(max_lines, kThreads), (size_t)e->sms * 8)),
+                     kThreads, 0, st>>>(sr);
+      CU(cudaGetLastError());
+      s.launches++;
+   }
+   if (timing) CU(cudaEventRecord(s.ev[E_K2_END], st));
 
    // ---- scan + K3/K4 --------------------------------------------------------
    uint32_t *tile_sum = s.d_fintiles, *tile_nz = tile_sum + fin_tiles, *tile_recbase = tile_nz + fin_tiles;
@@ -505,9 +518,9 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
          s.launches += 4;
       }
    }
-   if (timing) CU(cudaEventRecord(s.ev[3], st));
+   if (timing) CU(cudaEventRecord(s.ev[E_FIN_END], st));
    CU(cudaMemcpyAsync(s.h_ctr, ctr, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-   CU(cudaEventRecord(s.ev[4], st));
+   CU(cudaEventRecord(s.ev[E_DONE], st));
    return 0;
 }
 
@@ -516,7 +529,7 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
 {
    uint32_t reruns = 0;
    for (;;) {
-      CU(cudaEventSynchronize(s.ev[4]));
+      CU(cudaEventSynchronize(s.ev[E_DONE]));
       const int mode = mode_of(s.cur_options);
       const unsigned long long nlines = std::max(s.h_ctr[C_NLINES], s.h_ctr[C_NPSEUDO]);   // entries of ls
       const unsigned long long nev = s.h_ctr[C_EVENTS];
@@ -547,11 +560,13 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
       stats->launches = s.launches;
       stats->reruns = reruns;
       if (s.cur_options & SQB_TIMING) {
+         static const int span[6][2] = {{E_BEGIN, E_K1_END}, {E_K1_END, E_K2_END}, {E_K2_END, E_FIN_END},
+                                        {E_PACK_END, E_MATCH_END}, {E_PACK_BEGIN, E_PACK_END}, {E_BEGIN, E_K1C_END}};
          float ms = 0;
-         CU(cudaEventElapsedTime(&ms, s.ev[0], s.ev[3]));
+         CU(cudaEventElapsedTime(&ms, s.ev[E_BEGIN], s.ev[E_FIN_END]));
          stats->device_ms = ms;
-         for (int k = 0; k < 3; k++) {
-            CU(cudaEventElapsedTime(&ms, s.ev[k], s.ev[k + 1]));
+         for (int k = 0; k < 6; k++) {
+            CU(cudaEventElapsedTime(&ms, s.ev[span[k][0]], s.ev[span[k][1]]));
             stats->kernel_ms[k] = ms;
          }
       }
@@ -723,7 +738,7 @@ static int host_collect(sqb_engine *e, Slot &s, int options, uint64_t *line_base
    acc->launches += st.launches;
    acc->reruns += st.reruns;
    acc->device_ms += st.device_ms;
-   for (int k = 0; k < 4; k++) acc->kernel_ms[k] += st.kernel_ms[k];
+   for (int k = 0; k < 8; k++) acc->kernel_ms[k] += st.kernel_ms[k];
    return 0;
 }
 

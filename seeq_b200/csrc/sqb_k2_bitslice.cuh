@@ -68,7 +68,7 @@ __device__ __forceinline__ SegShape seg_shape(const uint32_t *ls, const uint32_t
                                               uint32_t nlines)
 {
    SegShape g{ls[l], 0xffffffffu, false, false};
-   if (lid) {
+   if (lid) {            // callers pass nullptr when K1 made no cut
       const uint32_t me = lid[l];
       g.cont = l > 0u && lid[l - 1u] == me;
       g.follow = l + 1u < nlines && lid[l + 1u] == me;
@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(kThreads) k15_tile_cols(const BsPrepArgs a)
    const uint32_t nlines = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
    const uint32_t ntiles = (nlines + kBsTileLines - 1) / kBsTileLines;
    const uint32_t wid = (blockIdx.x * kThreads + threadIdx.x) >> 5, nw = (gridDim.x * kThreads) >> 5;
+   const uint32_t *lid = a.ctr[C_NCUTS] != 0ull ? a.lid : nullptr;
    for (uint32_t t = wid; t < ntiles; t += nw) {
       uint32_t mx = 0;
       const uint32_t l0 = t * kBsTileLines;
@@ -93,8 +94,8 @@ __global__ void __launch_bounds__(kThreads) k15_tile_cols(const BsPrepArgs a)
          const uint32_t l = l0 + (uint32_t)k * 32u + (uint32_t)lane;
          if (l < nlines) {
             uint32_t len = a.ls[l + 1] - a.ls[l];
-            if (a.lid) {
-               const SegShape g = seg_shape(a.ls, a.lid, a.wup, l, nlines);
+            if (lid) {
+               const SegShape g = seg_shape(a.ls, lid, a.wup, l, nlines);
                len = g.follow ? g.limit : a.ls[l + 1] - g.begin;
             }
             mx = max(mx, len);
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(1024) k15_scan(const BsPrepArgs a)
       const unsigned long long cols = s_carry;
       // with segment cuts the entries of ls are segments: only the bit-sliced kernel knows them
       const bool want = nl_dev <= a.max_lines &&
-                        (a.lid != nullptr || (nl_dev >= a.gate.min_lines && mx <= a.gate.max_line + 1u));
+                        ((a.lid != nullptr && a.ctr[C_NCUTS] != 0ull) || (nl_dev >= a.gate.min_lines && mx <= a.gate.max_line + 1u));
       a.ctr[C_BS_COLS] = cols;
       a.ctr[C_BS_SELECTED] = !want ? 0ull : (cols <= a.planes_cap ? 1ull : 2ull);
    }
@@ -241,6 +242,7 @@ __global__ void __launch_bounds__(kThreads) k15_pack(const BsPackArgs a)
    const int lane = threadIdx.x & 31;
    const uint32_t nlines = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
    const uint32_t npairs = (nlines + 63u) / 64u;
+   const uint32_t *lid = a.ctr[C_NCUTS] != 0ull ? a.lid : nullptr;
    uint32_t keep[5], rot[5];
    {
       const uint32_t m[5] = {0x0000FFFFu, 0x00FF00FFu, 0x0F0F0F0Fu, 0x33333333u, 0x55555555u};
@@ -260,11 +262,11 @@ __global__ void __launch_bounds__(kThreads) k15_pack(const BsPackArgs a)
       const uint32_t la = pair * 64u + (uint32_t)lane, lb = la + 32u;
       NibbleStream sa, sb;
       SegShape ga{0u, 0xffffffffu, false, false}, gb{0u, 0xffffffffu, false, false};
-      if (la < nlines) ga = seg_shape(a.ls, a.lid, a.wup, la, nlines);
-      if (lb < nlines) gb = seg_shape(a.ls, a.lid, a.wup, lb, nlines);
+      if (la < nlines) ga = seg_shape(a.ls, lid, a.wup, la, nlines);
+      if (lb < nlines) gb = seg_shape(a.ls, lid, a.wup, lb, nlines);
       sa.open(a.codes, a.ncode16, ga.begin, la < nlines);
       sb.open(a.codes, a.ncode16, gb.begin, lb < nlines);
-      if (a.lid) {
+      if (lid) {
          const uint32_t ca = __ballot_sync(kFull, ga.cont), cb = __ballot_sync(kFull, gb.cont);
          const uint32_t fa = __ballot_sync(kFull, ga.follow), fb = __ballot_sync(kFull, gb.follow);
          if (lane == 0) {
@@ -282,8 +284,10 @@ __global__ void __launch_bounds__(kThreads) k15_pack(const BsPackArgs a)
          uint32_t wa[4], wb[4];
          sa.next(wa);
          sb.next(wb);
-         null_fill(wa, c0, ga.limit);
-         null_fill(wb, c0, gb.limit);
+         if (lid) {
+            null_fill(wa, c0, ga.limit);
+            null_fill(wb, c0, gb.limit);
+         }
 #pragma unroll
          for (int k = 0; k < 4; k++) {
             const uint32_t ta = warp_transpose32(wa[k], keep, rot);
@@ -369,6 +373,7 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
    }
 
    uint32_t my_matched = 0, my_events = 0;
+   const bool has_cuts = a.gmask != nullptr && a.ctr[C_NCUTS] != 0ull;
 
    for (uint32_t item = blockIdx.x * kBsWarps + warp; item < nitems; item += gridDim.x * kBsWarps) {
       const uint32_t tile = item / (uint32_t)G, q = item % (uint32_t)G;
@@ -384,7 +389,7 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
       }
       uint32_t lane_events = 0;
       uint32_t qmask = 0u, fmask = 0u;
-      if (a.gmask) {
+      if (has_cuts) {
          qmask = a.gmask[tile * 32u + group];
          fmask = a.gfollow[tile * 32u + group];
       }

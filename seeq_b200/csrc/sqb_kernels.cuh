@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(1024) k1_scan_tiles(const K1ScanArgs a)
    __shared__ unsigned long long s_warp[32], s_real[32];
    __shared__ uint32_t s_max[32];
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-   const bool cut = a.tile_real != nullptr;
+   const bool cut = a.tile_real != nullptr && a.ctr[C_NCUTS] != 0ull;     // K1 is complete: the count is final
    // warp w owns the contiguous run [w*per, (w+1)*per) and walks it 32 tiles at a
    // time (coalesced): first its totals, then -- after the 32 totals are scanned --
    // the exclusive prefix of every tile
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(kThreads) k1_gather(const K1GatherArgs a)
    const int lane = threadIdx.x & 31;
    const uint32_t wid = (blockIdx.x * kThreads + threadIdx.x) >> 5;
    const uint32_t nwarps = (gridDim.x * kThreads) >> 5;
-   const bool cut = a.codes != nullptr;
+   const bool cut = a.codes != nullptr && a.ctr[C_NCUTS] != 0ull;
    for (uint32_t t = wid; t < a.ntiles; t += nwarps) {
       const uint32_t cnt = a.tile_cnt[t], src = a.tile_off[t], dst = a.tile_base[t];
       if (!cut) {
@@ -1166,7 +1166,7 @@ struct LineOf {
 __device__ __forceinline__ LineOf line_of(const FinArgs &a, uint32_t p)
 {
    const uint32_t lp = a.ls[p];
-   if (a.lid == nullptr) return LineOf{p, lp, 0u};
+   if (a.lid == nullptr || a.ctr[C_NCUTS] == 0ull) return LineOf{p, lp, 0u};
    const uint32_t line = a.lid[p], lb = a.lbeg[p];
    const bool cont = p > 0u && a.lid[p - 1u] == line;
    return LineOf{line, lb, lp - (cont ? a.wup : 0u) - lb};

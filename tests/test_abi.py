@@ -66,7 +66,7 @@ def test_struct_layouts(B):
     assert C.sizeof(B.MatchT) == 24
     F = B.SeeqFileT
     assert [getattr(F, n).offset for n in ("flags", "line", "info", "fdi")] == [0, 8, 16, 24]
-    assert C.sizeof(B.StatsT) == 4 * 8 + 8 + 4 * 8 + 8 and C.sizeof(B.GenT) == 8 + 7 * 4 + 256 + 4
+    assert C.sizeof(B.StatsT) == 4 * 8 + 8 + 8 * 8 + 8 and C.sizeof(B.GenT) == 8 + 7 * 4 + 256 + 4
 
 
 def test_seeqnew_fields_and_errors(B):
