@@ -254,16 +254,20 @@ static int launch_k2(const sqb_engine *e, int mode, int grid, cudaStream_t st, c
 
 static int launch_finish(const sqb_engine *e, bool all, int grid, cudaStream_t st, const FinArgs &a, const Pattern &rp)
 {
+   // bytes fetched per round of the reverse pass (tuning knob)
+   static const int chunk = getenv("SEEQ_B200_REV_CHUNK") ? atoi(getenv("SEEQ_B200_REV_CHUNK")) : 8;
 #define SQB_FIN(W)                                                                  \
    case W:                                                                          \
       if (all) k34_finish_events<W><<<grid, kThreads, 0, st>>>(a, rp);              \
-      else k34_finish_lines<W><<<grid, kThreads, 0, st>>>(a, rp);                   \
+      else if (chunk <= 1) k34_finish_lines<W, 1><<<grid, kThreads, 0, st>>>(a, rp); \
+      else if (chunk <= 4) k34_finish_lines<W, 4><<<grid, kThreads, 0, st>>>(a, rp); \
+      else k34_finish_lines<W, 8><<<grid, kThreads, 0, st>>>(a, rp);                \
       break;
    switch (e->words) {
       SQB_FIN(1) SQB_FIN(2) SQB_FIN(4) SQB_FIN(8) SQB_FIN(16)
    default:
       if (all) k34_finish_events<32><<<grid, kThreads, 0, st>>>(a, rp);
-      else k34_finish_lines<32><<<grid, kThreads, 0, st>>>(a, rp);
+      else k34_finish_lines<32, 4><<<grid, kThreads, 0, st>>>(a, rp);
    }
 #undef SQB_FIN
    CU(cudaGetLastError());
@@ -634,6 +638,9 @@ sqb_engine_t *sqbEngineNew(const unsigned char *keys, int m, int tau, int device
       if (!strcmp(mk, "bitslice")) { e->bs_gate = BsGate{1u, 1u << 30}; e->bs_min_bytes = 1; }
    }
    if (const char *c = getenv("SEEQ_B200_CUTS")) e->cuts = atoi(c) != 0;
+   // the reverse pass touches one or two 32-byte sectors per record at random places:
+   // a smaller L2 fetch granularity keeps the DRAM traffic of that kernel down
+   if (const char *c = getenv("SEEQ_B200_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(c));
    return e;
 }
 

@@ -905,7 +905,7 @@ template <int W> __device__ __forceinline__ void rev_tables_load(RevTables<W> &t
    __syncthreads();
 }
 
-template <int W>
+template <int W, int kChunk = 8>
 __device__ __forceinline__ uint32_t reverse_start(const uint8_t *__restrict__ text, const uint32_t line_begin,
                                                   const uint32_t end, const int dist, const int m, const int tau,
                                                   const RevTables<W> &tab)
@@ -920,7 +920,6 @@ __device__ __forceinline__ uint32_t reverse_start(const uint8_t *__restrict__ te
    // the bytes are fetched eight at a time (independent loads) and then walked in
    // registers: a load per step would put the global latency on the dependency
    // chain of every step
-   constexpr int kChunk = 8;
    while (more) {
       const uint32_t left = end - j;                     // > 0
       uint8_t b[kChunk];
@@ -1178,7 +1177,7 @@ __device__ __forceinline__ LineOf line_of(const FinArgs &a, uint32_t p)
 // lines of a typical input have no match, and a thread per line would leave those
 // lanes idle through the whole pass -- and write the records, already in order,
 // behind the tile's first record (k_tile_sums / k_tile_scan).
-template <int W>
+template <int W, int CHUNK>
 __global__ void __launch_bounds__(kThreads) k34_finish_lines(const FinArgs a, const __grid_constant__ Pattern rpat)
 {
    __shared__ BlockScanSmem sc;
@@ -1212,7 +1211,7 @@ __global__ void __launch_bounds__(kThreads) k34_finish_lines(const FinArgs a, co
          r.line = c.x;
          r.end = c.z;
          r.dist = c.w;
-         r.start = reverse_start<W>(a.text, c.y, c.z, (int)c.w, rpat.m, rpat.tau, tab);
+         r.start = reverse_start<W, CHUNK>(a.text, c.y, c.z, (int)c.w, rpat.m, rpat.tau, tab);
          if (base + i < a.rec_cap) a.recs[base + i] = r;
       }
       __syncthreads();                                    // cand is reused by the next tile
