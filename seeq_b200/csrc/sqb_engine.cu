@@ -93,7 +93,9 @@ struct sqb_engine {
    int words = 1;                 // automaton words: 1, 2, 4, 8, 16 or 32
    unsigned char keys[kMaxWords * 32];
    bool bs_ok = false;            // the pattern fits the bit-sliced matcher
-   bool cuts = true;              // long lines may be cut into segments (SEEQ_B200_CUTS=0 disables)
+   int cuts = 1;                  // long lines are cut into segments: 0 never, 1 once a scan met lines longer
+                                  // than bs_max_line (then from that scan on), 2 always  (SEEQ_B200_CUTS)
+   bool cuts_wanted = false;      // a scan met long lines
    BsGate bs_gate{65536u, 4096u};
    uint32_t bs_min_bytes = 1u << 20;
    double cols_per_byte = 1.3 / 1024.0;   // tile columns per text byte (plane buffer guess)
@@ -255,7 +257,7 @@ static int launch_k2(const sqb_engine *e, int mode, int grid, cudaStream_t st, c
 static int launch_finish(const sqb_engine *e, bool all, int grid, cudaStream_t st, const FinArgs &a, const Pattern &rp)
 {
    // bytes fetched per round of the reverse pass (tuning knob)
-   static const int chunk = getenv("SEEQ_B200_REV_CHUNK") ? atoi(getenv("SEEQ_B200_REV_CHUNK")) : 8;
+   static const int chunk = getenv("SEEQ_B200_REV_CHUNK") ? atoi(getenv("SEEQ_B200_REV_CHUNK")) : 4;
 #define SQB_FIN(W)                                                                  \
    case W:                                                                          \
       if (all) k34_finish_events<W><<<grid, kThreads, 0, st>>>(a, rp);              \
@@ -291,12 +293,16 @@ static bool use_bitslice(const sqb_engine *e, int options, uint32_t n)
 // automaton.  Not with SQ_IGNORE (a warm-up could hold too few automaton inputs),
 // not in FASTA mode (a cut inside a long header line would be scanned), not when
 // the caller wants the line starts back, not in the count-only modes.
-static bool use_cuts(const sqb_engine *e, int options, uint32_t n)
+static bool cuts_allowed(const sqb_engine *e, int options, uint32_t n)
 {
-   if (!use_bitslice(e, options, n) || !e->cuts) return false;
+   if (!use_bitslice(e, options, n) || e->cuts == 0) return false;
    if (options & (SQB_FASTA | SQB_COUNT_ONLY | SQB_KEEP_LINES_INTERNAL)) return false;
    if ((options & OPT_NONDNA) == OPT_IGNORE) return false;
    return bs_warmup(e->m, e->tau) <= kCutWindow;
+}
+static bool use_cuts(const sqb_engine *e, int options, uint32_t n)
+{
+   return cuts_allowed(e, options, n) && (e->cuts == 2 || e->cuts_wanted);
 }
 
 template <int R, int G, int MODE> static int launch_bs2(bool skip, int grid, cudaStream_t st, const K2BsArgs &a, const BsPattern &p)
@@ -328,7 +334,7 @@ static int launch_bitslice(const sqb_engine *e, int mode, int options, size_t ma
    const int bsmode = (mode == M_ALL || mode == M_COUNTALL) ? BS_ALL : (mode == M_BEST ? BS_BEST : BS_FIRST);
    const bool skip = (options & OPT_NONDNA) == OPT_IGNORE;
    const int R = e->bs_pat.rows, G = e->bs_pat.parts;
-   int per_sm = G > 1 ? 2 : (R <= 16 ? 4 : 3);
+   int per_sm = G > 1 ? (R <= 24 ? 3 : 2) : (R <= 16 ? 4 : 3);
    if (const char *c = getenv("SEEQ_B200_BS_CTAS")) per_sm = std::max(1, atoi(c));
    // work items = (tile, 1/G of its groups), one warp each
    const int grid = (int)std::max<size_t>(1, std::min<size_t>(div_up(div_up(max_lines, kBsTileLines) * G, kBsWarps),
@@ -463,7 +469,8 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
       uint32_t *gmask = s.d_gmask, *gfollow = cut ? s.d_gmask + s.gmask_cap / 2 : nullptr;
       uint8_t *segstop = s.d_segflags;
       BsPrepArgs bp{s.d_ls, (uint32_t)lines_cap, n, ctr, tile_cols, tile_off, (uint32_t)max_tiles,
-                    (unsigned long long)(s.planes_cap / 32), e->bs_gate, cut ? s.d_lid : nullptr, wup};
+                    (unsigned long long)(s.planes_cap / 32), e->bs_gate, cut ? s.d_lid : nullptr, wup,
+                    (!cut && cuts_allowed(e, options, n)) ? 1 : 0};
       k15_tile_cols<<<(int)std::min<size_t>(div_up(max_tiles, kWarps), (size_t)e->sms * 8), kThreads, 0, st>>>(bp);
       k15_scan<<<1, 1024, 0, st>>>(bp);
       if (timing) CU(cudaEventRecord(s.ev[E_PACK_BEGIN], st));
@@ -540,6 +547,10 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
       bool again = false;
       if (nlines + 1 > s.line_cap) {
          e->lines_per_byte = (double)(nlines + 2) / (double)std::max<uint32_t>(s.cur_n, 1) * 1.05;
+         again = true;
+      }
+      if (s.h_ctr[C_BS_SELECTED] == 3ull) {          // long lines: cut them, in this scan and from now on
+         e->cuts_wanted = true;
          again = true;
       }
       if (s.h_ctr[C_BS_SELECTED] == 2ull) {          // plane buffer too small for the bit-sliced scan
@@ -637,10 +648,7 @@ sqb_engine_t *sqbEngineNew(const unsigned char *keys, int m, int tau, int device
       if (!strcmp(mk, "word")) e->bs_ok = false;
       if (!strcmp(mk, "bitslice")) { e->bs_gate = BsGate{1u, 1u << 30}; e->bs_min_bytes = 1; }
    }
-   if (const char *c = getenv("SEEQ_B200_CUTS")) e->cuts = atoi(c) != 0;
-   // the reverse pass touches one or two 32-byte sectors per record at random places:
-   // a smaller L2 fetch granularity keeps the DRAM traffic of that kernel down
-   if (const char *c = getenv("SEEQ_B200_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(c));
+   if (const char *c = getenv("SEEQ_B200_CUTS")) e->cuts = atoi(c);
    return e;
 }
 

@@ -53,6 +53,7 @@ struct BsPrepArgs {
    BsGate gate;
    const uint32_t *lid;           // line of every ls entry (segment cuts), or nullptr
    uint32_t wup;                  // warm-up bytes in front of a continuation segment
+   int cuts_possible;             // this scan could have cut its long lines but did not (see k15_scan)
 };
 
 // With segment cuts an entry l of ls is a CONTINUATION if it belongs to the same
@@ -108,7 +109,9 @@ __global__ void __launch_bounds__(kThreads) k15_tile_cols(const BsPrepArgs a)
 
 // exclusive scan of tile_cols (one CTA) and the decision: 1 = bit-sliced scan,
 // 0 = word-parallel kernels, 2 = bit-sliced but the plane buffer is too small
-// (the host repeats the scan with the exact size, ctr[C_BS_COLS])
+// (the host repeats the scan with the exact size, ctr[C_BS_COLS]), 3 = there are
+// long lines and the scan did not cut them: the host repeats it with segment
+// cuts (and keeps cutting from then on); no matcher runs
 __global__ void __launch_bounds__(1024) k15_scan(const BsPrepArgs a)
 {
    __shared__ unsigned long long s_warp[32];
@@ -155,7 +158,8 @@ __global__ void __launch_bounds__(1024) k15_scan(const BsPrepArgs a)
       const bool want = nl_dev <= a.max_lines &&
                         ((a.lid != nullptr && a.ctr[C_NCUTS] != 0ull) || (nl_dev >= a.gate.min_lines && mx <= a.gate.max_line + 1u));
       a.ctr[C_BS_COLS] = cols;
-      a.ctr[C_BS_SELECTED] = !want ? 0ull : (cols <= a.planes_cap ? 1ull : 2ull);
+      if (a.cuts_possible && nl_dev <= a.max_lines && mx > a.gate.max_line + 1u) a.ctr[C_BS_SELECTED] = 3ull;
+      else a.ctr[C_BS_SELECTED] = !want ? 0ull : (cols <= a.planes_cap ? 1ull : 2ull);
    }
 }
 
@@ -338,7 +342,7 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 // columns behind part 0 and receives the horizontal delta of the part below
 // with one pair of shuffles per column; only the last part reports.
 template <int R, int G, int MODE, bool SKIP>
-__global__ void __launch_bounds__(kBsThreads, G > 1 ? 2 : (R <= 16 ? 4 : 3))
+__global__ void __launch_bounds__(kBsThreads, G > 1 ? (R <= 24 ? 3 : 2) : (R <= 16 ? 4 : 3))
 k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
 {
    using Smem = typename std::conditional<MODE == BS_ALL, BsWarpSmemAll, BsWarpSmem>::type;

@@ -138,9 +138,9 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// CUT: long lines are cut into segments (sqb_tables.h).  The candidates A = 1024
-// (mod 2048) are the first bytes of lanes 8 and 24 of every warp, and "the line
-// has been running for 1024 bytes" = the eight lanes in front hold no line start:
+// CUT: long lines are cut into segments (sqb_tables.h).  The candidates A = 256
+// (mod 2048) are the first bytes of lanes 2 and 18 of every warp, and "the line
+// has been running for 256 bytes" = the two lanes in front hold no line start:
 // two shuffles of the warp scan decide it.
 template <bool CODES, bool CUT>
 __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, const __grid_constant__ ClassTable ct)
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, 
    __shared__ uint32_t s_base[2];
    __shared__ uint32_t s_last[2];
 
-   static_assert(kCutWindow == 8 * kK1LaneBytes && kCutStride == 16 * kK1LaneBytes, "cut candidates = lanes 8 and 24");
+   static_assert(kCutWindow == 2 * kK1LaneBytes && kCutStride == 16 * kK1LaneBytes, "cut candidates = lanes 2 and 18");
    const uint32_t n = a.n;
    const uint32_t ntiles = (n + kK1Tile - 1) / kK1Tile;
    const uint32_t n16 = (n + 15u) & ~15u;
@@ -273,11 +273,11 @@ __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, 
       uint32_t cut = 0, cutinc = 0;          // a cut at the first byte of this lane; cuts up to and including this lane
       if (CUT) {
          const uint32_t prev1 = __shfl_up_sync(kFull, inc, 1);
-         const uint32_t prev9 = __shfl_up_sync(kFull, inc, 9);
-         if ((lane == 8 || lane == 24) && pos0 < n) cut = (prev1 - (lane == 8 ? 0u : prev9)) == 0u ? 1u : 0u;
-         const uint32_t cut8 = __shfl_sync(kFull, cut, 8), cut24 = __shfl_sync(kFull, cut, 24);
-         cutinc = (lane >= 8 ? cut8 : 0u) + (lane >= 24 ? cut24 : 0u);
-         if (lane == 31) s_wcut[warp] = cut8 + cut24;
+         const uint32_t prev3 = __shfl_up_sync(kFull, inc, 3);
+         if ((lane == 2 || lane == 18) && pos0 < n) cut = (prev1 - (lane == 2 ? 0u : prev3)) == 0u ? 1u : 0u;
+         const uint32_t cut2 = __shfl_sync(kFull, cut, 2), cut18 = __shfl_sync(kFull, cut, 18);
+         cutinc = (lane >= 2 ? cut2 : 0u) + (lane >= 18 ? cut18 : 0u);
+         if (lane == 31) s_wcut[warp] = cut2 + cut18;
       }
       // the bulk store this warp issued one tile ago has long read its stage; make
       // sure before the stage is refilled below
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(1024) k1_scan_tiles(const K1ScanArgs a)
 //   lid[p]  = number of the line the entry belongs to
 //   lbeg[p] = start of that line
 // An entry is a line start iff it is 0 or follows a newline (bit 3 of the class
-// nibble in front of it); a cut never does (there is no line start in the 1024
+// nibble in front of it); a cut never does (there is no line start in the 256
 // bytes before it).
 struct K1GatherArgs {
    const uint32_t *ls_raw;

@@ -70,7 +70,10 @@ static inline bool bs_shape_for(int m, BsShape *out)
 // Long lines are cut into SEGMENTS so that they fill the lanes of the bit-sliced
 // matcher like short lines do.  A cut is made at every text offset A = kCutWindow
 // (mod kCutStride) whose line has been running for at least kCutWindow bytes (no
-// line start in the kCutWindow bytes before A).  The segment that starts at A
+// line start in the kCutWindow bytes before A).  The window only has to hold the
+// warm-up; a short one keeps the first segment of a line (kCutWindow .. kCutWindow
+// + kCutStride bytes) close to the length of the others, and the lanes of a tile
+// run as long as its longest segment.  The segment that starts at A
 // scans from A - warm-up with a fresh automaton and reports the events that end
 // after A; the segment before it scans up to and including byte A and reports
 // the events that end at or before A.  A warm-up of m + 2 tau + 2 automaton
@@ -78,7 +81,7 @@ static inline bool bs_shape_for(int m, BsShape *out)
 // inputs) and the suppress flag (a rising run of capped distances has at most
 // tau + 2 members) -- SURVEY.md 3.3, pinned by tests/test_bitslice_host.py.
 constexpr uint32_t kCutStride = 2048;
-constexpr uint32_t kCutWindow = 1024;
+constexpr uint32_t kCutWindow = 256;
 static inline uint32_t bs_warmup(int m, int tau) { return (uint32_t)(m + 2 * tau + 2); }
 
 // keys: one class byte per pattern position (bit0 A .. bit3 T, 0x1F = N).

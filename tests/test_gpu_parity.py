@@ -109,15 +109,15 @@ def test_buffers_all_modes(B, oracle, mrange, matcher):
 
 
 def long_line_buffer(rng, keys, tau, nlines, maxlen, junk):
-    """Ragged long lines (the matcher cuts them into segments at text offsets 1024 mod
+    """Ragged long lines (the matcher cuts them into segments at text offsets 256 mod
     2048), pattern instances planted at random and right across the cut offsets."""
     lines = []
     for _ in range(nlines):
-        n = rng.choice([rng.randint(0, 300), rng.randint(900, 3500), rng.randint(3000, maxlen)])
+        n = rng.choice([rng.randint(0, 300), rng.randint(200, 3500), rng.randint(3000, maxlen)])
         lines.append([rng.choice("ACGT") for _ in range(n)])
     buf = bytearray("\n".join("".join(l) for l in lines).encode() + b"\n")
     m = len(keys)
-    for a in range(1024, len(buf), 2048):
+    for a in range(256, len(buf), 2048):
         if rng.random() < 0.7:
             inst = plant(rng, keys, tau).encode()
             at = a - rng.randint(0, m + tau + 1) + rng.randint(0, 3)
@@ -135,8 +135,17 @@ def long_line_buffer(rng, keys, tau, nlines, maxlen, junk):
     return bytes(buf)
 
 
+@pytest.mark.parametrize("cuts", ["on-demand", "always"])
 @pytest.mark.parametrize("mrange", [(4, 12), (20, 32), (36, 48), (90, 110)])
-def test_long_lines(B, oracle, mrange, matcher):
+def test_long_lines(B, oracle, mrange, matcher, cuts, monkeypatch):
+    """Lines of up to 12 kB.  `always`: the bit-sliced matcher cuts them into segments
+    (SEEQ_B200_CUTS=2); `on-demand`: the engine's default -- with the thresholds of the
+    forced bit-sliced matcher lifted that is the un-cut bit-sliced scan, otherwise the
+    word-parallel kernels (the buffers are below the 1 MB the engine wants)."""
+    if cuts == "always":
+        monkeypatch.setenv("SEEQ_B200_CUTS", "2")
+    else:
+        monkeypatch.delenv("SEEQ_B200_CUTS", raising=False)
     rng = random.Random(mrange[0] * 131)
     for it in range(4):
         pattern = rand_pattern(rng, *mrange)
@@ -150,7 +159,9 @@ def test_long_lines(B, oracle, mrange, matcher):
 
 def test_long_lines_large(B, oracle):
     """More than the 1 MB the engine wants before it goes bit-sliced on its own: 10-kb
-    reads (BASELINE config 3 shape) with the engine's default choices."""
+    reads (BASELINE config 3 shape) with the engine's default choices -- the first scan
+    meets the long lines and is repeated with segment cuts (stats.reruns), the later ones
+    cut right away."""
     rng = random.Random(99)
     pattern = "".join(rng.choice("ACGT") for _ in range(40))
     keys, _ = oracle.parse(pattern)

@@ -21,6 +21,10 @@ except Exception as e:
     print("$wl failed", e)
 PY
 done
+# the two lines the driver takes at round end: our arm with defaults, the reference arm
+( time timeout 900 python bench.py ) > gpurun_out/${TAG}_bench_default.json 2> gpurun_out/${TAG}_bench_default.err
+( time timeout 900 python bench.py --impl reference --steps 3 --warmup 1 ) > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err
+tail -c 600 gpurun_out/${TAG}_bench_reference.json; grep real gpurun_out/${TAG}_bench_default.err gpurun_out/${TAG}_bench_reference.err
 bash tools/gpu_profile.sh $TAG cfg2 11 > gpurun_out/${TAG}_profile.log 2>&1
 tail -3 gpurun_out/${TAG}_profile.log
 bash tools/gpu_profile.sh $TAG cfg3 0 >> gpurun_out/${TAG}_profile.log 2>&1
