@@ -168,10 +168,14 @@ def cpu_reference_run(w, host_text: np.ndarray, nproc: int, seconds_target: floa
     for _ in range(max(1, steps)):
         t, result = run(sample, nproc)
         times.append(t)
+    # a sample the host cores finish in a fraction of a second is repeated (about 2 s of wall time)
+    while steps <= 1 and sum(times) < 2.0 and len(times) < 8:
+        t, result = run(sample, nproc)
+        times.append(t)
     t = float(np.mean(times))
     return dict(value=sample.size / t / 1e9, reads_per_s=reads / t, unit="GB/s", cores=nproc, kind=kind,
                 sample="%d reads (%.1f MB) of the same workload, %d processes over newline-aligned shards, "
-                       "%.2f s per step" % (reads, sample.size / 1e6, nproc, t),
+                       "%.2f s per pass, mean of %d passes" % (reads, sample.size / 1e6, nproc, t, len(times)),
                 seconds=t, result=int(result))
 
 
@@ -179,7 +183,7 @@ def cpu_reference_run(w, host_text: np.ndarray, nproc: int, seconds_target: floa
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
