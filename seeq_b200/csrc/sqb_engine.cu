@@ -60,6 +60,9 @@ struct Slot {
    uint32_t *d_lbeg = nullptr;  size_t lbeg_cap = 0;      //               start of that line
    uint32_t *d_gmask = nullptr; size_t gmask_cap = 0;     //               per group of 32 entries: continuations, followed
    uint8_t *d_segflags = nullptr; size_t segflags_cap = 0; //              segstop[], deadseg[]
+   uint32_t *d_act = nullptr;   size_t act_cap = 0;       // line filter: entries of ls the matcher looks at
+   uint8_t *d_lflags = nullptr; size_t lflags_cap = 0;    //              1 = dead on arrival
+   bool cur_filter = false;
    uint4 *d_planes = nullptr;   size_t planes_cap = 0;    // bit-planes, 32 uint4 per tile column
    uint32_t *d_bstiles = nullptr; size_t bstiles_cap = 0; // per match tile: columns, offset
    uint32_t *d_fintiles = nullptr; size_t fintiles_cap = 0; // per 1024-line tile: records, matched lines, first record
@@ -96,6 +99,9 @@ struct sqb_engine {
    int cuts = 1;                  // long lines are cut into segments: 0 never, 1 once a scan met lines longer
                                   // than bs_max_line (then from that scan on), 2 always  (SEEQ_B200_CUTS)
    bool cuts_wanted = false;      // a scan met long lines
+   int filter = 1;                // line filter (lines with a STOP in their first m - tau bytes are not packed):
+                                  // 0 never, 1 if the first filtered scan drops >= 25 % of the lines, 2 always
+   int filter_state = -1;         // filter == 1: -1 undecided (probe with the next scan), 0 off, 1 on
    BsGate bs_gate{65536u, 4096u};
    uint32_t bs_min_bytes = 1u << 20;
    double cols_per_byte = 1.3 / 1024.0;   // tile columns per text byte (plane buffer guess)
@@ -174,7 +180,7 @@ template <class T> static int pin_reserve(T **p, size_t *cap, size_t need)
 
 static void slot_free(Slot &s)
 {
-   cudaFree(s.d_text); cudaFree(s.d_ls); cudaFree(s.d_codes); cudaFree(s.d_ls_raw); cudaFree(s.d_tiles); cudaFree(s.d_lid); cudaFree(s.d_lbeg); cudaFree(s.d_gmask); cudaFree(s.d_segflags); cudaFree(s.d_planes); cudaFree(s.d_bstiles); cudaFree(s.d_fintiles); cudaFree(s.d_res); cudaFree(s.d_cnt); cudaFree(s.d_offs);
+   cudaFree(s.d_text); cudaFree(s.d_ls); cudaFree(s.d_codes); cudaFree(s.d_ls_raw); cudaFree(s.d_tiles); cudaFree(s.d_lid); cudaFree(s.d_lbeg); cudaFree(s.d_gmask); cudaFree(s.d_segflags); cudaFree(s.d_act); cudaFree(s.d_lflags); cudaFree(s.d_planes); cudaFree(s.d_bstiles); cudaFree(s.d_fintiles); cudaFree(s.d_res); cudaFree(s.d_cnt); cudaFree(s.d_offs);
    cudaFree(s.d_ev); cudaFree(s.d_recs); cudaFree(s.d_ctl);
    cudaFreeHost(s.h_ctr); cudaFreeHost(s.h_recs); cudaFreeHost(s.h_ls); cudaFreeHost(s.h_init);
    for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
@@ -300,6 +306,11 @@ static bool cuts_allowed(const sqb_engine *e, int options, uint32_t n)
    if ((options & OPT_NONDNA) == OPT_IGNORE) return false;
    return bs_warmup(e->m, e->tau) <= kCutWindow;
 }
+static bool use_filter(const sqb_engine *e, int options, uint32_t n)
+{
+   if (!use_bitslice(e, options, n) || e->filter == 0 || n >= 0x80000000u) return false;
+   return e->filter == 2 || e->filter_state != 0;
+}
 static bool use_cuts(const sqb_engine *e, int options, uint32_t n)
 {
    return cuts_allowed(e, options, n) && (e->cuts == 2 || e->cuts_wanted);
@@ -388,6 +399,8 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
    if (timing) CU(cudaEventRecord(s.ev[E_BEGIN], st));
    CU(cudaMemsetAsync(s.d_ctl, 0, ctl_words * sizeof(unsigned long long), st));
    const bool cut = !single && use_cuts(e, options, n);
+   const bool filter = !single && use_filter(e, options, n);
+   s.cur_filter = filter;
 
    // ---- K1 ------------------------------------------------------------------
    if (single) {
@@ -403,10 +416,15 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
          const size_t need = k1_tiles * (kK1Tile / 2) + 256;
          if (dev_reserve(&s.d_codes, &s.codes_cap, need)) return -1;
       }
-      if (dev_reserve(&s.d_tiles, &s.tiles_cap, 7 * k1_tiles)) return -1;
+      if (dev_reserve(&s.d_tiles, &s.tiles_cap, 9 * k1_tiles)) return -1;
       uint32_t *tile_cnt = s.d_tiles, *tile_off = tile_cnt + k1_tiles, *tile_base = tile_off + k1_tiles;
       uint32_t *tile_real = tile_base + k1_tiles, *tile_rbase = tile_real + k1_tiles;
       uint32_t *tile_last = tile_rbase + k1_tiles, *tile_lbeg = tile_last + k1_tiles;
+      uint32_t *tile_alive = tile_lbeg + k1_tiles, *tile_abase = tile_alive + k1_tiles;
+      if (filter) {
+         if (dev_reserve(&s.d_act, &s.act_cap, s.line_cap, 64)) return -1;
+         if (dev_reserve(&s.d_lflags, &s.lflags_cap, s.line_cap, 64)) return -1;
+      }
       if (cut) {
          if (dev_reserve(&s.d_lid, &s.lid_cap, s.line_cap, 64)) return -1;
          if (dev_reserve(&s.d_lbeg, &s.lbeg_cap, s.line_cap, 64)) return -1;
@@ -416,26 +434,33 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
       }
       const uint32_t ntiles = (uint32_t)div_up(n, kK1Tile);
       K1Args k1{d_text, n, s.d_ls_raw, (uint32_t)s.line_cap, want_codes ? (uint2 *)s.d_codes : nullptr, ctr,
-                tile_cnt, tile_off, tile_real, tile_last, (options & SQB_FASTA) ? 1 : 0};
+                tile_cnt, tile_off, tile_real, tile_last, tile_alive,
+                (uint32_t)std::min(8, std::max(1, e->m - e->tau)), (options & SQB_FASTA) ? 1 : 0};
       ClassTable ct;
       build_class_table(options, &ct);
       static bool attr = false;
       if (!attr) {
-         CU(cudaFuncSetAttribute(k1_scan_classify<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
-         CU(cudaFuncSetAttribute(k1_scan_classify<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
-         CU(cudaFuncSetAttribute(k1_scan_classify<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
+         CU(cudaFuncSetAttribute(k1_scan_classify<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
+         CU(cudaFuncSetAttribute(k1_scan_classify<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
+         CU(cudaFuncSetAttribute(k1_scan_classify<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
+         CU(cudaFuncSetAttribute(k1_scan_classify<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
+         CU(cudaFuncSetAttribute(k1_scan_classify<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
          attr = true;
       }
       const int grid = (int)std::min<size_t>(div_up(n, kK1Tile), (size_t)e->sms * 3);
-      if (cut) k1_scan_classify<true, true><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
-      else if (want_codes) k1_scan_classify<true, false><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
-      else k1_scan_classify<false, false><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
+      if (cut && filter) k1_scan_classify<true, true, true><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
+      else if (cut) k1_scan_classify<true, true, false><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
+      else if (filter) k1_scan_classify<true, false, true><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
+      else if (want_codes) k1_scan_classify<true, false, false><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
+      else k1_scan_classify<false, false, false><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
       CU(cudaGetLastError());
       if (timing) CU(cudaEventRecord(s.ev[E_K1C_END], st));
-      K1ScanArgs ks{tile_cnt, tile_base, ntiles, ctr, cut ? tile_real : nullptr, tile_rbase, tile_last, tile_lbeg};
+      K1ScanArgs ks{tile_cnt, tile_base, ntiles, ctr, cut ? tile_real : nullptr, tile_rbase, tile_last, tile_lbeg,
+                    filter ? tile_alive : nullptr, tile_abase};
       k1_scan_tiles<<<1, 1024, 0, st>>>(ks);
       K1GatherArgs kg{s.d_ls_raw, s.d_ls, (uint32_t)s.line_cap, tile_cnt, tile_off, tile_base, ntiles, n, ctr,
-                      cut ? s.d_codes : nullptr, tile_rbase, tile_lbeg, s.d_lid, s.d_lbeg};
+                      cut ? s.d_codes : nullptr, tile_rbase, tile_lbeg, s.d_lid, s.d_lbeg,
+                      filter ? tile_abase : nullptr, s.d_act, s.d_lflags};
       k1_gather<<<(int)std::min<size_t>(div_up(ntiles, kWarps), (size_t)e->sms * 8), kThreads, 0, st>>>(kg);
       CU(cudaGetLastError());
       s.launches += 3;
@@ -460,6 +485,8 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
       // the bit-sliced kernel stores only the lines that match
       if (mode == M_FIRST || mode == M_BEST)
          CU(cudaMemsetAsync(s.d_res, 0xFF, std::min<size_t>(lines_cap, (size_t)n + 1) * sizeof(unsigned long long), st));
+      if (mode == M_ALL && filter)      // the lines the filter drops are never written
+         CU(cudaMemsetAsync(s.d_cnt, 0, std::min<size_t>(lines_cap, (size_t)n + 1) * sizeof(uint32_t), st));
       const size_t max_tiles = div_up(lines_cap, kBsTileLines) + 1;
       if (dev_reserve(&s.d_bstiles, &s.bstiles_cap, 2 * max_tiles)) return -1;
       const size_t want_cols = (size_t)((double)n * e->cols_per_byte) + 4096;
@@ -470,20 +497,21 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
       uint8_t *segstop = s.d_segflags;
       BsPrepArgs bp{s.d_ls, (uint32_t)lines_cap, n, ctr, tile_cols, tile_off, (uint32_t)max_tiles,
                     (unsigned long long)(s.planes_cap / 32), e->bs_gate, cut ? s.d_lid : nullptr, wup,
-                    (!cut && cuts_allowed(e, options, n)) ? 1 : 0};
+                    (!cut && cuts_allowed(e, options, n)) ? 1 : 0, filter ? s.d_act : nullptr};
       k15_tile_cols<<<(int)std::min<size_t>(div_up(max_tiles, kWarps), (size_t)e->sms * 8), kThreads, 0, st>>>(bp);
       k15_scan<<<1, 1024, 0, st>>>(bp);
       if (timing) CU(cudaEventRecord(s.ev[E_PACK_BEGIN], st));
       BsPackArgs pk{(const uint4 *)s.d_codes, (uint32_t)(div_up(n, kK1Tile) * (kK1Tile / 32)), s.d_ls,
                     (uint32_t)lines_cap, ctr, tile_cols, tile_off, s.d_planes, cut ? s.d_lid : nullptr, wup,
-                    gmask, gfollow};
+                    gmask, gfollow, filter ? s.d_act : nullptr};
       k15_pack<<<(int)std::max<size_t>(1, std::min<size_t>(div_up(div_up(max_lines, 64), kWarps), (size_t)e->sms * 16)),
                  kThreads, 0, st>>>(pk);
       CU(cudaGetLastError());
       if (timing) CU(cudaEventRecord(s.ev[E_PACK_END], st));
       s.launches += 3;
       K2BsArgs kb{s.d_planes, tile_cols, tile_off, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_ev, k2.ev_cap,
-                  (mode == M_COUNT || mode == M_COUNTALL) ? 1 : 0, cut ? gmask : nullptr, gfollow, segstop, wup};
+                  (mode == M_COUNT || mode == M_COUNTALL) ? 1 : 0, cut ? gmask : nullptr, gfollow, segstop, wup,
+                  filter ? s.d_act : nullptr};
       if (launch_bitslice(e, mode, options, max_lines, st, kb)) return -1;
       s.launches++;
    }
@@ -495,7 +523,8 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
    if (timing) CU(cudaEventRecord(s.ev[E_MATCH_END], st));
    if (cut) {
       // one result per line out of the results per segment
-      SegReduceArgs sr{s.d_lid, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_segflags, s.d_segflags + s.line_cap, mode};
+      SegReduceArgs sr{s.d_lid, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_segflags, s.d_segflags + s.line_cap, mode,
+                       filter ? s.d_lflags : nullptr};
       k_seg_reduce<<<(int)std::max<size_t>(1, std::min<size_t>(div_up(max_lines, kThreads), (size_t)e->sms * 8)),
                      kThreads, 0, st>>>(sr);
       CU(cudaGetLastError());
@@ -566,6 +595,11 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
       if (slot_issue(e, s, s.cur_text, s.cur_n, s.cur_options, s.cur_stream)) return -1;
    }
    s.busy = false;
+   if (s.cur_filter && e->filter == 1 && e->filter_state < 0 && s.h_ctr[C_NPSEUDO] > 0) {
+      // the probe: keep filtering if it drops a quarter of the lines or more
+      const double live = (double)s.h_ctr[C_NACTIVE] / (double)s.h_ctr[C_NPSEUDO];
+      e->filter_state = live <= 0.75 ? 1 : 0;
+   }
    if (stats) {
       memset(stats, 0, sizeof *stats);
       stats->nbytes = s.cur_n;
@@ -649,6 +683,7 @@ sqb_engine_t *sqbEngineNew(const unsigned char *keys, int m, int tau, int device
       if (!strcmp(mk, "bitslice")) { e->bs_gate = BsGate{1u, 1u << 30}; e->bs_min_bytes = 1; }
    }
    if (const char *c = getenv("SEEQ_B200_CUTS")) e->cuts = atoi(c);
+   if (const char *c = getenv("SEEQ_B200_FILTER")) e->filter = atoi(c);
    return e;
 }
 

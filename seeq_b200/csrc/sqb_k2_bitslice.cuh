@@ -54,7 +54,15 @@ struct BsPrepArgs {
    const uint32_t *lid;           // line of every ls entry (segment cuts), or nullptr
    uint32_t wup;                  // warm-up bytes in front of a continuation segment
    int cuts_possible;             // this scan could have cut its long lines but did not (see k15_scan)
+   const uint32_t *act;           // line filter: the entries of ls to look at (nullptr: all of them)
 };
+
+// the bit-sliced kernels number the lines they look at 0 .. nact-1 ("slots": tile =
+// slot / 1024, group = slot / 32); with the line filter slot q is entry act[q] of ls
+__device__ __forceinline__ uint32_t bs_nslots(const unsigned long long *ctr, const uint32_t *act, uint32_t max_lines)
+{
+   return (uint32_t)min(ctr[act ? C_NACTIVE : C_NPSEUDO], (unsigned long long)max_lines);
+}
 
 // With segment cuts an entry l of ls is a CONTINUATION if it belongs to the same
 // line as the entry before it, and is FOLLOWED if the next entry continues it.
@@ -83,7 +91,8 @@ __device__ __forceinline__ SegShape seg_shape(const uint32_t *ls, const uint32_t
 __global__ void __launch_bounds__(kThreads) k15_tile_cols(const BsPrepArgs a)
 {
    const int lane = threadIdx.x & 31;
-   const uint32_t nlines = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
+   const uint32_t nents = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
+   const uint32_t nlines = bs_nslots(a.ctr, a.act, a.max_lines);
    const uint32_t ntiles = (nlines + kBsTileLines - 1) / kBsTileLines;
    const uint32_t wid = (blockIdx.x * kThreads + threadIdx.x) >> 5, nw = (gridDim.x * kThreads) >> 5;
    const uint32_t *lid = a.ctr[C_NCUTS] != 0ull ? a.lid : nullptr;
@@ -92,11 +101,12 @@ __global__ void __launch_bounds__(kThreads) k15_tile_cols(const BsPrepArgs a)
       const uint32_t l0 = t * kBsTileLines;
 #pragma unroll 4
       for (int k = 0; k < 32; k++) {
-         const uint32_t l = l0 + (uint32_t)k * 32u + (uint32_t)lane;
-         if (l < nlines) {
+         const uint32_t q = l0 + (uint32_t)k * 32u + (uint32_t)lane;
+         if (q < nlines) {
+            const uint32_t l = a.act ? a.act[q] : q;
             uint32_t len = a.ls[l + 1] - a.ls[l];
             if (lid) {
-               const SegShape g = seg_shape(a.ls, lid, a.wup, l, nlines);
+               const SegShape g = seg_shape(a.ls, lid, a.wup, l, nents);
                len = g.follow ? g.limit : a.ls[l + 1] - g.begin;
             }
             mx = max(mx, len);
@@ -119,7 +129,7 @@ __global__ void __launch_bounds__(1024) k15_scan(const BsPrepArgs a)
    __shared__ unsigned long long s_carry;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const unsigned long long nl_dev = a.ctr[C_NPSEUDO];
-   const uint32_t nlines = (uint32_t)min(nl_dev, (unsigned long long)a.max_lines);
+   const uint32_t nlines = bs_nslots(a.ctr, a.act, a.max_lines);
    const uint32_t ntiles = (nlines + kBsTileLines - 1) / kBsTileLines;
    if (tid == 0) s_carry = 0;
    __syncthreads();
@@ -173,7 +183,8 @@ struct BsPackArgs {
    uint4 *planes;                 // [tile_off + column][32 groups] {p0, p1, p2, -}
    const uint32_t *lid;           // segment cuts (or nullptr)
    uint32_t wup;
-   uint32_t *gmask, *gfollow;     // out, per group of 32 entries: continuations / followed segments
+   uint32_t *gmask, *gfollow;     // out, per group of 32 slots: continuations / followed segments
+   const uint32_t *act;           // line filter (or nullptr)
 };
 
 // class nibbles at columns >= limit of a followed segment become NULL (7): the
@@ -244,7 +255,8 @@ __global__ void __launch_bounds__(kThreads) k15_pack(const BsPackArgs a)
 {
    if (a.ctr[C_BS_SELECTED] != 1ull) return;
    const int lane = threadIdx.x & 31;
-   const uint32_t nlines = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
+   const uint32_t nents = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
+   const uint32_t nlines = bs_nslots(a.ctr, a.act, a.max_lines);
    const uint32_t npairs = (nlines + 63u) / 64u;
    const uint32_t *lid = a.ctr[C_NCUTS] != 0ull ? a.lid : nullptr;
    uint32_t keep[5], rot[5];
@@ -266,8 +278,8 @@ __global__ void __launch_bounds__(kThreads) k15_pack(const BsPackArgs a)
       const uint32_t la = pair * 64u + (uint32_t)lane, lb = la + 32u;
       NibbleStream sa, sb;
       SegShape ga{0u, 0xffffffffu, false, false}, gb{0u, 0xffffffffu, false, false};
-      if (la < nlines) ga = seg_shape(a.ls, lid, a.wup, la, nlines);
-      if (lb < nlines) gb = seg_shape(a.ls, lid, a.wup, lb, nlines);
+      if (la < nlines) ga = seg_shape(a.ls, lid, a.wup, a.act ? a.act[la] : la, nents);
+      if (lb < nlines) gb = seg_shape(a.ls, lid, a.wup, a.act ? a.act[lb] : lb, nents);
       sa.open(a.codes, a.ncode16, ga.begin, la < nlines);
       sb.open(a.codes, a.ncode16, gb.begin, lb < nlines);
       if (lid) {
@@ -320,6 +332,7 @@ struct K2BsArgs {
    const uint32_t *gmask, *gfollow;  // segment cuts: per group, continuations / followed segments (or nullptr)
    uint8_t *segstop;              // out: followed segments that ran into a STOP (the rest of the line is dead)
    uint32_t wup;                  // a continuation reports the events that end after its warm-up
+   const uint32_t *act;           // line filter: slot -> entry of ls (nullptr: identity)
 };
 
 struct BsWarpSmem {
@@ -357,7 +370,7 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const int part = lane / NG, gl = lane % NG;
    Smem &sm = reinterpret_cast<Smem *>(dyn)[warp];
-   const uint32_t nlines = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
+   const uint32_t nlines = bs_nslots(a.ctr, a.act, a.max_lines);
    const uint32_t ntiles = (nlines + kBsTileLines - 1) / kBsTileLines;
    const uint32_t nitems = ntiles * (uint32_t)G;          // (tile, quarter) pairs
 
@@ -488,7 +501,8 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
                while (e) {
                   const int r = __ffs(e) - 1;
                   e &= e - 1;
-                  const uint32_t line = line0 + group * 32u + (uint32_t)r;
+                  const uint32_t slot = line0 + group * 32u + (uint32_t)r;
+                  const uint32_t line = a.act ? a.act[slot] : slot;
                   const uint32_t rank = static_cast<BsWarpSmemAll &>(sm).cnt[gl * 32 + r]++;
                   if (!a.count_only) {
                      if (idx < a.ev_cap) a.ev[idx] = Event{line, rank, c, bs_value<B>(streak, r)};
@@ -502,22 +516,24 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
             while (e) {
                const int r = __ffs(e) - 1;
                e &= e - 1;
-               const uint32_t line = line0 + group * 32u + (uint32_t)r;
-               a.res[line] = ((unsigned long long)bs_value<B>(streak, r) << 32) | c;
+               const uint32_t slot = line0 + group * 32u + (uint32_t)r;
+               a.res[a.act ? a.act[slot] : slot] = ((unsigned long long)bs_value<B>(streak, r) << 32) | c;
             }
          }
          }
       }
       my_matched += (uint32_t)__popc(st.hit);
       my_events += lane_events;
-      for (uint32_t ss = st.stopped & fmask; ss; ss &= ss - 1u)
-         a.segstop[line0 + group * 32u + (uint32_t)(__ffs(ss) - 1)] = 1;
+      for (uint32_t ss = st.stopped & fmask; ss; ss &= ss - 1u) {
+         const uint32_t slot = line0 + group * 32u + (uint32_t)(__ffs(ss) - 1);
+         a.segstop[a.act ? a.act[slot] : slot] = 1;
+      }
       if (MODE == BS_ALL && !a.count_only) {
          __syncwarp();
 #pragma unroll 4
          for (int i = 0; i < NG; i++) {
-            const uint32_t line = line0 + (q * (uint32_t)NG + (uint32_t)i) * 32u + (uint32_t)lane;
-            if (line < nlines) a.cnt[line] = static_cast<BsWarpSmemAll &>(sm).cnt[i * 32 + lane];
+            const uint32_t slot = line0 + (q * (uint32_t)NG + (uint32_t)i) * 32u + (uint32_t)lane;
+            if (slot < nlines) a.cnt[a.act ? a.act[slot] : slot] = static_cast<BsWarpSmemAll &>(sm).cnt[i * 32 + lane];
          }
          __syncwarp();
       }

@@ -53,6 +53,7 @@ enum Counter {
    C_NPSEUDO = 10,   // entries of ls: counted lines + segment cuts (== C_NLINES without cuts)
    C_NCUTS = 11,     // segment cuts made by K1
    C_NZ_CORR = 12,   // SQ_ALL with cuts: segments with events beyond the first of their line
+   C_NACTIVE = 13,   // line filter: entries of ls the matcher has to look at
    C_COUNT = 16
 };
 
@@ -123,8 +124,12 @@ struct K1Args {
    uint32_t *tile_off;            // out: where the tile's segment starts in ls_raw
    uint32_t *tile_real;           // out (CUT): counted lines starting in each tile
    uint32_t *tile_last;           // out (CUT): 1 + the last line start inside the tile (0: none)
+   uint32_t *tile_alive;          // out (FILTER): entries of the tile that are not dead on arrival
+   uint32_t filter_k;             // FILTER: a STOP among the first filter_k (<= 8) bytes of a line kills it
    int fasta;
 };
+
+constexpr uint32_t kDeadBit = 0x80000000u;     // FILTER: flag in ls_raw (text < 2 GiB)
 
 // shared -> global bulk (TMA) store of the calling thread's bulk group
 __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes)
@@ -142,7 +147,14 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // (mod 2048) are the first bytes of lanes 2 and 18 of every warp, and "the line
 // has been running for 256 bytes" = the two lanes in front hold no line start:
 // two shuffles of the warp scan decide it.
-template <bool CODES, bool CUT>
+//
+// FILTER: a line with a STOP byte among its first m - tau bytes (the '@', '+' and
+// quality lines of FASTQ with -x 0; lines shorter than that) can never match
+// (libseeq.c:267-270: the scan of a line ends at the first illegal byte).  K1
+// flags such lines dead on arrival -- their first 8 class nibbles are at hand in
+// shared memory when the line start is emitted -- and the matcher packs only the
+// others into its tiles, which is a 4x denser tile for FASTQ.
+template <bool CODES, bool CUT, bool FILTER>
 __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, const __grid_constant__ ClassTable ct)
 {
    extern __shared__ __align__(128) uint8_t dyn[];            // 2 x kK1Stage, then the class table
@@ -152,6 +164,7 @@ __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, 
    __shared__ uint32_t s_wcut[kWarps];
    __shared__ uint32_t s_base[2];
    __shared__ uint32_t s_last[2];
+   __shared__ uint32_t s_alive[2];
 
    static_assert(kCutWindow == 2 * kK1LaneBytes && kCutStride == 16 * kK1LaneBytes, "cut candidates = lanes 2 and 18");
    const uint32_t n = a.n;
@@ -180,6 +193,7 @@ __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, 
       s_tile[0] = t;
       if (t < ntiles) issue(0, t);
       s_last[0] = s_last[1] = 0u;
+      s_alive[0] = s_alive[1] = 0u;
    }
    __syncthreads();
 
@@ -303,9 +317,15 @@ __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, 
          if (CUT) {
             a.tile_real[tile] = tile_total - tile_cuts;
             if (tile_cuts) atomicAdd(&a.ctr[C_NCUTS], (unsigned long long)tile_cuts);
+         }
+         if (CUT || FILTER) {
             // every warp has passed A: the emit of the previous tile (other stage) is complete
-            if (prev_tile != 0xffffffffu) a.tile_last[prev_tile] = s_last[stage ^ 1];
+            if (prev_tile != 0xffffffffu) {
+               if (CUT) a.tile_last[prev_tile] = s_last[stage ^ 1];
+               if (FILTER) a.tile_alive[prev_tile] = s_alive[stage ^ 1];
+            }
             s_last[stage ^ 1] = 0u;
+            s_alive[stage ^ 1] = 0u;
             prev_tile = tile;
          }
       }
@@ -329,14 +349,35 @@ __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, 
 
       // ---- emit (ordered inside the tile) -------------------------------------
       uint32_t mylast = 0;                          // CUT: 1 + the last LINE start emitted by this lane
+      uint32_t myalive = 0;                         // FILTER: entries of this lane that are not dead on arrival
+      // FILTER: kDeadBit if the line that starts at text position s holds a STOP among its
+      // first filter_k bytes.  The nibbles of the whole tile are in shared memory by now
+      // (in place, warp by warp); a window that leaves the warp's 4 KiB is not looked at.
+      auto dead_flag = [&](uint32_t s) -> uint32_t {
+         if (!FILTER) return 0u;
+         const uint32_t o = s - tile * kK1Tile;                           // <= kK1Tile
+         const uint32_t i = o & (kK1WarpBytes - 1u);                      // nibble index inside its warp
+         if (o >= kK1Tile || i + 8u > kK1WarpBytes) { myalive++; return 0u; }
+         const uint8_t *wb = buf + (o & ~(kK1WarpBytes - 1u));
+         const uint32_t a0 = (i >> 1) & ~3u;
+         const uint32_t w0 = *reinterpret_cast<const uint32_t *>(wb + a0);
+         const uint32_t w1 = *reinterpret_cast<const uint32_t *>(wb + a0 + 4u);
+         uint32_t win = __funnelshift_r(w0, w1, (i & 7u) * 4u);           // 8 nibbles from the line start on
+         if (a.filter_k < 8u) win &= (1u << (4u * a.filter_k)) - 1u;      // nibble 0 = A: never a STOP
+         const uint32_t y = (win ^ 0x55555555u) & 0x77777777u;            // zero nibble <=> class 5 (STOP)
+         const bool dead = ((y - 0x11111111u) & ~y & 0x88888888u) != 0u;
+         myalive += dead ? 0u : 1u;
+         return dead ? kDeadBit : 0u;
+      };
       if (first) {
-         if (idx < a.ls_cap) a.ls_raw[idx] = 0;
+         if (idx < a.ls_cap) a.ls_raw[idx] = 0u | dead_flag(0u);
          idx++;
          mylast = 1u;
       }
       if (CUT && cut) {                             // the segment start comes before the line starts of the lane
          if (idx < a.ls_cap) a.ls_raw[idx] = pos0;
          idx++;
+         myalive++;
       }
 #pragma unroll
       for (int q = 0; q < 4; q++) {
@@ -346,7 +387,8 @@ __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, 
          if ((bits & (bits - 1)) == 0) {           // one line start in these 32 bytes (the usual case)
             const int b = __ffs(bits) - 1;
             const uint32_t s = p + 8u * (uint32_t)(b & 3) + (uint32_t)(b >> 2);
-            if (idx < a.ls_cap) a.ls_raw[idx] = s;
+            const uint32_t fl = dead_flag(s);
+            if (idx < a.ls_cap) a.ls_raw[idx] = s | fl;
             idx++;
             mylast = s + 1u;
          } else {                                  // several: walk them in text order
@@ -357,7 +399,8 @@ __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, 
                   const int b = __ffs(be) - 1;
                   be &= be - 1;
                   const uint32_t s = p + 8u * (uint32_t)e + (uint32_t)(b >> 2);
-                  if (idx < a.ls_cap) a.ls_raw[idx] = s;
+                  const uint32_t fl = dead_flag(s);
+                  if (idx < a.ls_cap) a.ls_raw[idx] = s | fl;
                   idx++;
                   mylast = s + 1u;
                }
@@ -368,11 +411,18 @@ __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, 
          const uint32_t wl = __reduce_max_sync(kFull, mylast);
          if (lane == 0 && wl) atomicMax(&s_last[stage], wl);
       }
+      if (FILTER) {
+         const uint32_t wa = __reduce_add_sync(kFull, myalive);
+         if (lane == 0 && wa) atomicAdd(&s_alive[stage], wa);
+      }
    }
    if (CODES && store_pending) bulk_wait_all();
-   if (CUT) {
+   if (CUT || FILTER) {
       __syncthreads();
-      if (tid == 0 && prev_tile != 0xffffffffu) a.tile_last[prev_tile] = s_last[0] | s_last[1];   // the other one is 0
+      if (tid == 0 && prev_tile != 0xffffffffu) {                 // the slot of the other stage is 0
+         if (CUT) a.tile_last[prev_tile] = s_last[0] | s_last[1];
+         if (FILTER) a.tile_alive[prev_tile] = s_alive[0] + s_alive[1];
+      }
    }
 }
 
@@ -390,11 +440,13 @@ struct K1ScanArgs {
    uint32_t *tile_rbase;
    const uint32_t *tile_last;
    uint32_t *tile_lbeg;
+   const uint32_t *tile_alive;    // nullptr: no line filter
+   uint32_t *tile_abase;          // index in act[] of the first live entry of tile t; total -> ctr[C_NACTIVE]
 };
 
 __global__ void __launch_bounds__(1024) k1_scan_tiles(const K1ScanArgs a)
 {
-   __shared__ unsigned long long s_warp[32], s_real[32];
+   __shared__ unsigned long long s_warp[32], s_real[32], s_act[32];
    __shared__ uint32_t s_max[32];
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const bool cut = a.tile_real != nullptr && a.ctr[C_NCUTS] != 0ull;     // K1 is complete: the count is final
@@ -403,7 +455,8 @@ __global__ void __launch_bounds__(1024) k1_scan_tiles(const K1ScanArgs a)
    // the exclusive prefix of every tile
    const uint32_t per = ((a.ntiles + 1023u) / 1024u) * 32u;
    const uint32_t t0 = min((uint32_t)warp * per, a.ntiles), t1 = min(t0 + per, a.ntiles);
-   unsigned long long sum = 0, rsum = 0;
+   const bool filt = a.tile_alive != nullptr;
+   unsigned long long sum = 0, rsum = 0, asum = 0;
    uint32_t mx = 0;
 #pragma unroll 4
    for (uint32_t t = t0 + (uint32_t)lane; t < t1; t += 32) {
@@ -412,30 +465,35 @@ __global__ void __launch_bounds__(1024) k1_scan_tiles(const K1ScanArgs a)
          rsum += a.tile_real[t];
          mx = max(mx, a.tile_last[t]);
       }
+      if (filt) asum += a.tile_alive[t];
    }
 #pragma unroll
    for (int d = 16; d > 0; d >>= 1) {
       sum += __shfl_xor_sync(kFull, sum, d);
       rsum += __shfl_xor_sync(kFull, rsum, d);
+      asum += __shfl_xor_sync(kFull, asum, d);
    }
    mx = __reduce_max_sync(kFull, mx);
    if (lane == 0) {
       s_warp[warp] = sum;
       s_real[warp] = rsum;
+      s_act[warp] = asum;
       s_max[warp] = mx;
    }
    __syncthreads();
-   unsigned long long run = 0, tot = 0, rrun = 0, rtot = 0;
+   unsigned long long run = 0, tot = 0, rrun = 0, rtot = 0, arun = 0, atot = 0;
    uint32_t mrun = 0;
    for (int w = 0; w < 32; w++) {
-      const unsigned long long y = s_warp[w], z = s_real[w];
+      const unsigned long long y = s_warp[w], z = s_real[w], u = s_act[w];
       if (w < warp) {
          run += y;
          rrun += z;
+         arun += u;
          mrun = max(mrun, s_max[w]);
       }
       tot += y;
       rtot += z;
+      atot += u;
    }
    // line numbers are u32 (a batch is < 4 GiB of text)
 #pragma unroll 2
@@ -444,16 +502,19 @@ __global__ void __launch_bounds__(1024) k1_scan_tiles(const K1ScanArgs a)
       const uint32_t v = t < t1 ? a.tile_cnt[t] : 0u;
       const uint32_t rv = (cut && t < t1) ? a.tile_real[t] : 0u;
       const uint32_t lv = (cut && t < t1) ? a.tile_last[t] : 0u;
-      uint32_t x = v, rx = rv, lx = lv;
+      const uint32_t av = (filt && t < t1) ? a.tile_alive[t] : 0u;
+      uint32_t x = v, rx = rv, lx = lv, ax = av;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
          const uint32_t y = __shfl_up_sync(kFull, x, d);
          const uint32_t ry = __shfl_up_sync(kFull, rx, d);
          const uint32_t ly = __shfl_up_sync(kFull, lx, d);
+         const uint32_t ay = __shfl_up_sync(kFull, ax, d);
          if (lane >= d) {
             x += y;
             rx += ry;
             lx = max(lx, ly);
+            ax += ay;
          }
       }
       // exclusive running maximum: the inclusive one of the lane in front
@@ -465,14 +526,17 @@ __global__ void __launch_bounds__(1024) k1_scan_tiles(const K1ScanArgs a)
             a.tile_rbase[t] = (uint32_t)rrun + rx - rv;
             a.tile_lbeg[t] = max(mrun, lprev);
          }
+         if (filt) a.tile_abase[t] = (uint32_t)arun + ax - av;
       }
       run += __shfl_sync(kFull, x, 31);
       rrun += __shfl_sync(kFull, rx, 31);
+      arun += __shfl_sync(kFull, ax, 31);
       mrun = max(mrun, __shfl_sync(kFull, lx, 31));
    }
    if (tid == 0) {
       a.ctr[C_NPSEUDO] = tot;
       a.ctr[C_NLINES] = cut ? rtot : tot;
+      a.ctr[C_NACTIVE] = filt ? atot : tot;
    }
 }
 
@@ -494,6 +558,9 @@ struct K1GatherArgs {
    const uint8_t *codes;          // nullptr: no cuts
    const uint32_t *tile_rbase, *tile_lbeg;
    uint32_t *lid, *lbeg;
+   const uint32_t *tile_abase;    // nullptr: no line filter
+   uint32_t *act;                 // out (filter): the entries of ls the matcher looks at, in order
+   uint8_t *lflags;               // out (filter): 1 = dead on arrival
 };
 
 __global__ void __launch_bounds__(kThreads) k1_gather(const K1GatherArgs a)
@@ -502,11 +569,29 @@ __global__ void __launch_bounds__(kThreads) k1_gather(const K1GatherArgs a)
    const uint32_t wid = (blockIdx.x * kThreads + threadIdx.x) >> 5;
    const uint32_t nwarps = (gridDim.x * kThreads) >> 5;
    const bool cut = a.codes != nullptr && a.ctr[C_NCUTS] != 0ull;
+   const bool filt = a.tile_abase != nullptr;
    for (uint32_t t = wid; t < a.ntiles; t += nwarps) {
       const uint32_t cnt = a.tile_cnt[t], src = a.tile_off[t], dst = a.tile_base[t];
-      if (!cut) {
+      if (!cut && !filt) {
          for (uint32_t j = lane; j < cnt; j += 32)
             if (dst + j < a.ls_cap && src + j < a.ls_cap) a.ls[dst + j] = a.ls_raw[src + j];
+         continue;
+      }
+      uint32_t nact = filt ? a.tile_abase[t] : 0u;      // live entries before the current 32
+      if (!cut) {                                        // line filter only
+         for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+            const uint32_t j = j0 + (uint32_t)lane;
+            const bool ok = j < cnt && dst + j < a.ls_cap && src + j < a.ls_cap;
+            const uint32_t raw = ok ? a.ls_raw[src + j] : kDeadBit;
+            const bool live = !(raw & kDeadBit);
+            const uint32_t bal = __ballot_sync(kFull, live);
+            if (ok) {
+               a.ls[dst + j] = raw & ~kDeadBit;
+               a.lflags[dst + j] = live ? 0 : 1;
+               if (live) a.act[nact + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = dst + j;
+            }
+            nact += (uint32_t)__popc(bal);
+         }
          continue;
       }
       uint32_t nreal = a.tile_rbase[t];                 // line starts before the current 32 entries
@@ -514,7 +599,10 @@ __global__ void __launch_bounds__(kThreads) k1_gather(const K1GatherArgs a)
       for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
          const uint32_t j = j0 + (uint32_t)lane;
          const bool ok = j < cnt && dst + j < a.ls_cap && src + j < a.ls_cap;
-         const uint32_t pos = ok ? a.ls_raw[src + j] : 0u;
+         const uint32_t raw = ok ? a.ls_raw[src + j] : 0u;
+         const uint32_t pos = filt ? (raw & ~kDeadBit) : raw;
+         const bool live = ok && !(filt && (raw & kDeadBit));
+         const uint32_t lbal = __ballot_sync(kFull, live);
          bool real = false;
          if (ok) real = pos == 0u || ((a.codes[(pos - 1u) >> 1] >> ((((pos - 1u) & 1u) << 2) + 3u)) & 1u);
          const uint32_t bal = __ballot_sync(kFull, real);
@@ -530,7 +618,12 @@ __global__ void __launch_bounds__(kThreads) k1_gather(const K1GatherArgs a)
             a.ls[dst + j] = pos;
             a.lid[dst + j] = real ? rb : rb - 1u;
             a.lbeg[dst + j] = x - 1u;
+            if (filt) {
+               a.lflags[dst + j] = live ? 0 : 1;
+               if (live) a.act[nact + (uint32_t)__popc(lbal & ((1u << lane) - 1u))] = dst + j;
+            }
          }
+         nact += (uint32_t)__popc(lbal);
          nreal += (uint32_t)__popc(bal);
          lastp1 = __shfl_sync(kFull, x, 31);
       }
@@ -1061,6 +1154,7 @@ struct SegReduceArgs {
    const uint8_t *segstop;
    uint8_t *deadseg;              // out (SQ_ALL): segments whose events are to be dropped
    int mode;
+   const uint8_t *lflags;         // line filter: 1 = the line was dead on arrival and never scanned (or nullptr)
 };
 
 __global__ void __launch_bounds__(kThreads) k_seg_reduce(const SegReduceArgs a)
@@ -1071,7 +1165,8 @@ __global__ void __launch_bounds__(kThreads) k_seg_reduce(const SegReduceArgs a)
    for (uint32_t p = blockIdx.x * kThreads + threadIdx.x; p < np; p += gridDim.x * kThreads) {
       const uint32_t me = a.lid[p];
       if ((p > 0u && a.lid[p - 1u] == me) || p + 1u >= np || a.lid[p + 1u] != me) continue;   // heads of cut lines only
-      bool dead = false, have = false;
+      // a head segment the line filter dropped holds a STOP in its first bytes
+      bool dead = a.lflags != nullptr && a.lflags[p] != 0, have = false;
       uint32_t best_q = 0, best_d = 0, with_events = 0;
       for (uint32_t q = p; q < np && a.lid[q] == me; q++) {
          if (a.mode == M_ALL) {

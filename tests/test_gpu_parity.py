@@ -178,6 +178,49 @@ def test_long_lines_large(B, oracle):
     sq.close()
 
 
+def fastq_like(rng, keys, tau, nreads, maxlen):
+    """4-line records (@id, sequence, +, quality); some reads empty, some shorter than the
+    pattern, a few long ones; the quality alphabet '#'..'I' contains A, C and G."""
+    out = []
+    for r in range(nreads):
+        n = rng.choice([0, rng.randint(1, 12), rng.randint(30, maxlen), rng.randint(30, maxlen)])
+        seq = [rng.choice("ACGT") for _ in range(n)]
+        if n > 20 and rng.random() < 0.5:
+            at = rng.randrange(n)
+            seq[at:at] = list(plant(rng, keys, tau))
+        if rng.random() < 0.05 and seq:
+            seq[rng.randrange(len(seq))] = rng.choice("NX")
+        qual = "".join(chr(rng.randint(ord("#"), ord("I"))) for _ in range(len(seq)))
+        out += ["@r%d" % r, "".join(seq), "+", qual]
+    return ("\n".join(out) + "\n").encode()
+
+
+@pytest.mark.parametrize("filt", ["0", "1", "2"])
+@pytest.mark.parametrize("mrange", [(3, 9), (10, 30), (40, 60)])
+def test_fastq_like_line_filter(B, oracle, mrange, filt, monkeypatch):
+    """The line filter (lines with a STOP among their first m - tau bytes are not packed
+    into the matcher's tiles): never / decided by the first scan / always."""
+    monkeypatch.setenv("SEEQ_B200_MATCHER", "bitslice")
+    monkeypatch.setenv("SEEQ_B200_FILTER", filt)
+    rng = random.Random(mrange[1] * 17 + int(filt))
+    for it in range(4):
+        pattern = rand_pattern(rng, *mrange)
+        keys, _ = oracle.parse(pattern)
+        tau = rng.randint(0, min(len(keys) - 1, 3))
+        if it == 3:
+            monkeypatch.setenv("SEEQ_B200_CUTS", "2")          # long reads cut into segments, too
+        buf = fastq_like(rng, keys, tau, rng.randint(5, 900), 300 if it < 3 else 5000)
+        for mo in MATCH:
+            for nd in NONDNA:
+                check_buffer(B, oracle, pattern, tau, buf, mo | nd)
+        sq = B.Seeq(pattern, tau)
+        r_all, _, _ = oracle.buffer_scan(buf, keys, tau, SQ_ALL)
+        _, _, nm = oracle.buffer_scan(buf, keys, tau, SQ_FIRST)
+        assert sq.batch(buf, 0, SQ_COUNTMATCH) == len(r_all)
+        assert sq.batch(buf, 0, SQ_COUNTLINES) == nm
+        sq.close()
+
+
 def test_counts(B, oracle, matcher):
     rng = random.Random(4)
     for it in range(10):
