@@ -28,7 +28,7 @@ REFERENCE_DIR = os.environ.get("SEEQ_REFERENCE_DIR", "/root/reference")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
-CU_SOURCES = ["sqb_engine.cu"]
+CU_SOURCES = ["sqb_engine.cu", "sqb_engine_wm.cu"]
 C_SOURCES = ["seeq_api.c", "seeq_file.c"]
 HEADERS = sorted(os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".h", ".cuh"))) + \
           [os.path.join(INC, h) for h in ("libseeq.h", "seeq.h", "seeq_b200.h")]
@@ -52,13 +52,18 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     objs = []
+    jobs = []
     for src in CU_SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(objdir, src + ".o")
         if force or _newer(o, [s] + HEADERS):
-            _run([NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp",
-                  "-I" + INC, "-I" + CSRC, "-c", s, "-o", o] + (["-Xptxas", "-v"] if verbose else []))
+            jobs.append([NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp",
+                         "-I" + INC, "-I" + CSRC, "-c", s, "-o", o] + (["-Xptxas", "-v"] if verbose else []))
         objs.append(o)
+    if jobs:                                  # the translation units compile side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=len(jobs)) as pool:
+            list(pool.map(_run, jobs))
     for src in C_SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(objdir, src + ".o")

@@ -239,6 +239,112 @@ SQB_BS_HD uint32_t bs_step(BsState<R, 1> &st, const BsPattern &p, const EqOf &eq
    return bs_report<R, 1, MODE>(st, p, ph, mh, anybase, stopc, streak, quiet);
 }
 
+// ---------------------------------------------------------------------------
+// tau <= 2: the same automaton as bit-sliced NFA levels (Wu-Manber 1992) instead
+// of Myers' delta encoding.  r[d][j] = "a suffix of the text read so far matches
+// the first j+1 rows with at most d errors" (d = 0 .. tau), one bit per line:
+//
+//    r0[j]' = r0[j-1] & Eq[j]
+//    rd[j]' = (rd[j-1] & Eq[j]) | r(d-1)[j-1] | r(d-1)[j] | r(d-1)[j-1]'
+//              match              substitution   insertion    deletion
+//
+// with row -1 all ones (free start).  That is 2 tau + 1 LOP3 per row instead of
+// 6, and the capped distance of the last row comes for free in unary: "D <= d" is
+// r[d][R-1], so the ripple counter and the comparisons of the Myers version
+// disappear as well (cfg2, tau = 1: 59 instead of 115 logic ops per column).
+// D(i) = min{d : r[d][last]} or tau + 1 is exactly the capped NW value of the
+// reference (libseeq.c:779-786); the report state machine is the one of
+// bs_report, written for unary distances.
+// ---------------------------------------------------------------------------
+template <int R, int T> struct BsWmState {     // T = tau + 1 levels (2 or 3)
+   uint32_t r[T][R];
+   uint32_t lp[T];                             // streak: distance before this column <= d
+   uint32_t bd[T];                             // best distance so far <= d (BS_BEST)
+   uint32_t alive, flag, hit, stopped;
+};
+
+template <int R, int T> SQB_BS_HD void bs_wm_reset(BsWmState<R, T> &st, const BsPattern &p, uint32_t valid)
+{
+   const int pad = R - p.m;                     // wildcard rows at the bottom: always reachable
+#pragma unroll
+   for (int d = 0; d < T; d++) {
+#pragma unroll
+      for (int j = 0; j < R; j++) st.r[d][j] = (j < pad || j - pad + 1 <= d) ? ~0u : 0u;    // j+1-pad deletions
+      st.lp[d] = 0u;                            // the distance starts at tau + 1 (libseeq.c:240-244)
+      st.bd[d] = 0u;
+   }
+   st.alive = valid;
+   st.flag = 0u;
+   st.hit = 0u;
+   st.stopped = 0u;
+}
+
+// One text column.  Returns the event mask; streak[d] = "distance before this column
+// <= d" (unary: the distance of line r is the number of d with bit r of streak[d] clear).
+template <int R, int T, int MODE, bool SKIP, class EqOf>
+SQB_BS_HD uint32_t bs_wm_step(BsWmState<R, T> &st, const EqOf &eq, uint32_t anybase, uint32_t stopc, uint32_t skipc,
+                              uint32_t *streak, uint32_t quiet = 0u)
+{
+   (void)skipc;
+   uint32_t oldp[T], newp[T];                   // row j-1 before / after this column
+#pragma unroll
+   for (int d = 0; d < T; d++) oldp[d] = newp[d] = ~0u;
+#pragma unroll
+   for (int j = 0; j < R; j++) {
+      const uint32_t e = eq(j);
+      uint32_t old[T], nw[T];
+#pragma unroll
+      for (int d = 0; d < T; d++) old[d] = st.r[d][j];
+      nw[0] = oldp[0] & e;
+#pragma unroll
+      for (int d = 1; d < T; d++) nw[d] = (oldp[d] & e) | oldp[d - 1] | old[d - 1] | newp[d - 1];
+#pragma unroll
+      for (int d = 0; d < T; d++) {
+         if (SKIP) nw[d] = (old[d] & skipc) | (nw[d] & ~skipc);      // an ignored byte leaves the automaton untouched
+         st.r[d][j] = nw[d];
+         oldp[d] = old[d];
+         newp[d] = nw[d];
+      }
+   }
+   const uint32_t base = anybase & st.alive;    // lines that feed a base to the automaton
+   const uint32_t stop = stopc & st.alive;      // lines that end here (their distance becomes tau + 1)
+   const uint32_t active = base | stop;
+   uint32_t rise = 0u;                          // streak < new distance
+#pragma unroll
+   for (int d = 0; d < T; d++) {
+      streak[d] = st.lp[d];
+      rise |= st.lp[d] & ~(newp[d] & base);
+   }
+   st.flag &= rise | ~active;                   // libseeq.c:278  any non-rise clears the flag
+   uint32_t evt = active & st.lp[T - 1] & (st.lp[0] | rise) & ~st.flag;     // :286-288
+   st.flag |= evt;                              // also during a warm-up
+   evt &= ~quiet;
+   if (MODE == BS_BEST) {
+      uint32_t lt = 0u;                         // streak < best distance
+#pragma unroll
+      for (int d = 0; d < T; d++) lt |= st.lp[d] & ~st.bd[d];
+      evt &= lt;
+#pragma unroll
+      for (int d = 0; d < T; d++) st.bd[d] |= evt & st.lp[d];
+   }
+   st.hit |= evt;
+   st.stopped |= stop;
+   st.alive &= ~stop;
+   if (MODE == BS_FIRST) st.alive &= ~evt;      // :330
+#pragma unroll
+   for (int d = 0; d < T; d++) st.lp[d] = (base & newp[d]) | (~base & st.lp[d]);    // ignored bytes keep the streak
+   return evt;
+}
+
+// distance of line r from unary planes
+template <int T> SQB_BS_HD uint32_t bs_value_unary(const uint32_t *planes, int r)
+{
+   uint32_t v = 0;
+#pragma unroll
+   for (int d = 0; d < T; d++) v += ((planes[d] >> r) & 1u) ^ 1u;
+   return v;
+}
+
 // distance of line r from bit-planes
 template <int B> SQB_BS_HD uint32_t bs_value(const uint32_t *planes, int r)
 {

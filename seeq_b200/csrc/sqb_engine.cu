@@ -101,6 +101,7 @@ struct sqb_engine {
    bool cuts_wanted = false;      // a scan met long lines
    int filter = 1;                // line filter (lines with a STOP in their first m - tau bytes are not packed):
                                   // 0 never, 1 if the first filtered scan drops >= 25 % of the lines, 2 always
+   bool nfa_levels = true;        // tau <= 2: NFA-level automaton instead of Myers' (SEEQ_B200_NFA=0 disables)
    int filter_state = -1;         // filter == 1: -1 undecided (probe with the next scan), 0 off, 1 on
    BsGate bs_gate{65536u, 4096u};
    uint32_t bs_min_bytes = 1u << 20;
@@ -340,6 +341,10 @@ template <int R, int G> static int launch_bs1(int bsmode, bool skip, int grid, c
    }
 }
 
+// sqb_engine_wm.cu
+cudaError_t sqb_launch_bitslice_wm(int rows, int levels, int bsmode, bool skip, int grid, cudaStream_t st,
+                                   const K2BsArgs &a, const BsPattern &p);
+
 static int launch_bitslice(const sqb_engine *e, int mode, int options, size_t max_lines, cudaStream_t st, const K2BsArgs &a)
 {
    const int bsmode = (mode == M_ALL || mode == M_COUNTALL) ? BS_ALL : (mode == M_BEST ? BS_BEST : BS_FIRST);
@@ -350,6 +355,10 @@ static int launch_bitslice(const sqb_engine *e, int mode, int options, size_t ma
    // work items = (tile, 1/G of its groups), one warp each
    const int grid = (int)std::max<size_t>(1, std::min<size_t>(div_up(div_up(max_lines, kBsTileLines) * G, kBsWarps),
                                                                (size_t)e->sms * per_sm * 2));
+   if (G == 1 && e->tau <= 2 && e->nfa_levels) {          // small tau: the NFA-level automaton is cheaper
+      CU(sqb_launch_bitslice_wm(R, e->tau + 1, bsmode, skip, grid, st, a, e->bs_pat));
+      return 0;
+   }
 #define SQB_SHAPE(RR, GG) if (R == RR && G == GG) return launch_bs1<RR, GG>(bsmode, skip, grid, st, a, e->bs_pat);
    SQB_SHAPE(8, 1) SQB_SHAPE(12, 1) SQB_SHAPE(16, 1) SQB_SHAPE(24, 1) SQB_SHAPE(32, 1)
    SQB_SHAPE(20, 2) SQB_SHAPE(24, 2) SQB_SHAPE(32, 2)
@@ -684,6 +693,7 @@ sqb_engine_t *sqbEngineNew(const unsigned char *keys, int m, int tau, int device
    }
    if (const char *c = getenv("SEEQ_B200_CUTS")) e->cuts = atoi(c);
    if (const char *c = getenv("SEEQ_B200_FILTER")) e->filter = atoi(c);
+   if (const char *c = getenv("SEEQ_B200_NFA")) e->nfa_levels = atoi(c) != 0;
    return e;
 }
 

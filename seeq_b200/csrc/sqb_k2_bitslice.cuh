@@ -88,7 +88,7 @@ __device__ __forceinline__ SegShape seg_shape(const uint32_t *ls, const uint32_t
 }
 
 // columns of every tile = longest line (with its terminator) + 1; one warp per tile
-__global__ void __launch_bounds__(kThreads) k15_tile_cols(const BsPrepArgs a)
+static __global__ void __launch_bounds__(kThreads) k15_tile_cols(const BsPrepArgs a)
 {
    const int lane = threadIdx.x & 31;
    const uint32_t nents = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kThreads) k15_tile_cols(const BsPrepArgs a)
 // (the host repeats the scan with the exact size, ctr[C_BS_COLS]), 3 = there are
 // long lines and the scan did not cut them: the host repeats it with segment
 // cuts (and keeps cutting from then on); no matcher runs
-__global__ void __launch_bounds__(1024) k15_scan(const BsPrepArgs a)
+static __global__ void __launch_bounds__(1024) k15_scan(const BsPrepArgs a)
 {
    __shared__ unsigned long long s_warp[32];
    __shared__ uint32_t s_max[32];
@@ -251,7 +251,7 @@ struct NibbleStream {
    }
 };
 
-__global__ void __launch_bounds__(kThreads) k15_pack(const BsPackArgs a)
+static __global__ void __launch_bounds__(kThreads) k15_pack(const BsPackArgs a)
 {
    if (a.ctr[C_BS_SELECTED] != 1ull) return;
    const int lane = threadIdx.x & 31;
@@ -354,19 +354,27 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 // of one part read neighbouring uint4 of one plane column.  Part p runs p
 // columns behind part 0 and receives the horizontal delta of the part below
 // with one pair of shuffles per column; only the last part reports.
-template <int R, int G, int MODE, bool SKIP>
+//
+// WM > 0 selects the NFA-level automaton (bs_wm_step, tau = WM - 1 <= 2, G == 1)
+// instead of Myers' delta encoding: fewer logic ops per column for small tau.
+template <int R, int G, int MODE, bool SKIP, int WM = 0>
 __global__ void __launch_bounds__(kBsThreads, G > 1 ? (R <= 24 ? 3 : 2) : (R <= 16 ? 4 : 3))
 k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
 {
+   static_assert(WM == 0 || G == 1, "the NFA-level automaton is single-part");
    using Smem = typename std::conditional<MODE == BS_ALL, BsWarpSmemAll, BsWarpSmem>::type;
-   using State = BsState<R, G>;
+   using State = typename std::conditional<WM != 0, BsWmState<R, (WM ? WM : 1)>, BsState<R, G>>::type;
    extern __shared__ __align__(128) uint8_t dyn[];
    __shared__ uint32_t s_red[2][kBsWarps];
    __shared__ uint32_t s_off[G > 1 ? R * G : 1];
 
    if (a.ctr[C_BS_SELECTED] != 1ull) return;              // the word-parallel kernel takes this scan
    constexpr int NG = 32 / G;                             // groups per warp
-   constexpr int B = State::B;
+   constexpr int B = WM ? WM : BsState<R, G>::B;          // planes of the distance handed out with an event
+   auto value_of = [](const uint32_t *planes, int r) -> uint32_t {
+      if constexpr (WM != 0) return bs_value_unary<(WM ? WM : 1)>(planes, r);
+      else return bs_value<BsState<R, G>::B>(planes, r);
+   };
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const int part = lane / NG, gl = lane % NG;
    Smem &sm = reinterpret_cast<Smem *>(dyn)[warp];
@@ -399,12 +407,24 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
       const uint32_t left = nlines - line0;                              // > 0
       const uint32_t mine = left > group * 32u ? min(left - group * 32u, 32u) : 0u;
       State st;
-      bs_reset(st, pat, mine == 32u ? ~0u : ((1u << mine) - 1u), part);
+      if constexpr (WM != 0) bs_wm_reset(st, pat, mine == 32u ? ~0u : ((1u << mine) - 1u));
+      else bs_reset(st, pat, mine == 32u ? ~0u : ((1u << mine) - 1u), part);
       if (MODE == BS_ALL) {
 #pragma unroll
          for (int i = 0; i < 32; i++) static_cast<BsWarpSmemAll &>(sm).cnt[i * 32 + lane] = 0u;
       }
       uint32_t lane_events = 0;
+      // slot -> entry of ls.  With the line filter the 32 slots of a lane usually map to
+      // consecutive entries when the filter drops nothing around them: one look-up per
+      // tile then serves every event of the lane
+      const uint32_t slot0 = line0 + group * 32u;
+      uint32_t ent0 = slot0;
+      bool consecutive = true;
+      if (a.act && mine > 0u) {
+         ent0 = a.act[slot0];
+         consecutive = a.act[slot0 + mine - 1u] - ent0 == mine - 1u;
+      }
+      auto entry_of = [&](uint32_t r) -> uint32_t { return consecutive ? ent0 + r : a.act[slot0 + r]; };
       uint32_t qmask = 0u, fmask = 0u;
       if (has_cuts) {
          qmask = a.gmask[tile * 32u + group];
@@ -474,11 +494,16 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
             if (G > 1) return lds_u32(raddr[G > 1 ? j : 0]);
             return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(slot_base) + pat.slot_off[j]);
          };
-         bs_rows<R, G, SKIP>(st, eq, skip, ph, mh);
-         ph_prev = ph;
-         mh_prev = mh;
          uint32_t streak[B];
-         const uint32_t evt = bs_report<R, G, MODE>(st, pat, ph, mh, anybase, stop, streak, c <= a.wup ? qmask : 0u);
+         uint32_t evt;
+         if constexpr (WM != 0) {
+            evt = bs_wm_step<R, (WM ? WM : 1), MODE, SKIP>(st, eq, anybase, stop, skip, streak, c <= a.wup ? qmask : 0u);
+         } else {
+            bs_rows<R, G, SKIP>(st, eq, skip, ph, mh);
+            ph_prev = ph;
+            mh_prev = mh;
+            evt = bs_report<R, G, MODE>(st, pat, ph, mh, anybase, stop, streak, c <= a.wup ? qmask : 0u);
+         }
 
          // ---- events leave the bit-sliced world here (rare) ---------------------
          if (MODE == BS_ALL) {
@@ -501,11 +526,10 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
                while (e) {
                   const int r = __ffs(e) - 1;
                   e &= e - 1;
-                  const uint32_t slot = line0 + group * 32u + (uint32_t)r;
-                  const uint32_t line = a.act ? a.act[slot] : slot;
+                  const uint32_t line = entry_of((uint32_t)r);
                   const uint32_t rank = static_cast<BsWarpSmemAll &>(sm).cnt[gl * 32 + r]++;
                   if (!a.count_only) {
-                     if (idx < a.ev_cap) a.ev[idx] = Event{line, rank, c, bs_value<B>(streak, r)};
+                     if (idx < a.ev_cap) a.ev[idx] = Event{line, rank, c, value_of(streak, r)};
                      idx++;
                   }
                }
@@ -516,18 +540,14 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
             while (e) {
                const int r = __ffs(e) - 1;
                e &= e - 1;
-               const uint32_t slot = line0 + group * 32u + (uint32_t)r;
-               a.res[a.act ? a.act[slot] : slot] = ((unsigned long long)bs_value<B>(streak, r) << 32) | c;
+               a.res[entry_of((uint32_t)r)] = ((unsigned long long)value_of(streak, r) << 32) | c;
             }
          }
          }
       }
       my_matched += (uint32_t)__popc(st.hit);
       my_events += lane_events;
-      for (uint32_t ss = st.stopped & fmask; ss; ss &= ss - 1u) {
-         const uint32_t slot = line0 + group * 32u + (uint32_t)(__ffs(ss) - 1);
-         a.segstop[a.act ? a.act[slot] : slot] = 1;
-      }
+      for (uint32_t ss = st.stopped & fmask; ss; ss &= ss - 1u) a.segstop[entry_of((uint32_t)(__ffs(ss) - 1))] = 1;
       if (MODE == BS_ALL && !a.count_only) {
          __syncwarp();
 #pragma unroll 4

@@ -444,7 +444,7 @@ struct K1ScanArgs {
    uint32_t *tile_abase;          // index in act[] of the first live entry of tile t; total -> ctr[C_NACTIVE]
 };
 
-__global__ void __launch_bounds__(1024) k1_scan_tiles(const K1ScanArgs a)
+static __global__ void __launch_bounds__(1024) k1_scan_tiles(const K1ScanArgs a)
 {
    __shared__ unsigned long long s_warp[32], s_real[32], s_act[32];
    __shared__ uint32_t s_max[32];
@@ -563,7 +563,7 @@ struct K1GatherArgs {
    uint8_t *lflags;               // out (filter): 1 = dead on arrival
 };
 
-__global__ void __launch_bounds__(kThreads) k1_gather(const K1GatherArgs a)
+static __global__ void __launch_bounds__(kThreads) k1_gather(const K1GatherArgs a)
 {
    const int lane = threadIdx.x & 31;
    const uint32_t wid = (blockIdx.x * kThreads + threadIdx.x) >> 5;
@@ -1065,7 +1065,7 @@ struct TileSumArgs {
    uint32_t *tile_base;               // out of k_tile_scan
 };
 
-__global__ void __launch_bounds__(kThreads) k_tile_sums(const TileSumArgs a)
+static __global__ void __launch_bounds__(kThreads) k_tile_sums(const TileSumArgs a)
 {
    const int lane = threadIdx.x & 31;
    const uint32_t nlines = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
@@ -1091,7 +1091,7 @@ __global__ void __launch_bounds__(kThreads) k_tile_sums(const TileSumArgs a)
    }
 }
 
-__global__ void __launch_bounds__(1024) k_tile_scan(const TileSumArgs a)
+static __global__ void __launch_bounds__(1024) k_tile_scan(const TileSumArgs a)
 {
    __shared__ unsigned long long s_warp[32], s_nz[32];
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1157,7 +1157,7 @@ struct SegReduceArgs {
    const uint8_t *lflags;         // line filter: 1 = the line was dead on arrival and never scanned (or nullptr)
 };
 
-__global__ void __launch_bounds__(kThreads) k_seg_reduce(const SegReduceArgs a)
+static __global__ void __launch_bounds__(kThreads) k_seg_reduce(const SegReduceArgs a)
 {
    if (a.ctr[C_NCUTS] == 0ull) return;
    const uint32_t np = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
@@ -1213,7 +1213,7 @@ struct OffsArgs {
    const uint32_t *tile_base;
 };
 
-__global__ void __launch_bounds__(kThreads) k_offsets(const OffsArgs a)
+static __global__ void __launch_bounds__(kThreads) k_offsets(const OffsArgs a)
 {
    __shared__ BlockScanSmem sc;
    const uint32_t nlines = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);

@@ -290,3 +290,149 @@ extern "C" long bs_host_scan_cut(const char *buf, size_t n, const unsigned char 
    }
    return k;
 }
+
+
+// ---------------------------------------------------------------------------
+// tau <= 2: the NFA-level automaton (bs_wm_step), plain and with segment cuts.
+// cut == 0: every line is one segment.
+// ---------------------------------------------------------------------------
+template <int R, int T, int MODE, bool SKIP>
+static void run_group_wm(const std::vector<uint8_t> &cls, size_t n, const std::vector<Seg> &segs, size_t l0, size_t l1,
+                         uint32_t wup, const BsPattern &p, std::vector<std::vector<Ev>> &per_seg,
+                         std::vector<uint8_t> &segstop)
+{
+   BsWmState<R, T> st;
+   const int nl = (int)(l1 - l0);
+   bs_wm_reset(st, p, nl == 32 ? ~0u : ((1u << nl) - 1u));
+   uint32_t contmask = 0, followmask = 0;
+   std::vector<size_t> s0(nl), len(nl);
+   for (int r = 0; r < nl; r++) {
+      const Seg &sg = segs[l0 + r];
+      if (sg.cont) contmask |= 1u << r;
+      if (sg.follow) followmask |= 1u << r;
+      s0[r] = sg.start - (sg.cont ? wup : 0);
+      const size_t next = l0 + r + 1 < segs.size() ? segs[l0 + r + 1].start : n;
+      len[r] = (next - sg.start) + (sg.cont ? wup : 0) + (sg.follow ? 1 : 0);
+   }
+   uint32_t streak[4];
+   for (size_t col = 0; st.alive; col++) {
+      uint32_t p0 = 0, p1 = 0, p2 = 0;
+      for (int r = 0; r < nl; r++) {
+         uint8_t c;
+         if (segs[l0 + r].follow && col >= len[r]) c = kClsNull;
+         else {
+            const size_t pos = s0[r] + col;
+            c = pos >= n ? kClsStop : (cls[pos] & 7);
+         }
+         p0 |= (uint32_t)(c & 1) << r;
+         p1 |= (uint32_t)((c >> 1) & 1) << r;
+         p2 |= (uint32_t)((c >> 2) & 1) << r;
+      }
+      for (int r = nl; r < 32; r++) { p0 |= 1u << r; p2 |= 1u << r; }     // STOP
+      uint32_t slots[BS_SLOTS], anybase, stop, skip;
+      bs_classes(p0, p1, p2, p, slots, anybase, stop, skip);
+      auto eq = [&](int j) { return slots[p.slot[j]]; };
+      const uint32_t quiet = col <= wup ? contmask : 0u;
+      const uint32_t evt = bs_wm_step<R, T, MODE, SKIP>(st, eq, anybase, stop, skip, streak, quiet);
+      for (int r = 0; r < nl; r++)
+         if ((evt >> r) & 1u) {
+            const Seg &sg = segs[l0 + r];
+            per_seg[l0 + r].push_back(Ev{(uint64_t)sg.line, (uint64_t)(s0[r] + col - sg.lbeg), bs_value_unary<T>(streak, r)});
+         }
+      // a followed segment whose columns are used up is over (the kernel stops at the tile's last column)
+      bool any = false;
+      for (int r = 0; r < nl; r++)
+         if (((st.alive >> r) & 1u) && !(segs[l0 + r].follow && col + 1 >= len[r] + 1)) any = true;
+      if (!any) break;
+   }
+   for (int r = 0; r < nl; r++)
+      if (((st.stopped & followmask) >> r) & 1u) segstop[l0 + r] = 1;
+}
+
+extern "C" long bs_host_scan_wm(const char *buf, size_t n, const unsigned char *keys, int m, int tau, int options,
+                                size_t stride, size_t window, uint64_t *out, long cap, long *ncuts)
+{
+   BsPattern p;
+   if (!build_bs_pattern(keys, m, tau, &p) || p.parts != 1 || tau > 2) return -1;
+   const bool skipmode = (options & OPT_NONDNA) == OPT_IGNORE;
+   const bool cut = stride != 0;
+   if (cut && skipmode) return -1;
+   const uint32_t wup = bs_warmup(m, tau);
+   if (cut && wup > window) return -1;
+   ClassTable ct;
+   build_class_table(options, &ct);
+   std::vector<uint8_t> cls(n);
+   for (size_t i = 0; i < n; i++) cls[i] = ct.code[(unsigned char)buf[i]];
+   std::vector<Seg> segs;
+   {
+      std::vector<uint8_t> is_cut(n + 1, 0);
+      *ncuts = 0;
+      if (cut)
+         for (size_t a = window; a < n; a += stride) {
+            bool any = a - window == 0;
+            for (size_t q = a - window; q + 1 <= a && !any; q++) any = buf[q] == '\n';
+            if (!any) { is_cut[a] = 1; (*ncuts)++; }
+         }
+      size_t line = 0, lbeg = 0;
+      bool have = false;
+      for (size_t i = 0; i < n; i++) {
+         if (i == 0 || buf[i - 1] == '\n') {
+            if (have) line++;
+            have = true;
+            lbeg = i;
+            segs.push_back(Seg{i, line, lbeg, false, false});
+         } else if (is_cut[i]) {
+            segs.push_back(Seg{i, line, lbeg, true, false});
+         }
+      }
+      for (size_t k = 0; k + 1 < segs.size(); k++) segs[k].follow = segs[k + 1].cont;
+   }
+   const int match = options & OPT_MATCH;
+   const int mode = match == OPT_ALL ? BS_ALL : (match == OPT_BEST ? BS_BEST : BS_FIRST);
+   std::vector<std::vector<Ev>> per_seg(segs.size());
+   std::vector<uint8_t> segstop(segs.size(), 0);
+   for (size_t l0 = 0; l0 < segs.size(); l0 += 32) {
+      const size_t l1 = std::min(segs.size(), l0 + 32);
+#define WM3(R, T, M)                                                                                    \
+   if (mode == M) {                                                                                     \
+      if (skipmode) run_group_wm<R, T, M, true>(cls, n, segs, l0, l1, wup, p, per_seg, segstop);        \
+      else run_group_wm<R, T, M, false>(cls, n, segs, l0, l1, wup, p, per_seg, segstop);                \
+   }
+#define WM2(R, T) if (p.rows == R && tau + 1 == T) { WM3(R, T, BS_FIRST) WM3(R, T, BS_BEST) WM3(R, T, BS_ALL) }
+#define WM1(R) WM2(R, 1) WM2(R, 2) WM2(R, 3)
+      WM1(8) WM1(12) WM1(16) WM1(24) WM1(32)
+#undef WM1
+#undef WM2
+#undef WM3
+   }
+   long k = 0;
+   for (size_t s = 0; s < segs.size();) {
+      size_t e = s + 1;
+      while (e < segs.size() && segs[e].cont) e++;
+      bool dead = false, have = false;
+      Ev best{0, 0, 0};
+      for (size_t q = s; q < e; q++) {
+         if (!dead) {
+            for (size_t i = 0; i < per_seg[q].size(); i++) {
+               const Ev &ev = per_seg[q][i];
+               if (mode == BS_ALL) {
+                  if (k >= cap) return -2;
+                  out[3 * k] = ev.line + 1; out[3 * k + 1] = ev.end; out[3 * k + 2] = ev.dist; k++;
+               } else if (mode == BS_FIRST) {
+                  if (!have) { best = ev; have = true; }
+               } else {
+                  const bool last_of_seg = i + 1 == per_seg[q].size();
+                  if (last_of_seg && (!have || ev.dist < best.dist)) { best = ev; have = true; }
+               }
+            }
+         }
+         if (segstop[q]) dead = true;
+      }
+      if (mode != BS_ALL && have) {
+         if (k >= cap) return -2;
+         out[3 * k] = best.line + 1; out[3 * k + 1] = best.end; out[3 * k + 2] = best.dist; k++;
+      }
+      s = e;
+   }
+   return k;
+}

@@ -28,6 +28,8 @@ def harness(tmp_path_factory):
     L.bs_host_scan_cut.restype = C.c_long
     L.bs_host_scan_cut.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_size_t,
                                    C.c_size_t, C.POINTER(C.c_uint64), C.c_long, C.POINTER(C.c_long)]
+    L.bs_host_scan_wm.restype = C.c_long
+    L.bs_host_scan_wm.argtypes = L.bs_host_scan_cut.argtypes
     return L
 
 
@@ -143,3 +145,54 @@ def test_cut_segments_equal_oracle(harness, oracle, mrange, stride, window):
                 checked += 1
                 cuts += ncuts.value
     assert checked > 30 and cuts > 100
+
+
+@pytest.mark.parametrize("mrange,stride,window", [((1, 8), 0, 0), ((9, 12), 0, 0), ((13, 32), 0, 0),
+                                                   ((2, 10), 64, 32), ((8, 32), 256, 128)])
+def test_nfa_level_automaton_equals_oracle(harness, oracle, mrange, stride, window):
+    """tau <= 2: the NFA-level formulation (bs_wm_step) reproduces the oracle's events, on
+    whole lines (stride 0) and on lines cut into segments."""
+    rng = random.Random(mrange[1] * 13 + stride)
+    checked = 0
+    for it in range(40):
+        pattern = rand_pattern(rng, *mrange)
+        keys, _ = oracle.parse(pattern)
+        if not keys:
+            continue
+        tau = rng.randint(0, min(len(keys) - 1, 2))
+        if stride and len(keys) + 2 * tau + 2 > window:
+            continue
+        plant = "".join(rng.choice([c for b, c in ((1, "A"), (2, "C"), (4, "G"), (8, "T")) if k & b] or ["A"])
+                        for k in keys)
+        alphabet = ["ACGT", "ACGTN", "ACGTNXacgu-"][it % 3]
+        if stride:
+            lines = []
+            for _ in range(rng.randint(1, 40)):
+                n = rng.choice([rng.randint(0, window), rng.randint(window, 5 * stride)])
+                s = [rng.choice(alphabet[:4] if rng.random() < 0.98 else alphabet) for _ in range(n)]
+                for _ in range(rng.randint(0, 1 + n // (3 * len(keys) + 20))):
+                    at = rng.randrange(n + 1)
+                    q = list(plant)
+                    for _ in range(rng.randint(0, tau + 1)):
+                        if q:
+                            k = rng.randrange(len(q))
+                            q[k:k + 1] = rng.choice([[], [rng.choice("ACGT")], [q[k], rng.choice("ACGT")]])
+                    s[at:at] = q
+                lines.append("".join(s))
+            buf = "\n".join(lines).encode() + (b"\n" if it % 2 == 0 else b"")
+        else:
+            buf = make_buffer(rng, rng.randint(1, 150), 60 + 3 * len(keys), alphabet, plant, it % 2 == 0)
+        out = np.zeros((len(buf) + 64, 3), dtype=np.uint64)
+        ncuts = C.c_long(0)
+        for mo in (SQ_FIRST, SQ_BEST, SQ_ALL):
+            for nd in (SQ_FAIL, SQ_CONVERT, SQ_IGNORE):
+                n = harness.bs_host_scan_wm(buf, len(buf), keys, len(keys), tau, mo | nd, stride, window,
+                                            out.ctypes.data_as(C.POINTER(C.c_uint64)), out.shape[0], C.byref(ncuts))
+                if n == -1:
+                    continue
+                assert n >= 0
+                exp, _, _ = oracle.buffer_scan(buf, keys, tau, mo | nd)
+                exp = exp[:, [0, 2, 3]]
+                assert np.array_equal(out[:n], exp), (pattern, tau, mo, nd, buf[:120])
+                checked += 1
+    assert checked > 100

@@ -16,12 +16,11 @@ except Exception as e:
     print("$name failed", e)
 PY
 }
-WL=cfg5 run cfg5_auto X=1
-WL=cfg5 run cfg5_nofilter SEEQ_B200_FILTER=0
-WL=cfg2 run cfg2_auto X=1
-WL=cfg2 run cfg2_nofilter SEEQ_B200_FILTER=0
+WL=cfg2 run cfg2_nfa X=1
+WL=cfg2 run cfg2_myers SEEQ_B200_NFA=0
+WL=cfg1 run cfg1_nfa X=1
+WL=cfg1 run cfg1_myers SEEQ_B200_NFA=0
+WL=cfg5 run cfg5_nfa X=1
+WL=cfg5 run cfg5_myers SEEQ_B200_NFA=0
 WL=cfg2 run cfg2_filter SEEQ_B200_FILTER=2
-WL=cfg1 run cfg1_auto X=1
-WL=cfg3 run cfg3_auto X=1
-WL=cfg4 run cfg4_auto X=1
 ls $OUT | wc -l
