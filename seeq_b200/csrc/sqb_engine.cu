@@ -350,12 +350,14 @@ static int launch_bitslice(const sqb_engine *e, int mode, int options, size_t ma
    const int bsmode = (mode == M_ALL || mode == M_COUNTALL) ? BS_ALL : (mode == M_BEST ? BS_BEST : BS_FIRST);
    const bool skip = (options & OPT_NONDNA) == OPT_IGNORE;
    const int R = e->bs_pat.rows, G = e->bs_pat.parts;
+   const bool nfa = G == 1 && e->tau <= 2 && e->nfa_levels;
    int per_sm = G > 1 ? (R <= 24 ? 3 : 2) : (R <= 16 ? 4 : 3);
+   if (nfa) per_sm = R * (e->tau + 1) <= 24 ? 6 : (R * (e->tau + 1) <= 48 ? 4 : 3);      // = the kernels' launch bounds
    if (const char *c = getenv("SEEQ_B200_BS_CTAS")) per_sm = std::max(1, atoi(c));
    // work items = (tile, 1/G of its groups), one warp each
    const int grid = (int)std::max<size_t>(1, std::min<size_t>(div_up(div_up(max_lines, kBsTileLines) * G, kBsWarps),
                                                                (size_t)e->sms * per_sm * 2));
-   if (G == 1 && e->tau <= 2 && e->nfa_levels) {          // small tau: the NFA-level automaton is cheaper
+   if (nfa) {                                             // small tau: the NFA-level automaton is cheaper
       CU(sqb_launch_bitslice_wm(R, e->tau + 1, bsmode, skip, grid, st, a, e->bs_pat));
       return 0;
    }

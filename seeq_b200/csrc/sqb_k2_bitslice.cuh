@@ -336,7 +336,10 @@ struct K2BsArgs {
 };
 
 struct BsWarpSmem {
-   uint32_t slots[BS_SLOTS][32];
+   // Eq slots of the column in flight, [buffer][slot][lane].  Two buffers, used by the
+   // even and odd columns (G == 1): the slot stores of column c+1 do not have to wait
+   // for the Eq loads of column c
+   uint32_t slots[2][BS_SLOTS][32];
 };
 struct BsWarpSmemAll : BsWarpSmem {
    uint32_t cnt[32 * 32];         // events per line of the warp's groups (BS_ALL)
@@ -358,7 +361,7 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 // WM > 0 selects the NFA-level automaton (bs_wm_step, tau = WM - 1 <= 2, G == 1)
 // instead of Myers' delta encoding: fewer logic ops per column for small tau.
 template <int R, int G, int MODE, bool SKIP, int WM = 0>
-__global__ void __launch_bounds__(kBsThreads, G > 1 ? (R <= 24 ? 3 : 2) : (R <= 16 ? 4 : 3))
+__global__ void __launch_bounds__(kBsThreads, WM ? (R * WM <= 24 ? 6 : (R * WM <= 48 ? 4 : 3)) : (G > 1 ? (R <= 24 ? 3 : 2) : (R <= 16 ? 4 : 3)))
 k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
 {
    static_assert(WM == 0 || G == 1, "the NFA-level automaton is single-part");
@@ -382,8 +385,9 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
    const uint32_t ntiles = (nlines + kBsTileLines - 1) / kBsTileLines;
    const uint32_t nitems = ntiles * (uint32_t)G;          // (tile, quarter) pairs
 
-   sm.slots[BS_ONES][lane] = ~0u;
-   const uint32_t *slot_base = &sm.slots[0][lane];
+   sm.slots[0][BS_ONES][lane] = ~0u;
+   sm.slots[1][BS_ONES][lane] = ~0u;
+   const uint32_t *slot_base = &sm.slots[0][0][lane];
    // shared-memory address of the Eq mask of every row of this lane's part: with
    // G > 1 the slot of a row differs between the lanes of a warp, so the addresses
    // live in registers (from a staged copy of the table: a per-lane index into the
@@ -469,20 +473,19 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
             anybase = ~p2 | nn;
             stop = p2 & ~p1 & p0;
             skip = p2 & p1 & ~p0;
-            sm.slots[BS_A][lane] = na;
-            sm.slots[BS_C][lane] = nc;
-            sm.slots[BS_G][lane] = ng;
-            sm.slots[BS_T][lane] = nt;
-            sm.slots[BS_N][lane] = nn;
-            sm.slots[BS_ANY][lane] = anybase;
+            auto &sl = sm.slots[G == 1 ? (k & 1) : 0];
+            sl[BS_A][lane] = na;
+            sl[BS_C][lane] = nc;
+            sl[BS_G][lane] = ng;
+            sl[BS_T][lane] = nt;
+            sl[BS_N][lane] = nn;
+            sl[BS_ANY][lane] = anybase;
             if (pat.ncustom > 0)
-               sm.slots[BS_CUSTOM0][lane] = (na & pat.custom[0][0]) | (nc & pat.custom[0][1]) |
-                                            (ng & pat.custom[0][2]) | (nt & pat.custom[0][3]) |
-                                            (nn & pat.custom[0][4]);
+               sl[BS_CUSTOM0][lane] = (na & pat.custom[0][0]) | (nc & pat.custom[0][1]) | (ng & pat.custom[0][2]) |
+                                      (nt & pat.custom[0][3]) | (nn & pat.custom[0][4]);
             if (pat.ncustom > 1)
-               sm.slots[BS_CUSTOM1][lane] = (na & pat.custom[1][0]) | (nc & pat.custom[1][1]) |
-                                            (ng & pat.custom[1][2]) | (nt & pat.custom[1][3]) |
-                                            (nn & pat.custom[1][4]);
+               sl[BS_CUSTOM1][lane] = (na & pat.custom[1][0]) | (nc & pat.custom[1][1]) | (ng & pat.custom[1][2]) |
+                                      (nt & pat.custom[1][3]) | (nn & pat.custom[1][4]);
          }
          uint32_t ph = 0u, mh = 0u;
          if (G > 1) {
@@ -492,7 +495,8 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
          }
          auto eq = [&](int j) -> uint32_t {
             if (G > 1) return lds_u32(raddr[G > 1 ? j : 0]);
-            return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(slot_base) + pat.slot_off[j]);
+            return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(slot_base) +
+                                                       (k & 1) * (int)sizeof(sm.slots[0]) + pat.slot_off[j]);
          };
          uint32_t streak[B];
          uint32_t evt;
