@@ -246,7 +246,11 @@ def main():
     eng = B.Engine.borrowed(sq.engine())
 
     # this rank's slice of the global read stream, generated on the device
-    stream = torch.cuda.current_stream()
+    # a stream of our own: the legacy default stream has handle 0, which the C-ABI reads as
+    # "use the engine's stream"; both slots must run on ONE stream so that the scans follow
+    # each other on the device and the CUDA events bracket them
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     d_text = torch.empty(nbytes + 64, dtype=torch.uint8, device="cuda")
     first_read = rank * reads
     assert L.sqbGenDevice(C.byref(g), first_read, reads, d_text.data_ptr(), stream.cuda_stream) == 0, B.last_error()
@@ -254,16 +258,23 @@ def main():
 
     opt = w["options"] | (B.SQB_COUNT_ONLY if w["count"] else 0)
 
-    def step(timing=False):
-        return eng.scan_device(d_text.data_ptr(), nbytes, opt | (B.SQB_TIMING if timing else 0), stream.cuda_stream)
+    # One step = one scan.  Two scans may be in flight (sqbScanDeviceIssue / Wait, one slot of
+    # result arrays each): step i+1 is queued on the same stream before the host waits for
+    # step i, so the device never idles between steps while the host reads the counters back.
+    def issue(i, timing=False):
+        eng.scan_device_issue(i & 1, d_text.data_ptr(), nbytes, opt | (B.SQB_TIMING if timing else 0), stream.cuda_stream)
+
+    def wait(i):
+        return eng.scan_device_wait(i & 1)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        st = step()
+    for i in range(args.warmup):
+        issue(i)
+        st = wait(i)
     clocks = Clocks(local_rank)
     barrier()
     if rank == 0:
@@ -271,10 +282,9 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k2_ms, k1_ms, fin_ms, launches = [], [], [], 0
     match_ms, pack_ms, k1c_ms = [], [], []
-    barrier()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        st = step(timing=True)
+
+    def account(st):
+        nonlocal launches
         k1_ms.append(st.kernel_ms[0])
         k2_ms.append(st.kernel_ms[1])
         fin_ms.append(st.kernel_ms[2])
@@ -282,6 +292,16 @@ def main():
         pack_ms.append(st.kernel_ms[4])
         k1c_ms.append(st.kernel_ms[5])
         launches += st.launches
+
+    barrier()
+    ev0.record(stream)
+    issue(0, timing=True)
+    for i in range(1, args.steps):
+        issue(i, timing=True)
+        st = wait(i - 1)
+        account(st)
+    st = wait(args.steps - 1)
+    account(st)
     ev1.record(stream)
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)

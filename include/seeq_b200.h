@@ -86,7 +86,16 @@ int            sqbMaxPatternLength (void);
 int sqbScanDevice (sqb_engine_t * e, const void * d_text, size_t nbytes,
                    int options, void * stream, sqb_stats_t * stats);
 
-/* results of the last sqbScanDevice, resident on the device */
+/* The same in two halves, for callers that keep the device busy: up to two scans
+ * may be in flight (slot 0 and 1, each with its own result arrays); Issue returns
+ * as soon as the kernels are queued on `stream` (NULL: the slot's own stream),
+ * Wait blocks until the scan of that slot is complete and fills stats.  A slot
+ * must be waited for before it is issued again. */
+int sqbScanDeviceIssue (sqb_engine_t * e, int slot, const void * d_text, size_t nbytes,
+                        int options, void * stream);
+int sqbScanDeviceWait  (sqb_engine_t * e, int slot, sqb_stats_t * stats);
+
+/* results of the last sqbScanDevice / sqbScanDeviceWait, resident on the device */
 const sqb_rec_t * sqbDeviceRecords    (sqb_engine_t * e);
 const uint32_t  * sqbDeviceLineStarts (sqb_engine_t * e);   /* nlines+1 entries */
 int sqbFetchRecords    (sqb_engine_t * e, sqb_rec_t * dst, uint64_t first, uint64_t count);

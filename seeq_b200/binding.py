@@ -87,6 +87,8 @@ SYMBOLS = {
     "sqbDeviceCount": (C.c_int, []),
     "sqbMaxPatternLength": (C.c_int, []),
     "sqbScanDevice": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(StatsT)]),
+    "sqbScanDeviceIssue": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "sqbScanDeviceWait": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(StatsT)]),
     "sqbDeviceRecords": (C.c_void_p, [C.c_void_p]),
     "sqbDeviceLineStarts": (C.c_void_p, [C.c_void_p]),
     "sqbFetchRecords": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
@@ -237,6 +239,16 @@ class Engine:
         st = StatsT()
         if self.L.sqbScanDevice(self.e, d_ptr, nbytes, options, stream, C.byref(st)):
             raise RuntimeError("sqbScanDevice failed: " + last_error())
+        return st
+
+    def scan_device_issue(self, slot: int, d_ptr: int, nbytes: int, options: int, stream: int = 0) -> None:
+        if self.L.sqbScanDeviceIssue(self.e, slot, d_ptr, nbytes, options, stream):
+            raise RuntimeError("sqbScanDeviceIssue failed: " + last_error())
+
+    def scan_device_wait(self, slot: int) -> StatsT:
+        st = StatsT()
+        if self.L.sqbScanDeviceWait(self.e, slot, C.byref(st)):
+            raise RuntimeError("sqbScanDeviceWait failed: " + last_error())
         return st
 
     def scan_host(self, buf, options: int) -> StatsT:

@@ -112,7 +112,8 @@ struct sqb_engine {
    double lines_per_byte = 1.0 / 24.0;
    double events_per_byte = 1.0 / 64.0;
    // results of the last sqbScanHost
-   std::vector<sqb_rec_t> host_recs;
+   sqb_rec_t *host_recs = nullptr;     // pinned; the records of the last sqbScanHost, all chunks, in order
+   size_t host_recs_cap = 0, host_recs_n = 0;
    std::vector<uint64_t> host_lines;
    int last_slot = 0;
    sqb_stats_t last_stats;
@@ -704,6 +705,7 @@ void sqbEngineFree(sqb_engine_t *e)
    if (e == NULL) return;
    cudaSetDevice(e->device);
    for (auto &s : e->slot) slot_free(s);
+   if (e->host_recs) cudaFreeHost(e->host_recs);
    delete e;
 }
 
@@ -725,6 +727,28 @@ int sqbScanDevice(sqb_engine_t *e, const void *d_text, size_t nbytes, int option
    cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
    if (slot_issue(e, s, (const uint8_t *)d_text, (uint32_t)nbytes, options, st)) return -1;
    if (slot_finish(e, s, &e->last_stats)) return -1;
+   if (stats) *stats = e->last_stats;
+   return 0;
+}
+
+int sqbScanDeviceIssue(sqb_engine_t *e, int slot, const void *d_text, size_t nbytes, int options, void *stream)
+{
+   if (slot < 0 || slot > 1) { set_err("sqbScanDeviceIssue: slot %d out of range", slot); return -1; }
+   if (nbytes == 0 || nbytes >= kMaxBatch) { set_err("sqbScanDeviceIssue: %zu bytes are outside the batch limits", nbytes); return -1; }
+   if (((uintptr_t)d_text & 15) != 0) { set_err("sqbScanDeviceIssue: text pointer must be 16-byte aligned"); return -1; }
+   CU(cudaSetDevice(e->device));
+   Slot &s = e->slot[slot];
+   if (slot_init(s)) return -1;
+   if (s.busy) { set_err("sqbScanDeviceIssue: slot %d has a scan in flight", slot); return -1; }
+   return slot_issue(e, s, (const uint8_t *)d_text, (uint32_t)nbytes, options, stream ? (cudaStream_t)stream : s.stream);
+}
+
+int sqbScanDeviceWait(sqb_engine_t *e, int slot, sqb_stats_t *stats)
+{
+   if (slot < 0 || slot > 1 || !e->slot[slot].busy) { set_err("sqbScanDeviceWait: no scan in flight in slot %d", slot); return -1; }
+   CU(cudaSetDevice(e->device));
+   e->last_slot = slot;
+   if (slot_finish(e, e->slot[slot], &e->last_stats)) return -1;
    if (stats) *stats = e->last_stats;
    return 0;
 }
@@ -766,9 +790,19 @@ static int host_collect(sqb_engine *e, Slot &s, int options, uint64_t *line_base
    sqb_stats_t st;
    if (slot_finish(e, s, &st)) return -1;
    const bool count_only = options & SQB_COUNT_ONLY;
+   // the records go straight into the (pinned) result array of the scan
    if (!count_only && st.nrecs > 0) {
-      if (pin_reserve(&s.h_recs, &s.h_rec_cap, (size_t)st.nrecs)) return -1;
-      CU(cudaMemcpyAsync(s.h_recs, s.d_recs, st.nrecs * sizeof(Rec), cudaMemcpyDeviceToHost, s.stream));
+      const size_t need = e->host_recs_n + (size_t)st.nrecs;
+      if (need > e->host_recs_cap) {
+         sqb_rec_t *bigger = nullptr;
+         const size_t cap = need + need / 2 + (1u << 16);
+         CU(cudaMallocHost((void **)&bigger, cap * sizeof(sqb_rec_t)));
+         if (e->host_recs_n) memcpy(bigger, e->host_recs, e->host_recs_n * sizeof(sqb_rec_t));
+         if (e->host_recs) CU(cudaFreeHost(e->host_recs));
+         e->host_recs = bigger;
+         e->host_recs_cap = cap;
+      }
+      CU(cudaMemcpyAsync(e->host_recs + e->host_recs_n, s.d_recs, st.nrecs * sizeof(Rec), cudaMemcpyDeviceToHost, s.stream));
    }
    if ((options & SQB_KEEP_LINES_INTERNAL) && st.nlines > 0) {
       if (pin_reserve(&s.h_ls, &s.h_ls_cap, (size_t)st.nlines)) return -1;
@@ -776,16 +810,11 @@ static int host_collect(sqb_engine *e, Slot &s, int options, uint64_t *line_base
    }
    CU(cudaStreamSynchronize(s.stream));
    if (!count_only && st.nrecs > 0) {
-      const size_t old = e->host_recs.size();
-      e->host_recs.resize(old + st.nrecs);
-      const uint32_t lb = (uint32_t)*line_base;
-      sqb_rec_t *dst = e->host_recs.data() + old;
-      for (uint64_t k = 0; k < st.nrecs; k++) {
-         dst[k].line = s.h_recs[k].line + lb;
-         dst[k].start = s.h_recs[k].start;
-         dst[k].end = s.h_recs[k].end;
-         dst[k].dist = s.h_recs[k].dist;
-      }
+      const uint32_t lb = (uint32_t)*line_base;        // lines of a chunk are numbered from 0 on the device
+      sqb_rec_t *dst = e->host_recs + e->host_recs_n;
+      if (lb)
+         for (uint64_t k = 0; k < st.nrecs; k++) dst[k].line += lb;
+      e->host_recs_n += (size_t)st.nrecs;
    }
    if ((options & SQB_KEEP_LINES_INTERNAL) && st.nlines > 0) {
       const size_t old = e->host_lines.size();
@@ -808,7 +837,7 @@ int sqbScanHost(sqb_engine_t *e, const char *text, size_t nbytes, int options, s
 {
    CU(cudaSetDevice(e->device));
    for (auto &s : e->slot) if (slot_init(s)) return -1;
-   e->host_recs.clear();
+   e->host_recs_n = 0;
    e->host_lines.clear();
    sqb_stats_t acc;
    memset(&acc, 0, sizeof acc);
@@ -867,8 +896,8 @@ int sqbScanHost(sqb_engine_t *e, const char *text, size_t nbytes, int options, s
 
 const sqb_rec_t *sqbHostRecords(sqb_engine_t *e, uint64_t *count)
 {
-   if (count) *count = e->host_recs.size();
-   return e->host_recs.data();
+   if (count) *count = e->host_recs_n;
+   return e->host_recs;
 }
 
 int sqbHostLineStarts(sqb_engine_t *e, const uint64_t **starts, uint64_t *count)
