@@ -257,15 +257,24 @@ def main():
     torch.cuda.synchronize()
 
     opt = w["options"] | (B.SQB_COUNT_ONLY if w["count"] else 0)
+    # a shard of 2 GiB or more (cfg5 at 12.5 GB per GPU: --reads 39800000) is scanned in newline-aligned
+    # chunks by sqbScanDeviceLarge; its records travel to the host while the next chunk is matched
+    big = nbytes >= (1 << 31)
 
     # One step = one scan.  Two scans may be in flight (sqbScanDeviceIssue / Wait, one slot of
     # result arrays each): step i+1 is queued on the same stream before the host waits for
     # step i, so the device never idles between steps while the host reads the counters back.
+    big_stats = {}
+
     def issue(i, timing=False):
-        eng.scan_device_issue(i & 1, d_text.data_ptr(), nbytes, opt | (B.SQB_TIMING if timing else 0), stream.cuda_stream)
+        o = opt | (B.SQB_TIMING if timing else 0)
+        if big:
+            big_stats[i] = eng.scan_device_large(d_text.data_ptr(), nbytes, o, stream.cuda_stream)
+        else:
+            eng.scan_device_issue(i & 1, d_text.data_ptr(), nbytes, o, stream.cuda_stream)
 
     def wait(i):
-        return eng.scan_device_wait(i & 1)
+        return big_stats.pop(i) if big else eng.scan_device_wait(i & 1)
 
     def barrier():
         if world > 1:
@@ -323,7 +332,14 @@ def main():
 
     # ---------------- end to end through the C-ABI with host buffers ---------
     e2e = None
-    if not args.no_e2e:
+    host_ok = True
+    if big:
+        try:
+            avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
+        except (OSError, IndexError, ValueError):
+            avail = 0
+        host_ok = avail > 3 * nbytes * max(1, world)
+    if not args.no_e2e and host_ok:
         h_ptr = L.sqbHostAlloc(nbytes + 64)
         assert h_ptr, B.last_error()
         torch.cuda.synchronize()

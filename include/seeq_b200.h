@@ -95,6 +95,15 @@ int sqbScanDeviceIssue (sqb_engine_t * e, int slot, const void * d_text, size_t 
                         int options, void * stream);
 int sqbScanDeviceWait  (sqb_engine_t * e, int slot, sqb_stats_t * stats);
 
+/* A device-resident buffer of ANY size (a 12.5 GB shard of a 100 GB read set): cut into
+ * newline-aligned chunks below 2 GiB ($SEEQ_B200_DEVICE_CHUNK_MB, default 1536) that are scanned
+ * where they lie, back to back on `stream` (NULL: a stream of the engine); counts are summed and
+ * the records of all chunks are delivered like sqbScanHost's, with buffer-global line indices
+ * (sqbHostRecords; sqbHostLineStarts with SQB_KEEP_LINES).  d_text needs no alignment (the
+ * 16-byte vector it lies in must be readable, as inside any CUDA allocation). */
+int sqbScanDeviceLarge (sqb_engine_t * e, const void * d_text, size_t nbytes,
+                        int options, void * stream, sqb_stats_t * stats);
+
 /* results of the last sqbScanDevice / sqbScanDeviceWait, resident on the device */
 const sqb_rec_t * sqbDeviceRecords    (sqb_engine_t * e);
 const uint32_t  * sqbDeviceLineStarts (sqb_engine_t * e);   /* nlines+1 entries */

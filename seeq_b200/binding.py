@@ -89,6 +89,7 @@ SYMBOLS = {
     "sqbScanDevice": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(StatsT)]),
     "sqbScanDeviceIssue": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "sqbScanDeviceWait": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(StatsT)]),
+    "sqbScanDeviceLarge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(StatsT)]),
     "sqbDeviceRecords": (C.c_void_p, [C.c_void_p]),
     "sqbDeviceLineStarts": (C.c_void_p, [C.c_void_p]),
     "sqbFetchRecords": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
@@ -239,6 +240,13 @@ class Engine:
         st = StatsT()
         if self.L.sqbScanDevice(self.e, d_ptr, nbytes, options, stream, C.byref(st)):
             raise RuntimeError("sqbScanDevice failed: " + last_error())
+        return st
+
+    def scan_device_large(self, d_ptr: int, nbytes: int, options: int, stream: int = 0) -> StatsT:
+        """Any size; records via host_records() (buffer-global line indices)."""
+        st = StatsT()
+        if self.L.sqbScanDeviceLarge(self.e, d_ptr, nbytes, options, stream, C.byref(st)):
+            raise RuntimeError("sqbScanDeviceLarge failed: " + last_error())
         return st
 
     def scan_device_issue(self, slot: int, d_ptr: int, nbytes: int, options: int, stream: int = 0) -> None:

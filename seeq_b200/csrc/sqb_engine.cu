@@ -7,6 +7,13 @@
 // per byte in SQ_ALL) are guessed generously, detected exactly by the kernels
 // (which keep counting past the capacity) and, if ever exceeded, the scan is
 // repeated once with exact sizes (stats->reruns).
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include <cerrno>
 #include <cstdarg>
 #include <cstdio>
@@ -81,6 +88,7 @@ struct Slot {
    // description of the scan in flight
    const uint8_t *cur_text = nullptr;
    uint32_t cur_n = 0;
+   uint32_t cur_skip = 0;       // the buffer proper starts cur_skip (< 16) bytes into cur_text (K1Args::skip)
    int cur_options = 0;
    cudaStream_t cur_stream = nullptr;
    uint32_t launches = 0;
@@ -117,6 +125,8 @@ struct sqb_engine {
    std::vector<uint64_t> host_lines;
    int last_slot = 0;
    sqb_stats_t last_stats;
+   unsigned long long *d_word = nullptr, *h_word = nullptr;     // device_cuts: one word each
+   cudaStream_t big_stream = nullptr;                           // sqbScanDeviceLarge: the kernels of all chunks
 };
 
 // ---------------------------------------------------------------------------
@@ -154,6 +164,90 @@ static void build_pattern(const sqb_engine *e, int options, bool reverse, Patter
 }
 
 // ---------------------------------------------------------------------------
+// NUMA placement of pinned host memory
+// ---------------------------------------------------------------------------
+// Pinned buffers (the text a caller stages with sqbHostAlloc, the record arrays) are the
+// two ends of every PCIe transfer.  On a two-socket host with 8 GPUs a buffer that lives
+// on the other socket makes every DMA cross the inter-socket link, and with one process
+// per GPU all of them do at once.  For the duration of an allocation the calling thread
+// is therefore moved onto the CPUs of the GPU's NUMA node (sysfs: numa_node of the PCI
+// device, cpulist of the node) and its memory policy set to prefer that node; both are
+// restored afterwards.  No-op where sysfs has no answer (VMs), or with SEEQ_B200_NUMA=0.
+struct NumaScope {
+   cpu_set_t old_set;
+   bool moved = false, policy = false;
+
+   static int node_of(int device)
+   {
+      static int cache[64];
+      static bool known[64];
+      if (device < 0 || device >= 64) return -1;
+      if (known[device]) return cache[device];
+      int node = -1;
+      const char *env = getenv("SEEQ_B200_NUMA");
+      char bus[64] = "";
+      if (!(env && atoi(env) == 0) && cudaDeviceGetPCIBusId(bus, sizeof bus, device) == cudaSuccess) {
+         for (char *c = bus; *c; c++) if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+         char path[160];
+         snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+         if (FILE *f = fopen(path, "r")) {
+            if (fscanf(f, "%d", &node) != 1) node = -1;
+            fclose(f);
+         }
+      } else {
+         cudaGetLastError();
+      }
+      cache[device] = node;
+      known[device] = true;
+      return node;
+   }
+
+   explicit NumaScope(int device)
+   {
+      const int node = node_of(device);
+      if (node < 0) return;
+      char path[96];
+      snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+      FILE *f = fopen(path, "r");
+      if (f == nullptr) return;
+      cpu_set_t want, cur;
+      CPU_ZERO(&want);
+      int a = 0, b = 0;
+      char sep = 0;
+      while (fscanf(f, "%d", &a) == 1) {             // "0-31,64-95"
+         b = a;
+         if (fscanf(f, "%c", &sep) == 1 && sep == '-') {
+            if (fscanf(f, "%d", &b) != 1) b = a;
+            if (fscanf(f, "%c", &sep) != 1) sep = 0;
+         }
+         for (int c = a; c <= b && c < CPU_SETSIZE; c++) CPU_SET(c, &want);
+         if (sep != ',') break;
+      }
+      fclose(f);
+      if (sched_getaffinity(0, sizeof old_set, &old_set) != 0) return;
+      CPU_AND(&cur, &want, &old_set);
+      if (CPU_COUNT(&cur) > 0 && !CPU_EQUAL(&cur, &old_set)) moved = sched_setaffinity(0, sizeof cur, &cur) == 0;
+      if (node < 64) {
+         unsigned long mask = 1ul << node;
+         policy = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 65ul) == 0;
+      }
+   }
+   ~NumaScope()
+   {
+      if (policy) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+      if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
+   }
+};
+
+static cudaError_t pinned_alloc(void **p, size_t bytes)
+{
+   int device = 0;
+   if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); device = 0; }
+   NumaScope scope(device);
+   return cudaMallocHost(p, bytes);
+}
+
+// ---------------------------------------------------------------------------
 // memory helpers
 // ---------------------------------------------------------------------------
 template <class T> static int dev_reserve(T **p, size_t *cap, size_t need, size_t slack_div = 8)
@@ -175,7 +269,7 @@ template <class T> static int pin_reserve(T **p, size_t *cap, size_t need)
    *p = nullptr;
    *cap = 0;
    const size_t want = need + need / 4 + 1024;
-   CU(cudaMallocHost((void **)p, want * sizeof(T)));
+   CU(pinned_alloc((void **)p, want * sizeof(T)));
    *cap = want;
    return 0;
 }
@@ -194,8 +288,8 @@ static int slot_init(Slot &s)
 {
    if (s.stream) return 0;
    CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-   CU(cudaMallocHost((void **)&s.h_ctr, C_COUNT * sizeof(unsigned long long)));
-   CU(cudaMallocHost((void **)&s.h_init, 4 * sizeof(uint32_t)));
+   CU(pinned_alloc((void **)&s.h_ctr, C_COUNT * sizeof(unsigned long long)));
+   CU(pinned_alloc((void **)&s.h_init, 4 * sizeof(uint32_t)));
    for (auto &ev : s.ev) CU(cudaEventCreate(&ev));
    return 0;
 }
@@ -371,13 +465,15 @@ static int launch_bitslice(const sqb_engine *e, int mode, int options, size_t ma
    return -1;
 }
 
-static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n, int options, cudaStream_t st)
+static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n, int options, cudaStream_t st,
+                      uint32_t skip = 0)
 {
    const int mode = mode_of(options);
    const bool single = options & SQB_SINGLE_LINE;
    const bool timing = options & SQB_TIMING;
    s.cur_text = d_text;
    s.cur_n = n;
+   s.cur_skip = skip;
    s.cur_options = options;
    s.cur_stream = st;
    s.launches = 0;
@@ -447,7 +543,7 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
       const uint32_t ntiles = (uint32_t)div_up(n, kK1Tile);
       K1Args k1{d_text, n, s.d_ls_raw, (uint32_t)s.line_cap, want_codes ? (uint2 *)s.d_codes : nullptr, ctr,
                 tile_cnt, tile_off, tile_real, tile_last, tile_alive,
-                (uint32_t)std::min(8, std::max(1, e->m - e->tau)), (options & SQB_FASTA) ? 1 : 0};
+                (uint32_t)std::min(8, std::max(1, e->m - e->tau)), (options & SQB_FASTA) ? 1 : 0, skip};
       ClassTable ct;
       build_class_table(options, &ct);
       static bool attr = false;
@@ -604,7 +700,7 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
       }
       if (!again) break;
       if (++reruns > 3) { set_err("capacity re-run did not converge"); return -1; }
-      if (slot_issue(e, s, s.cur_text, s.cur_n, s.cur_options, s.cur_stream)) return -1;
+      if (slot_issue(e, s, s.cur_text, s.cur_n, s.cur_options, s.cur_stream, s.cur_skip)) return -1;
    }
    s.busy = false;
    if (s.cur_filter && e->filter == 1 && e->filter_state < 0 && s.h_ctr[C_NPSEUDO] > 0) {
@@ -633,6 +729,21 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
       }
    }
    return 0;
+}
+
+// last (or first) '\n' of text[lo, hi): *out = max (min) over 1 + its position
+static __global__ void k_find_newline(const uint8_t *text, unsigned long long lo, unsigned long long hi, int last,
+                                      unsigned long long *out)
+{
+   unsigned long long best = last ? 0ull : ~0ull;
+   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+   for (unsigned long long p = lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p < hi; p += stride)
+      if (text[p] == '\n') {
+         if (last) best = p + 1ull;
+         else { best = p + 1ull; break; }
+      }
+   if (last) { if (best) atomicMax(out, best); }
+   else if (best != ~0ull) atomicMin(out, best);
 }
 
 // ---------------------------------------------------------------------------
@@ -706,6 +817,9 @@ void sqbEngineFree(sqb_engine_t *e)
    cudaSetDevice(e->device);
    for (auto &s : e->slot) slot_free(s);
    if (e->host_recs) cudaFreeHost(e->host_recs);
+   if (e->d_word) cudaFree(e->d_word);
+   if (e->h_word) cudaFreeHost(e->h_word);
+   if (e->big_stream) cudaStreamDestroy(e->big_stream);
    delete e;
 }
 
@@ -784,6 +898,16 @@ static size_t host_chunk_bytes(void)
    return mb << 20;
 }
 
+// device-resident buffers: chunks below 2 GiB keep the line filter available (kDeadBit)
+static size_t device_chunk_bytes(void)
+{
+   const char *env = getenv("SEEQ_B200_DEVICE_CHUNK_MB");
+   size_t mb = env ? (size_t)atol(env) : 1536;
+   if (mb < 1) mb = 1;
+   if (mb > 2040) mb = 2040;
+   return mb << 20;
+}
+
 // collect the results of the chunk in flight in slot s (in chunk order)
 static int host_collect(sqb_engine *e, Slot &s, int options, uint64_t *line_base, sqb_stats_t *acc)
 {
@@ -796,7 +920,7 @@ static int host_collect(sqb_engine *e, Slot &s, int options, uint64_t *line_base
       if (need > e->host_recs_cap) {
          sqb_rec_t *bigger = nullptr;
          const size_t cap = need + need / 2 + (1u << 16);
-         CU(cudaMallocHost((void **)&bigger, cap * sizeof(sqb_rec_t)));
+         CU(pinned_alloc((void **)&bigger, cap * sizeof(sqb_rec_t)));
          if (e->host_recs_n) memcpy(bigger, e->host_recs, e->host_recs_n * sizeof(sqb_rec_t));
          if (e->host_recs) CU(cudaFreeHost(e->host_recs));
          e->host_recs = bigger;
@@ -833,7 +957,55 @@ static int host_collect(sqb_engine *e, Slot &s, int options, uint64_t *line_base
    return 0;
 }
 
-int sqbScanHost(sqb_engine_t *e, const char *text, size_t nbytes, int options, sqb_stats_t *stats)
+// Chunk boundaries of a DEVICE-resident buffer: cuts[0] = 0 < cuts[1] < ... = nbytes, every inner cut
+// just behind a '\n'.  The last newline of a window is looked for in its final 1 MiB, then 64 MiB,
+// then all of it; a window without any is extended to the next newline.
+static int device_cuts(sqb_engine *e, const uint8_t *d_text, size_t nbytes, size_t chunk, std::vector<size_t> &cuts)
+{
+   Slot &s = e->slot[0];
+   if (e->d_word == nullptr) {
+      CU(cudaMalloc((void **)&e->d_word, sizeof(unsigned long long)));
+      CU(pinned_alloc((void **)&e->h_word, sizeof(unsigned long long)));
+   }
+   auto find = [&](size_t lo, size_t hi, bool last, size_t *where) -> int {
+      *e->h_word = last ? 0ull : ~0ull;
+      CU(cudaMemcpyAsync(e->d_word, e->h_word, sizeof(unsigned long long), cudaMemcpyHostToDevice, s.stream));
+      const int grid = (int)std::max<size_t>(1, std::min<size_t>(div_up(hi - lo, 256 * 16), (size_t)e->sms * 8));
+      k_find_newline<<<grid, 256, 0, s.stream>>>(d_text, lo, hi, last ? 1 : 0, e->d_word);
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(e->h_word, e->d_word, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+      CU(cudaStreamSynchronize(s.stream));
+      *where = (size_t)*e->h_word;            // 1 + position; 0 / ~0: none
+      return 0;
+   };
+   cuts.assign(1, 0);
+   size_t pos = 0;
+   while (nbytes - pos > chunk) {
+      size_t at = 0;
+      const size_t hi = pos + chunk;
+      for (size_t win : {(size_t)1 << 20, (size_t)64 << 20, chunk}) {
+         const size_t lo = hi - std::min(win, chunk);
+         if (find(lo, hi, true, &at)) return -1;
+         if (at != 0 || lo == pos) break;
+      }
+      if (at == 0) {
+         if (find(hi, nbytes, false, &at)) return -1;
+         if (at == (size_t)~0ull) break;                 // no newline left: the rest is one chunk
+      }
+      if (at >= nbytes) break;
+      cuts.push_back(at);
+      pos = at;
+   }
+   cuts.push_back(nbytes);
+   return 0;
+}
+
+// The chunk pipeline behind sqbScanHost and sqbScanDeviceLarge: newline-aligned chunks, two slots,
+// the results of chunk k are collected while chunk k+1 runs.  Host text is copied into the slot's
+// device buffer; device text is scanned where it lies (a chunk that does not start on a 16-byte
+// boundary starts `skip` bytes into its aligned address, K1Args::skip).
+static int scan_chunks(sqb_engine *e, const char *text, size_t nbytes, int options, sqb_stats_t *stats,
+                       bool on_device, cudaStream_t user_stream)
 {
    CU(cudaSetDevice(e->device));
    for (auto &s : e->slot) if (slot_init(s)) return -1;
@@ -842,19 +1014,25 @@ int sqbScanHost(sqb_engine_t *e, const char *text, size_t nbytes, int options, s
    sqb_stats_t acc;
    memset(&acc, 0, sizeof acc);
    const bool single = options & SQB_SINGLE_LINE;
-   const size_t chunk = host_chunk_bytes();
+   const size_t chunk = on_device ? device_chunk_bytes() : host_chunk_bytes();
+   std::vector<size_t> cuts;
+   if (on_device && !single && device_cuts(e, (const uint8_t *)text, nbytes, chunk, cuts)) return -1;
+   // device text: the kernels of all chunks follow each other on ONE stream (the caller's, or one of
+   // the engine's own) while the slots' streams carry the record copies of the chunk before
+   if (on_device && user_stream == nullptr) {
+      if (e->big_stream == nullptr) CU(cudaStreamCreateWithFlags(&e->big_stream, cudaStreamNonBlocking));
+      user_stream = e->big_stream;
+   }
    uint64_t line_base = 0;
    size_t pos = 0;
    int c = 0;
    int pending[2] = {0, 0};
-   // FASTA is a property of the whole stream (seeq.c:243-253), not of a chunk
-   if (!single && !(options & SQB_FASTA)) {
-      /* caller decides; nothing to do */
-   }
    while (pos < nbytes || (single && c == 0)) {
       size_t len;
       if (single) {
          len = nbytes;
+      } else if (on_device) {
+         len = cuts[(size_t)c + 1] - pos;
       } else {
          len = nbytes - pos;
          if (len > chunk) {
@@ -864,18 +1042,29 @@ int sqbScanHost(sqb_engine_t *e, const char *text, size_t nbytes, int options, s
             len = nl ? (size_t)(nl - (text + pos)) + 1 : nbytes - pos;
          }
       }
-      if (len >= kMaxBatch) { set_err("a single line of %zu bytes exceeds the batch limit of %zu", len, (size_t)kMaxBatch); return -1; }
+      if (len + 16 >= kMaxBatch) { set_err("a single line of %zu bytes exceeds the batch limit of %zu", len, (size_t)kMaxBatch); return -1; }
       Slot &s = e->slot[c & 1];
       if (pending[c & 1]) {
          if (host_collect(e, s, options, &line_base, &acc)) return -1;
          pending[c & 1] = 0;
       }
-      if (dev_reserve(&s.d_text, &s.text_cap, len + 64)) return -1;
-      s.chunk_off = pos;
-      if (len) CU(cudaMemcpyAsync(s.d_text, text + pos, len, cudaMemcpyHostToDevice, s.stream));
-      if (len || single) {
-         if (slot_issue(e, s, s.d_text, (uint32_t)len, options, s.stream)) return -1;
-         pending[c & 1] = 1;
+      if (on_device) {
+         const uint32_t skip = single ? 0u : (uint32_t)((uintptr_t)(text + pos) & 15u);
+         if (single && ((uintptr_t)text & 15u)) { set_err("device text must be 16-byte aligned"); return -1; }
+         s.chunk_off = pos - skip;
+         if (len || single) {
+            if (slot_issue(e, s, (const uint8_t *)text + pos - skip, (uint32_t)(len + skip), options, user_stream,
+                           skip)) return -1;
+            pending[c & 1] = 1;
+         }
+      } else {
+         if (dev_reserve(&s.d_text, &s.text_cap, len + 64)) return -1;
+         s.chunk_off = pos;
+         if (len) CU(cudaMemcpyAsync(s.d_text, text + pos, len, cudaMemcpyHostToDevice, s.stream));
+         if (len || single) {
+            if (slot_issue(e, s, s.d_text, (uint32_t)len, options, s.stream)) return -1;
+            pending[c & 1] = 1;
+         }
       }
       pos += len;
       c++;
@@ -889,9 +1078,22 @@ int sqbScanHost(sqb_engine_t *e, const char *text, size_t nbytes, int options, s
          pending[idx] = 0;
       }
    }
+   acc.nbytes = nbytes;          // (a device chunk counts its alignment bytes)
    e->last_stats = acc;
    if (stats) *stats = acc;
    return 0;
+}
+
+int sqbScanHost(sqb_engine_t *e, const char *text, size_t nbytes, int options, sqb_stats_t *stats)
+{
+   return scan_chunks(e, text, nbytes, options, stats, false, nullptr);
+}
+
+int sqbScanDeviceLarge(sqb_engine_t *e, const void *d_text, size_t nbytes, int options, void *stream,
+                       sqb_stats_t *stats)
+{
+   if (options & SQB_SINGLE_LINE) { set_err("sqbScanDeviceLarge: not for single lines"); return -1; }
+   return scan_chunks(e, (const char *)d_text, nbytes, options, stats, true, (cudaStream_t)stream);
 }
 
 const sqb_rec_t *sqbHostRecords(sqb_engine_t *e, uint64_t *count)
@@ -910,7 +1112,7 @@ int sqbHostLineStarts(sqb_engine_t *e, const uint64_t **starts, uint64_t *count)
 void *sqbHostAlloc(size_t nbytes)
 {
    void *p = NULL;
-   if (cudaMallocHost(&p, nbytes ? nbytes : 1) != cudaSuccess) {
+   if (pinned_alloc(&p, nbytes ? nbytes : 1) != cudaSuccess) {
       set_err("cudaMallocHost(%zu) failed", nbytes);
       cudaGetLastError();
       return NULL;

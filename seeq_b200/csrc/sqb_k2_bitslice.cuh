@@ -218,9 +218,17 @@ struct NibbleStream {
    const uint4 *codes;
    uint32_t chunk, last;          // next 16-byte chunk to load, last valid chunk
    uint32_t ws, bs;               // word and bit shift of the line start inside its first chunk
-   uint4 prev;
+   uint4 prev, cur;               // the two chunks the next call combines: cur is loaded one call ahead,
+                                  // its latency hides behind the transposes of the block before
    bool valid;
 
+   __device__ __forceinline__ uint4 load()
+   {
+      uint4 v = cur;
+      if (valid) v = codes[chunk];
+      chunk = min(chunk + 1u, last);
+      return v;
+   }
    __device__ __forceinline__ void open(const uint4 *c, uint32_t ncode16, uint32_t begin, bool ok)
    {
       codes = c;
@@ -229,14 +237,12 @@ struct NibbleStream {
       chunk = min(begin >> 5, last);
       ws = (begin & 31u) >> 3;
       bs = (begin & 7u) * 4u;
-      prev = valid ? codes[chunk] : make_uint4(0x55555555u, 0x55555555u, 0x55555555u, 0x55555555u);
-      chunk = min(chunk + 1u, last);
+      cur = make_uint4(0x55555555u, 0x55555555u, 0x55555555u, 0x55555555u);
+      prev = load();
+      cur = load();
    }
    __device__ __forceinline__ void next(uint32_t (&out)[4])
    {
-      uint4 cur = prev;
-      if (valid) cur = codes[chunk];
-      chunk = min(chunk + 1u, last);
       const uint32_t w[8] = {prev.x, prev.y, prev.z, prev.w, cur.x, cur.y, cur.z, cur.w};
       uint32_t u[5];
 #pragma unroll
@@ -248,10 +254,11 @@ struct NibbleStream {
 #pragma unroll
       for (int i = 0; i < 4; i++) out[i] = __funnelshift_r(u[i], u[i + 1], bs);
       prev = cur;
+      cur = load();
    }
 };
 
-static __global__ void __launch_bounds__(kThreads) k15_pack(const BsPackArgs a)
+static __global__ void __launch_bounds__(kThreads, 4) k15_pack(const BsPackArgs a)
 {
    if (a.ctr[C_BS_SELECTED] != 1ull) return;
    const int lane = threadIdx.x & 31;

@@ -127,6 +127,9 @@ struct K1Args {
    uint32_t *tile_alive;          // out (FILTER): entries of the tile that are not dead on arrival
    uint32_t filter_k;             // FILTER: a STOP among the first filter_k (<= 8) bytes of a line kills it
    int fasta;
+   uint32_t skip;                 // 0..15: the buffer proper starts at text + skip (text is the 16-byte aligned
+                                  // address below it); the bytes in front are not looked at, byte skip-1 acts
+                                  // as the '\n' in front of the first line
 };
 
 constexpr uint32_t kDeadBit = 0x80000000u;     // FILTER: flag in ls_raw (text < 2 GiB)
@@ -226,6 +229,16 @@ __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, 
          lo[k] = l;
          hi[k] = h;
       }
+      if (a.skip != 0u && pos0 == 0u) {     // the bytes in front of the buffer: STOP, the last one a newline
+         const uint32_t nl = a.skip - 1u;            // 0..14, in vector 0 (lane 0: rot == 0)
+#pragma unroll
+         for (int j = 0; j < 8; j++) {
+            if ((uint32_t)j <= nl)
+               lo[0] = (lo[0] & ~(0xFu << (4 * j))) | ((uint32_t)(kClsStop | ((uint32_t)j == nl ? kClsNewline : 0)) << (4 * j));
+            if (8u + (uint32_t)j <= nl)
+               hi[0] = (hi[0] & ~(0xFu << (4 * j))) | ((uint32_t)(kClsStop | (8u + (uint32_t)j == nl ? kClsNewline : 0)) << (4 * j));
+         }
+      }
       if (pos0 + kK1LaneBytes > n) {        // bytes at or beyond n are STOP and never newlines
 #pragma unroll
          for (int k = 0; k < 8; k++) {
@@ -273,7 +286,8 @@ __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, 
          }
       }
       // the first line of the buffer has no newline in front of it
-      const uint32_t first = (tile == 0 && tid == 0 && n > 0 && !(a.fasta && buf[0] == '>')) ? 1u : 0u;
+      // (with a.skip > 0 the newline at skip-1 opens it like any other line)
+      const uint32_t first = (tile == 0 && tid == 0 && n > 0 && a.skip == 0u && !(a.fasta && buf[0] == '>')) ? 1u : 0u;
 
       // ---- one prefix over the lanes of the warp, then over the warps ------------
       const uint32_t cnt = (uint32_t)(__popc(c[0]) + __popc(c[1]) + __popc(c[2]) + __popc(c[3])) + first;
