@@ -95,6 +95,20 @@ struct Slot {
    bool busy = false;
    // host-path bookkeeping
    size_t chunk_off = 0;
+   // the scan as a CUDA graph: a scan that repeats the one before it (same text, size, options,
+   // stream and engine state) is captured once and replayed with one launch from then on
+   struct GraphKey {
+      const uint8_t *text = nullptr;
+      uint32_t n = 0, skip = 0;
+      int options = -1;
+      cudaStream_t st = nullptr;
+      unsigned long long version = 0;
+      bool operator==(const GraphKey &o) const
+      { return text == o.text && n == o.n && skip == o.skip && options == o.options && st == o.st && version == o.version; }
+   } gkey;
+   cudaGraphExec_t gexec = nullptr;
+   uint32_t glaunches = 0;
+   bool gbroken = false;          // a capture failed once: this slot stays eager
 };
 
 struct sqb_engine {
@@ -127,6 +141,8 @@ struct sqb_engine {
    sqb_stats_t last_stats;
    unsigned long long *d_word = nullptr, *h_word = nullptr;     // device_cuts: one word each
    cudaStream_t big_stream = nullptr;                           // sqbScanDeviceLarge: the kernels of all chunks
+   bool graphs = true;                                          // SEEQ_B200_GRAPHS=0 disables graph replay
+   unsigned long long version = 1;                              // bumped whenever a capacity guess or a mode changes
 };
 
 // ---------------------------------------------------------------------------
@@ -280,6 +296,7 @@ static void slot_free(Slot &s)
    cudaFree(s.d_ev); cudaFree(s.d_recs); cudaFree(s.d_ctl);
    cudaFreeHost(s.h_ctr); cudaFreeHost(s.h_recs); cudaFreeHost(s.h_ls); cudaFreeHost(s.h_init);
    for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
+   if (s.gexec) cudaGraphExecDestroy(s.gexec);
    if (s.stream) cudaStreamDestroy(s.stream);
    s = Slot();
 }
@@ -465,8 +482,8 @@ static int launch_bitslice(const sqb_engine *e, int mode, int options, size_t ma
    return -1;
 }
 
-static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n, int options, cudaStream_t st,
-                      uint32_t skip = 0)
+static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n, int options, cudaStream_t st,
+                        uint32_t skip)
 {
    const int mode = mode_of(options);
    const bool single = options & SQB_SINGLE_LINE;
@@ -668,6 +685,54 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
    }
    if (timing) CU(cudaEventRecord(s.ev[E_FIN_END], st));
    CU(cudaMemcpyAsync(s.h_ctr, ctr, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+   return 0;
+}
+
+// Queue one scan on `st`.  The first scan of a kind is enqueued call by call; when the next one
+// repeats it exactly, the same calls are recorded into a CUDA graph (stream capture: every
+// capacity is in place by then, so no allocation happens underneath) and from then on a scan is
+// ONE graph launch -- the ~15 launches and memsets of a step cost the host nothing, and the
+// device runs them back to back.  Not with SQB_TIMING (the caller wants events around single
+// kernels) and not for single strings.
+static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n, int options, cudaStream_t st,
+                      uint32_t skip = 0)
+{
+   Slot::GraphKey key;
+   key.text = d_text; key.n = n; key.skip = skip; key.options = options; key.st = st; key.version = e->version;
+   const bool eligible = e->graphs && !s.gbroken && !(options & (SQB_TIMING | SQB_SINGLE_LINE)) && st != nullptr;
+   if (eligible && key == s.gkey) {
+      if (s.gexec == nullptr) {
+         cudaGraph_t graph = nullptr;
+         bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+         if (ok) {
+            const int rc = slot_enqueue(e, s, d_text, n, options, st, skip);
+            const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            ok = rc == 0 && ce == cudaSuccess && graph != nullptr;
+            if (ok) ok = cudaGraphInstantiate(&s.gexec, graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+         }
+         if (!ok) {
+            cudaGetLastError();
+            if (s.gexec) { cudaGraphExecDestroy(s.gexec); s.gexec = nullptr; }
+            s.gbroken = true;
+         } else {
+            s.glaunches = s.launches;
+         }
+      }
+      if (s.gexec != nullptr) {
+         s.cur_text = d_text; s.cur_n = n; s.cur_skip = skip; s.cur_options = options; s.cur_stream = st;
+         s.launches = s.glaunches;
+         s.busy = true;
+         CU(cudaGraphLaunch(s.gexec, st));
+         CU(cudaEventRecord(s.ev[E_DONE], st));
+         return 0;
+      }
+   } else if (s.gexec != nullptr) {
+      cudaGraphExecDestroy(s.gexec);
+      s.gexec = nullptr;
+   }
+   s.gkey = eligible ? key : Slot::GraphKey();
+   if (slot_enqueue(e, s, d_text, n, options, st, skip)) return -1;
    CU(cudaEventRecord(s.ev[E_DONE], st));
    return 0;
 }
@@ -699,6 +764,7 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
          again = true;
       }
       if (!again) break;
+      e->version++;
       if (++reruns > 3) { set_err("capacity re-run did not converge"); return -1; }
       if (slot_issue(e, s, s.cur_text, s.cur_n, s.cur_options, s.cur_stream, s.cur_skip)) return -1;
    }
@@ -707,6 +773,7 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
       // the probe: keep filtering if it drops a quarter of the lines or more
       const double live = (double)s.h_ctr[C_NACTIVE] / (double)s.h_ctr[C_NPSEUDO];
       e->filter_state = live <= 0.75 ? 1 : 0;
+      e->version++;
    }
    if (stats) {
       memset(stats, 0, sizeof *stats);
@@ -808,6 +875,7 @@ sqb_engine_t *sqbEngineNew(const unsigned char *keys, int m, int tau, int device
    if (const char *c = getenv("SEEQ_B200_CUTS")) e->cuts = atoi(c);
    if (const char *c = getenv("SEEQ_B200_FILTER")) e->filter = atoi(c);
    if (const char *c = getenv("SEEQ_B200_NFA")) e->nfa_levels = atoi(c) != 0;
+   if (const char *c = getenv("SEEQ_B200_GRAPHS")) e->graphs = atoi(c) != 0;
    return e;
 }
 

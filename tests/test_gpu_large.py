@@ -272,3 +272,40 @@ def test_full_size_properties(B, oracle, cfg):
         sq.close()
     finally:
         L.sqbDeviceFree(d_text)
+
+
+def test_repeated_scans_replay_a_graph(B, oracle):
+    """A scan that repeats the one before it is captured into a CUDA graph and replayed: same
+    results as the call-by-call scan, and a replay follows the CONTENT of the buffer (the graph
+    holds addresses and sizes, not data)."""
+    rng = random.Random(77)
+    pattern, tau = "GATCGGAAGAGC", 2
+    keys, _ = oracle.parse(pattern)
+    sq = B.Seeq(pattern, tau)
+    eng = B.Engine.borrowed(sq.engine())
+    L = B.lib()
+    bufs = [make_buffer(rng, keys, tau, 40000, 150, "ACGTN") for _ in range(2)]
+    n = min(len(b) for b in bufs)
+    bufs = [b[:n - 1] + b"\n" for b in bufs]
+    d = DevBuf(B, bufs[0])
+    for mo in (SQ_BEST, SQ_ALL):
+        for rep in range(5):
+            data = bufs[rep >= 3]                      # same address and size, other bytes
+            if rep == 3:
+                arr = np.frombuffer(data, dtype=np.uint8)
+                assert L.sqbMemcpyH2D(d.ptr, arr.ctypes.data, n) == 0
+            exp, nl, nm = oracle.buffer_scan(data, keys, tau, mo)
+            st = eng.scan_device(d.ptr, n, mo)
+            got = eng.fetch_records(st.nrecs)
+            assert (st.nlines, st.nmatched) == (nl, nm)
+            assert rec_rows(got) == [tuple(int(x) for x in row) for row in exp], (mo, rep)
+        arr = np.frombuffer(bufs[0], dtype=np.uint8)
+        assert L.sqbMemcpyH2D(d.ptr, arr.ctypes.data, n) == 0
+    # two scans in flight, both slots replaying
+    for rep in range(4):
+        eng.scan_device_issue(0, d.ptr, n, SQ_BEST)
+        eng.scan_device_issue(1, d.ptr, n, SQ_BEST)
+        a, b = eng.scan_device_wait(0), eng.scan_device_wait(1)
+        assert (a.nlines, a.nmatched, a.nrecs) == (b.nlines, b.nmatched, b.nrecs)
+    d.free()
+    sq.close()
