@@ -104,7 +104,7 @@ def test_large_small_chunks_fasta_and_fastq(B, oracle, monkeypatch):
     keys, _ = oracle.parse(pattern)
     # FASTA: headers are skipped and not counted
     lines = []
-    for r in range(24000):
+    for r in range(40000):
         if r % 3 == 0:
             lines.append(">seq%d GATCGGAAGAGC" % r)
         lines.append("".join(rng.choice("ACGT") for _ in range(rng.randint(0, 120))) +
@@ -116,7 +116,7 @@ def test_large_small_chunks_fasta_and_fastq(B, oracle, monkeypatch):
     # FASTQ-like: the line filter drops three lines out of four
     for filt in ("1", "2"):
         monkeypatch.setenv("SEEQ_B200_FILTER", filt)
-        fq = fastq_like(rng, keys, 2, 12000, 150)
+        fq = fastq_like(rng, keys, 2, 24000, 150)
         assert len(fq) > (2 << 20)
         for mo in (SQ_FIRST, SQ_ALL):
             check_large(B, oracle, pattern, 2, fq, mo)
