@@ -105,6 +105,87 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, BlockScanSm
 }
 
 // ---------------------------------------------------------------------------
+// exclusive prefix sums of a whole array by ONE CTA of 1024 threads
+// ---------------------------------------------------------------------------
+// The per-tile arrays of a scan (tens of thousands of entries) are turned into offsets by a
+// single CTA between two grid-wide kernels, so what counts is latency: every round loads 8192
+// entries with coalesced, independent loads into shared memory, each thread then owns 8
+// CONTIGUOUS entries (padded index: conflict-free), one block scan of the 1024 thread sums
+// places them, and the offsets leave through shared memory again, coalesced.
+constexpr uint32_t kCtaScanRound = 8192;
+struct CtaScanSmem {
+   uint32_t stage[kCtaScanRound + kCtaScanRound / 32];
+   unsigned long long warp_sum[32];
+   uint32_t warp_max[32];
+};
+
+// out[i] = (uint32_t)(sum of in[0..i)); returns the total to every thread; *maxv (optional) = max in[]
+__device__ __forceinline__ unsigned long long cta_scan_u32(const uint32_t *in, uint32_t *out, uint32_t n,
+                                                           CtaScanSmem &sm, uint32_t *maxv = nullptr)
+{
+   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;      // blockDim.x == 1024
+   unsigned long long carry = 0;
+   uint32_t mx = 0;
+   for (uint32_t base = 0; base < n; base += kCtaScanRound) {
+#pragma unroll
+      for (uint32_t k = 0; k < 8; k++) {
+         const uint32_t idx = k * 1024u + tid, i = base + idx;
+         sm.stage[idx + (idx >> 5)] = i < n ? in[i] : 0u;
+      }
+      __syncthreads();
+      uint32_t loc[8];
+      unsigned long long sum = 0;
+#pragma unroll
+      for (uint32_t k = 0; k < 8; k++) {
+         const uint32_t idx = tid * 8u + k;
+         loc[k] = sm.stage[idx + (idx >> 5)];
+         sum += loc[k];
+         mx = max(mx, loc[k]);
+      }
+      unsigned long long x = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+         const unsigned long long y = __shfl_up_sync(kFull, x, d);
+         if (lane >= (uint32_t)d) x += y;
+      }
+      if (lane == 31u) sm.warp_sum[warp] = x;
+      __syncthreads();
+      unsigned long long before = 0, tot = 0;
+#pragma unroll 8
+      for (uint32_t w = 0; w < 32; w++) {
+         const unsigned long long y = sm.warp_sum[w];
+         if (w < warp) before += y;
+         tot += y;
+      }
+      unsigned long long run = carry + before + x - sum;
+#pragma unroll
+      for (uint32_t k = 0; k < 8; k++) {
+         const uint32_t idx = tid * 8u + k;
+         sm.stage[idx + (idx >> 5)] = (uint32_t)run;
+         run += loc[k];
+      }
+      __syncthreads();
+#pragma unroll
+      for (uint32_t k = 0; k < 8; k++) {
+         const uint32_t idx = k * 1024u + tid, i = base + idx;
+         if (i < n) out[i] = sm.stage[idx + (idx >> 5)];
+      }
+      carry += tot;
+      __syncthreads();
+   }
+   if (maxv) {
+      mx = __reduce_max_sync(kFull, mx);
+      if (lane == 0u) sm.warp_max[warp] = mx;
+      __syncthreads();
+      uint32_t m2 = 0;
+      for (uint32_t w = 0; w < 32; w++) m2 = max(m2, sm.warp_max[w]);
+      *maxv = m2;
+      __syncthreads();
+   }
+   return carry;
+}
+
+// ---------------------------------------------------------------------------
 // decoupled look-back: tile `tile` publishes its aggregate and obtains the sum
 // of the aggregates of all earlier tiles.  status[] must be zero before the
 // launch.  Word layout: bits 63:62 = 0 empty / 1 aggregate / 2 inclusive

@@ -798,6 +798,14 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
    return 0;
 }
 
+// records of a chunk -> buffer-global line numbers
+static __global__ void k_add_line_base(Rec *recs, unsigned long long n, uint32_t base)
+{
+   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+        i += (unsigned long long)gridDim.x * blockDim.x)
+      recs[i].line += base;
+}
+
 // last (or first) '\n' of text[lo, hi): *out = max (min) over 1 + its position
 static __global__ void k_find_newline(const uint8_t *text, unsigned long long lo, unsigned long long hi, int last,
                                       unsigned long long *out)
@@ -994,6 +1002,13 @@ static int host_collect(sqb_engine *e, Slot &s, int options, uint64_t *line_base
          e->host_recs = bigger;
          e->host_recs_cap = cap;
       }
+      // lines of a chunk are numbered from 0 on the device: rebase them there, before the copy
+      // (the scan is complete; the slot's stream carries only this)
+      if (*line_base) {
+         k_add_line_base<<<(int)std::min<size_t>(div_up((size_t)st.nrecs, 256), (size_t)e->sms * 8), 256, 0, s.stream>>>(
+            s.d_recs, st.nrecs, (uint32_t)*line_base);
+         CU(cudaGetLastError());
+      }
       CU(cudaMemcpyAsync(e->host_recs + e->host_recs_n, s.d_recs, st.nrecs * sizeof(Rec), cudaMemcpyDeviceToHost, s.stream));
    }
    if ((options & SQB_KEEP_LINES_INTERNAL) && st.nlines > 0) {
@@ -1001,13 +1016,7 @@ static int host_collect(sqb_engine *e, Slot &s, int options, uint64_t *line_base
       CU(cudaMemcpyAsync(s.h_ls, s.d_ls, st.nlines * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
    }
    CU(cudaStreamSynchronize(s.stream));
-   if (!count_only && st.nrecs > 0) {
-      const uint32_t lb = (uint32_t)*line_base;        // lines of a chunk are numbered from 0 on the device
-      sqb_rec_t *dst = e->host_recs + e->host_recs_n;
-      if (lb)
-         for (uint64_t k = 0; k < st.nrecs; k++) dst[k].line += lb;
-      e->host_recs_n += (size_t)st.nrecs;
-   }
+   if (!count_only && st.nrecs > 0) e->host_recs_n += (size_t)st.nrecs;
    if ((options & SQB_KEEP_LINES_INTERNAL) && st.nlines > 0) {
       const size_t old = e->host_lines.size();
       e->host_lines.resize(old + st.nlines);

@@ -124,46 +124,13 @@ static __global__ void __launch_bounds__(kThreads) k15_tile_cols(const BsPrepArg
 // cuts (and keeps cutting from then on); no matcher runs
 static __global__ void __launch_bounds__(1024) k15_scan(const BsPrepArgs a)
 {
-   __shared__ unsigned long long s_warp[32];
-   __shared__ uint32_t s_max[32];
-   __shared__ unsigned long long s_carry;
-   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   __shared__ CtaScanSmem cs;
    const unsigned long long nl_dev = a.ctr[C_NPSEUDO];
    const uint32_t nlines = bs_nslots(a.ctr, a.act, a.max_lines);
    const uint32_t ntiles = (nlines + kBsTileLines - 1) / kBsTileLines;
-   if (tid == 0) s_carry = 0;
-   __syncthreads();
-   uint32_t mymax = 0;
-   for (uint32_t t0 = 0; t0 < ntiles; t0 += 1024) {
-      const uint32_t t = t0 + tid;
-      const unsigned long long v = t < ntiles ? a.tile_cols[t] : 0u;
-      mymax = max(mymax, (uint32_t)v);
-      unsigned long long x = v;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-         const unsigned long long y = __shfl_up_sync(kFull, x, d);
-         if (lane >= d) x += y;
-      }
-      if (lane == 31) s_warp[warp] = x;
-      __syncthreads();
-      unsigned long long before = s_carry, tot = 0;
-      for (int w = 0; w < 32; w++) {
-         const unsigned long long y = s_warp[w];
-         if (w < warp) before += y;
-         tot += y;
-      }
-      if (t < ntiles) a.tile_off[t] = (uint32_t)(before + x - v);      // total <= text bytes < 2^32
-      __syncthreads();
-      if (tid == 0) s_carry += tot;
-      __syncthreads();
-   }
-   mymax = __reduce_max_sync(kFull, mymax);
-   if (lane == 0) s_max[warp] = mymax;
-   __syncthreads();
-   if (tid == 0) {
-      uint32_t mx = 0;
-      for (int w = 0; w < 32; w++) mx = max(mx, s_max[w]);
-      const unsigned long long cols = s_carry;
+   uint32_t mx = 0;
+   const unsigned long long cols = cta_scan_u32(a.tile_cols, a.tile_off, ntiles, cs, &mx);   // total <= text bytes < 2^32
+   if (threadIdx.x == 0) {
       // with segment cuts the entries of ls are segments: only the bit-sliced kernel knows them
       const bool want = nl_dev <= a.max_lines &&
                         ((a.lid != nullptr && a.ctr[C_NCUTS] != 0ull) || (nl_dev >= a.gate.min_lines && mx <= a.gate.max_line + 1u));

@@ -393,32 +393,31 @@ __global__ void __launch_bounds__(kThreads, 3) k1_scan_classify(const K1Args a, 
          idx++;
          myalive++;
       }
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-         const uint32_t bits = c[q];
-         if (bits == 0) continue;
-         const uint32_t p = pos0 + 32u * (uint32_t)q + 1u;
-         if ((bits & (bits - 1)) == 0) {           // one line start in these 32 bytes (the usual case)
-            const int b = __ffs(bits) - 1;
-            const uint32_t s = p + 8u * (uint32_t)(b & 3) + (uint32_t)(b >> 2);
+      // One line start per lane and round: the warp runs as many rounds as its busiest lane has
+      // starts (FASTQ-like text: 3-4), all lanes in step.  The starts of a lane are taken in BIT
+      // order of c[q], which is not text order (bit 4i+e <=> byte 8e+i); the place of each among
+      // the starts of its lane comes from a popc over the bits that precede it in the text.
+      {
+         const uint32_t r1 = (uint32_t)__popc(c[0]), r2 = r1 + (uint32_t)__popc(c[1]), r3 = r2 + (uint32_t)__popc(c[2]);
+         uint32_t w0 = c[0], w1 = c[1], w2 = c[2], w3 = c[3];
+         for (uint32_t left = cnt - first; left != 0u; left--) {
+            const uint32_t q = w0 ? 0u : (w1 ? 1u : (w2 ? 2u : 3u));
+            const uint32_t cur = w0 ? w0 : (w1 ? w1 : (w2 ? w2 : w3));
+            const uint32_t orig = q == 0u ? c[0] : (q == 1u ? c[1] : (q == 2u ? c[2] : c[3]));
+            const uint32_t rbase = q == 0u ? 0u : (q == 1u ? r1 : (q == 2u ? r2 : r3));
+            const uint32_t b = (uint32_t)__ffs(cur) - 1u, e = b & 3u;
+            const uint32_t rest = cur & (cur - 1u);
+            if (q == 0u) w0 = rest;
+            else if (q == 1u) w1 = rest;
+            else if (q == 2u) w2 = rest;
+            else w3 = rest;
+            // starts of this word in front of byte 8e+i: all of the bytes 8e'+i' with e' < e, and i' < i of e
+            const uint32_t before_b = (0x11111111u * ((1u << e) - 1u)) | ((0x11111111u << e) & ((1u << (b & ~3u)) - 1u));
+            const uint32_t at = idx + rbase + (uint32_t)__popc(orig & before_b);
+            const uint32_t s = pos0 + 32u * q + 1u + 8u * e + (b >> 2);
             const uint32_t fl = dead_flag(s);
-            if (idx < a.ls_cap) a.ls_raw[idx] = s | fl;
-            idx++;
-            mylast = s + 1u;
-         } else {                                  // several: walk them in text order
-#pragma unroll 1
-            for (int e = 0; e < 4; e++) {
-               uint32_t be = bits & (0x11111111u << e);
-               while (be) {
-                  const int b = __ffs(be) - 1;
-                  be &= be - 1;
-                  const uint32_t s = p + 8u * (uint32_t)e + (uint32_t)(b >> 2);
-                  const uint32_t fl = dead_flag(s);
-                  if (idx < a.ls_cap) a.ls_raw[idx] = s | fl;
-                  idx++;
-                  mylast = s + 1u;
-               }
-            }
+            if (at < a.ls_cap) a.ls_raw[at] = s | fl;
+            mylast = max(mylast, s + 1u);
          }
       }
       if (CUT) {
@@ -464,6 +463,18 @@ static __global__ void __launch_bounds__(1024) k1_scan_tiles(const K1ScanArgs a)
    __shared__ uint32_t s_max[32];
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const bool cut = a.tile_real != nullptr && a.ctr[C_NCUTS] != 0ull;     // K1 is complete: the count is final
+   if (!cut) {                            // the usual case: one or two plain prefix sums
+      __shared__ CtaScanSmem cs;
+      const unsigned long long total = cta_scan_u32(a.tile_cnt, a.tile_base, a.ntiles, cs);
+      unsigned long long alive = total;
+      if (a.tile_alive != nullptr) alive = cta_scan_u32(a.tile_alive, a.tile_abase, a.ntiles, cs);
+      if (threadIdx.x == 0) {
+         a.ctr[C_NPSEUDO] = total;
+         a.ctr[C_NLINES] = total;
+         a.ctr[C_NACTIVE] = alive;
+      }
+      return;
+   }
    // warp w owns the contiguous run [w*per, (w+1)*per) and walks it 32 tiles at a
    // time (coalesced): first its totals, then -- after the 32 totals are scanned --
    // the exclusive prefix of every tile
@@ -1107,40 +1118,21 @@ static __global__ void __launch_bounds__(kThreads) k_tile_sums(const TileSumArgs
 
 static __global__ void __launch_bounds__(1024) k_tile_scan(const TileSumArgs a)
 {
-   __shared__ unsigned long long s_warp[32], s_nz[32];
+   __shared__ CtaScanSmem cs;
+   __shared__ unsigned long long s_nz[32];
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const uint32_t nlines = (uint32_t)min(a.ctr[C_NPSEUDO], (unsigned long long)a.max_lines);
    const uint32_t ntiles = (nlines + kFinTile - 1) / kFinTile;
-   const uint32_t per = (ntiles + 1023u) / 1024u;
-   const uint32_t t0 = min((uint32_t)tid * per, ntiles), t1 = min(t0 + per, ntiles);
-   unsigned long long sum = 0, nz = 0;
-   for (uint32_t t = t0; t < t1; t++) {
-      sum += a.tile_sum[t];
-      nz += a.tile_nz[t];
-   }
-   unsigned long long x = sum;
+   unsigned long long nz = 0;
+   for (uint32_t t = (uint32_t)tid; t < ntiles; t += 1024u) nz += a.tile_nz[t];
 #pragma unroll
-   for (int d = 1; d < 32; d <<= 1) {
-      const unsigned long long y = __shfl_up_sync(kFull, x, d);
-      if (lane >= d) x += y;
-   }
-   nz = __reduce_add_sync(kFull, (uint32_t)nz);          // a tile has <= 1024 lines, a warp <= 2^20
-   if (lane == 31) s_warp[warp] = x;
+   for (int d = 16; d > 0; d >>= 1) nz += __shfl_xor_sync(kFull, nz, d);
    if (lane == 0) s_nz[warp] = nz;
-   __syncthreads();
-   unsigned long long before = 0, tot = 0, tnz = 0;
-   for (int w = 0; w < 32; w++) {
-      const unsigned long long y = s_warp[w];
-      if (w < warp) before += y;
-      tot += y;
-      tnz += s_nz[w];
-   }
-   unsigned long long run = before + x - sum;
-   for (uint32_t t = t0; t < t1; t++) {
-      a.tile_base[t] = (uint32_t)run;                    // records of a batch fit 32 bits (checked by the host)
-      run += a.tile_sum[t];
-   }
+   // records of a batch fit 32 bits (checked by the host)
+   const unsigned long long tot = cta_scan_u32(a.tile_sum, a.tile_base, ntiles, cs);      // syncs: s_nz is visible
    if (tid == 0) {
+      unsigned long long tnz = 0;
+      for (int w = 0; w < 32; w++) tnz += s_nz[w];
       a.ctr[C_NRECS] = tot;
       a.ctr[C_NMATCHED] = tnz - a.ctr[C_NZ_CORR];        // SQ_ALL with cuts: lines, not segments, with records
    }

@@ -128,8 +128,8 @@ def test_large_small_chunks_long_lines(B, oracle, monkeypatch):
     rng = random.Random(31337)
     pattern = "".join(rng.choice("ACGT") for _ in range(40))
     keys, _ = oracle.parse(pattern)
-    buf = long_line_buffer(rng, keys, 4, 900, 10000, junk=5)
-    assert len(buf) > (3 << 20)
+    buf = long_line_buffer(rng, keys, 4, 1100, 10000, junk=5)
+    assert len(buf) > (2 << 20)
     for mo in (SQ_FIRST, SQ_BEST, SQ_ALL):
         check_large(B, oracle, pattern, 4, buf, mo | SQ_CONVERT)
 
