@@ -107,7 +107,7 @@ struct Slot {
       { return text == o.text && n == o.n && skip == o.skip && options == o.options && st == o.st && version == o.version; }
    } gkey;
    cudaGraphExec_t gexec = nullptr;
-   uint32_t glaunches = 0;
+   uint32_t glaunches = 0, grepeats = 0;
    bool gbroken = false;          // a capture failed once: this slot stays eager
 };
 
@@ -688,19 +688,22 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
    return 0;
 }
 
-// Queue one scan on `st`.  The first scan of a kind is enqueued call by call; when the next one
-// repeats it exactly, the same calls are recorded into a CUDA graph (stream capture: every
+// Queue one scan on `st`.  A scan is enqueued call by call; when the same scan has been asked for
+// three times in a row, the same calls are recorded into a CUDA graph (stream capture: every
 // capacity is in place by then, so no allocation happens underneath) and from then on a scan is
 // ONE graph launch -- the ~15 launches and memsets of a step cost the host nothing, and the
 // device runs them back to back.  Not with SQB_TIMING (the caller wants events around single
 // kernels) and not for single strings.
 static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n, int options, cudaStream_t st,
-                      uint32_t skip = 0)
+                      uint32_t skip = 0, bool may_replay = false)
 {
    Slot::GraphKey key;
    key.text = d_text; key.n = n; key.skip = skip; key.options = options; key.st = st; key.version = e->version;
-   const bool eligible = e->graphs && !s.gbroken && !(options & (SQB_TIMING | SQB_SINGLE_LINE)) && st != nullptr;
-   if (eligible && key == s.gkey) {
+   // only the direct device scans replay (the chunk pipelines scan a different chunk every time, and
+   // two chunks of equal size in a row would pay for an instantiation that is used once), and only
+   // from the third identical scan on
+   const bool eligible = may_replay && e->graphs && !s.gbroken && !(options & (SQB_TIMING | SQB_SINGLE_LINE)) && st != nullptr;
+   if (eligible && key == s.gkey && ++s.grepeats >= 2) {
       if (s.gexec == nullptr) {
          cudaGraph_t graph = nullptr;
          bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess;
@@ -731,6 +734,7 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
       cudaGraphExecDestroy(s.gexec);
       s.gexec = nullptr;
    }
+   if (!(eligible && key == s.gkey)) s.grepeats = 0;
    s.gkey = eligible ? key : Slot::GraphKey();
    if (slot_enqueue(e, s, d_text, n, options, st, skip)) return -1;
    CU(cudaEventRecord(s.ev[E_DONE], st));
@@ -915,7 +919,7 @@ int sqbScanDevice(sqb_engine_t *e, const void *d_text, size_t nbytes, int option
       return 0;
    }
    cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
-   if (slot_issue(e, s, (const uint8_t *)d_text, (uint32_t)nbytes, options, st)) return -1;
+   if (slot_issue(e, s, (const uint8_t *)d_text, (uint32_t)nbytes, options, st, 0, true)) return -1;
    if (slot_finish(e, s, &e->last_stats)) return -1;
    if (stats) *stats = e->last_stats;
    return 0;
@@ -930,7 +934,7 @@ int sqbScanDeviceIssue(sqb_engine_t *e, int slot, const void *d_text, size_t nby
    Slot &s = e->slot[slot];
    if (slot_init(s)) return -1;
    if (s.busy) { set_err("sqbScanDeviceIssue: slot %d has a scan in flight", slot); return -1; }
-   return slot_issue(e, s, (const uint8_t *)d_text, (uint32_t)nbytes, options, stream ? (cudaStream_t)stream : s.stream);
+   return slot_issue(e, s, (const uint8_t *)d_text, (uint32_t)nbytes, options, stream ? (cudaStream_t)stream : s.stream, 0, true);
 }
 
 int sqbScanDeviceWait(sqb_engine_t *e, int slot, sqb_stats_t *stats)

@@ -168,11 +168,16 @@ __device__ __forceinline__ void null_fill(uint32_t (&w)[4], uint32_t c0, uint32_
 }
 
 // 32x32 bit transpose across the warp: on return lane j holds, in bit i, bit j
-// of lane i's input.  keep[s] / rot[s] are per-lane constants of stage s.
-__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, const uint32_t (&keep)[5], const uint32_t (&rot)[5])
+// of lane i's input.  keep[s] / rot[s] are per-lane constants of stage s.  The
+// first two stages exchange whole half-words and bytes: one PRMT each (sel16 /
+// sel8, per-lane selectors) instead of mask + funnel shift + merge.
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, const uint32_t (&keep)[5], const uint32_t (&rot)[5],
+                                                     uint32_t sel16, uint32_t sel8)
 {
+   x = __byte_perm(x, __shfl_xor_sync(kFull, x, 16), sel16);
+   x = __byte_perm(x, __shfl_xor_sync(kFull, x, 8), sel8);
 #pragma unroll
-   for (int s = 0; s < 5; s++) {
+   for (int s = 2; s < 5; s++) {
       const uint32_t y = __shfl_xor_sync(kFull, x, 16 >> s);
       x = (x & keep[s]) | (__funnelshift_l(y, y, rot[s]) & ~keep[s]);
    }
@@ -243,6 +248,8 @@ static __global__ void __launch_bounds__(kThreads, 4) k15_pack(const BsPackArgs 
          rot[s] = (lane & d) ? 32u - d : d;
       }
    }
+   // stage 0: low half of x | low half of y << 16, or (lanes 16..31) y >> 16 | high half of x; stage 1 alike per byte
+   const uint32_t sel16 = (lane & 16) ? 0x3276u : 0x5410u, sel8 = (lane & 8) ? 0x3715u : 0x6240u;
    const uint32_t wid = (blockIdx.x * kThreads + threadIdx.x) >> 5, nw = (gridDim.x * kThreads) >> 5;
    for (uint32_t pair = wid; pair < npairs; pair += nw) {
       const uint32_t tile = pair >> 4;                          // 16 pairs of groups per tile
@@ -280,8 +287,8 @@ static __global__ void __launch_bounds__(kThreads, 4) k15_pack(const BsPackArgs 
          }
 #pragma unroll
          for (int k = 0; k < 4; k++) {
-            const uint32_t ta = warp_transpose32(wa[k], keep, rot);
-            const uint32_t tb = warp_transpose32(wb[k], keep, rot);
+            const uint32_t ta = warp_transpose32(wa[k], keep, rot, sel16, sel8);
+            const uint32_t tb = warp_transpose32(wb[k], keep, rot, sel16, sel8);
             // lane j holds plane (j&3) of column (j>>2): pair up planes 0|1 and 2|3
             const uint32_t give = (lane & 1) ? ta : tb;
             const uint32_t got = __shfl_xor_sync(kFull, give, 1);
