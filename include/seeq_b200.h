@@ -142,6 +142,24 @@ long seeqBatchMatch (struct seeq_t * sq, const char * text, size_t nbytes,
 /* the engine behind a seeq_t (created on first use); NULL if no device */
 sqb_engine_t * seeqEngine (struct seeq_t * sq);
 
+/* ---- pattern sets: several patterns over ONE pass of the text -------------------------- */
+/* Adapter / barcode sets (the extension the reference's authors name, doc/response.tex:358-360).
+ * The text crosses PCIe once and is tokenized (K1) and packed into bit-planes once; every
+ * pattern then runs its own matcher (K2) and finishing kernels (K3/K4) on the staged planes.
+ * Results are those of npatterns independent scans: one stats entry per pattern (caller's
+ * order), records of pattern p via sqbHostRecords(sqbMultiEngine(mp, p), &n), with
+ * buffer-global line indices.  Any buffer size; device text needs no alignment. */
+typedef struct sqb_multi sqb_multi_t;
+sqb_multi_t  * sqbMultiNew    (int npatterns, const unsigned char * const * keys, const int * m,
+                               const int * tau, int device);
+void           sqbMultiFree   (sqb_multi_t * mp);
+int            sqbMultiCount  (sqb_multi_t * mp);
+sqb_engine_t * sqbMultiEngine (sqb_multi_t * mp, int pattern);
+int sqbMultiScanHost   (sqb_multi_t * mp, const char * text, size_t nbytes, int options,
+                        sqb_stats_t * stats /* [npatterns] */);
+int sqbMultiScanDevice (sqb_multi_t * mp, const void * d_text, size_t nbytes, int options,
+                        void * stream, sqb_stats_t * stats /* [npatterns] */);
+
 /* ---- multi-GPU helper ------------------------------------------------------ */
 /* Newline-aligned byte range of shard `rank` of `world` over a buffer: the
  * boundary k*nbytes/world is moved forward to just after the next '\n'. */

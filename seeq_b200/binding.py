@@ -103,6 +103,12 @@ SYMBOLS = {
     "sqbDeviceFree": (None, [C.c_void_p]),
     "sqbMemcpyH2D": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "sqbMemcpyD2H": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "sqbMultiNew": (C.c_void_p, [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]),
+    "sqbMultiFree": (None, [C.c_void_p]),
+    "sqbMultiCount": (C.c_int, [C.c_void_p]),
+    "sqbMultiEngine": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "sqbMultiScanHost": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(StatsT)]),
+    "sqbMultiScanDevice": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(StatsT)]),
     "seeqBatchMatch": (C.c_long, [_SEEQ, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                   C.POINTER(C.c_void_p), C.POINTER(StatsT)]),
     "seeqEngine": (C.c_void_p, [_SEEQ]),
@@ -297,6 +303,51 @@ class Engine:
         if count and self.L.sqbFetchLineStarts(self.e, out.ctypes.data, first, count):
             raise RuntimeError("sqbFetchLineStarts failed: " + last_error())
         return out
+
+
+class Multi:
+    """sqb_multi_t: a pattern set scanned over one pass of the text."""
+
+    def __init__(self, keys_list, taus, device: int = -1):
+        self.L = lib()
+        n = len(keys_list)
+        self.n = n
+        self._keep = [bytes(k) for k in keys_list]
+        arr = (C.c_char_p * n)(*self._keep)
+        ms = (C.c_int * n)(*[len(k) for k in self._keep])
+        ts = (C.c_int * n)(*taus)
+        self.mp = self.L.sqbMultiNew(n, arr, ms, ts, device)
+        if not self.mp:
+            raise RuntimeError("sqbMultiNew failed: " + last_error())
+
+    def close(self):
+        if getattr(self, "mp", None):
+            self.L.sqbMultiFree(self.mp)
+        self.mp = None
+
+    __del__ = close
+
+    def scan_host(self, buf, options: int):
+        addr, n, keep = _ptr(buf)
+        st = (StatsT * self.n)()
+        if self.L.sqbMultiScanHost(self.mp, addr, n, options, st):
+            raise RuntimeError("sqbMultiScanHost failed: " + last_error())
+        return list(st)
+
+    def scan_host_ptr(self, addr: int, n: int, options: int):
+        st = (StatsT * self.n)()
+        if self.L.sqbMultiScanHost(self.mp, addr, n, options, st):
+            raise RuntimeError("sqbMultiScanHost failed: " + last_error())
+        return list(st)
+
+    def scan_device(self, d_ptr: int, nbytes: int, options: int, stream: int = 0):
+        st = (StatsT * self.n)()
+        if self.L.sqbMultiScanDevice(self.mp, d_ptr, nbytes, options, stream, st):
+            raise RuntimeError("sqbMultiScanDevice failed: " + last_error())
+        return list(st)
+
+    def records(self, pattern: int) -> np.ndarray:
+        return Engine.borrowed(self.L.sqbMultiEngine(self.mp, pattern)).host_records()
 
 
 def make_gen(seed: int, line_len: int, plant: str = "", plant_per_1024: int = 0, max_edits: int = 0,

@@ -70,6 +70,8 @@ struct Slot {
    uint32_t *d_act = nullptr;   size_t act_cap = 0;       // line filter: entries of ls the matcher looks at
    uint8_t *d_lflags = nullptr; size_t lflags_cap = 0;    //              1 = dead on arrival
    bool cur_filter = false;
+   bool cur_bitslice = false;     // this scan produced class nibbles and bit-planes (a front others may share)
+   const Slot *cur_front = nullptr; // multi-pattern: the slot whose K1 / pack output this scan reads (or nullptr)
    uint4 *d_planes = nullptr;   size_t planes_cap = 0;    // bit-planes, 32 uint4 per tile column
    uint32_t *d_bstiles = nullptr; size_t bstiles_cap = 0; // per match tile: columns, offset
    uint32_t *d_fintiles = nullptr; size_t fintiles_cap = 0; // per 1024-line tile: records, matched lines, first record
@@ -125,6 +127,8 @@ struct sqb_engine {
                                   // 0 never, 1 if the first filtered scan drops >= 25 % of the lines, 2 always
    bool nfa_levels = true;        // tau <= 2: NFA-level automaton instead of Myers' (SEEQ_B200_NFA=0 disables)
    int filter_state = -1;         // filter == 1: -1 undecided (probe with the next scan), 0 off, 1 on
+   int filter_k = 1;              // a STOP among the first filter_k bytes kills a line: min(8, m - tau); the leader
+                                  // of a pattern set uses the smallest of the set
    BsGate bs_gate{65536u, 4096u};
    uint32_t bs_min_bytes = 1u << 20;
    double cols_per_byte = 1.3 / 1024.0;   // tile columns per text byte (plane buffer guess)
@@ -482,8 +486,11 @@ static int launch_bitslice(const sqb_engine *e, int mode, int options, size_t ma
    return -1;
 }
 
+// front != nullptr: the slot of ANOTHER engine that has scanned (or is scanning, earlier on the same
+// stream) the same text with the same options; its line starts, line filter and bit-planes are read
+// instead of being computed again (several patterns over one pass of the text).
 static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n, int options, cudaStream_t st,
-                        uint32_t skip)
+                        uint32_t skip, const Slot *front)
 {
    const int mode = mode_of(options);
    const bool single = options & SQB_SINGLE_LINE;
@@ -493,15 +500,19 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
    s.cur_skip = skip;
    s.cur_options = options;
    s.cur_stream = st;
+   s.cur_front = front;
    s.launches = 0;
    s.busy = true;
+   const Slot &f = front ? *front : s;                      // owner of ls, act, lflags, planes, bstiles
 
    // ---- capacities ----------------------------------------------------------
-   size_t want_lines = single ? 2 : (size_t)((double)n * e->lines_per_byte) + 1024;
-   if (want_lines > (size_t)n + 2) want_lines = (size_t)n + 2;
-   if (dev_reserve(&s.d_ls, &s.line_cap, want_lines)) return -1;
-   if (!single && dev_reserve(&s.d_ls_raw, &s.ls_raw_cap, s.line_cap, 64)) return -1;
-   const size_t lines_cap = s.line_cap - 1;                 // one entry is the sentinel
+   if (!front) {
+      size_t want_lines = single ? 2 : (size_t)((double)n * e->lines_per_byte) + 1024;
+      if (want_lines > (size_t)n + 2) want_lines = (size_t)n + 2;
+      if (dev_reserve(&s.d_ls, &s.line_cap, want_lines)) return -1;
+      if (!single && dev_reserve(&s.d_ls_raw, &s.ls_raw_cap, s.line_cap, 64)) return -1;
+   }
+   const size_t lines_cap = f.line_cap - 1;                 // one entry is the sentinel
    if (mode == M_FIRST || mode == M_BEST) {
       if (dev_reserve(&s.d_res, &s.res_cap, lines_cap, 64)) return -1;
       if (dev_reserve(&s.d_recs, &s.rec_cap, lines_cap, 64)) return -1;
@@ -523,12 +534,17 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
 
    if (timing) CU(cudaEventRecord(s.ev[E_BEGIN], st));
    CU(cudaMemsetAsync(s.d_ctl, 0, ctl_words * sizeof(unsigned long long), st));
-   const bool cut = !single && use_cuts(e, options, n);
-   const bool filter = !single && use_filter(e, options, n);
+   const bool cut = !single && !front && use_cuts(e, options, n);
+   const bool filter = front ? front->cur_filter : (!single && use_filter(e, options, n));
    s.cur_filter = filter;
 
    // ---- K1 ------------------------------------------------------------------
-   if (single) {
+   if (front) {
+      // the front's counters: lines, entries, the matcher decision, live entries
+      CU(cudaMemcpyAsync(ctr + C_NLINES, front->d_ctl + C_NLINES, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+      CU(cudaMemcpyAsync(ctr + C_BS_SELECTED, front->d_ctl + C_BS_SELECTED,
+                         (C_NACTIVE + 1 - C_BS_SELECTED) * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+   } else if (single) {
       s.h_init[0] = 0;
       s.h_init[1] = n;
       CU(cudaMemcpyAsync(s.d_ls, s.h_init, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
@@ -560,7 +576,7 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
       const uint32_t ntiles = (uint32_t)div_up(n, kK1Tile);
       K1Args k1{d_text, n, s.d_ls_raw, (uint32_t)s.line_cap, want_codes ? (uint2 *)s.d_codes : nullptr, ctr,
                 tile_cnt, tile_off, tile_real, tile_last, tile_alive,
-                (uint32_t)std::min(8, std::max(1, e->m - e->tau)), (options & SQB_FASTA) ? 1 : 0, skip};
+                (uint32_t)e->filter_k, (options & SQB_FASTA) ? 1 : 0, skip};
       ClassTable ct;
       build_class_table(options, &ct);
       static bool attr = false;
@@ -590,7 +606,7 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
       CU(cudaGetLastError());
       s.launches += 3;
    }
-   if (timing && single) CU(cudaEventRecord(s.ev[E_K1C_END], st));
+   if (timing && (single || front)) CU(cudaEventRecord(s.ev[E_K1C_END], st));
    if (timing) CU(cudaEventRecord(s.ev[E_K1_END], st));
 
    // ---- K2 ------------------------------------------------------------------
@@ -599,8 +615,9 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
    build_pattern(e, options, true, &rev);
    const size_t max_lines = single ? 1 : std::min<size_t>(lines_cap, n);
    const int lines_per_cta = e->words <= 2 ? kThreads : kThreads / e->words;
-   const bool bitslice = !single && use_bitslice(e, options, n);
-   K2Args k2{d_text, n, s.d_ls, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_ev,
+   const bool bitslice = !single && use_bitslice(e, options, n) && (!front || front->cur_bitslice);
+   s.cur_bitslice = bitslice && !front;
+   K2Args k2{d_text, n, f.d_ls, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_ev,
              (uint32_t)std::min<size_t>(s.ev_cap, 0xffffffffu), bitslice ? 1 : 0};
    if (timing && !bitslice) {
       CU(cudaEventRecord(s.ev[E_PACK_BEGIN], st));
@@ -613,30 +630,35 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
       if (mode == M_ALL && filter)      // the lines the filter drops are never written
          CU(cudaMemsetAsync(s.d_cnt, 0, std::min<size_t>(lines_cap, (size_t)n + 1) * sizeof(uint32_t), st));
       const size_t max_tiles = div_up(lines_cap, kBsTileLines) + 1;
-      if (dev_reserve(&s.d_bstiles, &s.bstiles_cap, 2 * max_tiles)) return -1;
-      const size_t want_cols = (size_t)((double)n * e->cols_per_byte) + 4096;
-      if (dev_reserve(&s.d_planes, &s.planes_cap, want_cols * 32, 16)) return -1;
-      uint32_t *tile_cols = s.d_bstiles, *tile_off = tile_cols + max_tiles;
+      if (!front) {
+         if (dev_reserve(&s.d_bstiles, &s.bstiles_cap, 2 * max_tiles)) return -1;
+         const size_t want_cols = (size_t)((double)n * e->cols_per_byte) + 4096;
+         if (dev_reserve(&s.d_planes, &s.planes_cap, want_cols * 32, 16)) return -1;
+      }
+      uint32_t *tile_cols = f.d_bstiles, *tile_off = tile_cols + max_tiles;
       const uint32_t wup = bs_warmup(e->m, e->tau);
       uint32_t *gmask = s.d_gmask, *gfollow = cut ? s.d_gmask + s.gmask_cap / 2 : nullptr;
       uint8_t *segstop = s.d_segflags;
-      BsPrepArgs bp{s.d_ls, (uint32_t)lines_cap, n, ctr, tile_cols, tile_off, (uint32_t)max_tiles,
-                    (unsigned long long)(s.planes_cap / 32), e->bs_gate, cut ? s.d_lid : nullptr, wup,
-                    (!cut && cuts_allowed(e, options, n)) ? 1 : 0, filter ? s.d_act : nullptr};
-      k15_tile_cols<<<(int)std::min<size_t>(div_up(max_tiles, kWarps), (size_t)e->sms * 8), kThreads, 0, st>>>(bp);
-      k15_scan<<<1, 1024, 0, st>>>(bp);
-      if (timing) CU(cudaEventRecord(s.ev[E_PACK_BEGIN], st));
-      BsPackArgs pk{(const uint4 *)s.d_codes, (uint32_t)(div_up(n, kK1Tile) * (kK1Tile / 32)), s.d_ls,
-                    (uint32_t)lines_cap, ctr, tile_cols, tile_off, s.d_planes, cut ? s.d_lid : nullptr, wup,
-                    gmask, gfollow, filter ? s.d_act : nullptr};
-      k15_pack<<<(int)std::max<size_t>(1, std::min<size_t>(div_up(div_up(max_lines, 64), kWarps), (size_t)e->sms * 16)),
-                 kThreads, 0, st>>>(pk);
-      CU(cudaGetLastError());
+      if (timing && front) CU(cudaEventRecord(s.ev[E_PACK_BEGIN], st));
+      if (!front) {
+         BsPrepArgs bp{s.d_ls, (uint32_t)lines_cap, n, ctr, tile_cols, tile_off, (uint32_t)max_tiles,
+                       (unsigned long long)(s.planes_cap / 32), e->bs_gate, cut ? s.d_lid : nullptr, wup,
+                       (!cut && cuts_allowed(e, options, n)) ? 1 : 0, filter ? s.d_act : nullptr};
+         k15_tile_cols<<<(int)std::min<size_t>(div_up(max_tiles, kWarps), (size_t)e->sms * 8), kThreads, 0, st>>>(bp);
+         k15_scan<<<1, 1024, 0, st>>>(bp);
+         if (timing) CU(cudaEventRecord(s.ev[E_PACK_BEGIN], st));
+         BsPackArgs pk{(const uint4 *)s.d_codes, (uint32_t)(div_up(n, kK1Tile) * (kK1Tile / 32)), s.d_ls,
+                       (uint32_t)lines_cap, ctr, tile_cols, tile_off, s.d_planes, cut ? s.d_lid : nullptr, wup,
+                       gmask, gfollow, filter ? s.d_act : nullptr};
+         k15_pack<<<(int)std::max<size_t>(1, std::min<size_t>(div_up(div_up(max_lines, 64), kWarps), (size_t)e->sms * 16)),
+                    kThreads, 0, st>>>(pk);
+         CU(cudaGetLastError());
+         s.launches += 3;
+      }
       if (timing) CU(cudaEventRecord(s.ev[E_PACK_END], st));
-      s.launches += 3;
-      K2BsArgs kb{s.d_planes, tile_cols, tile_off, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_ev, k2.ev_cap,
+      K2BsArgs kb{f.d_planes, tile_cols, tile_off, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_ev, k2.ev_cap,
                   (mode == M_COUNT || mode == M_COUNTALL) ? 1 : 0, cut ? gmask : nullptr, gfollow, segstop, wup,
-                  filter ? s.d_act : nullptr};
+                  filter ? f.d_act : nullptr};
       if (launch_bitslice(e, mode, options, max_lines, st, kb)) return -1;
       s.launches++;
    }
@@ -659,7 +681,7 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
 
    // ---- scan + K3/K4 --------------------------------------------------------
    uint32_t *tile_sum = s.d_fintiles, *tile_nz = tile_sum + fin_tiles, *tile_recbase = tile_nz + fin_tiles;
-   FinArgs fa{d_text, s.d_ls, (uint32_t)lines_cap, s.d_res, s.d_offs, s.d_ev, k2.ev_cap, s.d_recs,
+   FinArgs fa{d_text, f.d_ls, (uint32_t)lines_cap, s.d_res, s.d_offs, s.d_ev, k2.ev_cap, s.d_recs,
               (uint32_t)std::min<size_t>(s.rec_cap, 0xffffffffu), ctr, tile_recbase,
               cut ? s.d_lid : nullptr, cut ? s.d_lbeg : nullptr,
               (cut && mode == M_ALL) ? s.d_segflags + s.line_cap : nullptr, bs_warmup(e->m, e->tau)};
@@ -695,20 +717,20 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
 // device runs them back to back.  Not with SQB_TIMING (the caller wants events around single
 // kernels) and not for single strings.
 static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n, int options, cudaStream_t st,
-                      uint32_t skip = 0, bool may_replay = false)
+                      uint32_t skip = 0, bool may_replay = false, const Slot *front = nullptr)
 {
    Slot::GraphKey key;
    key.text = d_text; key.n = n; key.skip = skip; key.options = options; key.st = st; key.version = e->version;
    // only the direct device scans replay (the chunk pipelines scan a different chunk every time, and
    // two chunks of equal size in a row would pay for an instantiation that is used once), and only
    // from the third identical scan on
-   const bool eligible = may_replay && e->graphs && !s.gbroken && !(options & (SQB_TIMING | SQB_SINGLE_LINE)) && st != nullptr;
+   const bool eligible = may_replay && !front && e->graphs && !s.gbroken && !(options & (SQB_TIMING | SQB_SINGLE_LINE)) && st != nullptr;
    if (eligible && key == s.gkey && ++s.grepeats >= 2) {
       if (s.gexec == nullptr) {
          cudaGraph_t graph = nullptr;
          bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess;
          if (ok) {
-            const int rc = slot_enqueue(e, s, d_text, n, options, st, skip);
+            const int rc = slot_enqueue(e, s, d_text, n, options, st, skip, nullptr);
             const cudaError_t ce = cudaStreamEndCapture(st, &graph);
             ok = rc == 0 && ce == cudaSuccess && graph != nullptr;
             if (ok) ok = cudaGraphInstantiate(&s.gexec, graph, 0) == cudaSuccess;
@@ -724,6 +746,7 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
       }
       if (s.gexec != nullptr) {
          s.cur_text = d_text; s.cur_n = n; s.cur_skip = skip; s.cur_options = options; s.cur_stream = st;
+         s.cur_front = nullptr;
          s.launches = s.glaunches;
          s.busy = true;
          CU(cudaGraphLaunch(s.gexec, st));
@@ -736,7 +759,7 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
    }
    if (!(eligible && key == s.gkey)) s.grepeats = 0;
    s.gkey = eligible ? key : Slot::GraphKey();
-   if (slot_enqueue(e, s, d_text, n, options, st, skip)) return -1;
+   if (slot_enqueue(e, s, d_text, n, options, st, skip, front)) return -1;
    CU(cudaEventRecord(s.ev[E_DONE], st));
    return 0;
 }
@@ -751,15 +774,16 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
       const unsigned long long nlines = std::max(s.h_ctr[C_NLINES], s.h_ctr[C_NPSEUDO]);   // entries of ls
       const unsigned long long nev = s.h_ctr[C_EVENTS];
       bool again = false;
-      if (nlines + 1 > s.line_cap) {
+      const bool follower = s.cur_front != nullptr;         // the front's owner repeats a scan whose front was short
+      if (!follower && nlines + 1 > s.line_cap) {
          e->lines_per_byte = (double)(nlines + 2) / (double)std::max<uint32_t>(s.cur_n, 1) * 1.05;
          again = true;
       }
-      if (s.h_ctr[C_BS_SELECTED] == 3ull) {          // long lines: cut them, in this scan and from now on
+      if (!follower && s.h_ctr[C_BS_SELECTED] == 3ull) {          // long lines: cut them, in this scan and from now on
          e->cuts_wanted = true;
          again = true;
       }
-      if (s.h_ctr[C_BS_SELECTED] == 2ull) {          // plane buffer too small for the bit-sliced scan
+      if (!follower && s.h_ctr[C_BS_SELECTED] == 2ull) {          // plane buffer too small for the bit-sliced scan
          e->cols_per_byte = (double)(s.h_ctr[C_BS_COLS] + 64) / (double)std::max<uint32_t>(s.cur_n, 1) * 1.05;
          again = true;
       }
@@ -770,10 +794,10 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
       if (!again) break;
       e->version++;
       if (++reruns > 3) { set_err("capacity re-run did not converge"); return -1; }
-      if (slot_issue(e, s, s.cur_text, s.cur_n, s.cur_options, s.cur_stream, s.cur_skip)) return -1;
+      if (slot_issue(e, s, s.cur_text, s.cur_n, s.cur_options, s.cur_stream, s.cur_skip, false, s.cur_front)) return -1;
    }
    s.busy = false;
-   if (s.cur_filter && e->filter == 1 && e->filter_state < 0 && s.h_ctr[C_NPSEUDO] > 0) {
+   if (!s.cur_front && s.cur_filter && e->filter == 1 && e->filter_state < 0 && s.h_ctr[C_NPSEUDO] > 0) {
       // the probe: keep filtering if it drops a quarter of the lines or more
       const double live = (double)s.h_ctr[C_NACTIVE] / (double)s.h_ctr[C_NPSEUDO];
       e->filter_state = live <= 0.75 ? 1 : 0;
@@ -872,6 +896,7 @@ sqb_engine_t *sqbEngineNew(const unsigned char *keys, int m, int tau, int device
    e->m = m;
    e->tau = tau;
    memcpy(e->keys, keys, (size_t)m);
+   e->filter_k = std::min(8, std::max(1, m - tau));
    const int words = (m + 31) / 32;
    e->words = 1;
    while (e->words < words) e->words *= 2;
@@ -1081,19 +1106,25 @@ static int device_cuts(sqb_engine *e, const uint8_t *d_text, size_t nbytes, size
    return 0;
 }
 
-// The chunk pipeline behind sqbScanHost and sqbScanDeviceLarge: newline-aligned chunks, two slots,
-// the results of chunk k are collected while chunk k+1 runs.  Host text is copied into the slot's
-// device buffer; device text is scanned where it lies (a chunk that does not start on a 16-byte
-// boundary starts `skip` bytes into its aligned address, K1Args::skip).
-static int scan_chunks(sqb_engine *e, const char *text, size_t nbytes, int options, sqb_stats_t *stats,
+// The chunk pipeline behind sqbScanHost, sqbScanDeviceLarge and the multi-pattern scans:
+// newline-aligned chunks, two slots, the results of chunk k are collected while chunk k+1 runs.
+// Host text is copied into the slot's device buffer; device text is scanned where it lies (a chunk
+// that does not start on a 16-byte boundary starts `skip` bytes into its aligned address,
+// K1Args::skip).  With P > 1 engines (a pattern set), engs[0] scans every chunk in full and the
+// others read its line starts, line filter and bit-planes (slot_enqueue: front) on the same stream.
+static int scan_chunks(sqb_engine **engs, int P, const char *text, size_t nbytes, int options, sqb_stats_t *stats,
                        bool on_device, cudaStream_t user_stream)
 {
+   sqb_engine *e = engs[0];
    CU(cudaSetDevice(e->device));
-   for (auto &s : e->slot) if (slot_init(s)) return -1;
-   e->host_recs_n = 0;
-   e->host_lines.clear();
-   sqb_stats_t acc;
-   memset(&acc, 0, sizeof acc);
+   std::vector<sqb_stats_t> acc((size_t)P);
+   std::vector<uint64_t> line_base((size_t)P, 0);
+   for (int p = 0; p < P; p++) {
+      for (auto &s : engs[p]->slot) if (slot_init(s)) return -1;
+      engs[p]->host_recs_n = 0;
+      engs[p]->host_lines.clear();
+      memset(&acc[(size_t)p], 0, sizeof(sqb_stats_t));
+   }
    const bool single = options & SQB_SINGLE_LINE;
    const size_t chunk = on_device ? device_chunk_bytes() : host_chunk_bytes();
    std::vector<size_t> cuts;
@@ -1104,7 +1135,22 @@ static int scan_chunks(sqb_engine *e, const char *text, size_t nbytes, int optio
       if (e->big_stream == nullptr) CU(cudaStreamCreateWithFlags(&e->big_stream, cudaStreamNonBlocking));
       user_stream = e->big_stream;
    }
-   uint64_t line_base = 0;
+   // results of the chunk in flight in slot k, leader first: if the leader had to repeat its scan
+   // (a capacity guess was low) the others have read a front that was cut short and go again
+   auto collect = [&](int k) -> int {
+      Slot &ls = e->slot[k];
+      const uint32_t before = acc[0].reruns;
+      if (host_collect(e, ls, options, &line_base[0], &acc[0])) return -1;
+      for (int p = 1; p < P; p++) {
+         Slot &fs = engs[p]->slot[k];
+         if (acc[0].reruns != before) {
+            if (slot_finish(engs[p], fs, nullptr)) return -1;
+            if (slot_issue(engs[p], fs, ls.cur_text, ls.cur_n, options, ls.cur_stream, ls.cur_skip, false, &ls)) return -1;
+         }
+         if (host_collect(engs[p], fs, options, &line_base[(size_t)p], &acc[(size_t)p])) return -1;
+      }
+      return 0;
+   };
    size_t pos = 0;
    int c = 0;
    int pending[2] = {0, 0};
@@ -1124,57 +1170,127 @@ static int scan_chunks(sqb_engine *e, const char *text, size_t nbytes, int optio
          }
       }
       if (len + 16 >= kMaxBatch) { set_err("a single line of %zu bytes exceeds the batch limit of %zu", len, (size_t)kMaxBatch); return -1; }
-      Slot &s = e->slot[c & 1];
-      if (pending[c & 1]) {
-         if (host_collect(e, s, options, &line_base, &acc)) return -1;
-         pending[c & 1] = 0;
+      const int k = c & 1;
+      Slot &s = e->slot[k];
+      if (pending[k]) {
+         if (collect(k)) return -1;
+         pending[k] = 0;
       }
+      const uint8_t *d_chunk = nullptr;
+      uint32_t skip = 0;
+      cudaStream_t st = s.stream;
       if (on_device) {
-         const uint32_t skip = single ? 0u : (uint32_t)((uintptr_t)(text + pos) & 15u);
+         skip = single ? 0u : (uint32_t)((uintptr_t)(text + pos) & 15u);
          if (single && ((uintptr_t)text & 15u)) { set_err("device text must be 16-byte aligned"); return -1; }
-         s.chunk_off = pos - skip;
-         if (len || single) {
-            if (slot_issue(e, s, (const uint8_t *)text + pos - skip, (uint32_t)(len + skip), options, user_stream,
-                           skip)) return -1;
-            pending[c & 1] = 1;
-         }
+         d_chunk = (const uint8_t *)text + pos - skip;
+         st = user_stream;
       } else {
          if (dev_reserve(&s.d_text, &s.text_cap, len + 64)) return -1;
-         s.chunk_off = pos;
          if (len) CU(cudaMemcpyAsync(s.d_text, text + pos, len, cudaMemcpyHostToDevice, s.stream));
-         if (len || single) {
-            if (slot_issue(e, s, s.d_text, (uint32_t)len, options, s.stream)) return -1;
-            pending[c & 1] = 1;
+         d_chunk = s.d_text;
+      }
+      if (len || single) {
+         for (int p = 0; p < P; p++) {
+            Slot &ps = engs[p]->slot[k];
+            ps.chunk_off = pos - skip;
+            if (slot_issue(engs[p], ps, d_chunk, (uint32_t)(len + skip), options, st, skip, false, p ? &s : nullptr)) return -1;
          }
+         pending[k] = 1;
       }
       pos += len;
       c++;
       if (single) break;
    }
    // drain in chunk order
-   for (int k = 0; k < 2; k++) {
-      const int idx = (c + k) & 1;
-      if (pending[idx]) {
-         if (host_collect(e, e->slot[idx], options, &line_base, &acc)) return -1;
-         pending[idx] = 0;
+   for (int j = 0; j < 2; j++) {
+      const int k = (c + j) & 1;
+      if (pending[k]) {
+         if (collect(k)) return -1;
+         pending[k] = 0;
       }
    }
-   acc.nbytes = nbytes;          // (a device chunk counts its alignment bytes)
-   e->last_stats = acc;
-   if (stats) *stats = acc;
+   for (int p = 0; p < P; p++) {
+      acc[(size_t)p].nbytes = nbytes;          // (a device chunk counts its alignment bytes)
+      engs[p]->last_stats = acc[(size_t)p];
+      if (stats) stats[p] = acc[(size_t)p];
+   }
    return 0;
 }
 
 int sqbScanHost(sqb_engine_t *e, const char *text, size_t nbytes, int options, sqb_stats_t *stats)
 {
-   return scan_chunks(e, text, nbytes, options, stats, false, nullptr);
+   return scan_chunks(&e, 1, text, nbytes, options, stats, false, nullptr);
 }
 
 int sqbScanDeviceLarge(sqb_engine_t *e, const void *d_text, size_t nbytes, int options, void *stream,
                        sqb_stats_t *stats)
 {
    if (options & SQB_SINGLE_LINE) { set_err("sqbScanDeviceLarge: not for single lines"); return -1; }
-   return scan_chunks(e, (const char *)d_text, nbytes, options, stats, true, (cudaStream_t)stream);
+   return scan_chunks(&e, 1, (const char *)d_text, nbytes, options, stats, true, (cudaStream_t)stream);
+}
+
+// ---- pattern sets ---------------------------------------------------------------
+struct sqb_multi {
+   std::vector<sqb_engine *> engs;     // engs[0] is the leader (its K1 / pack output is shared)
+   std::vector<int> order;             // order[i] = caller's index of engs[i]
+   std::vector<sqb_stats_t> tmp;
+};
+
+sqb_multi_t *sqbMultiNew(int npatterns, const unsigned char *const *keys, const int *m, const int *tau, int device)
+{
+   if (npatterns < 1 || keys == NULL || m == NULL || tau == NULL) { set_err("sqbMultiNew: invalid arguments"); return NULL; }
+   sqb_multi *mp = new sqb_multi();
+   int fk = 8;
+   for (int i = 0; i < npatterns; i++) {
+      sqb_engine *e = sqbEngineNew(keys[i], m[i], tau[i], device);
+      if (e == NULL) { sqbMultiFree(mp); return NULL; }
+      e->cuts = 0;                     // segment cuts depend on the pattern (warm-up): long lines run un-cut
+      fk = std::min(fk, e->filter_k);
+      mp->engs.push_back(e);
+      mp->order.push_back(i);
+   }
+   // the leader must produce bit-planes if anyone is to read them
+   for (size_t i = 0; i < mp->engs.size(); i++)
+      if (mp->engs[i]->bs_ok) { std::swap(mp->engs[0], mp->engs[i]); std::swap(mp->order[0], mp->order[i]); break; }
+   mp->engs[0]->filter_k = fk;         // dead for the shortest pattern of the set = dead for all of them
+   mp->tmp.resize(mp->engs.size());
+   return mp;
+}
+
+void sqbMultiFree(sqb_multi_t *mp)
+{
+   if (mp == NULL) return;
+   for (sqb_engine *e : mp->engs) sqbEngineFree(e);
+   delete mp;
+}
+
+int sqbMultiCount(sqb_multi_t *mp) { return (int)mp->engs.size(); }
+
+sqb_engine_t *sqbMultiEngine(sqb_multi_t *mp, int pattern)
+{
+   for (size_t i = 0; i < mp->engs.size(); i++) if (mp->order[i] == pattern) return mp->engs[i];
+   set_err("sqbMultiEngine: pattern %d out of range", pattern);
+   return NULL;
+}
+
+static int multi_scan(sqb_multi *mp, const char *text, size_t nbytes, int options, sqb_stats_t *stats, bool on_device,
+                      cudaStream_t st)
+{
+   if (options & SQB_SINGLE_LINE) { set_err("pattern sets are for buffers of lines"); return -1; }
+   const int P = (int)mp->engs.size();
+   if (scan_chunks(mp->engs.data(), P, text, nbytes, options, mp->tmp.data(), on_device, st)) return -1;
+   if (stats) for (int i = 0; i < P; i++) stats[mp->order[(size_t)i]] = mp->tmp[(size_t)i];
+   return 0;
+}
+
+int sqbMultiScanHost(sqb_multi_t *mp, const char *text, size_t nbytes, int options, sqb_stats_t *stats)
+{
+   return multi_scan(mp, text, nbytes, options, stats, false, nullptr);
+}
+
+int sqbMultiScanDevice(sqb_multi_t *mp, const void *d_text, size_t nbytes, int options, void *stream, sqb_stats_t *stats)
+{
+   return multi_scan(mp, (const char *)d_text, nbytes, options, stats, true, (cudaStream_t)stream);
 }
 
 const sqb_rec_t *sqbHostRecords(sqb_engine_t *e, uint64_t *count)
