@@ -101,7 +101,7 @@ extern "C" long bs_host_scan(const char *buf, size_t n, const unsigned char *key
 #define SHAPE(R, G) if (p.rows == R && p.parts == G) run_rows<R, G>(mode, skip, cls, n, begin, l0, l1, p, ev);
       SHAPE(8, 1) SHAPE(12, 1) SHAPE(16, 1) SHAPE(24, 1) SHAPE(32, 1)
       SHAPE(20, 2) SHAPE(24, 2) SHAPE(32, 2)
-      SHAPE(20, 4) SHAPE(24, 4) SHAPE(28, 4) SHAPE(32, 4)
+      SHAPE(20, 4) SHAPE(24, 4) SHAPE(26, 4) SHAPE(28, 4) SHAPE(32, 4)
 #undef SHAPE
    }
    std::stable_sort(ev.begin(), ev.end(), [](const Ev &a, const Ev &b) { return a.line < b.line; });
@@ -254,7 +254,7 @@ extern "C" long bs_host_scan_cut(const char *buf, size_t n, const unsigned char 
    }
       SHAPE(8, 1) SHAPE(12, 1) SHAPE(16, 1) SHAPE(24, 1) SHAPE(32, 1)
       SHAPE(20, 2) SHAPE(24, 2) SHAPE(32, 2)
-      SHAPE(20, 4) SHAPE(24, 4) SHAPE(28, 4) SHAPE(32, 4)
+      SHAPE(20, 4) SHAPE(24, 4) SHAPE(26, 4) SHAPE(28, 4) SHAPE(32, 4)
 #undef SHAPE
    }
    // k_seg_reduce: one result per real line, segments behind a STOP are dead

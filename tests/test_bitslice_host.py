@@ -69,7 +69,7 @@ def make_buffer(rng, nlines, maxlen, alphabet, plant, final_newline):
 
 
 @pytest.mark.parametrize("mrange", [(1, 8), (9, 12), (13, 16), (17, 24), (25, 32), (33, 40), (41, 64),
-                                    (65, 80), (81, 112), (113, 128)])
+                                    (65, 80), (81, 96), (97, 104), (105, 112), (113, 128)])
 def test_bitsliced_events_equal_oracle(harness, oracle, mrange):
     rng = random.Random(mrange[1] * 31)
     checked = 0
