@@ -174,6 +174,7 @@ def cpu_reference_run(w, host_text: np.ndarray, nproc: int, seconds_target: floa
         times.append(t)
     t = float(np.mean(times))
     return dict(value=sample.size / t / 1e9, reads_per_s=reads / t, unit="GB/s", cores=nproc, kind=kind,
+                one_core_value=rate1 / 1e9,
                 sample="%d reads (%.1f MB) of the same workload, %d processes over newline-aligned shards, "
                        "%.2f s per pass, mean of %d passes" % (reads, sample.size / 1e6, nproc, t, len(times)),
                 seconds=t, result=int(result))
@@ -270,8 +271,8 @@ def main():
 
     def issue(i, timing=False):
         o = opt | (B.SQB_TIMING if timing else 0)
-        if big:
-            big_stats[i] = eng.scan_device_large(d_text.data_ptr(), nbytes, o, stream.cuda_stream)
+        if big:      # like the one-batch scans of this arm, the records stay in HBM
+            big_stats[i] = eng.scan_device_large(d_text.data_ptr(), nbytes, o | B.SQB_DEVICE_RESULTS, stream.cuda_stream)
         else:
             eng.scan_device_issue(i & 1, d_text.data_ptr(), nbytes, o, stream.cuda_stream)
 
@@ -409,7 +410,10 @@ def main():
     traffic_path = os.path.join(ROOT, "profiles", "k2_traffic.json")
     if os.path.exists(traffic_path):
         try:
-            roofline["traffic"] = json.load(open(traffic_path)).get(args.workload, {}).get(dominant)
+            tj = json.load(open(traffic_path))
+            roofline["traffic"] = tj.get(args.workload, {}).get(dominant)
+            # SURVEY 8(d), secondary: integer-pipe utilisation of the kernels from the same ncu capture
+            roofline["ncu_pipes"] = tj.get("_pipes", {}).get(args.workload)
         except (ValueError, OSError):
             pass
 
@@ -420,7 +424,7 @@ def main():
         host = B.gen_host(g, sample_reads)
         r = cpu_reference_run(w, host, cores, seconds_target=12.0)
         cpu = {"value": r["value"], "unit": "GB/s", "reads_per_s": r["reads_per_s"], "cores": r["cores"],
-               "kind": r["kind"], "sample": r["sample"]}
+               "kind": r["kind"], "sample": r["sample"], "one_core_GBps": r["one_core_value"]}
 
     out = {"metric": "reads_scanned_GBps", "value": value, "unit": "GB/s", "reads_per_s": reads_per_s,
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -430,6 +434,8 @@ def main():
                       "lines_per_gpu": int(nlines), "records_per_gpu": int(nrecs),
                       "matched_lines_per_gpu": int(nmatched), "total_lines": int(tot_lines),
                       "total_records": int(tot_recs), "l2_policy": "input (%.2f GB) larger than L2 (126 MB)" % (nbytes / 1e9),
+                      "scan": ("sqbScanDeviceLarge: newline-aligned chunks of <= 1536 MiB, records kept in HBM"
+                               if big else "sqbScanDeviceIssue/Wait: one batch, two scans in flight, graph replay"),
                       "sharding": "newline-aligned byte ranges, one rank per GPU, no data-path collective"},
            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
            "scan_reruns": int(reruns), "clocks": clk}

@@ -65,6 +65,9 @@ typedef struct {
 #define SQB_SINGLE_LINE  0x0400  /* the buffer is ONE line (string API)      */
 #define SQB_TIMING       0x0800  /* fill kernel_ms[] (adds event records)    */
 #define SQB_KEEP_LINES   0x1000  /* sqbScanHost: also return line offsets    */
+#define SQB_DEVICE_RESULTS 0x2000 /* chunked scans (sqbScanDeviceLarge, sqbScanHost, pattern sets): the records
+                                   * of all chunks stay in HBM (sqbDeviceRecordsAll) instead of travelling to
+                                   * the pinned host array (sqbHostRecords)                                     */
 
 /* ---- engine life cycle --------------------------------------------------- */
 /* keys: one class byte per pattern position as produced by the parser
@@ -103,6 +106,8 @@ int sqbScanDeviceWait  (sqb_engine_t * e, int slot, sqb_stats_t * stats);
  * 16-byte vector it lies in must be readable, as inside any CUDA allocation). */
 int sqbScanDeviceLarge (sqb_engine_t * e, const void * d_text, size_t nbytes,
                         int options, void * stream, sqb_stats_t * stats);
+/* with SQB_DEVICE_RESULTS: all records of the last chunked scan, in order, on the device */
+const sqb_rec_t * sqbDeviceRecordsAll (sqb_engine_t * e, uint64_t * count);
 
 /* results of the last sqbScanDevice / sqbScanDeviceWait, resident on the device */
 const sqb_rec_t * sqbDeviceRecords    (sqb_engine_t * e);

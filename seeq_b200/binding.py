@@ -21,6 +21,7 @@ SQ_FAIL, SQ_CONVERT, SQ_IGNORE = 0, 4, 8
 SQ_LINES, SQ_STREAM = 0, 0x10
 SQ_ANY, SQ_MATCH, SQ_NOMATCH, SQ_COUNTLINES, SQ_COUNTMATCH = 0, 1, 2, 3, 4
 SQB_COUNT_ONLY, SQB_FASTA, SQB_SINGLE_LINE, SQB_TIMING, SQB_KEEP_LINES = 0x100, 0x200, 0x400, 0x800, 0x1000
+SQB_DEVICE_RESULTS = 0x2000
 
 REC_DTYPE = np.dtype([("line", "<u4"), ("start", "<u4"), ("end", "<u4"), ("dist", "<u4")])
 
@@ -90,6 +91,7 @@ SYMBOLS = {
     "sqbScanDeviceIssue": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "sqbScanDeviceWait": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(StatsT)]),
     "sqbScanDeviceLarge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(StatsT)]),
+    "sqbDeviceRecordsAll": (C.c_void_p, [C.c_void_p, _u64p]),
     "sqbDeviceRecords": (C.c_void_p, [C.c_void_p]),
     "sqbDeviceLineStarts": (C.c_void_p, [C.c_void_p]),
     "sqbFetchRecords": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
@@ -126,9 +128,10 @@ def lib() -> C.CDLL:
     """Load (building if necessary) libseeq_b200.so and type its entry points."""
     global _lib
     if _lib is None:
-        if not os.path.exists(_build.LIB):
+        path = os.environ.get("SEEQ_B200_LIB") or _build.LIB      # experiments: another build of the library
+        if path == _build.LIB and not os.path.exists(path):
             _build.build_library()
-        L = C.CDLL(_build.LIB)
+        L = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)       # AttributeError = symbol missing
             fn.restype = res
@@ -282,6 +285,15 @@ class Engine:
         n = C.c_uint64(0)
         p = self.L.sqbHostRecords(self.e, C.byref(n))
         return _as_recs(p, n.value)
+
+    def device_records_all(self) -> np.ndarray:
+        """Records of the last chunked scan run with SQB_DEVICE_RESULTS, copied back."""
+        n = C.c_uint64(0)
+        p = self.L.sqbDeviceRecordsAll(self.e, C.byref(n))
+        out = np.zeros(n.value, dtype=REC_DTYPE)
+        if n.value and self.L.sqbMemcpyD2H(out.ctypes.data, p, n.value * 16):
+            raise RuntimeError("sqbMemcpyD2H failed: " + last_error())
+        return out
 
     def host_line_starts(self) -> np.ndarray:
         n = C.c_uint64(0)

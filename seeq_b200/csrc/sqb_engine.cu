@@ -143,6 +143,8 @@ struct sqb_engine {
    std::vector<uint64_t> host_lines;
    int last_slot = 0;
    sqb_stats_t last_stats;
+   Rec *d_all_recs = nullptr;          // SQB_DEVICE_RESULTS: the records of all chunks of the last chunked scan
+   size_t d_all_cap = 0, d_all_n = 0;
    unsigned long long *d_word = nullptr, *h_word = nullptr;     // device_cuts: one word each
    cudaStream_t big_stream = nullptr;                           // sqbScanDeviceLarge: the kernels of all chunks
    bool graphs = true;                                          // SEEQ_B200_GRAPHS=0 disables graph replay
@@ -467,7 +469,7 @@ static int launch_bitslice(const sqb_engine *e, int mode, int options, size_t ma
    const bool skip = (options & OPT_NONDNA) == OPT_IGNORE;
    const int R = e->bs_pat.rows, G = e->bs_pat.parts;
    const bool nfa = G == 1 && e->tau <= 2 && e->nfa_levels;
-   int per_sm = G > 1 ? (R <= 24 ? 3 : 2) : (R <= 16 ? 4 : 3);
+   int per_sm = G > 1 ? (R <= 24 ? SQB_G2_CTAS : 2) : (R <= 16 ? 4 : 3);
    if (nfa) per_sm = R * (e->tau + 1) <= 24 ? 6 : (R * (e->tau + 1) <= 48 ? 4 : 3);      // = the kernels' launch bounds
    if (const char *c = getenv("SEEQ_B200_BS_CTAS")) per_sm = std::max(1, atoi(c));
    // work items = (tile, 1/G of its groups), one warp each
@@ -826,12 +828,15 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
    return 0;
 }
 
-// records of a chunk -> buffer-global line numbers
-static __global__ void k_add_line_base(Rec *recs, unsigned long long n, uint32_t base)
+// records of a chunk -> buffer-global line numbers (in place, or into the array of all chunks)
+static __global__ void k_add_line_base(Rec *dst, const Rec *src, unsigned long long n, uint32_t base)
 {
    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-        i += (unsigned long long)gridDim.x * blockDim.x)
-      recs[i].line += base;
+        i += (unsigned long long)gridDim.x * blockDim.x) {
+      Rec r = src[i];
+      r.line += base;
+      dst[i] = r;
+   }
 }
 
 // last (or first) '\n' of text[lo, hi): *out = max (min) over 1 + its position
@@ -922,6 +927,7 @@ void sqbEngineFree(sqb_engine_t *e)
    cudaSetDevice(e->device);
    for (auto &s : e->slot) slot_free(s);
    if (e->host_recs) cudaFreeHost(e->host_recs);
+   if (e->d_all_recs) cudaFree(e->d_all_recs);
    if (e->d_word) cudaFree(e->d_word);
    if (e->h_word) cudaFreeHost(e->h_word);
    if (e->big_stream) cudaStreamDestroy(e->big_stream);
@@ -1019,8 +1025,26 @@ static int host_collect(sqb_engine *e, Slot &s, int options, uint64_t *line_base
    sqb_stats_t st;
    if (slot_finish(e, s, &st)) return -1;
    const bool count_only = options & SQB_COUNT_ONLY;
+   const bool on_device = options & SQB_DEVICE_RESULTS;
+   if (!count_only && on_device && st.nrecs > 0) {
+      // the records stay in HBM: appended, rebased, to the device array of the whole scan
+      const size_t need = e->d_all_n + (size_t)st.nrecs;
+      if (need > e->d_all_cap) {
+         Rec *bigger = nullptr;
+         const size_t cap = need + need / 2 + (1u << 16);
+         CU(cudaMalloc((void **)&bigger, cap * sizeof(Rec)));
+         if (e->d_all_n) CU(cudaMemcpy(bigger, e->d_all_recs, e->d_all_n * sizeof(Rec), cudaMemcpyDeviceToDevice));
+         if (e->d_all_recs) CU(cudaFree(e->d_all_recs));
+         e->d_all_recs = bigger;
+         e->d_all_cap = cap;
+      }
+      k_add_line_base<<<(int)std::min<size_t>(div_up((size_t)st.nrecs, 256), (size_t)e->sms * 8), 256, 0, s.stream>>>(
+         e->d_all_recs + e->d_all_n, s.d_recs, st.nrecs, (uint32_t)*line_base);
+      CU(cudaGetLastError());
+      e->d_all_n += (size_t)st.nrecs;
+   }
    // the records go straight into the (pinned) result array of the scan
-   if (!count_only && st.nrecs > 0) {
+   if (!count_only && !on_device && st.nrecs > 0) {
       const size_t need = e->host_recs_n + (size_t)st.nrecs;
       if (need > e->host_recs_cap) {
          sqb_rec_t *bigger = nullptr;
@@ -1035,7 +1059,7 @@ static int host_collect(sqb_engine *e, Slot &s, int options, uint64_t *line_base
       // (the scan is complete; the slot's stream carries only this)
       if (*line_base) {
          k_add_line_base<<<(int)std::min<size_t>(div_up((size_t)st.nrecs, 256), (size_t)e->sms * 8), 256, 0, s.stream>>>(
-            s.d_recs, st.nrecs, (uint32_t)*line_base);
+            s.d_recs, s.d_recs, st.nrecs, (uint32_t)*line_base);
          CU(cudaGetLastError());
       }
       CU(cudaMemcpyAsync(e->host_recs + e->host_recs_n, s.d_recs, st.nrecs * sizeof(Rec), cudaMemcpyDeviceToHost, s.stream));
@@ -1045,7 +1069,7 @@ static int host_collect(sqb_engine *e, Slot &s, int options, uint64_t *line_base
       CU(cudaMemcpyAsync(s.h_ls, s.d_ls, st.nlines * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
    }
    CU(cudaStreamSynchronize(s.stream));
-   if (!count_only && st.nrecs > 0) e->host_recs_n += (size_t)st.nrecs;
+   if (!count_only && !on_device && st.nrecs > 0) e->host_recs_n += (size_t)st.nrecs;
    if ((options & SQB_KEEP_LINES_INTERNAL) && st.nlines > 0) {
       const size_t old = e->host_lines.size();
       e->host_lines.resize(old + st.nlines);
@@ -1122,6 +1146,7 @@ static int scan_chunks(sqb_engine **engs, int P, const char *text, size_t nbytes
    for (int p = 0; p < P; p++) {
       for (auto &s : engs[p]->slot) if (slot_init(s)) return -1;
       engs[p]->host_recs_n = 0;
+      engs[p]->d_all_n = 0;
       engs[p]->host_lines.clear();
       memset(&acc[(size_t)p], 0, sizeof(sqb_stats_t));
    }
@@ -1291,6 +1316,12 @@ int sqbMultiScanHost(sqb_multi_t *mp, const char *text, size_t nbytes, int optio
 int sqbMultiScanDevice(sqb_multi_t *mp, const void *d_text, size_t nbytes, int options, void *stream, sqb_stats_t *stats)
 {
    return multi_scan(mp, (const char *)d_text, nbytes, options, stats, true, (cudaStream_t)stream);
+}
+
+const sqb_rec_t *sqbDeviceRecordsAll(sqb_engine_t *e, uint64_t *count)
+{
+   if (count) *count = e->d_all_n;
+   return (const sqb_rec_t *)e->d_all_recs;
 }
 
 const sqb_rec_t *sqbHostRecords(sqb_engine_t *e, uint64_t *count)

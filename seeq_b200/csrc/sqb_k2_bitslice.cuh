@@ -40,6 +40,9 @@ constexpr int kBsWarps   = 4;                       // warps per CTA of the matc
 constexpr int kBsThreads = kBsWarps * 32;
 constexpr int kBsTileLines = 1024;                  // lines per warp tile
 constexpr int kBsBlock   = 4;                       // columns per prefetch block of the match kernel
+#ifndef SQB_G2_CTAS
+#define SQB_G2_CTAS 3                               // CTAs per SM of the multi-part matcher with R <= 24 (A/B knob)
+#endif
 
 struct BsPrepArgs {
    const uint32_t *ls;
@@ -342,7 +345,7 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 // WM > 0 selects the NFA-level automaton (bs_wm_step, tau = WM - 1 <= 2, G == 1)
 // instead of Myers' delta encoding: fewer logic ops per column for small tau.
 template <int R, int G, int MODE, bool SKIP, int WM = 0>
-__global__ void __launch_bounds__(kBsThreads, WM ? (R * WM <= 24 ? 6 : (R * WM <= 48 ? 4 : 3)) : (G > 1 ? (R <= 24 ? 3 : 2) : (R <= 16 ? 4 : 3)))
+__global__ void __launch_bounds__(kBsThreads, WM ? (R * WM <= 24 ? 6 : (R * WM <= 48 ? 4 : 3)) : (G > 1 ? (R <= 24 ? SQB_G2_CTAS : 2) : (R <= 16 ? 4 : 3)))
 k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
 {
    static_assert(WM == 0 || G == 1, "the NFA-level automaton is single-part");

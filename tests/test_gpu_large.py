@@ -74,6 +74,10 @@ def check_large(B, oracle, pattern, tau, buf, opt, keep_lines=False):
                 want.append(pos)
             pos += len(ln) + 1
         assert starts.tolist() == want
+    # the records kept in HBM are the same records
+    st3 = eng.scan_device_large(d.ptr, d.n, opt | flags | B.SQB_DEVICE_RESULTS)
+    assert (st3.nlines, st3.nmatched, st3.nrecs) == (nl, nm, len(exp))
+    assert rec_rows(eng.device_records_all()) == exp and eng.host_records().size == 0
     # count-only agrees
     st2 = eng.scan_device_large(d.ptr, d.n, opt | flags | B.SQB_COUNT_ONLY)
     assert (st2.nlines, st2.nmatched) == (nl, nm)

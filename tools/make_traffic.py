@@ -17,6 +17,7 @@ def main():
     for arg in sys.argv[1:]:
         wl, path = arg.split("=")
         per = {}
+        pipes = {}
         for k in json.load(open(path))["kernels"]:
             for needle, name in NAMES:
                 if needle in k["kernel"]:
@@ -24,7 +25,12 @@ def main():
                          k["dram_write"] * UNIT[k.get("dram_write_unit", "byte")])
                     if b > per.get(name, 0):          # the gated no-op launch of the other matcher moves nothing
                         per[name] = int(b)
+                        pipes[name] = {"alu_pipe_pct": round(k.get("alu_pipe_pct", 0.0), 1),
+                                       "issue_active_pct": round(k.get("issue_active_pct", 0.0), 1),
+                                       "dram_pct_of_peak": round(k.get("dram_pct_of_peak", 0.0), 1),
+                                       "warp_instructions": int(k.get("warp_instructions", 0))}
         out[wl] = per
+        out.setdefault("_pipes", {})[wl] = pipes
     out["_source"] = {a.split("=")[0]: a.split("=")[1] for a in sys.argv[1:]}
     json.dump(out, open("profiles/k2_traffic.json", "w"), indent=1)
     print(json.dumps(out, indent=1))
