@@ -40,6 +40,9 @@ constexpr int kBsWarps   = 4;                       // warps per CTA of the matc
 constexpr int kBsThreads = kBsWarps * 32;
 constexpr int kBsTileLines = 1024;                  // lines per warp tile
 constexpr int kBsBlock   = 4;                       // columns per prefetch block of the match kernel
+#ifndef SQB_PACK_CTAS
+#define SQB_PACK_CTAS 4                             // CTAs per SM of k15_pack (A/B knob: 5 -> 51 registers, 6 -> 42)
+#endif
 #ifndef SQB_G2_CTAS
 #define SQB_G2_CTAS 3                               // CTAs per SM of the multi-part matcher with R <= 24 (A/B knob)
 #endif
@@ -233,7 +236,7 @@ struct NibbleStream {
    }
 };
 
-static __global__ void __launch_bounds__(kThreads, 4) k15_pack(const BsPackArgs a)
+static __global__ void __launch_bounds__(kThreads, SQB_PACK_CTAS) k15_pack(const BsPackArgs a)
 {
    if (a.ctr[C_BS_SELECTED] != 1ull) return;
    const int lane = threadIdx.x & 31;
