@@ -285,7 +285,7 @@ def main():
         torch.cuda.synchronize()
 
     for i in range(args.warmup):
-        issue(i)
+        issue(i, timing=os.environ.get("SEEQ_B200_BENCH_TIMING", "1") != "0")
         st = wait(i)
     clocks = Clocks(local_rank)
     barrier()
@@ -305,30 +305,33 @@ def main():
         k1c_ms.append(st.kernel_ms[5])
         launches += st.launches
 
+    # every timed step records the engine's CUDA events around its single kernels (SQB_TIMING; as
+    # nodes of the replayed graph): the per-kernel times of the roofline come from the timed region
+    timing = os.environ.get("SEEQ_B200_BENCH_TIMING", "1") != "0"
     barrier()
     ev0.record(stream)
-    issue(0)
+    issue(0, timing=timing)
     for i in range(1, args.steps):
-        issue(i)
+        issue(i, timing=timing)
         st = wait(i - 1)
-        launches += st.launches
+        account(st)
         reruns += st.reruns
     st = wait(args.steps - 1)
-    launches += st.launches
+    account(st)
     reruns += st.reruns
     ev1.record(stream)
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     clk = clocks.stop() if rank == 0 else None
     nlines, nmatched, nrecs = st.nlines, st.nmatched, st.nrecs
-    # the per-kernel breakdown comes from extra steps OUTSIDE the timed region: SQB_TIMING makes the
-    # engine record CUDA events on its stream around the single kernels (and launch them one by one)
-    launches_timed = launches
-    for i in range(min(5, args.steps)):
-        issue(i, timing=True)
-        account(wait(i))
-    launches = launches_timed
-    torch.cuda.synchronize()
+    if not timing:                     # A/B: the breakdown from extra steps after the timed region
+        launches_timed = launches
+        k2_ms, k1_ms, fin_ms, match_ms, pack_ms, k1c_ms = [], [], [], [], [], []
+        for i in range(min(5, args.steps)):
+            issue(i, timing=True)
+            account(wait(i))
+        launches = launches_timed
+        torch.cuda.synchronize()
 
     # the tiny exchanges: global line base, totals; time = max over ranks
     from seeq_b200 import shard

@@ -716,8 +716,8 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
 // three times in a row, the same calls are recorded into a CUDA graph (stream capture: every
 // capacity is in place by then, so no allocation happens underneath) and from then on a scan is
 // ONE graph launch -- the ~15 launches and memsets of a step cost the host nothing, and the
-// device runs them back to back.  Not with SQB_TIMING (the caller wants events around single
-// kernels) and not for single strings.
+// device runs them back to back.  With SQB_TIMING the event records around the single kernels
+// are nodes of the graph.  Not for single strings.
 static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n, int options, cudaStream_t st,
                       uint32_t skip = 0, bool may_replay = false, const Slot *front = nullptr)
 {
@@ -726,7 +726,7 @@ static int slot_issue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n,
    // only the direct device scans replay (the chunk pipelines scan a different chunk every time, and
    // two chunks of equal size in a row would pay for an instantiation that is used once), and only
    // from the third identical scan on
-   const bool eligible = may_replay && !front && e->graphs && !s.gbroken && !(options & (SQB_TIMING | SQB_SINGLE_LINE)) && st != nullptr;
+   const bool eligible = may_replay && !front && e->graphs && !s.gbroken && !(options & SQB_SINGLE_LINE) && st != nullptr;
    if (eligible && key == s.gkey && ++s.grepeats >= 2) {
       if (s.gexec == nullptr) {
          cudaGraph_t graph = nullptr;
@@ -820,7 +820,8 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
          CU(cudaEventElapsedTime(&ms, s.ev[E_BEGIN], s.ev[E_FIN_END]));
          stats->device_ms = ms;
          for (int k = 0; k < 6; k++) {
-            CU(cudaEventElapsedTime(&ms, s.ev[span[k][0]], s.ev[span[k][1]]));
+            // (a follower of a pattern set has no K1 / pack of its own: empty spans)
+            if (cudaEventElapsedTime(&ms, s.ev[span[k][0]], s.ev[span[k][1]]) != cudaSuccess) { cudaGetLastError(); ms = 0; }
             stats->kernel_ms[k] = ms;
          }
       }

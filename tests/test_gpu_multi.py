@@ -110,3 +110,27 @@ def test_pattern_set_small_and_single(B, oracle):
     check_set(B, oracle, pats, buf, SQ_BEST, device=False)
     check_set(B, oracle, pats, buf, SQ_FIRST | SQ_CONVERT, device=True)
     check_set(B, oracle, pats, b"", SQ_FIRST, device=False)
+
+
+def test_pattern_set_leader_repeats_its_scan(B, oracle, monkeypatch):
+    """Lines of ~6 bytes: more lines per byte than the engine guesses, so the leader's first scan of
+    every chunk runs out of room and is repeated with exact sizes (stats.reruns) -- the other patterns
+    of the set have read a front that was cut short and must go again."""
+    monkeypatch.setenv("SEEQ_B200_CHUNK_MB", "1")
+    monkeypatch.setenv("SEEQ_B200_MATCHER", "bitslice")
+    rng = random.Random(808)
+    pats = pattern_set(rng, oracle, [(4, 5), (3, 4), (6, 8)])
+    lines = ["".join(rng.choice("ACGT") for _ in range(rng.randint(0, 12))) for _ in range(330000)]
+    buf = ("\n".join(lines) + "\n").encode()
+    assert len(buf) > (2 << 20)
+    mp = B.Multi([k for _, k, _ in pats], [t for _, _, t in pats])
+    stats = mp.scan_host(buf, SQ_BEST)
+    assert sum(st.reruns for st in stats) > 0
+    for i, (p, keys, tau) in enumerate(pats):
+        exp, nl, nm = oracle.buffer_scan(buf, keys, tau, SQ_BEST)
+        exp = np.asarray(exp, dtype=np.uint64).reshape(-1, 4)
+        r = mp.records(i)
+        got = np.stack([r["line"].astype(np.uint64) + 1, r["start"], r["end"], r["dist"]], axis=1).astype(np.uint64)
+        assert (stats[i].nlines, stats[i].nmatched) == (nl, nm), (i, p)
+        assert np.array_equal(got, exp), (i, p)
+    mp.close()
