@@ -488,6 +488,17 @@ static int launch_bitslice(const sqb_engine *e, int mode, int options, size_t ma
    return -1;
 }
 
+// cudaEventRecord that also works while `st` is being captured into a graph: there a plain record
+// is only a dependency edge of the capture; the EXTERNAL flavour becomes an event-record node
+// that really stamps the event every time the graph runs (SQB_TIMING inside a replayed scan)
+static cudaError_t record_event(cudaEvent_t ev, cudaStream_t st)
+{
+   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+   if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive)
+      return cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal);
+   return cudaEventRecord(ev, st);
+}
+
 // front != nullptr: the slot of ANOTHER engine that has scanned (or is scanning, earlier on the same
 // stream) the same text with the same options; its line starts, line filter and bit-planes are read
 // instead of being computed again (several patterns over one pass of the text).
@@ -534,7 +545,7 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
    if (dev_reserve(&s.d_fintiles, &s.fintiles_cap, 3 * fin_tiles)) return -1;
    unsigned long long *ctr = s.d_ctl;
 
-   if (timing) CU(cudaEventRecord(s.ev[E_BEGIN], st));
+   if (timing) CU(record_event(s.ev[E_BEGIN], st));
    CU(cudaMemsetAsync(s.d_ctl, 0, ctl_words * sizeof(unsigned long long), st));
    const bool cut = !single && !front && use_cuts(e, options, n);
    const bool filter = front ? front->cur_filter : (!single && use_filter(e, options, n));
@@ -597,7 +608,7 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
       else if (want_codes) k1_scan_classify<true, false, false><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
       else k1_scan_classify<false, false, false><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
       CU(cudaGetLastError());
-      if (timing) CU(cudaEventRecord(s.ev[E_K1C_END], st));
+      if (timing) CU(record_event(s.ev[E_K1C_END], st));
       K1ScanArgs ks{tile_cnt, tile_base, ntiles, ctr, cut ? tile_real : nullptr, tile_rbase, tile_last, tile_lbeg,
                     filter ? tile_alive : nullptr, tile_abase};
       k1_scan_tiles<<<1, 1024, 0, st>>>(ks);
@@ -608,8 +619,8 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
       CU(cudaGetLastError());
       s.launches += 3;
    }
-   if (timing && (single || front)) CU(cudaEventRecord(s.ev[E_K1C_END], st));
-   if (timing) CU(cudaEventRecord(s.ev[E_K1_END], st));
+   if (timing && (single || front)) CU(record_event(s.ev[E_K1C_END], st));
+   if (timing) CU(record_event(s.ev[E_K1_END], st));
 
    // ---- K2 ------------------------------------------------------------------
    Pattern fwd, rev;
@@ -622,8 +633,8 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
    K2Args k2{d_text, n, f.d_ls, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_ev,
              (uint32_t)std::min<size_t>(s.ev_cap, 0xffffffffu), bitslice ? 1 : 0};
    if (timing && !bitslice) {
-      CU(cudaEventRecord(s.ev[E_PACK_BEGIN], st));
-      CU(cudaEventRecord(s.ev[E_PACK_END], st));
+      CU(record_event(s.ev[E_PACK_BEGIN], st));
+      CU(record_event(s.ev[E_PACK_END], st));
    }
    if (bitslice) {
       // the bit-sliced kernel stores only the lines that match
@@ -641,14 +652,14 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
       const uint32_t wup = bs_warmup(e->m, e->tau);
       uint32_t *gmask = s.d_gmask, *gfollow = cut ? s.d_gmask + s.gmask_cap / 2 : nullptr;
       uint8_t *segstop = s.d_segflags;
-      if (timing && front) CU(cudaEventRecord(s.ev[E_PACK_BEGIN], st));
+      if (timing && front) CU(record_event(s.ev[E_PACK_BEGIN], st));
       if (!front) {
          BsPrepArgs bp{s.d_ls, (uint32_t)lines_cap, n, ctr, tile_cols, tile_off, (uint32_t)max_tiles,
                        (unsigned long long)(s.planes_cap / 32), e->bs_gate, cut ? s.d_lid : nullptr, wup,
                        (!cut && cuts_allowed(e, options, n)) ? 1 : 0, filter ? s.d_act : nullptr};
          k15_tile_cols<<<(int)std::min<size_t>(div_up(max_tiles, kWarps), (size_t)e->sms * 8), kThreads, 0, st>>>(bp);
          k15_scan<<<1, 1024, 0, st>>>(bp);
-         if (timing) CU(cudaEventRecord(s.ev[E_PACK_BEGIN], st));
+         if (timing) CU(record_event(s.ev[E_PACK_BEGIN], st));
          BsPackArgs pk{(const uint4 *)s.d_codes, (uint32_t)(div_up(n, kK1Tile) * (kK1Tile / 32)), s.d_ls,
                        (uint32_t)lines_cap, ctr, tile_cols, tile_off, s.d_planes, cut ? s.d_lid : nullptr, wup,
                        gmask, gfollow, filter ? s.d_act : nullptr};
@@ -657,7 +668,7 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
          CU(cudaGetLastError());
          s.launches += 3;
       }
-      if (timing) CU(cudaEventRecord(s.ev[E_PACK_END], st));
+      if (timing) CU(record_event(s.ev[E_PACK_END], st));
       K2BsArgs kb{f.d_planes, tile_cols, tile_off, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_ev, k2.ev_cap,
                   (mode == M_COUNT || mode == M_COUNTALL) ? 1 : 0, cut ? gmask : nullptr, gfollow, segstop, wup,
                   filter ? f.d_act : nullptr};
@@ -669,7 +680,7 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
       if (launch_k2(e, mode, grid, st, k2, fwd)) return -1;
       s.launches++;
    }
-   if (timing) CU(cudaEventRecord(s.ev[E_MATCH_END], st));
+   if (timing) CU(record_event(s.ev[E_MATCH_END], st));
    if (cut) {
       // one result per line out of the results per segment
       SegReduceArgs sr{s.d_lid, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_segflags, s.d_segflags + s.line_cap, mode,
@@ -679,7 +690,7 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
       CU(cudaGetLastError());
       s.launches++;
    }
-   if (timing) CU(cudaEventRecord(s.ev[E_K2_END], st));
+   if (timing) CU(record_event(s.ev[E_K2_END], st));
 
    // ---- scan + K3/K4 --------------------------------------------------------
    uint32_t *tile_sum = s.d_fintiles, *tile_nz = tile_sum + fin_tiles, *tile_recbase = tile_nz + fin_tiles;
@@ -707,7 +718,7 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
          s.launches += 4;
       }
    }
-   if (timing) CU(cudaEventRecord(s.ev[E_FIN_END], st));
+   if (timing) CU(record_event(s.ev[E_FIN_END], st));
    CU(cudaMemcpyAsync(s.h_ctr, ctr, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
    return 0;
 }
