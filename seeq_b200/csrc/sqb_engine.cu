@@ -614,7 +614,8 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
       k1_scan_tiles<<<1, 1024, 0, st>>>(ks);
       K1GatherArgs kg{s.d_ls_raw, s.d_ls, (uint32_t)s.line_cap, tile_cnt, tile_off, tile_base, ntiles, n, ctr,
                       cut ? s.d_codes : nullptr, tile_rbase, tile_lbeg, s.d_lid, s.d_lbeg,
-                      filter ? tile_abase : nullptr, s.d_act, s.d_lflags};
+                      filter ? tile_abase : nullptr, s.d_act, s.d_lflags,
+                      (want_codes && (mode == M_FIRST || mode == M_BEST)) ? s.d_res : nullptr};
       k1_gather<<<(int)std::min<size_t>(div_up(ntiles, kWarps), (size_t)e->sms * 8), kThreads, 0, st>>>(kg);
       CU(cudaGetLastError());
       s.launches += 3;
@@ -637,8 +638,9 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
       CU(record_event(s.ev[E_PACK_END], st));
    }
    if (bitslice) {
-      // the bit-sliced kernel stores only the lines that match
-      if (mode == M_FIRST || mode == M_BEST)
+      // the bit-sliced kernel stores only the lines that match: k1_gather has preset the results of
+      // its own scan, a scan that rides on another engine's front presets its own
+      if ((mode == M_FIRST || mode == M_BEST) && front)
          CU(cudaMemsetAsync(s.d_res, 0xFF, std::min<size_t>(lines_cap, (size_t)n + 1) * sizeof(unsigned long long), st));
       if (mode == M_ALL && filter)      // the lines the filter drops are never written
          CU(cudaMemsetAsync(s.d_cnt, 0, std::min<size_t>(lines_cap, (size_t)n + 1) * sizeof(uint32_t), st));

@@ -586,6 +586,8 @@ struct K1GatherArgs {
    const uint32_t *tile_abase;    // nullptr: no line filter
    uint32_t *act;                 // out (filter): the entries of ls the matcher looks at, in order
    uint8_t *lflags;               // out (filter): 1 = dead on arrival
+   unsigned long long *res_init;  // out (or nullptr): per-entry result preset to kNoMatch -- the bit-sliced matcher
+                                  // stores only the entries that match, and this saves a memset of 8 B per line
 };
 
 static __global__ void __launch_bounds__(kThreads) k1_gather(const K1GatherArgs a)
@@ -599,7 +601,10 @@ static __global__ void __launch_bounds__(kThreads) k1_gather(const K1GatherArgs 
       const uint32_t cnt = a.tile_cnt[t], src = a.tile_off[t], dst = a.tile_base[t];
       if (!cut && !filt) {
          for (uint32_t j = lane; j < cnt; j += 32)
-            if (dst + j < a.ls_cap && src + j < a.ls_cap) a.ls[dst + j] = a.ls_raw[src + j];
+            if (dst + j < a.ls_cap && src + j < a.ls_cap) {
+               a.ls[dst + j] = a.ls_raw[src + j];
+               if (a.res_init && dst + j + 1u < a.ls_cap) a.res_init[dst + j] = kNoMatch;
+            }
          continue;
       }
       uint32_t nact = filt ? a.tile_abase[t] : 0u;      // live entries before the current 32
@@ -612,6 +617,7 @@ static __global__ void __launch_bounds__(kThreads) k1_gather(const K1GatherArgs 
             const uint32_t bal = __ballot_sync(kFull, live);
             if (ok) {
                a.ls[dst + j] = raw & ~kDeadBit;
+               if (a.res_init && dst + j + 1u < a.ls_cap) a.res_init[dst + j] = kNoMatch;
                a.lflags[dst + j] = live ? 0 : 1;
                if (live) a.act[nact + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = dst + j;
             }
@@ -641,6 +647,7 @@ static __global__ void __launch_bounds__(kThreads) k1_gather(const K1GatherArgs 
          x = max(x, lastp1);
          if (ok) {
             a.ls[dst + j] = pos;
+            if (a.res_init && dst + j + 1u < a.ls_cap) a.res_init[dst + j] = kNoMatch;
             a.lid[dst + j] = real ? rb : rb - 1u;
             a.lbeg[dst + j] = x - 1u;
             if (filt) {

@@ -1,6 +1,6 @@
 #!/bin/bash
 # tools/gpu_round5.sh TAG -- full GPU suite, all configs, the two lines the driver takes, ncu of the cfg2 step
-TAG=${1:-r1p}
+TAG=${1:-r1x}
 OUT=gpurun_out
 mkdir -p $OUT
 timeout 1700 python -m pytest tests -m gpu -q --durations=4 > $OUT/${TAG}_pytest_gpu.log 2>&1; tail -12 $OUT/${TAG}_pytest_gpu.log
