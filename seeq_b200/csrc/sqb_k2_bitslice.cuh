@@ -43,6 +43,12 @@ constexpr int kBsBlock   = 4;                       // columns per prefetch bloc
 #ifndef SQB_PACK_CTAS
 #define SQB_PACK_CTAS 4                             // CTAs per SM of k15_pack (A/B knob: 5 -> 51 registers, 6 -> 42)
 #endif
+#ifndef SQB_G2_BLOCK
+#define SQB_G2_BLOCK 4                              // prefetch block of the multi-part matcher (A/B knob)
+#endif
+#ifndef SQB_G2_RADDR_SMEM
+#define SQB_G2_RADDR_SMEM 0                         // 1: Eq slot addresses of the multi-part matcher from shared memory
+#endif                                              //    instead of R registers (A/B knob)
 #ifndef SQB_G2_CTAS
 #define SQB_G2_CTAS 3                               // CTAs per SM of the multi-part matcher with R <= 24 (A/B knob)
 #endif
@@ -360,6 +366,7 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
 
    if (a.ctr[C_BS_SELECTED] != 1ull) return;              // the word-parallel kernel takes this scan
    constexpr int NG = 32 / G;                             // groups per warp
+   constexpr int kBsBlock = G > 1 ? SQB_G2_BLOCK : sqb::kBsBlock;   // (shadows the namespace constant)
    constexpr int B = WM ? WM : BsState<R, G>::B;          // planes of the distance handed out with an event
    auto value_of = [](const uint32_t *planes, int r) -> uint32_t {
       if constexpr (WM != 0) return bs_value_unary<(WM ? WM : 1)>(planes, r);
@@ -379,13 +386,15 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
    // G > 1 the slot of a row differs between the lanes of a warp, so the addresses
    // live in registers (from a staged copy of the table: a per-lane index into the
    // kernel parameters would serialise in the constant bank)
-   uint32_t raddr[G > 1 ? R : 1];
+   uint32_t raddr[(G > 1 && !SQB_G2_RADDR_SMEM) ? R : 1];
+   const uint32_t sb = smem_addr(slot_base);
    if (G > 1) {
       for (int i = tid; i < R * G; i += kBsThreads) s_off[i] = pat.slot_off[i];
       __syncthreads();
-      const uint32_t sb = smem_addr(slot_base);
+      if (!SQB_G2_RADDR_SMEM) {
 #pragma unroll
-      for (int j = 0; j < R; j++) raddr[j] = sb + s_off[part * R + j];
+         for (int j = 0; j < R; j++) raddr[(G > 1 && !SQB_G2_RADDR_SMEM) ? j : 0] = sb + s_off[part * R + j];
+      }
    }
 
    uint32_t my_matched = 0, my_events = 0;
@@ -481,7 +490,10 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
             if (part == 0) ph = mh = 0u;
          }
          auto eq = [&](int j) -> uint32_t {
-            if (G > 1) return lds_u32(raddr[G > 1 ? j : 0]);
+            if (G > 1) {
+               if (SQB_G2_RADDR_SMEM) return lds_u32(sb + s_off[(G > 1 ? part * R + j : 0)]);
+               return lds_u32(raddr[(G > 1 && !SQB_G2_RADDR_SMEM) ? j : 0]);
+            }
             return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(slot_base) +
                                                        (k & 1) * (int)sizeof(sm.slots[0]) + pat.slot_off[j]);
          };
