@@ -44,7 +44,7 @@ constexpr int kBsBlock   = 4;                       // columns per prefetch bloc
 #define SQB_PACK_CTAS 4                             // CTAs per SM of k15_pack (A/B knob: 5 -> 51 registers, 6 -> 42)
 #endif
 #ifndef SQB_G2_BLOCK
-#define SQB_G2_BLOCK 4                              // prefetch block of the multi-part matcher (A/B knob)
+#define SQB_G2_BLOCK 6                              // prefetch block of the multi-part matcher (r1y, r1z: 2 -12 %, 6 +1.5 %, 8 -10 %)
 #endif
 #ifndef SQB_G2_RADDR_SMEM
 #define SQB_G2_RADDR_SMEM 0                         // 1: Eq slot addresses of the multi-part matcher from shared memory
