@@ -137,6 +137,8 @@ def test_matching_fails_loudly_without_a_device(B):
         sq.batch(b"ACGT\n", 0, 0)
     with pytest.raises(RuntimeError):
         B.Engine(b"\x01\x02", 0)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        B.Multi([b"\x01\x02\x04", b"\x08\x01"], [1, 0])        # a pattern set needs its engines
     sq.close()
 
 
