@@ -480,7 +480,7 @@ static int launch_bitslice(const sqb_engine *e, int mode, int options, size_t ma
       return 0;
    }
 #define SQB_SHAPE(RR, GG) if (R == RR && G == GG) return launch_bs1<RR, GG>(bsmode, skip, grid, st, a, e->bs_pat);
-   SQB_SHAPE(8, 1) SQB_SHAPE(12, 1) SQB_SHAPE(16, 1) SQB_SHAPE(24, 1) SQB_SHAPE(32, 1)
+   SQB_SHAPE(8, 1) SQB_SHAPE(10, 1) SQB_SHAPE(12, 1) SQB_SHAPE(16, 1) SQB_SHAPE(24, 1) SQB_SHAPE(32, 1)
    SQB_SHAPE(20, 2) SQB_SHAPE(24, 2) SQB_SHAPE(32, 2)
    SQB_SHAPE(20, 4) SQB_SHAPE(24, 4) SQB_SHAPE(26, 4) SQB_SHAPE(28, 4) SQB_SHAPE(32, 4)
 #undef SQB_SHAPE

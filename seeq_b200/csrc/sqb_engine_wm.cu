@@ -37,6 +37,7 @@ cudaError_t sqb_launch_bitslice_wm(int rows, int levels, int bsmode, bool skip, 
 {
    switch (rows) {
    case 8: return launch1<8>(levels, bsmode, skip, grid, st, a, p);
+   case 10: return launch1<10>(levels, bsmode, skip, grid, st, a, p);
    case 12: return launch1<12>(levels, bsmode, skip, grid, st, a, p);
    case 16: return launch1<16>(levels, bsmode, skip, grid, st, a, p);
    case 24: return launch1<24>(levels, bsmode, skip, grid, st, a, p);
