@@ -65,6 +65,12 @@ typedef struct {
 #define SQB_SINGLE_LINE  0x0400  /* the buffer is ONE line (string API)      */
 #define SQB_TIMING       0x0800  /* fill kernel_ms[] (adds event records)    */
 #define SQB_KEEP_LINES   0x1000  /* sqbScanHost: also return line offsets    */
+#define SQB_FASTQ        0x4000  /* the buffer holds 4-line records (@id, sequence, +, quality) and starts at
+                                   * one: only the SEQUENCE line of every record (line index 1 mod 4) is matched,
+                                   * the other lines count as lines and never match -- no false hits in quality
+                                   * strings, and the matcher's tiles hold sequence lines only with every -x mode.
+                                   * Chunked scans cut at record boundaries ('@' line, '+' two lines on).
+                                   * The reference has no such mode (it scans every line, seeq.c:358-391).     */
 #define SQB_DEVICE_RESULTS 0x2000 /* chunked scans (sqbScanDeviceLarge, sqbScanHost, pattern sets): the records
                                    * of all chunks stay in HBM (sqbDeviceRecordsAll) instead of travelling to
                                    * the pinned host array (sqbHostRecords)                                     */

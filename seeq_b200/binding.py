@@ -22,6 +22,7 @@ SQ_LINES, SQ_STREAM = 0, 0x10
 SQ_ANY, SQ_MATCH, SQ_NOMATCH, SQ_COUNTLINES, SQ_COUNTMATCH = 0, 1, 2, 3, 4
 SQB_COUNT_ONLY, SQB_FASTA, SQB_SINGLE_LINE, SQB_TIMING, SQB_KEEP_LINES = 0x100, 0x200, 0x400, 0x800, 0x1000
 SQB_DEVICE_RESULTS = 0x2000
+SQB_FASTQ = 0x4000
 
 REC_DTYPE = np.dtype([("line", "<u4"), ("start", "<u4"), ("end", "<u4"), ("dist", "<u4")])
 

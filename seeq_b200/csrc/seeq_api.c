@@ -219,7 +219,7 @@ long seeqBatchMatch(seeq_t *sq, const char *text, size_t nbytes, int match_opt, 
    seeqerr = 0;
    sqb_engine_t *eng = seeqEngine(sq);
    if (eng == NULL) return -1;
-   int opt = match_opt & (MASK_MATCH | MASK_NONDNA | SQB_FASTA | SQB_TIMING | SQB_KEEP_LINES);
+   int opt = match_opt & (MASK_MATCH | MASK_NONDNA | SQB_FASTA | SQB_FASTQ | SQB_TIMING | SQB_KEEP_LINES);
    if (file_opt == 4)      opt = (opt & ~MASK_MATCH) | SQ_ALL | SQB_COUNT_ONLY;     /* SQ_COUNTMATCH */
    else if (file_opt == 3) opt = (opt & ~MASK_MATCH) | SQ_FIRST | SQB_COUNT_ONLY;   /* SQ_COUNTLINES */
    else if (file_opt != 0) { errno = EINVAL; return -1; }

@@ -421,7 +421,7 @@ static bool use_bitslice(const sqb_engine *e, int options, uint32_t n)
 static bool cuts_allowed(const sqb_engine *e, int options, uint32_t n)
 {
    if (!use_bitslice(e, options, n) || e->cuts == 0) return false;
-   if (options & (SQB_FASTA | SQB_COUNT_ONLY | SQB_KEEP_LINES_INTERNAL)) return false;
+   if (options & (SQB_FASTA | SQB_FASTQ | SQB_COUNT_ONLY | SQB_KEEP_LINES_INTERNAL)) return false;
    if ((options & OPT_NONDNA) == OPT_IGNORE) return false;
    return bs_warmup(e->m, e->tau) <= kCutWindow;
 }
@@ -548,7 +548,12 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
    if (timing) CU(record_event(s.ev[E_BEGIN], st));
    CU(cudaMemsetAsync(s.d_ctl, 0, ctl_words * sizeof(unsigned long long), st));
    const bool cut = !single && !front && use_cuts(e, options, n);
-   const bool filter = front ? front->cur_filter : (!single && use_filter(e, options, n));
+   // SQB_FASTQ: the line filter by record structure -- the matcher is handed the sequence lines only
+   // (entry index 1 mod 4; k1_scan_tiles / k1_gather), K1 itself computes no dead-on-arrival flags
+   const bool fastq = !single && (options & SQB_FASTQ);
+   const bool filter = front ? front->cur_filter
+                             : (!single && (fastq ? use_bitslice(e, options, n) : use_filter(e, options, n)));
+   const bool k1_filter = filter && !fastq;
    s.cur_filter = filter;
 
    // ---- K1 ------------------------------------------------------------------
@@ -602,20 +607,20 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
          attr = true;
       }
       const int grid = (int)std::min<size_t>(div_up(n, kK1Tile), (size_t)e->sms * 3);
-      if (cut && filter) k1_scan_classify<true, true, true><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
+      if (cut && k1_filter) k1_scan_classify<true, true, true><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
       else if (cut) k1_scan_classify<true, true, false><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
-      else if (filter) k1_scan_classify<true, false, true><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
+      else if (k1_filter) k1_scan_classify<true, false, true><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
       else if (want_codes) k1_scan_classify<true, false, false><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
       else k1_scan_classify<false, false, false><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
       CU(cudaGetLastError());
       if (timing) CU(record_event(s.ev[E_K1C_END], st));
       K1ScanArgs ks{tile_cnt, tile_base, ntiles, ctr, cut ? tile_real : nullptr, tile_rbase, tile_last, tile_lbeg,
-                    filter ? tile_alive : nullptr, tile_abase};
+                    filter ? tile_alive : nullptr, tile_abase, fastq ? 1 : 0};
       k1_scan_tiles<<<1, 1024, 0, st>>>(ks);
       K1GatherArgs kg{s.d_ls_raw, s.d_ls, (uint32_t)s.line_cap, tile_cnt, tile_off, tile_base, ntiles, n, ctr,
                       cut ? s.d_codes : nullptr, tile_rbase, tile_lbeg, s.d_lid, s.d_lbeg,
                       filter ? tile_abase : nullptr, s.d_act, s.d_lflags,
-                      (want_codes && (mode == M_FIRST || mode == M_BEST)) ? s.d_res : nullptr};
+                      (want_codes && (mode == M_FIRST || mode == M_BEST)) ? s.d_res : nullptr, fastq ? 1 : 0};
       k1_gather<<<(int)std::min<size_t>(div_up(ntiles, kWarps), (size_t)e->sms * 8), kThreads, 0, st>>>(kg);
       CU(cudaGetLastError());
       s.launches += 3;
@@ -632,7 +637,7 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
    const bool bitslice = !single && use_bitslice(e, options, n) && (!front || front->cur_bitslice);
    s.cur_bitslice = bitslice && !front;
    K2Args k2{d_text, n, f.d_ls, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_ev,
-             (uint32_t)std::min<size_t>(s.ev_cap, 0xffffffffu), bitslice ? 1 : 0};
+             (uint32_t)std::min<size_t>(s.ev_cap, 0xffffffffu), bitslice ? 1 : 0, fastq ? 1 : 0};
    if (timing && !bitslice) {
       CU(record_event(s.ev[E_PACK_BEGIN], st));
       CU(record_event(s.ev[E_PACK_END], st));
@@ -812,7 +817,8 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
       if (slot_issue(e, s, s.cur_text, s.cur_n, s.cur_options, s.cur_stream, s.cur_skip, false, s.cur_front)) return -1;
    }
    s.busy = false;
-   if (!s.cur_front && s.cur_filter && e->filter == 1 && e->filter_state < 0 && s.h_ctr[C_NPSEUDO] > 0) {
+   if (!s.cur_front && s.cur_filter && !(s.cur_options & SQB_FASTQ) && e->filter == 1 && e->filter_state < 0 &&
+       s.h_ctr[C_NPSEUDO] > 0) {
       // the probe: keep filtering if it drops a quarter of the lines or more
       const double live = (double)s.h_ctr[C_NACTIVE] / (double)s.h_ctr[C_NPSEUDO];
       e->filter_state = live <= 0.75 ? 1 : 0;
@@ -1101,11 +1107,34 @@ static int host_collect(sqb_engine *e, Slot &s, int options, uint64_t *line_base
    return 0;
 }
 
+// SQB_FASTQ: chunks must start at record boundaries (the matcher takes the lines 1 mod 4 of a chunk).
+// The start of the last record that begins at or before `cut` (a line start) inside text[lo, nbytes): a
+// line that starts with '@' whose next-but-one line starts with '+'.  Exact for well-formed 4-line
+// records: a quality line may start with '@', but two lines on comes a sequence line, never a '+'.
+// Looks at the 64 lines in front of `cut` at most; (size_t)-1 if there is no such line.
+static size_t fastq_record_start(const char *text, size_t lo, size_t cut, size_t nbytes)
+{
+   size_t q = cut;
+   for (int tries = 0; tries < 64; tries++) {
+      if (q < nbytes && text[q] == '@') {
+         const char *nl1 = (const char *)memchr(text + q, '\n', nbytes - q);
+         const char *nl2 = nl1 ? (const char *)memchr(nl1 + 1, '\n', (size_t)(text + nbytes - (nl1 + 1))) : NULL;
+         if (nl2 && (size_t)(nl2 + 1 - text) < nbytes && nl2[1] == '+') return q;
+      }
+      if (q <= lo) break;
+      const char *prev = q >= lo + 2 ? (const char *)memrchr(text + lo, '\n', q - 1 - lo) : NULL;
+      q = prev ? (size_t)(prev - text) + 1 : lo;
+   }
+   return (size_t)-1;
+}
+
 // Chunk boundaries of a DEVICE-resident buffer: cuts[0] = 0 < cuts[1] < ... = nbytes, every inner cut
 // just behind a '\n'.  The last newline of a window is looked for in its final 1 MiB, then 64 MiB,
 // then all of it; a window without any is extended to the next newline.
-static int device_cuts(sqb_engine *e, const uint8_t *d_text, size_t nbytes, size_t chunk, std::vector<size_t> &cuts)
+static int device_cuts(sqb_engine *e, const uint8_t *d_text, size_t nbytes, size_t chunk, int options,
+                       std::vector<size_t> &cuts)
 {
+   std::vector<char> win;
    Slot &s = e->slot[0];
    if (e->d_word == nullptr) {
       CU(cudaMalloc((void **)&e->d_word, sizeof(unsigned long long)));
@@ -1137,6 +1166,19 @@ static int device_cuts(sqb_engine *e, const uint8_t *d_text, size_t nbytes, size
          if (at == (size_t)~0ull) break;                 // no newline left: the rest is one chunk
       }
       if (at >= nbytes) break;
+      if (options & SQB_FASTQ) {
+         // back to a record boundary: the heuristic runs on the host over a window around the cut
+         const size_t half = 32u << 10;
+         const size_t w0 = at - pos > half ? at - half : pos, w1 = std::min(nbytes, at + half);
+         win.resize(w1 - w0);
+         CU(cudaMemcpy(win.data(), d_text + w0, w1 - w0, cudaMemcpyDeviceToHost));
+         const size_t q = fastq_record_start(win.data(), 0, at - w0, w1 - w0);
+         if (q == (size_t)-1 || w0 + q <= pos) {
+            set_err("SQB_FASTQ: no record boundary ('@' line, '+' two lines on) in the 32 KiB in front of byte %zu", at);
+            return -1;
+         }
+         at = w0 + q;
+      }
       cuts.push_back(at);
       pos = at;
    }
@@ -1167,7 +1209,7 @@ static int scan_chunks(sqb_engine **engs, int P, const char *text, size_t nbytes
    const bool single = options & SQB_SINGLE_LINE;
    const size_t chunk = on_device ? device_chunk_bytes() : host_chunk_bytes();
    std::vector<size_t> cuts;
-   if (on_device && !single && device_cuts(e, (const uint8_t *)text, nbytes, chunk, cuts)) return -1;
+   if (on_device && !single && device_cuts(e, (const uint8_t *)text, nbytes, chunk, options, cuts)) return -1;
    // device text: the kernels of all chunks follow each other on ONE stream (the caller's, or one of
    // the engine's own) while the slots' streams carry the record copies of the chunk before
    if (on_device && user_stream == nullptr) {
@@ -1206,6 +1248,14 @@ static int scan_chunks(sqb_engine **engs, int P, const char *text, size_t nbytes
             const char *nl = (const char *)memrchr(text + pos, '\n', chunk);
             if (nl == NULL) nl = (const char *)memchr(text + pos + chunk, '\n', nbytes - pos - chunk);
             len = nl ? (size_t)(nl - (text + pos)) + 1 : nbytes - pos;
+            if ((options & SQB_FASTQ) && pos + len < nbytes) {
+               const size_t q = fastq_record_start(text, pos, pos + len, nbytes);
+               if (q == (size_t)-1 || q <= pos) {
+                  set_err("SQB_FASTQ: no record boundary ('@' line, '+' two lines on) in front of byte %zu", pos + len);
+                  return -1;
+               }
+               len = q - pos;
+            }
          }
       }
       if (len + 16 >= kMaxBatch) { set_err("a single line of %zu bytes exceeds the batch limit of %zu", len, (size_t)kMaxBatch); return -1; }

@@ -453,8 +453,10 @@ struct K1ScanArgs {
    uint32_t *tile_rbase;
    const uint32_t *tile_last;
    uint32_t *tile_lbeg;
-   const uint32_t *tile_alive;    // nullptr: no line filter
+   uint32_t *tile_alive;          // nullptr: no line filter
    uint32_t *tile_abase;          // index in act[] of the first live entry of tile t; total -> ctr[C_NACTIVE]
+   int fastq;                     // the live entries are the sequence lines of 4-line records (entry index 1 mod 4):
+                                  // tile_alive is computed here, from tile_base and tile_cnt
 };
 
 static __global__ void __launch_bounds__(1024) k1_scan_tiles(const K1ScanArgs a)
@@ -467,6 +469,14 @@ static __global__ void __launch_bounds__(1024) k1_scan_tiles(const K1ScanArgs a)
       __shared__ CtaScanSmem cs;
       const unsigned long long total = cta_scan_u32(a.tile_cnt, a.tile_base, a.ntiles, cs);
       unsigned long long alive = total;
+      if (a.tile_alive != nullptr && a.fastq) {
+         // entries i < x with i = 1 (mod 4): (x + 2) / 4
+         for (uint32_t t = threadIdx.x; t < a.ntiles; t += 1024u) {
+            const uint32_t b = a.tile_base[t], e = b + a.tile_cnt[t];
+            a.tile_alive[t] = (e + 2u) / 4u - (b + 2u) / 4u;
+         }
+         __syncthreads();
+      }
       if (a.tile_alive != nullptr) alive = cta_scan_u32(a.tile_alive, a.tile_abase, a.ntiles, cs);
       if (threadIdx.x == 0) {
          a.ctr[C_NPSEUDO] = total;
@@ -588,6 +598,7 @@ struct K1GatherArgs {
    uint8_t *lflags;               // out (filter): 1 = dead on arrival
    unsigned long long *res_init;  // out (or nullptr): per-entry result preset to kNoMatch -- the bit-sliced matcher
                                   // stores only the entries that match, and this saves a memset of 8 B per line
+   int fastq;                     // filter by record structure: entry p is live iff p = 1 (mod 4)
 };
 
 static __global__ void __launch_bounds__(kThreads) k1_gather(const K1GatherArgs a)
@@ -613,10 +624,10 @@ static __global__ void __launch_bounds__(kThreads) k1_gather(const K1GatherArgs 
             const uint32_t j = j0 + (uint32_t)lane;
             const bool ok = j < cnt && dst + j < a.ls_cap && src + j < a.ls_cap;
             const uint32_t raw = ok ? a.ls_raw[src + j] : kDeadBit;
-            const bool live = !(raw & kDeadBit);
+            const bool live = ok && (a.fastq ? ((dst + j) & 3u) == 1u : !(raw & kDeadBit));
             const uint32_t bal = __ballot_sync(kFull, live);
             if (ok) {
-               a.ls[dst + j] = raw & ~kDeadBit;
+               a.ls[dst + j] = a.fastq ? raw : (raw & ~kDeadBit);
                if (a.res_init && dst + j + 1u < a.ls_cap) a.res_init[dst + j] = kNoMatch;
                a.lflags[dst + j] = live ? 0 : 1;
                if (live) a.act[nact + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = dst + j;
@@ -682,6 +693,8 @@ struct K2Args {
    Event *ev;                   // M_ALL: unordered events
    uint32_t ev_cap;
    int gate;                    // 1: leave the scan to the bit-sliced kernel when it is selected
+   int fastq;                   // 1: only the sequence lines of 4-line records (line index 1 mod 4) are scanned;
+                                //    the others are treated as empty lines
 };
 
 template <int W> struct LutEntry;
@@ -826,11 +839,12 @@ __global__ void __launch_bounds__(kThreads) k2_forward_thread(const K2Args a, co
       }
       if (line < l1) {
          uint32_t mt, ne;
-         const uint32_t limit = min(t_end, n);
+         const bool off = a.fastq && (line & 3u) != 1u;          // an empty line: no byte, no event (tau < m)
+         const uint32_t limit = off ? begin : min(t_end, n);
          if (staged)
             scan_line<W, MODE>(SmemReader{stage - a0}, line, begin, limit, lut, pat.m, pat.tau, a, mt, ne);
          else
-            scan_line<W, MODE>(GlobalReader{a.text}, line, begin, n, lut, pat.m, pat.tau, a, mt, ne);
+            scan_line<W, MODE>(GlobalReader{a.text}, line, begin, off ? begin : n, lut, pat.m, pat.tau, a, mt, ne);
          my_matched += mt;
          my_events += ne;
       }
@@ -897,7 +911,7 @@ __global__ void __launch_bounds__(kThreads) k2_forward_lanes(const K2Args a, con
 
    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const uint32_t line = tile * kLinesPerBlock + (uint32_t)(tid / G);
-      bool done = line >= nlines;
+      bool done = line >= nlines || (a.fastq && (line & 3u) != 1u);      // not a sequence line: nothing to scan
       const uint32_t begin = done ? 0u : a.ls[line];
       uint32_t p = begin;
       uint32_t pv = pv0, mv = 0;
