@@ -61,6 +61,14 @@ WORKLOADS = {
     "cfg5": dict(desc="seeq -e -d 2 GATCGGAAGAGC, FASTQ-like 4-line records", pattern="GATCGGAAGAGC", tau=2,
                  options=SQ_FIRST, count=False, reads=4_000_000,
                  gen=dict(seed=5, line_len=150, plant="GATCGGAAGAGC", plant_per_1024=307, max_edits=2, fastq=True)),
+    # beyond BASELINE.json: config 5 with -x 1 (every byte is scannable, the dead-on-arrival filter drops nothing),
+    # as the reference would scan it, and record-aware (SQB_FASTQ: sequence lines only)
+    "cfg5x1": dict(desc="seeq -e -x 1 -d 2 GATCGGAAGAGC, FASTQ-like 4-line records, every line scanned",
+                   pattern="GATCGGAAGAGC", tau=2, options=SQ_FIRST | SQ_CONVERT, count=False, reads=4_000_000,
+                   gen=dict(seed=5, line_len=150, plant="GATCGGAAGAGC", plant_per_1024=307, max_edits=2, fastq=True)),
+    "cfg5x1q": dict(desc="the same, record-aware (SQB_FASTQ: sequence lines only)",
+                    pattern="GATCGGAAGAGC", tau=2, options=SQ_FIRST | SQ_CONVERT | 0x4000, count=False, reads=4_000_000,
+                    gen=dict(seed=5, line_len=150, plant="GATCGGAAGAGC", plant_per_1024=307, max_edits=2, fastq=True)),
 }
 
 
