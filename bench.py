@@ -1,20 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the seeq matching path on B200 (BASELINE.json metric).
 
-  python bench.py --gpus 1 --steps K --warmup W [--workload cfg2] [--impl reference]
+  python bench.py --gpus 1 --steps K --warmup W [--workload cfg2] [--reads R] [--impl reference]
 
-A *step* is one pass of the hot path (K1 line scan -> K2 forward matcher ->
+A *step* is one pass of the hot path (K1 line scan -> bit-plane pack -> K2 forward matcher ->
 K3 reverse pass / K4 ordered compaction) over one batch of synthetic reads.
 Default workload = BASELINE.json configs[1] (cfg2): `seeq -b -l -p -k -d 1
 A[CG]TNNGATC` over 10 M synthetic 150-nt reads (1.51 GB per GPU; weak scaling:
-every rank scans its own 10 M reads of one global read stream).
+every rank scans its own 10 M reads of one global read stream).  A shard of 2 GiB
+or more (`--workload cfg5 --reads 39800000`: one GPU's share of BASELINE config 5)
+goes through sqbScanDeviceLarge.
 
 One JSON line is printed by rank 0:
-  value        GB/s of reads scanned, whole job, input resident in HBM
+  value        GB/s of reads scanned, whole job, input resident in HBM: CUDA events
+               around K steps on the stream the scans are queued on, max over ranks;
+               two scans in flight, a repeated scan replays as a CUDA graph
   e2e          same metric through the C-ABI with HOST buffers (sqbScanHost:
                pinned host text -> H2D -> kernels -> records D2H inside the timed
                region)
-  roofline     dominant kernel (K2) against the measured HBM copy peak
+  roofline     the slowest single kernel of the step against the measured HBM copy
+               peak: algorithmic bytes / its duration, from CUDA events the engine
+               records around its kernels INSIDE the timed region (every other step);
+               per-kernel times, DRAM traffic and pipe utilisation from the committed
+               ncu capture next to it
   cpu_baseline the unmodified reference (oracle/_ref) on the host cores, on a
                bounded sample of the same workload
 `--impl reference` times the reference's own CPU implementation instead.
@@ -397,7 +405,7 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---------------- roofline of the dominant kernel (K2) ------------------
+    # ---------------- roofline of the slowest kernel of the step ------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak = float(json.load(open(peaks_path))["hbm_gbs"])
