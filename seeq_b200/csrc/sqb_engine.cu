@@ -7,6 +7,10 @@
 // per byte in SQ_ALL) are guessed generously, detected exactly by the kernels
 // (which keep counting past the capacity) and, if ever exceeded, the scan is
 // repeated once with exact sizes (stats->reruns).
+//
+// On top of the single scan (slot_enqueue / slot_issue / slot_finish): graph replay of
+// repeated scans, the chunk pipeline (scan_chunks) behind sqbScanHost, sqbScanDeviceLarge
+// and the pattern sets (sqbMulti*), NUMA-aware pinned allocations.
 #ifndef _GNU_SOURCE
 #define _GNU_SOURCE
 #endif

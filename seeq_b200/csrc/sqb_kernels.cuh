@@ -1,16 +1,24 @@
 // sqb_kernels.cuh -- the hand-written sm_100a kernels of the matching path.
 //
-//   k1_line_scan          K1  newline / line-offset scan (TMA-staged tiles,
-//                             16-byte loads, warp-aggregated prefix, look-back)
+//   k1_scan_classify      K1  newline / line-offset scan + class nibbles (TMA-staged
+//                             tiles, 16-byte loads, warp-aggregated prefix, line
+//                             starts allocated per tile with one atomic)
+//   k1_scan_tiles             exclusive scans over the K1 tiles (one CTA, staged)
+//   k1_gather                 tile segments -> line order; line filter (dead-on-arrival
+//                             flags or FASTQ record structure); results preset
 //   k2_forward_thread     K2  Myers/Hyyro forward matcher, one read per thread
 //                             (pattern <= 64 positions: 1 or 2 words)
 //   k2_forward_lanes      K2  blocked multi-word automaton across warp lanes
 //                             (pattern > 64 positions; carries via ballot)
-//   k_scan_counts             exclusive scan of per-line event counts (SQ_ALL)
+//   k_tile_sums / _scan       records per 1024-line tile -> first record of each tile
+//   k_seg_reduce              segment cuts: one result per line
 //   k34_finish_lines      K3+K4 for SQ_FIRST / SQ_BEST: reverse pass + ordered
 //                             ballot/popc compaction of one record per line
 //   k34_finish_events     K3+K4 for SQ_ALL: reverse pass per event + ordered
 //                             scatter to offs[line] + rank
+//
+// (The production matcher for patterns of up to 128 positions -- the bit-plane pack
+// and the line-bit-sliced automaton -- lives in sqb_k2_bitslice.cuh / sqb_bitslice.h.)
 //
 // Semantics restated from /root/reference/src/libseeq.c:171-352.
 #pragma once
