@@ -1052,6 +1052,10 @@ template <int W> __device__ __forceinline__ void rev_tables_load(RevTables<W> &t
    __syncthreads();
 }
 
+#ifndef SQB_REV_WINDOW
+#define SQB_REV_WINDOW 0
+#endif
+
 template <int W, int kChunk = 8>
 __device__ __forceinline__ uint32_t reverse_start(const uint8_t *__restrict__ text, const uint32_t line_begin,
                                                   const uint32_t end, const int dist, const int m, const int tau,
@@ -1064,6 +1068,49 @@ __device__ __forceinline__ uint32_t reverse_start(const uint8_t *__restrict__ te
    uint32_t j = 0, skipped = 0;
    const uint8_t *p = text + line_begin + end;           // the pass reads p[-1], p[-2], ...
    bool more = end > 0;
+#if SQB_REV_WINDOW
+   // A/B build (-DSQB_REV_WINDOW=1, not the default): the last 16 bytes in front of `end` in
+   // ONE round trip -- the two aligned 16-byte vectors that hold them, realigned in registers -- instead of up to
+   // four rounds of byte loads; a pass that is not over after 16 bytes carries on in the loop below.
+   if (more && line_begin + end >= 16u) {
+      const size_t a0 = (size_t)line_begin + end - 16u;                 // first byte of the window (offset in text)
+      const uint4 *vec = reinterpret_cast<const uint4 *>(text + (a0 & ~(size_t)15));
+      const uint4 v0 = __ldg(vec);                                      // (text is readable to the next multiple of 16:
+      const uint4 v1 = (a0 & 15u) ? __ldg(vec + 1) : make_uint4(0u, 0u, 0u, 0u);   //  an aligned window ends with v0)
+      const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      const uint32_t ws = ((uint32_t)a0 & 15u) >> 2, bs = ((uint32_t)a0 & 3u) * 8u;
+      uint32_t u[5], win[4];
+#pragma unroll
+      for (int i = 0; i < 5; i++) {
+         const uint32_t lo = (ws & 1u) ? w[i + 1] : w[i];
+         const uint32_t hi = (ws & 1u) ? w[(i + 3) & 7] : w[i + 2];
+         u[i] = (ws & 2u) ? hi : lo;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) win[i] = __funnelshift_r(u[i], u[i + 1], bs);   // win = bytes a0 .. a0+15
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+         if (more) {
+            j++;
+            const uint8_t c = tab.cls[(win[3 - (i >> 2)] >> (8 * (3 - (i & 3)))) & 0xffu];   // byte end-1-i
+            last_d = d;
+            if ((c & 0x30) == kKindBase) {
+               skipped = 0;
+               uint32_t eq[W];
+#pragma unroll
+               for (int w2 = 0; w2 < W; w2++) eq[w2] = tab.eq[c & 7][w2];
+               uint32_t rise, fall;
+               bv_step<W>(bv, eq, rise, fall);
+               score += (int)rise - (int)fall;
+               d = min(score, tau + 1);
+            } else {
+               skipped++;
+            }
+            more = d > dist && j < end;
+         }
+      }
+   }
+#endif
    // the bytes are fetched eight at a time (independent loads) and then walked in
    // registers: a load per step would put the global latency on the dependency
    // chain of every step
