@@ -43,6 +43,11 @@ constexpr int kBsBlock   = 4;                       // columns per prefetch bloc
 #ifndef SQB_PACK_CTAS
 #define SQB_PACK_CTAS 4                             // CTAs per SM of k15_pack (A/B knob: 5 -> 51 registers, 6 -> 42)
 #endif
+#ifndef SQB_PLANE_PAIRS
+#define SQB_PLANE_PAIRS 0                           // A/B build: planes of a tile laid out
+#endif                                              // [pair of groups][column][2 groups] instead of [column][32 groups]:
+                                                    // the pack's stores coalesce (8 columns x 32 B side by side = 2 data-pipe
+                                                    // wavefronts per STG.64 instead of 8), the matcher's lanes read 32-B pieces
 #ifndef SQB_G2_BLOCK
 #define SQB_G2_BLOCK 6                              // prefetch block of the multi-part matcher (r1y, r1z: 2 -12 %, 6 +1.5 %, 8 -10 %)
 #endif
@@ -289,6 +294,7 @@ static __global__ void __launch_bounds__(kThreads, SQB_PACK_CTAS) k15_pack(const
       //   even lanes: group g0,     planes (j&2), (j&2)+1 of column j>>2
       //   odd  lanes: group g0 + 1, the same planes
       const uint32_t slot16 = (g0 + (uint32_t)(lane & 1)) * 2u + (uint32_t)((lane >> 1) & 1);   // in 8-byte units
+      (void)slot16;                                     // (unused in the SQB_PLANE_PAIRS build)
       for (uint32_t c0 = 0; c0 < ncols; c0 += 32) {
          uint32_t wa[4], wb[4];
          sa.next(wa);
@@ -306,7 +312,13 @@ static __global__ void __launch_bounds__(kThreads, SQB_PACK_CTAS) k15_pack(const
             const uint32_t got = __shfl_xor_sync(kFull, give, 1);
             const uint2 v = (lane & 1) ? make_uint2(got, tb) : make_uint2(ta, got);
             const uint32_t col = c0 + 8u * (uint32_t)k + (uint32_t)(lane >> 2);
+#if SQB_PLANE_PAIRS
+            // (g0 is even: the warp's pair of groups is pair g0 / 2 of the tile)
+            if (col < ncols)
+               reinterpret_cast<uint2 *>(out + ((size_t)(g0 >> 1) * ncols + col) * 2u)[(lane & 1) * 2 + ((lane >> 1) & 1)] = v;
+#else
             if (col < ncols) reinterpret_cast<uint2 *>(out + (size_t)col * 32u)[slot16] = v;
+#endif
          }
       }
    }
@@ -432,14 +444,18 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
       }
       const uint32_t ncols = a.tile_cols[tile];
       const uint32_t niter = ncols + (uint32_t)(G - 1);
+#if SQB_PLANE_PAIRS
+      const uint4 *col = a.planes + (size_t)a.tile_off[tile] * 32u + (size_t)(group >> 1) * ncols * 2u + (group & 1u);
+#else
       const uint4 *col = a.planes + (size_t)a.tile_off[tile] * 32u + group;
+#endif
 
       // columns are consumed in blocks of kBsBlock; the next block is in flight while
       // this one is matched (global latency >> one column of work).  Iteration t of
       // part p is column t - p; before the line start that is a NULL column.
       auto fetch = [&](uint32_t t) {
          const int c = (int)t - part;
-         uint4 v = col[(size_t)min((uint32_t)max(c, 0), ncols - 1u) * 32u];          // ncols >= 1
+         uint4 v = col[(size_t)min((uint32_t)max(c, 0), ncols - 1u) * (SQB_PLANE_PAIRS ? 2u : 32u)];          // ncols >= 1
          if (G > 1 && c < 0) v = make_uint4(~0u, ~0u, ~0u, 0u);
          return v;
       };
