@@ -1111,27 +1111,6 @@ static int host_collect(sqb_engine *e, Slot &s, int options, uint64_t *line_base
    return 0;
 }
 
-// SQB_FASTQ: chunks must start at record boundaries (the matcher takes the lines 1 mod 4 of a chunk).
-// The start of the last record that begins at or before `cut` (a line start) inside text[lo, nbytes): a
-// line that starts with '@' whose next-but-one line starts with '+'.  Exact for well-formed 4-line
-// records: a quality line may start with '@', but two lines on comes a sequence line, never a '+'.
-// Looks at the 64 lines in front of `cut` at most; (size_t)-1 if there is no such line.
-static size_t fastq_record_start(const char *text, size_t lo, size_t cut, size_t nbytes)
-{
-   size_t q = cut;
-   for (int tries = 0; tries < 64; tries++) {
-      if (q < nbytes && text[q] == '@') {
-         const char *nl1 = (const char *)memchr(text + q, '\n', nbytes - q);
-         const char *nl2 = nl1 ? (const char *)memchr(nl1 + 1, '\n', (size_t)(text + nbytes - (nl1 + 1))) : NULL;
-         if (nl2 && (size_t)(nl2 + 1 - text) < nbytes && nl2[1] == '+') return q;
-      }
-      if (q <= lo) break;
-      const char *prev = q >= lo + 2 ? (const char *)memrchr(text + lo, '\n', q - 1 - lo) : NULL;
-      q = prev ? (size_t)(prev - text) + 1 : lo;
-   }
-   return (size_t)-1;
-}
-
 // Chunk boundaries of a DEVICE-resident buffer: cuts[0] = 0 < cuts[1] < ... = nbytes, every inner cut
 // just behind a '\n'.  The last newline of a window is looked for in its final 1 MiB, then 64 MiB,
 // then all of it; a window without any is extended to the next newline.

@@ -5,6 +5,7 @@
 #ifndef SQB_TABLES_H_
 #define SQB_TABLES_H_
 
+#include <stddef.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -130,6 +131,35 @@ static inline bool build_bs_pattern(const unsigned char *keys, int m, int tau, B
    }
    for (int k = 0; k < kBsBestBits; k++) p->best_plane[k] = ((tau + 1) >> k) & 1 ? ~0u : 0u;
    return true;
+}
+
+// (memrchr is a GNU extension; a plain loop keeps this header portable -- the search is a few lines long)
+static inline const void *sqb_memrchr(const void *s, int c, size_t n)
+{
+   const unsigned char *p = (const unsigned char *)s + n;
+   while (n--) if (*--p == (unsigned char)c) return p;
+   return nullptr;
+}
+
+// SQB_FASTQ: chunks must start at record boundaries (the matcher takes the lines 1 mod 4 of a chunk).
+// The start of the last record that begins at or before `cut` (a line start) inside text[lo, nbytes): a
+// line that starts with '@' whose next-but-one line starts with '+'.  Exact for well-formed 4-line
+// records: a quality line may start with '@', but two lines on comes a sequence line, never a '+'.
+// Looks at the 64 lines in front of `cut` at most; (size_t)-1 if there is no such line.
+static inline size_t fastq_record_start(const char *text, size_t lo, size_t cut, size_t nbytes)
+{
+   size_t q = cut;
+   for (int tries = 0; tries < 64; tries++) {
+      if (q < nbytes && text[q] == '@') {
+         const char *nl1 = (const char *)memchr(text + q, '\n', nbytes - q);
+         const char *nl2 = nl1 ? (const char *)memchr(nl1 + 1, '\n', (size_t)(text + nbytes - (nl1 + 1))) : NULL;
+         if (nl2 && (size_t)(nl2 + 1 - text) < nbytes && nl2[1] == '+') return q;
+      }
+      if (q <= lo) break;
+      const char *prev = q >= lo + 2 ? (const char *)sqb_memrchr(text + lo, '\n', q - 1 - lo) : NULL;
+      q = prev ? (size_t)(prev - text) + 1 : lo;
+   }
+   return (size_t)-1;
 }
 
 }  // namespace sqb

@@ -436,3 +436,10 @@ extern "C" long bs_host_scan_wm(const char *buf, size_t n, const unsigned char *
    }
    return k;
 }
+
+// SQB_FASTQ chunk alignment (sqb_tables.h: fastq_record_start), as the chunk pipeline calls it
+extern "C" long bs_fastq_record_start(const char *text, size_t lo, size_t cut, size_t nbytes)
+{
+   const size_t q = sqb::fastq_record_start(text, lo, cut, nbytes);
+   return q == (size_t)-1 ? -1L : (long)q;
+}

@@ -30,6 +30,8 @@ def harness(tmp_path_factory):
                                    C.c_size_t, C.POINTER(C.c_uint64), C.c_long, C.POINTER(C.c_long)]
     L.bs_host_scan_wm.restype = C.c_long
     L.bs_host_scan_wm.argtypes = L.bs_host_scan_cut.argtypes
+    L.bs_fastq_record_start.restype = C.c_long
+    L.bs_fastq_record_start.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t]
     return L
 
 
@@ -196,3 +198,44 @@ def test_nfa_level_automaton_equals_oracle(harness, oracle, mrange, stride, wind
                 assert np.array_equal(out[:n], exp), (pattern, tau, mo, nd, buf[:120])
                 checked += 1
     assert checked > 100
+
+
+def test_fastq_chunk_cuts_are_record_starts(harness):
+    """SQB_FASTQ: a chunked scan cuts the text at the last record start at or in front of a
+    newline-aligned position (sqb_tables.h: fastq_record_start -- a line that starts with '@' whose
+    next-but-one line starts with '+').  On well-formed records with hostile quality strings (they
+    start with '@' or '+' and contain both) every cut is a record start, and the nearest one."""
+    rng = random.Random(2026)
+    recs = []
+    for r in range(4000):
+        n = rng.choice([0, 1, rng.randint(2, 150)])
+        seq = "".join(rng.choice("ACGTN") for _ in range(n))
+        qual = [chr(rng.randint(33, 74)) for _ in range(n)]
+        if qual and rng.random() < 0.5:
+            qual[0] = rng.choice("@+")
+        recs.append("@%s\n%s\n+%s\n%s\n" % (rng.choice(["r%d" % r, "@@", "+", ""]), seq, rng.choice(["", "r%d" % r]), "".join(qual)))
+    buf = "".join(recs).encode()
+    starts, pos = [], 0
+    for rec in recs:
+        starts.append(pos)
+        pos += len(rec)
+    starts_set = set(starts)
+    line_starts = [0] + [i + 1 for i, b in enumerate(buf) if b == 10 and i + 1 < len(buf)]
+    checked = 0
+    for _ in range(3000):
+        cut = rng.choice(line_starts)
+        lo = rng.choice([0, starts[rng.randrange(len(starts))]])
+        if lo > cut:
+            lo = 0
+        q = harness.bs_fastq_record_start(buf, lo, cut, len(buf))
+        want = max((s for s in starts if lo <= s <= cut), default=None)
+        # the last record of the buffer has no line two on from its quality line to look at: it is
+        # recognised by its '+' line like the others; only a cut inside the last TWO lines of the
+        # buffer can fall back to the record before
+        assert q != -1 and q in starts_set and lo <= q <= cut, (lo, cut, q)
+        assert q == want, (lo, cut, q, want)
+        checked += 1
+    assert checked == 3000
+    # text without records: no boundary
+    plain = ("\n".join("".join(rng.choice("ACGT") for _ in range(80)) for _ in range(500)) + "\n").encode()
+    assert harness.bs_fastq_record_start(plain, 0, 81 * 200, len(plain)) == -1
