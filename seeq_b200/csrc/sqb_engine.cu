@@ -238,18 +238,13 @@ struct NumaScope {
       if (f == nullptr) return;
       cpu_set_t want, cur;
       CPU_ZERO(&want);
-      int a = 0, b = 0;
-      char sep = 0;
-      while (fscanf(f, "%d", &a) == 1) {             // "0-31,64-95"
-         b = a;
-         if (fscanf(f, "%c", &sep) == 1 && sep == '-') {
-            if (fscanf(f, "%d", &b) != 1) b = a;
-            if (fscanf(f, "%c", &sep) != 1) sep = 0;
-         }
-         for (int c = a; c <= b && c < CPU_SETSIZE; c++) CPU_SET(c, &want);
-         if (sep != ',') break;
-      }
+      char line[4096] = "";
+      const bool got = fgets(line, sizeof line, f) != nullptr;
       fclose(f);
+      if (!got) return;
+      unsigned char listed[CPU_SETSIZE];
+      if (parse_cpulist(line, listed, CPU_SETSIZE) == 0) return;          // "0-31,64-95"
+      for (int c = 0; c < CPU_SETSIZE; c++) if (listed[c]) CPU_SET(c, &want);
       if (sched_getaffinity(0, sizeof old_set, &old_set) != 0) return;
       CPU_AND(&cur, &want, &old_set);
       if (CPU_COUNT(&cur) > 0 && !CPU_EQUAL(&cur, &old_set)) moved = sched_setaffinity(0, sizeof cur, &cur) == 0;

@@ -133,6 +133,29 @@ static inline bool build_bs_pattern(const unsigned char *keys, int m, int tau, B
    return true;
 }
 
+// sysfs cpulist ("0-31,64-95\n") -> one byte per CPU (1 = listed); returns the number of CPUs listed
+static inline int parse_cpulist(const char *s, unsigned char *cpus, int maxcpus)
+{
+   int count = 0;
+   memset(cpus, 0, (size_t)maxcpus);
+   while (*s) {
+      while (*s == ',' || *s == ' ' || *s == '\n' || *s == '\t') s++;
+      if (*s < '0' || *s > '9') break;
+      long a = 0, b;
+      while (*s >= '0' && *s <= '9') a = a * 10 + (*s++ - '0');
+      b = a;
+      if (*s == '-') {
+         s++;
+         if (*s < '0' || *s > '9') break;
+         b = 0;
+         while (*s >= '0' && *s <= '9') b = b * 10 + (*s++ - '0');
+      }
+      for (long c = a; c <= b && c < maxcpus; c++)
+         if (!cpus[c]) { cpus[c] = 1; count++; }
+   }
+   return count;
+}
+
 // (memrchr is a GNU extension; a plain loop keeps this header portable -- the search is a few lines long)
 static inline const void *sqb_memrchr(const void *s, int c, size_t n)
 {

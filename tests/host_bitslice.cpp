@@ -443,3 +443,9 @@ extern "C" long bs_fastq_record_start(const char *text, size_t lo, size_t cut, s
    const size_t q = sqb::fastq_record_start(text, lo, cut, nbytes);
    return q == (size_t)-1 ? -1L : (long)q;
 }
+
+// sysfs cpulist parser of the NUMA placement (sqb_tables.h: parse_cpulist)
+extern "C" int bs_parse_cpulist(const char *s, unsigned char *cpus, int maxcpus)
+{
+   return sqb::parse_cpulist(s, cpus, maxcpus);
+}

@@ -30,6 +30,8 @@ def harness(tmp_path_factory):
                                    C.c_size_t, C.POINTER(C.c_uint64), C.c_long, C.POINTER(C.c_long)]
     L.bs_host_scan_wm.restype = C.c_long
     L.bs_host_scan_wm.argtypes = L.bs_host_scan_cut.argtypes
+    L.bs_parse_cpulist.restype = C.c_int
+    L.bs_parse_cpulist.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
     L.bs_fastq_record_start.restype = C.c_long
     L.bs_fastq_record_start.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t]
     return L
@@ -239,3 +241,16 @@ def test_fastq_chunk_cuts_are_record_starts(harness):
     # text without records: no boundary
     plain = ("\n".join("".join(rng.choice("ACGT") for _ in range(80)) for _ in range(500)) + "\n").encode()
     assert harness.bs_fastq_record_start(plain, 0, 81 * 200, len(plain)) == -1
+
+
+@pytest.mark.parametrize("text,want", [
+    ("0-31,64-95\n", list(range(32)) + list(range(64, 96))),
+    ("0\n", [0]), ("3,5,7-9", [3, 5, 7, 8, 9]), ("", []), ("\n", []), ("0-3,2-5\n", [0, 1, 2, 3, 4, 5]),
+    ("1020-1030\n", [1020, 1021, 1022, 1023]), ("7-", [])])
+def test_cpulist_parser_of_the_numa_placement(harness, text, want):
+    """Pinned host memory is allocated on the CPUs of the GPU's NUMA node (sqb_engine.cu: NumaScope);
+    the node's sysfs cpulist is parsed by sqb_tables.h: parse_cpulist."""
+    buf = C.create_string_buffer(1024)
+    n = harness.bs_parse_cpulist(text.encode(), buf, 1024)
+    got = [i for i in range(1024) if buf.raw[i] == 1]
+    assert (n, got) == (len(want), want)
