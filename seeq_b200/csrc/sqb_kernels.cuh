@@ -1069,7 +1069,7 @@ __device__ __forceinline__ uint32_t reverse_start(const uint8_t *__restrict__ te
    const uint8_t *p = text + line_begin + end;           // the pass reads p[-1], p[-2], ...
    bool more = end > 0;
 #if SQB_REV_WINDOW
-   // A/B build (-DSQB_REV_WINDOW=1, not the default; DESIGN.md 12, item 4): the last 16 bytes in front of `end` in
+   // A/B build (-DSQB_REV_WINDOW=1, not the default; DESIGN.md 12, item 5): the last 16 bytes in front of `end` in
    // ONE round trip -- the two aligned 16-byte vectors that hold them, realigned in registers -- instead of up to
    // four rounds of byte loads; a pass that is not over after 16 bytes carries on in the loop below.
    if (more && line_begin + end >= 16u) {

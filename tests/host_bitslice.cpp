@@ -17,6 +17,13 @@ struct Ev { uint64_t line, end, dist; };
 // One group of <= 32 lines through a G-part automaton, driven like the kernel:
 // part p works on column t - p at iteration t (NULL columns while the pipeline
 // fills) and receives the horizontal delta part p-1 produced one iteration ago.
+// g_skew generalises the pipeline: part p runs p * g_skew columns behind and takes
+// what part p-1 produced g_skew iterations ago.  The kernels use 1; a skew of 2
+// takes the hand-over off the critical path between consecutive columns of a lane
+// (the parts of two consecutive columns could then be interleaved).
+static int g_skew = 1;
+extern "C" void bs_set_skew(int skew) { g_skew = skew < 1 ? 1 : skew; }
+
 template <int R, int G, int MODE, bool SKIP>
 static void run_group(const std::vector<uint8_t> &cls, size_t n, const std::vector<size_t> &begin, size_t l0,
                       size_t l1, const BsPattern &p, std::vector<Ev> &out)
@@ -24,16 +31,19 @@ static void run_group(const std::vector<uint8_t> &cls, size_t n, const std::vect
    BsState<R, G> st[G];
    const int nl = (int)(l1 - l0);
    for (int g = 0; g < G; g++) bs_reset(st[g], p, nl == 32 ? ~0u : ((1u << nl) - 1u), g);
+   const int skew = g_skew;
+   std::vector<uint32_t> hist_ph((size_t)skew * G, 0u), hist_mh((size_t)skew * G, 0u);   // outputs of the last `skew` iterations
    uint32_t out_ph[G] = {0}, out_mh[G] = {0};
    uint32_t streak[8];
    for (long t = 0; st[G - 1].alive; t++) {
       uint32_t in_ph[G], in_mh[G];
+      const size_t slot = (size_t)(t % skew) * G;          // holds the outputs of iteration t - skew
       for (int g = 0; g < G; g++) {
-         in_ph[g] = g ? out_ph[g - 1] : 0u;
-         in_mh[g] = g ? out_mh[g - 1] : 0u;
+         in_ph[g] = g ? hist_ph[slot + g - 1] : 0u;
+         in_mh[g] = g ? hist_mh[slot + g - 1] : 0u;
       }
       for (int g = 0; g < G; g++) {
-         const long col = t - g;
+         const long col = t - (long)g * skew;
          uint32_t p0 = 0, p1 = 0, p2 = 0;
          for (int r = 0; r < nl; r++) {
             const size_t b = begin[l0 + r], a = b & ~(size_t)15;
@@ -51,6 +61,8 @@ static void run_group(const std::vector<uint8_t> &cls, size_t n, const std::vect
          bs_rows<R, G, SKIP>(st[g], eq, skip, ph, mh);
          out_ph[g] = ph;
          out_mh[g] = mh;
+         hist_ph[slot + g] = ph;                             // read again at iteration t + skew
+         hist_mh[slot + g] = mh;
          if (g == G - 1) {
             const uint32_t evt = bs_report<R, G, MODE>(st[g], p, ph, mh, anybase, stop, streak);
             for (int r = 0; r < nl; r++)

@@ -254,3 +254,37 @@ def test_cpulist_parser_of_the_numa_placement(harness, text, want):
     n = harness.bs_parse_cpulist(text.encode(), buf, 1024)
     got = [i for i in range(1024) if buf.raw[i] == 1]
     assert (n, got) == (len(want), want)
+
+
+@pytest.mark.parametrize("mrange", [(33, 64), (65, 128)])
+def test_multi_part_pipeline_with_a_skew_of_two(harness, oracle, mrange):
+    """The hand-over between the parts of a multi-part automaton does not depend on the parts running
+    exactly one column apart: with part p running 2 p columns behind and reading what part p-1 produced
+    two iterations ago, the events are the same (the kernels use a skew of 1)."""
+    harness.bs_set_skew.argtypes = [C.c_int]
+    harness.bs_set_skew.restype = None
+    harness.bs_set_skew(2)
+    try:
+        rng = random.Random(mrange[0] * 13)
+        checked = 0
+        for it in range(10):
+            pattern = rand_pattern(rng, *mrange)
+            keys, _ = oracle.parse(pattern)
+            tau = rng.randint(0, min(len(keys) - 1, 3 + len(keys) // 8, 14))
+            plant = "".join(rng.choice([c for b, c in ((1, "A"), (2, "C"), (4, "G"), (8, "T")) if k & b] or ["A"])
+                            for k in keys)
+            alphabet = ["ACGT", "ACGTN", "ACGTNXacgu-"][it % 3]
+            buf = make_buffer(rng, rng.randint(1, 150), 60 + 3 * len(keys), alphabet, plant, it % 2 == 0)
+            out = np.zeros((len(buf) + 64, 3), dtype=np.uint64)
+            for mo in (SQ_FIRST, SQ_BEST, SQ_ALL):
+                for nd in (SQ_FAIL, SQ_CONVERT, SQ_IGNORE):
+                    n = harness.bs_host_scan(buf, len(buf), keys, len(keys), tau, mo | nd,
+                                             out.ctypes.data_as(C.POINTER(C.c_uint64)), out.shape[0])
+                    if n == -1:
+                        continue
+                    exp, _, _ = oracle.buffer_scan(buf, keys, tau, mo | nd)
+                    assert np.array_equal(out[:n], exp[:, [0, 2, 3]]), (pattern, tau, mo, nd)
+                    checked += 1
+        assert checked > 30
+    finally:
+        harness.bs_set_skew(1)
