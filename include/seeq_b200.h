@@ -57,7 +57,14 @@ typedef struct {
                          * k1_scan_classify                                    */
    uint32_t launches;   /* kernels launched by this scan                     */
    uint32_t reruns;     /* scans repeated because a capacity guess was low   */
+   uint32_t path;       /* which kernels served the (last chunk of the) scan: SQB_PATH_* bits */
+   uint32_t devices;    /* GPUs that took part (sqbScanHost with SEEQ_B200_DEVICES)          */
 } sqb_stats_t;
+
+#define SQB_PATH_BITSLICE 0x1   /* line-bit-sliced matcher (k2_bitslice), else the word-parallel kernels  */
+#define SQB_PATH_FUSED    0x2   /* fused tokenise + bit-plane pack (k12_scan_pack), else K1 + k15_pack    */
+#define SQB_PATH_CUTS     0x4   /* long lines cut into segments                                          */
+#define SQB_PATH_FILTER   0x8   /* line filter on (dead-on-arrival lines / FASTQ records not packed)     */
 
 /* flags, OR-ed into `options` next to the SQ_* bits of libseeq.h */
 #define SQB_COUNT_ONLY   0x0100  /* no records: nmatched and nrecs only      */

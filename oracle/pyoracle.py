@@ -170,6 +170,9 @@ class Reference:
         L.ref_bench.restype = C.c_double
         L.ref_bench.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int,
                                 C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
+        L.ref_bench_ck.restype = C.c_double
+        L.ref_bench_ck.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long), u64p]
         self.L = L
 
     def string_match(self, pattern, tau, text, options, cap=4096):
@@ -211,3 +214,25 @@ class Reference:
         s = self.L.ref_bench(ptr, n_in, _as_bytes(pattern), tau, options, mode,
                              nproc, C.byref(total))
         return s, total.value
+
+    def bench_ck(self, buf, pattern, tau, options, mode, nproc):
+        """-> (wall seconds, summed result, checksum of the records: see records_checksum)."""
+        ptr, n_in = self._ptr(buf)
+        total = C.c_long(0)
+        ck = C.c_uint64(0)
+        s = self.L.ref_bench_ck(ptr, n_in, _as_bytes(pattern), tau, options, mode,
+                                nproc, C.byref(total), C.byref(ck))
+        return s, total.value, ck.value
+
+
+CK_P = (0x9E3779B97F4A7C15, 0xC2B2AE3D27D4EB4F, 0x165667B19E3779F9, 0x27D4EB2F165667C5, 0x85EBCA77C2B2AE63)
+
+
+def records_checksum(line1, start, end, dist) -> int:
+    """The checksum of oracle/ref_driver.c (ref_bench_ck) over arrays of records; line1 = 1-based
+    buffer-global line numbers.  Arithmetic mod 2^64 (numpy uint64 wraps)."""
+    with np.errstate(over="ignore"):
+        p = [np.uint64(x) for x in CK_P]
+        a = (np.asarray(line1, dtype=np.uint64) * p[0] + np.asarray(start, dtype=np.uint64) * p[1] +
+             np.asarray(end, dtype=np.uint64) * p[2] + np.asarray(dist, dtype=np.uint64) * p[3] + p[4])
+        return int(a.sum(dtype=np.uint64))

@@ -52,7 +52,10 @@ class SeeqArgT(C.Structure):
 class StatsT(C.Structure):
     _fields_ = [("nbytes", C.c_uint64), ("nlines", C.c_uint64), ("nmatched", C.c_uint64),
                 ("nrecs", C.c_uint64), ("device_ms", C.c_double), ("kernel_ms", C.c_double * 8),
-                ("launches", C.c_uint32), ("reruns", C.c_uint32)]
+                ("launches", C.c_uint32), ("reruns", C.c_uint32), ("path", C.c_uint32), ("devices", C.c_uint32)]
+
+
+SQB_PATH_BITSLICE, SQB_PATH_FUSED, SQB_PATH_CUTS, SQB_PATH_FILTER = 1, 2, 4, 8
 
 
 class GenT(C.Structure):

@@ -76,6 +76,30 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(tag: str, defines, verbose: bool = False) -> str:
+    """An A/B build of the library with extra -D flags -> seeq_b200/libseeq_b200_<tag>.so (git-ignored; travels
+    to the GPU box; selected with SEEQ_B200_LIB, see tools/gpu_session.sh `ab`)."""
+    objdir = os.path.join(HERE, "build_" + tag)
+    os.makedirs(objdir, exist_ok=True)
+    lib = os.path.join(HERE, "libseeq_b200_%s.so" % tag)
+    objs, jobs = [], []
+    for src in CU_SOURCES:
+        o = os.path.join(objdir, src + ".o")
+        jobs.append([NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp", *defines,
+                     "-I" + INC, "-I" + CSRC, "-c", os.path.join(CSRC, src), "-o", o] + (["-Xptxas", "-v"] if verbose else []))
+        objs.append(o)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(jobs)) as pool:
+        list(pool.map(_run, jobs))
+    for src in C_SOURCES:
+        o = os.path.join(objdir, src + ".o")
+        _run(["gcc", "-std=c99", "-O2", "-fPIC", "-Wall", "-Wextra", "-I" + INC, "-I" + CSRC, "-c",
+              os.path.join(CSRC, src), "-o", o])
+        objs.append(o)
+    _run([NVCC, *ARCH, "-shared", "-o", lib, *objs, "-Xcompiler", "-fopenmp", "-lgomp"])
+    return lib
+
+
 def build_relinks(force: bool = False) -> dict:
     """Re-link the reference front-ends against our library (no source copied)."""
     out = {}
@@ -91,12 +115,16 @@ def build_relinks(force: bool = False) -> dict:
         _run(["gcc", "-std=gnu99", "-O2", "-w", "-ftrivial-auto-var-init=zero", "-I" + INC,
               main_c, "-o", cli, "-L" + HERE, "-lseeq_b200", rpath])
     out["cli"] = cli
+    # the CPython module: seeqmodule.c is compiled where it lies (included by path from our wrapper
+    # translation unit, which adds the batched method SeeqObject.matchBatch)
     mod_c = os.path.join(src, "seeqmodule.c")
+    wrap_c = os.path.join(CSRC, "seeqmodule_b200.c")
     ext = sysconfig.get_config_var("EXT_SUFFIX") or ".so"
     mod = os.path.join(RELINK, "seeq" + ext)
-    if force or _newer(mod, [mod_c, LIB]):
+    if force or _newer(mod, [mod_c, wrap_c, LIB]):
         _run(["gcc", "-std=gnu99", "-O2", "-w", "-fPIC", "-shared", "-DMAJOR_VERSION=1", "-DMINOR_VERSION=2",
-              "-I" + INC, "-I" + sysconfig.get_paths()["include"], mod_c, "-o", mod,
+              "-DSQB_REFERENCE_MODULE=\"" + mod_c + "\"",
+              "-I" + INC, "-I" + sysconfig.get_paths()["include"], wrap_c, "-o", mod,
               "-L" + HERE, "-lseeq_b200", rpath])
     out["module"] = mod
     return out
@@ -108,5 +136,8 @@ def build_all(force: bool = False, verbose: bool = False) -> None:
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "variant":      # python seeq_b200/build.py variant TAG -DX=1 ...
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+        sys.exit(0)
     build_all(force="-B" in sys.argv, verbose="-v" in sys.argv)
     print(LIB)

@@ -159,6 +159,15 @@ sqb_engine_t *seeqEngine(seeq_t *sq)
    sqb_seeq_t *p = (sqb_seeq_t *)sq;
    if (p->magic != SQB_SEEQ_MAGIC) { errno = EINVAL; return NULL; }
    if (p->engine == NULL) {
+      /* seeqNew accepts a pattern of any length, as the reference does (libseeq.c:43-138); the blocked
+       * automaton serves up to sqbMaxPatternLength() positions.  A longer pattern is not a missing
+       * device: say so with an errno of its own (E2BIG) instead of ENODEV */
+      if (sq->wlen > sqbMaxPatternLength()) {
+         fprintf(stderr, "seeq-b200: pattern of %d positions exceeds the %d supported by the GPU matcher\n",
+                 sq->wlen, sqbMaxPatternLength());
+         errno = E2BIG;
+         return NULL;
+      }
       p->engine = sqbEngineNew((const unsigned char *)sq->keys, sq->wlen, sq->tau, -1);
       if (p->engine == NULL) {
          fprintf(stderr, "seeq-b200: %s\n", sqbLastError());

@@ -177,6 +177,9 @@ static int chunk_load(sqb_file_t *f)
    f->cur_line = f->cur_rec = 0;
    f->nlines = f->nrecs = 0;
    f->res_valid = 0;
+   f->hdr_scan = f->hdr_off = 0;
+   f->hdr_seen = 0;
+   f->hdr_dirty = 1;
    if (f->eof && carry == 0) return 0;
 
    size_t want = f->target;
@@ -273,31 +276,44 @@ static size_t line_length(const sqb_file_t *f, size_t off)
    return nl ? (size_t)(nl - (f->buf + off)) : f->len - off;
 }
 
-/* FASTA: sqfile->info = last header line before chunk offset `off` */
+/* FASTA: sqfile->info = last header line before chunk offset `off` (a line start).  The cursor walks
+ * forward from the line served before; info is rewritten only when the header in force changes. */
 static int update_info(sqb_file_t *f, size_t off)
 {
-   size_t end = off;
-   while (end > 0) {
-      const size_t s = line_start_before(f->buf, end);
-      if (f->buf[s] == '>') {
-         size_t n = end - s;
-         if (n && f->buf[s + n - 1] == '\n') n--;
-         char *h = malloc(n + 1);
-         if (h == NULL) { seeqerr = 666; return -1; }
-         memcpy(h, f->buf + s, n);
-         h[n] = 0;
-         free(f->pub.info);
-         f->pub.info = h;
-         return 0;
-      }
-      end = s;
+   if (off < f->hdr_scan) {                         /* (not on the iterator's path: start over) */
+      f->hdr_scan = 0;
+      f->hdr_seen = 0;
+      f->hdr_dirty = 1;
    }
-   if (f->last_header) {
-      char *h = strdup(f->last_header);
+   size_t p = f->hdr_scan;
+   while (p < off) {
+      if (f->buf[p] == '>') {
+         f->hdr_off = p;
+         f->hdr_seen = 1;
+         f->hdr_dirty = 1;
+      }
+      const char *nl = memchr(f->buf + p, '\n', off - p);
+      if (nl == NULL) break;                        /* off is a line start: not reached */
+      p = (size_t)(nl - f->buf) + 1;
+   }
+   f->hdr_scan = off;
+   if (!f->hdr_dirty) return 0;
+   char *h = NULL;
+   if (f->hdr_seen) {
+      const size_t n = line_length(f, f->hdr_off);
+      h = malloc(n + 1);
+      if (h == NULL) { seeqerr = 666; return -1; }  /* seeq.c:370 */
+      memcpy(h, f->buf + f->hdr_off, n);
+      h[n] = 0;
+   } else if (f->last_header) {
+      h = strdup(f->last_header);
       if (h == NULL) { seeqerr = 666; return -1; }
+   }
+   if (h) {
       free(f->pub.info);
       f->pub.info = h;
    }
+   f->hdr_dirty = 0;
    return 0;
 }
 

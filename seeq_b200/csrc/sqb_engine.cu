@@ -23,6 +23,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <set>
+#include <utility>
 #include <vector>
 
 #include "seeq_b200.h"
@@ -54,6 +57,19 @@ static void set_err(const char *fmt, ...)
          return -1;                                                                    \
       }                                                                                \
    } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE attribute of a kernel: the opt-in
+// is made once per (kernel, device), from whichever host thread gets there first (engines of several
+// devices may live in one process, one host thread each: sqbScanHost with SEEQ_B200_DEVICES)
+static bool first_use(const void *fn)
+{
+   static std::mutex mu;
+   static std::set<std::pair<const void *, int>> seen;
+   int dev = 0;
+   if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+   std::lock_guard<std::mutex> lock(mu);
+   return seen.insert(std::make_pair(fn, dev)).second;
+}
 
 // ---------------------------------------------------------------------------
 // CUDA events of a scan (SQB_TIMING records all of them, otherwise only E_DONE)
@@ -197,11 +213,13 @@ static void build_pattern(const sqb_engine *e, int options, bool reverse, Patter
 // on the other socket makes every DMA cross the inter-socket link, and with one process
 // per GPU all of them do at once.  For the duration of an allocation the calling thread
 // is therefore moved onto the CPUs of the GPU's NUMA node (sysfs: numa_node of the PCI
-// device, cpulist of the node) and its memory policy set to prefer that node; both are
-// restored afterwards.  No-op where sysfs has no answer (VMs), or with SEEQ_B200_NUMA=0.
+// device, cpulist of the node) and its memory policy set to prefer that node; the affinity
+// mask and the caller's policy (get_mempolicy) are put back afterwards.  No-op where sysfs has no answer (VMs), or with SEEQ_B200_NUMA=0.
 struct NumaScope {
    cpu_set_t old_set;
    bool moved = false, policy = false;
+   int old_mode = 0;                       // the caller's memory policy (numactl --membind / --interleave ...)
+   unsigned long old_mask[16] = {};        // 1024 nodes
 
    static int node_of(int device)
    {
@@ -250,12 +268,16 @@ struct NumaScope {
       if (CPU_COUNT(&cur) > 0 && !CPU_EQUAL(&cur, &old_set)) moved = sched_setaffinity(0, sizeof cur, &cur) == 0;
       if (node < 64) {
          unsigned long mask = 1ul << node;
+         if (syscall(SYS_get_mempolicy, &old_mode, old_mask, sizeof old_mask * 8ul, nullptr, 0ul) != 0) return;
          policy = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 65ul) == 0;
       }
    }
    ~NumaScope()
    {
-      if (policy) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+      if (policy) {                        // exactly what the caller had (MPOL_DEFAULT takes no node mask)
+         if (old_mode == 0) syscall(SYS_set_mempolicy, 0, nullptr, 0ul);
+         else syscall(SYS_set_mempolicy, old_mode, old_mask, sizeof old_mask * 8ul);
+      }
       if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
    }
 };
@@ -332,12 +354,9 @@ template <int W> static int launch_k2_thread(int mode, int grid, cudaStream_t st
 {
 #define SQB_CASE(M)                                                                              \
    case M: {                                                                                     \
-      static bool attr = false;                                                                  \
-      if (!attr) {                                                                               \
+      if (first_use((const void *)k2_forward_thread<W, M>))                                      \
          CU(cudaFuncSetAttribute(k2_forward_thread<W, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                  (int)kK2Stage));                                                \
-         attr = true;                                                                            \
-      }                                                                                          \
       k2_forward_thread<W, M><<<grid, kThreads, kK2Stage, st>>>(a, p);                            \
       break;                                                                                     \
    }
@@ -437,11 +456,9 @@ static bool use_cuts(const sqb_engine *e, int options, uint32_t n)
 template <int R, int G, int MODE> static int launch_bs2(bool skip, int grid, cudaStream_t st, const K2BsArgs &a, const BsPattern &p)
 {
    const size_t smem = (MODE == BS_ALL ? sizeof(BsWarpSmemAll) : sizeof(BsWarpSmem)) * kBsWarps;
-   static bool attr = false;
-   if (!attr) {
+   if (first_use((const void *)k2_bitslice<R, G, MODE, true>)) {
       CU(cudaFuncSetAttribute(k2_bitslice<R, G, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       CU(cudaFuncSetAttribute(k2_bitslice<R, G, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = true;
    }
    if (skip) k2_bitslice<R, G, MODE, true><<<grid, kBsThreads, smem, st>>>(a, p);
    else k2_bitslice<R, G, MODE, false><<<grid, kBsThreads, smem, st>>>(a, p);
@@ -596,14 +613,12 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
                 (uint32_t)e->filter_k, (options & SQB_FASTA) ? 1 : 0, skip};
       ClassTable ct;
       build_class_table(options, &ct);
-      static bool attr = false;
-      if (!attr) {
+      if (first_use((const void *)k1_scan_classify<true, true, true>)) {
          CU(cudaFuncSetAttribute(k1_scan_classify<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
          CU(cudaFuncSetAttribute(k1_scan_classify<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
          CU(cudaFuncSetAttribute(k1_scan_classify<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
          CU(cudaFuncSetAttribute(k1_scan_classify<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
          CU(cudaFuncSetAttribute(k1_scan_classify<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
-         attr = true;
       }
       const int grid = (int)std::min<size_t>(div_up(n, kK1Tile), (size_t)e->sms * 3);
       if (cut && k1_filter) k1_scan_classify<true, true, true><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
@@ -831,6 +846,9 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
       stats->nrecs = s.h_ctr[C_NRECS];
       stats->launches = s.launches;
       stats->reruns = reruns;
+      stats->devices = 1;
+      stats->path = (s.h_ctr[C_BS_SELECTED] == 1ull ? SQB_PATH_BITSLICE : 0u) | (s.h_ctr[C_NCUTS] ? SQB_PATH_CUTS : 0u) |
+                    (s.cur_filter ? SQB_PATH_FILTER : 0u);
       if (s.cur_options & SQB_TIMING) {
          static const int span[6][2] = {{E_BEGIN, E_K1_END}, {E_K1_END, E_K2_END}, {E_K2_END, E_FIN_END},
                                         {E_PACK_END, E_MATCH_END}, {E_PACK_BEGIN, E_PACK_END}, {E_BEGIN, E_K1C_END}};
@@ -1101,6 +1119,8 @@ static int host_collect(sqb_engine *e, Slot &s, int options, uint64_t *line_base
    acc->nrecs += st.nrecs;
    acc->launches += st.launches;
    acc->reruns += st.reruns;
+   acc->path = st.path;
+   acc->devices = 1;
    acc->device_ms += st.device_ms;
    for (int k = 0; k < 8; k++) acc->kernel_ms[k] += st.kernel_ms[k];
    return 0;

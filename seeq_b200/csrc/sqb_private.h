@@ -53,6 +53,13 @@ typedef struct {
    size_t         line_base;    /* counted lines before the resident chunk    */
    size_t         target;       /* bytes to read per chunk                    */
    char         * last_header;  /* FASTA: last header seen before the chunk   */
+   /* FASTA: forward cursor over the headers of the resident chunk.  Lines are handed out in increasing
+    * order, so the header in force for a line is found by walking on from the previous line served:
+    * O(chunk) per chunk in total (the reference keeps the last header as it reads, seeq.c:367-374) */
+   size_t         hdr_scan;     /* a line start: everything before it has been examined    */
+   size_t         hdr_off;      /* offset of the last header line before hdr_scan          */
+   int            hdr_seen;     /* 1: hdr_off is valid (else the header is last_header)    */
+   int            hdr_dirty;    /* 1: pub.info does not show the header in force           */
 } sqb_file_t;
 
 int  sqb_parse_pattern (const char * text, char * keys);

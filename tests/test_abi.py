@@ -66,7 +66,7 @@ def test_struct_layouts(B):
     assert C.sizeof(B.MatchT) == 24
     F = B.SeeqFileT
     assert [getattr(F, n).offset for n in ("flags", "line", "info", "fdi")] == [0, 8, 16, 24]
-    assert C.sizeof(B.StatsT) == 4 * 8 + 8 + 8 * 8 + 8 and C.sizeof(B.GenT) == 8 + 7 * 4 + 256 + 4
+    assert C.sizeof(B.StatsT) == 4 * 8 + 8 + 8 * 8 + 16 and C.sizeof(B.GenT) == 8 + 7 * 4 + 256 + 4
 
 
 def test_seeqnew_fields_and_errors(B):
@@ -155,3 +155,28 @@ def test_shard_range_agrees_with_numpy_statement(B):
             assert want[0][0] == 0 and want[-1][1] == n
             for (b0, e0), (b1, e1) in zip(want, want[1:]):
                 assert e0 == b1 and (b1 == 0 or b1 == n or buf[b1 - 1] == 0x0A)
+
+
+def test_relinked_module_has_the_batched_method():
+    """seeq_b200/_relink/seeq*.so (the reference's seeqmodule.c compiled in place + matchBatch): imports,
+    keeps the reference's surface (seeqmodule.c:986-1014, :1097-1103) and fails loudly without a device."""
+    import glob
+    import importlib.util
+    from seeq_b200 import build
+    build.build_library()
+    out = build.build_relinks()
+    if "module" not in out:
+        pytest.skip("reference tree absent: the module cannot be re-linked here")
+    mods = glob.glob(os.path.join(os.path.dirname(out["module"]), "seeq*.so"))
+    spec = importlib.util.spec_from_file_location("seeq", mods[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    m = mod.compile("CGCTAATTAATGGAAT", 3)
+    for name in ("match", "matchBest", "matchAll", "matchIter", "matchPrefix", "matchSuffix", "matchBatch"):
+        assert callable(getattr(m, name)), name
+    with pytest.raises(mod.exception):
+        m.matchBatch(b"ACGT\n", mode="fastest")
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(mod.clibexception):
+            m.matchBatch(b"ACGT\nGGGGCGCTAATAATGGAATGGGG\n")

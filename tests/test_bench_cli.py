@@ -28,7 +28,10 @@ def test_reference_arm_prints_the_contract_line():
     assert d["higher_is_better"] is True and d["gpu_launches"] == 0 and d["value"] > 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["workload"].startswith("cfg2")
+    # the default workload is the metric's own shape (BASELINE.json: "d=2, 20-nt pattern")
+    assert d["config"]["workload"].startswith("metric") and d["config"]["distance"] == 2 and len(d["config"]["pattern"]) == 20
+    assert set(d["config"]) == {"workload", "pattern", "distance", "reads_per_gpu", "bytes_per_gpu", "line_len",
+                                "l2_policy", "sharding"}
 
 
 def test_reference_arm_other_ranks_do_nothing():

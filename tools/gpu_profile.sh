@@ -7,7 +7,7 @@ TAG=${1:-r1}
 WL=${2:-cfg2}
 OUT=gpurun_out
 mkdir -p $OUT
-BENCH="python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
+BENCH="python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-configs"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file $OUT/${TAG}_${WL}_launches.csv $BENCH > $OUT/${TAG}_${WL}_launches.log 2>&1
 # skip the generator + 3 warm-up steps, then capture one full step
