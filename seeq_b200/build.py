@@ -28,7 +28,11 @@ REFERENCE_DIR = os.environ.get("SEEQ_REFERENCE_DIR", "/root/reference")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
-CU_SOURCES = ["sqb_engine.cu", "sqb_engine_wm.cu"]
+# (source, extra defines, object name): the matcher instances are spread over translation units that compile side by side
+CU_UNITS = [("sqb_engine.cu", [], "sqb_engine.cu.o"),
+            ("sqb_engine_wm.cu", ["-DSQB_WM_FUSED=0"], "sqb_engine_wm.cu.o"),
+            ("sqb_engine_wm.cu", ["-DSQB_WM_FUSED=1"], "sqb_engine_wmf.cu.o"),
+            ("sqb_engine_bsf.cu", [], "sqb_engine_bsf.cu.o")]
 C_SOURCES = ["seeq_api.c", "seeq_file.c"]
 HEADERS = sorted(os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".h", ".cuh"))) + \
           [os.path.join(INC, h) for h in ("libseeq.h", "seeq.h", "seeq_b200.h")]
@@ -53,11 +57,11 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     objs = []
     jobs = []
-    for src in CU_SOURCES:
+    for src, defs, oname in CU_UNITS:
         s = os.path.join(CSRC, src)
-        o = os.path.join(objdir, src + ".o")
+        o = os.path.join(objdir, oname)
         if force or _newer(o, [s] + HEADERS):
-            jobs.append([NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp",
+            jobs.append([NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp", *defs,
                          "-I" + INC, "-I" + CSRC, "-c", s, "-o", o] + (["-Xptxas", "-v"] if verbose else []))
         objs.append(o)
     if jobs:                                  # the translation units compile side by side
@@ -83,9 +87,9 @@ def build_variant(tag: str, defines, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     lib = os.path.join(HERE, "libseeq_b200_%s.so" % tag)
     objs, jobs = [], []
-    for src in CU_SOURCES:
-        o = os.path.join(objdir, src + ".o")
-        jobs.append([NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp", *defines,
+    for src, defs, oname in CU_UNITS:
+        o = os.path.join(objdir, oname)
+        jobs.append([NVCC, *ARCH, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fopenmp", *defs, *defines,
                      "-I" + INC, "-I" + CSRC, "-c", os.path.join(CSRC, src), "-o", o] + (["-Xptxas", "-v"] if verbose else []))
         objs.append(o)
     from concurrent.futures import ThreadPoolExecutor

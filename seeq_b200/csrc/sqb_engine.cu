@@ -32,6 +32,7 @@
 #include "sqb_gen.h"
 #include "sqb_kernels.cuh"
 #include "sqb_k2_bitslice.cuh"
+#include "sqb_k12_fused.cuh"
 
 using namespace sqb;
 
@@ -61,7 +62,9 @@ static void set_err(const char *fmt, ...)
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE attribute of a kernel: the opt-in
 // is made once per (kernel, device), from whichever host thread gets there first (engines of several
 // devices may live in one process, one host thread each: sqbScanHost with SEEQ_B200_DEVICES)
-static bool first_use(const void *fn)
+bool sqb_first_use(const void *fn);
+static bool first_use(const void *fn) { return sqb_first_use(fn); }
+bool sqb_first_use(const void *fn)
 {
    static std::mutex mu;
    static std::set<std::pair<const void *, int>> seen;
@@ -94,6 +97,9 @@ struct Slot {
    const Slot *cur_front = nullptr; // multi-pattern: the slot whose K1 / pack output this scan reads (or nullptr)
    uint4 *d_planes = nullptr;   size_t planes_cap = 0;    // bit-planes, 32 uint4 per tile column
    uint32_t *d_bstiles = nullptr; size_t bstiles_cap = 0; // per match tile: columns, offset
+   GroupDesc *d_gdesc = nullptr; size_t gdesc_cap = 0;    // fused tokenise + pack: one descriptor per group of 32 lines
+   uint16_t *d_gent = nullptr;  size_t gent_cap = 0;      //   line filter: local entry index of every slot
+   bool cur_fused = false;
    uint32_t *d_fintiles = nullptr; size_t fintiles_cap = 0; // per 1024-line tile: records, matched lines, first record
    unsigned long long *d_res = nullptr; size_t res_cap = 0;
    uint32_t *d_cnt = nullptr;   size_t cnt_cap = 0;
@@ -152,6 +158,12 @@ struct sqb_engine {
    BsGate bs_gate{65536u, 4096u};
    uint32_t bs_min_bytes = 1u << 20;
    double cols_per_byte = 1.3 / 1024.0;   // tile columns per text byte (plane buffer guess)
+   // fused tokenise + pack (sqb_k12_fused.cuh): 1 = use it where it applies, 0 = never (SEEQ_B200_FUSED=0, a
+   // pattern set, or a scan that met something the fused kernel does not handle: from then on the
+   // two-kernel path serves this engine)
+   int fused = 1;
+   uint32_t fused_ov = 512;               // overlap staged behind a tile; 4096 after a scan met longer lines
+   double units_per_byte = 0.0255;        // plane units (16 B) per text byte: 3 bits per byte + padding
    BsPattern bs_pat;
    Slot slot[2];
    // lines / events per byte seen so far (capacity guesses)
@@ -319,7 +331,7 @@ template <class T> static int pin_reserve(T **p, size_t *cap, size_t need)
 
 static void slot_free(Slot &s)
 {
-   cudaFree(s.d_text); cudaFree(s.d_ls); cudaFree(s.d_codes); cudaFree(s.d_ls_raw); cudaFree(s.d_tiles); cudaFree(s.d_lid); cudaFree(s.d_lbeg); cudaFree(s.d_gmask); cudaFree(s.d_segflags); cudaFree(s.d_act); cudaFree(s.d_lflags); cudaFree(s.d_planes); cudaFree(s.d_bstiles); cudaFree(s.d_fintiles); cudaFree(s.d_res); cudaFree(s.d_cnt); cudaFree(s.d_offs);
+   cudaFree(s.d_text); cudaFree(s.d_ls); cudaFree(s.d_codes); cudaFree(s.d_ls_raw); cudaFree(s.d_tiles); cudaFree(s.d_lid); cudaFree(s.d_lbeg); cudaFree(s.d_gmask); cudaFree(s.d_segflags); cudaFree(s.d_act); cudaFree(s.d_lflags); cudaFree(s.d_planes); cudaFree(s.d_bstiles); cudaFree(s.d_gdesc); cudaFree(s.d_gent); cudaFree(s.d_fintiles); cudaFree(s.d_res); cudaFree(s.d_cnt); cudaFree(s.d_offs);
    cudaFree(s.d_ev); cudaFree(s.d_recs); cudaFree(s.d_ctl);
    cudaFreeHost(s.h_ctr); cudaFreeHost(s.h_recs); cudaFreeHost(s.h_ls); cudaFreeHost(s.h_init);
    for (auto &ev : s.ev) if (ev) cudaEventDestroy(ev);
@@ -452,6 +464,15 @@ static bool use_cuts(const sqb_engine *e, int options, uint32_t n)
 {
    return cuts_allowed(e, options, n) && (e->cuts == 2 || e->cuts_wanted);
 }
+// the fused tokenise + pack kernel serves the bit-sliced scans of single-part automata over plain lines:
+// no FASTA header rule, no record structure, no segment cuts (an engine that has met long lines cuts
+// them on the two-kernel path), not inside a pattern set
+static bool use_fused(const sqb_engine *e, int options, uint32_t n)
+{
+   if (!e->fused || !use_bitslice(e, options, n) || e->bs_pat.parts != 1) return false;
+   if (options & (SQB_FASTA | SQB_FASTQ)) return false;
+   return !use_cuts(e, options, n);
+}
 
 template <int R, int G, int MODE> static int launch_bs2(bool skip, int grid, cudaStream_t st, const K2BsArgs &a, const BsPattern &p)
 {
@@ -475,9 +496,13 @@ template <int R, int G> static int launch_bs1(int bsmode, bool skip, int grid, c
    }
 }
 
-// sqb_engine_wm.cu
+// sqb_engine_wm.cu (compiled twice: planes of k15_pack / group planes of the fused kernel), sqb_engine_bsf.cu
 cudaError_t sqb_launch_bitslice_wm(int rows, int levels, int bsmode, bool skip, int grid, cudaStream_t st,
                                    const K2BsArgs &a, const BsPattern &p);
+cudaError_t sqb_launch_bitslice_wm_fused(int rows, int levels, int bsmode, bool skip, int grid, cudaStream_t st,
+                                         const K2BsArgs &a, const BsPattern &p);
+cudaError_t sqb_launch_bitslice_myers_fused(int rows, int bsmode, bool skip, int grid, cudaStream_t st,
+                                            const K2BsArgs &a, const BsPattern &p);
 
 static int launch_bitslice(const sqb_engine *e, int mode, int options, size_t max_lines, cudaStream_t st, const K2BsArgs &a)
 {
@@ -491,8 +516,14 @@ static int launch_bitslice(const sqb_engine *e, int mode, int options, size_t ma
    // work items = (tile, 1/G of its groups), one warp each
    const int grid = (int)std::max<size_t>(1, std::min<size_t>(div_up(div_up(max_lines, kBsTileLines) * G, kBsWarps),
                                                                (size_t)e->sms * per_sm * 2));
+   const bool fused = a.gdesc != nullptr;                 // (single-part automata only: use_fused)
    if (nfa) {                                             // small tau: the NFA-level automaton is cheaper
-      CU(sqb_launch_bitslice_wm(R, e->tau + 1, bsmode, skip, grid, st, a, e->bs_pat));
+      if (fused) CU(sqb_launch_bitslice_wm_fused(R, e->tau + 1, bsmode, skip, grid, st, a, e->bs_pat));
+      else CU(sqb_launch_bitslice_wm(R, e->tau + 1, bsmode, skip, grid, st, a, e->bs_pat));
+      return 0;
+   }
+   if (fused) {
+      CU(sqb_launch_bitslice_myers_fused(R, bsmode, skip, grid, st, a, e->bs_pat));
       return 0;
    }
 #define SQB_SHAPE(RR, GG) if (R == RR && G == GG) return launch_bs1<RR, GG>(bsmode, skip, grid, st, a, e->bs_pat);
@@ -571,6 +602,8 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
                              : (!single && (fastq ? use_bitslice(e, options, n) : use_filter(e, options, n)));
    const bool k1_filter = filter && !fastq;
    s.cur_filter = filter;
+   const bool fused = !single && !front && use_fused(e, options, n);
+   s.cur_fused = fused;
 
    // ---- K1 ------------------------------------------------------------------
    if (front) {
@@ -587,7 +620,7 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
       CU(cudaMemcpyAsync(ctr + C_NPSEUDO, s.h_ctr + C_NLINES, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
    } else {
       const bool want_codes = use_bitslice(e, options, n);
-      if (want_codes) {
+      if (want_codes && !fused) {
          const size_t need = k1_tiles * (kK1Tile / 2) + 256;
          if (dev_reserve(&s.d_codes, &s.codes_cap, need)) return -1;
       }
@@ -596,7 +629,7 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
       uint32_t *tile_real = tile_base + k1_tiles, *tile_rbase = tile_real + k1_tiles;
       uint32_t *tile_last = tile_rbase + k1_tiles, *tile_lbeg = tile_last + k1_tiles;
       uint32_t *tile_alive = tile_lbeg + k1_tiles, *tile_abase = tile_alive + k1_tiles;
-      if (filter) {
+      if (filter && !fused) {
          if (dev_reserve(&s.d_act, &s.act_cap, s.line_cap, 64)) return -1;
          if (dev_reserve(&s.d_lflags, &s.lflags_cap, s.line_cap, 64)) return -1;
       }
@@ -608,11 +641,29 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
          CU(cudaMemsetAsync(s.d_segflags, 0, 2 * s.line_cap, st));
       }
       const uint32_t ntiles = (uint32_t)div_up(n, kK1Tile);
+      ClassTable ct;
+      build_class_table(options, &ct);
+      const int grid = (int)std::min<size_t>(div_up(n, kK1Tile), (size_t)e->sms * 3);
+      if (fused) {
+         // groups: 32 lines each, plus one partial group per K1 tile at most
+         if (dev_reserve(&s.d_gdesc, &s.gdesc_cap, s.line_cap / 32 + k1_tiles + 64, 64)) return -1;
+         if (filter && dev_reserve(&s.d_gent, &s.gent_cap, s.gdesc_cap * 32, 64)) return -1;
+         const size_t want_units = (size_t)((double)n * e->units_per_byte) + 4096;
+         if (dev_reserve(&s.d_planes, &s.planes_cap, want_units, 16)) return -1;
+         K12Args ka{d_text, n, s.d_ls_raw, (uint32_t)s.line_cap, ctr, tile_cnt, tile_off, tile_alive,
+                    (uint32_t)e->filter_k, skip, e->fused_ov, s.d_gdesc, (uint32_t)std::min<size_t>(s.gdesc_cap, 0xffffffffu),
+                    s.d_gent, s.d_planes, (uint32_t)std::min<size_t>(s.planes_cap, 0xffffffffu)};
+         if (first_use((const void *)k12_scan_pack<true>)) {
+            CU(cudaFuncSetAttribute(k12_scan_pack<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k12_smem_bytes(kFMaxOverlap)));
+            CU(cudaFuncSetAttribute(k12_scan_pack<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k12_smem_bytes(kFMaxOverlap)));
+         }
+         const size_t smem = k12_smem_bytes(e->fused_ov);
+         if (filter) k12_scan_pack<true><<<grid, kThreads, smem, st>>>(ka, ct);
+         else k12_scan_pack<false><<<grid, kThreads, smem, st>>>(ka, ct);
+      } else {
       K1Args k1{d_text, n, s.d_ls_raw, (uint32_t)s.line_cap, want_codes ? (uint2 *)s.d_codes : nullptr, ctr,
                 tile_cnt, tile_off, tile_real, tile_last, tile_alive,
                 (uint32_t)e->filter_k, (options & SQB_FASTA) ? 1 : 0, skip};
-      ClassTable ct;
-      build_class_table(options, &ct);
       if (first_use((const void *)k1_scan_classify<true, true, true>)) {
          CU(cudaFuncSetAttribute(k1_scan_classify<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
          CU(cudaFuncSetAttribute(k1_scan_classify<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
@@ -620,20 +671,22 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
          CU(cudaFuncSetAttribute(k1_scan_classify<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
          CU(cudaFuncSetAttribute(k1_scan_classify<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kK1Smem));
       }
-      const int grid = (int)std::min<size_t>(div_up(n, kK1Tile), (size_t)e->sms * 3);
       if (cut && k1_filter) k1_scan_classify<true, true, true><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
       else if (cut) k1_scan_classify<true, true, false><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
       else if (k1_filter) k1_scan_classify<true, false, true><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
       else if (want_codes) k1_scan_classify<true, false, false><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
       else k1_scan_classify<false, false, false><<<grid, kThreads, kK1Smem, st>>>(k1, ct);
+      }
       CU(cudaGetLastError());
       if (timing) CU(record_event(s.ev[E_K1C_END], st));
       K1ScanArgs ks{tile_cnt, tile_base, ntiles, ctr, cut ? tile_real : nullptr, tile_rbase, tile_last, tile_lbeg,
-                    filter ? tile_alive : nullptr, tile_abase, fastq ? 1 : 0};
+                    filter ? tile_alive : nullptr, tile_abase, fastq ? 1 : 0,
+                    fused ? 1 : 0, (uint32_t)std::min<size_t>(s.planes_cap, 0xffffffffu),
+                    (uint32_t)std::min<size_t>(s.gdesc_cap, 0xffffffffu), e->bs_gate};
       k1_scan_tiles<<<1, 1024, 0, st>>>(ks);
       K1GatherArgs kg{s.d_ls_raw, s.d_ls, (uint32_t)s.line_cap, tile_cnt, tile_off, tile_base, ntiles, n, ctr,
                       cut ? s.d_codes : nullptr, tile_rbase, tile_lbeg, s.d_lid, s.d_lbeg,
-                      filter ? tile_abase : nullptr, s.d_act, s.d_lflags,
+                      filter ? tile_abase : nullptr, fused ? nullptr : s.d_act, s.d_lflags,
                       (want_codes && (mode == M_FIRST || mode == M_BEST)) ? s.d_res : nullptr, fastq ? 1 : 0};
       k1_gather<<<(int)std::min<size_t>(div_up(ntiles, kWarps), (size_t)e->sms * 8), kThreads, 0, st>>>(kg);
       CU(cudaGetLastError());
@@ -664,7 +717,7 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
       if (mode == M_ALL && filter)      // the lines the filter drops are never written
          CU(cudaMemsetAsync(s.d_cnt, 0, std::min<size_t>(lines_cap, (size_t)n + 1) * sizeof(uint32_t), st));
       const size_t max_tiles = div_up(lines_cap, kBsTileLines) + 1;
-      if (!front) {
+      if (!front && !fused) {
          if (dev_reserve(&s.d_bstiles, &s.bstiles_cap, 2 * max_tiles)) return -1;
          const size_t want_cols = (size_t)((double)n * e->cols_per_byte) + 4096;
          if (dev_reserve(&s.d_planes, &s.planes_cap, want_cols * 32, 16)) return -1;
@@ -673,8 +726,8 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
       const uint32_t wup = bs_warmup(e->m, e->tau);
       uint32_t *gmask = s.d_gmask, *gfollow = cut ? s.d_gmask + s.gmask_cap / 2 : nullptr;
       uint8_t *segstop = s.d_segflags;
-      if (timing && front) CU(record_event(s.ev[E_PACK_BEGIN], st));
-      if (!front) {
+      if (timing && (front || fused)) CU(record_event(s.ev[E_PACK_BEGIN], st));
+      if (!front && !fused) {
          BsPrepArgs bp{s.d_ls, (uint32_t)lines_cap, n, ctr, tile_cols, tile_off, (uint32_t)max_tiles,
                        (unsigned long long)(s.planes_cap / 32), e->bs_gate, cut ? s.d_lid : nullptr, wup,
                        (!cut && cuts_allowed(e, options, n)) ? 1 : 0, filter ? s.d_act : nullptr};
@@ -692,7 +745,9 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
       if (timing) CU(record_event(s.ev[E_PACK_END], st));
       K2BsArgs kb{f.d_planes, tile_cols, tile_off, (uint32_t)lines_cap, ctr, s.d_res, s.d_cnt, s.d_ev, k2.ev_cap,
                   (mode == M_COUNT || mode == M_COUNTALL) ? 1 : 0, cut ? gmask : nullptr, gfollow, segstop, wup,
-                  filter ? f.d_act : nullptr};
+                  (filter && !fused) ? f.d_act : nullptr,
+                  fused ? s.d_gdesc : nullptr, (uint32_t)std::min<size_t>(s.gdesc_cap, 0xffffffffu),
+                  (fused && filter) ? s.d_gent : nullptr, fused ? s.d_tiles + 2 * k1_tiles : nullptr};
       if (launch_bitslice(e, mode, options, max_lines, st, kb)) return -1;
       s.launches++;
    }
@@ -818,7 +873,15 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
          again = true;
       }
       if (!follower && s.h_ctr[C_BS_SELECTED] == 2ull) {          // plane buffer too small for the bit-sliced scan
-         e->cols_per_byte = (double)(s.h_ctr[C_BS_COLS] + 64) / (double)std::max<uint32_t>(s.cur_n, 1) * 1.05;
+         if (s.cur_fused) e->units_per_byte = (double)(s.h_ctr[C_BS_COLS] + 64) / (double)std::max<uint32_t>(s.cur_n, 1) * 1.05;
+         else e->cols_per_byte = (double)(s.h_ctr[C_BS_COLS] + 64) / (double)std::max<uint32_t>(s.cur_n, 1) * 1.05;
+         again = true;
+      }
+      if (!follower && s.h_ctr[C_BS_SELECTED] == 4ull) {
+         // the fused kernel met a line beyond its overlap (or a tile with too many line starts): a wider
+         // overlap once, then the two-kernel path for this engine
+         if (e->fused_ov < kFMaxOverlap) e->fused_ov = kFMaxOverlap;
+         else e->fused = 0;
          again = true;
       }
       if (mode == M_ALL && nev > s.ev_cap) {
@@ -827,7 +890,7 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
       }
       if (!again) break;
       e->version++;
-      if (++reruns > 3) { set_err("capacity re-run did not converge"); return -1; }
+      if (++reruns > 6) { set_err("capacity re-run did not converge"); return -1; }
       if (slot_issue(e, s, s.cur_text, s.cur_n, s.cur_options, s.cur_stream, s.cur_skip, false, s.cur_front)) return -1;
    }
    s.busy = false;
@@ -848,6 +911,7 @@ static int slot_finish(sqb_engine *e, Slot &s, sqb_stats_t *stats)
       stats->reruns = reruns;
       stats->devices = 1;
       stats->path = (s.h_ctr[C_BS_SELECTED] == 1ull ? SQB_PATH_BITSLICE : 0u) | (s.h_ctr[C_NCUTS] ? SQB_PATH_CUTS : 0u) |
+                    ((s.cur_fused && s.h_ctr[C_BS_SELECTED] == 1ull) ? SQB_PATH_FUSED : 0u) |
                     (s.cur_filter ? SQB_PATH_FILTER : 0u);
       if (s.cur_options & SQB_TIMING) {
          static const int span[6][2] = {{E_BEGIN, E_K1_END}, {E_K1_END, E_K2_END}, {E_K2_END, E_FIN_END},
@@ -955,6 +1019,8 @@ sqb_engine_t *sqbEngineNew(const unsigned char *keys, int m, int tau, int device
    if (const char *c = getenv("SEEQ_B200_FILTER")) e->filter = atoi(c);
    if (const char *c = getenv("SEEQ_B200_NFA")) e->nfa_levels = atoi(c) != 0;
    if (const char *c = getenv("SEEQ_B200_GRAPHS")) e->graphs = atoi(c) != 0;
+   if (const char *c = getenv("SEEQ_B200_FUSED")) e->fused = atoi(c) != 0;
+   if (const char *c = getenv("SEEQ_B200_FUSED_OV")) e->fused_ov = std::min<uint32_t>(kFMaxOverlap, std::max(16, atoi(c)) & ~15u);
    return e;
 }
 
@@ -1332,6 +1398,7 @@ sqb_multi_t *sqbMultiNew(int npatterns, const unsigned char *const *keys, const 
       sqb_engine *e = sqbEngineNew(keys[i], m[i], tau[i], device);
       if (e == NULL) { sqbMultiFree(mp); return NULL; }
       e->cuts = 0;                     // segment cuts depend on the pattern (warm-up): long lines run un-cut
+      e->fused = 0;                    // the followers read the leader's planes[tile][column][group]
       fk = std::min(fk, e->filter_k);
       mp->engs.push_back(e);
       mp->order.push_back(i);

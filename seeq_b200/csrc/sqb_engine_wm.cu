@@ -1,15 +1,26 @@
 // sqb_engine_wm.cu -- instantiations of the bit-sliced matcher with the NFA-level
 // automaton (tau <= 2, patterns of up to 32 positions; sqb_bitslice.h: bs_wm_step).
 // A translation unit of its own so that it compiles next to sqb_engine.cu.
+// Compiled twice (seeq_b200/build.py): -DSQB_WM_FUSED=0 (planes of k15_pack) and -DSQB_WM_FUSED=1 (group
+// planes of the fused tokenise + pack kernel, sqb_k12_fused.cuh).
 #include "sqb_k2_bitslice.cuh"
 
 using namespace sqb;
 
+#ifndef SQB_WM_FUSED
+#define SQB_WM_FUSED 0
+#endif
+#if SQB_WM_FUSED
+#define SQB_WM_ENTRY sqb_launch_bitslice_wm_fused
+#else
+#define SQB_WM_ENTRY sqb_launch_bitslice_wm
+#endif
+
 template <int R, int T, int MODE> static cudaError_t launch3(bool skip, int grid, cudaStream_t st, const K2BsArgs &a, const BsPattern &p)
 {
    const size_t smem = (MODE == BS_ALL ? sizeof(BsWarpSmemAll) : sizeof(BsWarpSmem)) * kBsWarps;      // < 48 KiB
-   if (skip) k2_bitslice<R, 1, MODE, true, T><<<grid, kBsThreads, smem, st>>>(a, p);
-   else k2_bitslice<R, 1, MODE, false, T><<<grid, kBsThreads, smem, st>>>(a, p);
+   if (skip) k2_bitslice<R, 1, MODE, true, T, SQB_WM_FUSED != 0><<<grid, kBsThreads, smem, st>>>(a, p);
+   else k2_bitslice<R, 1, MODE, false, T, SQB_WM_FUSED != 0><<<grid, kBsThreads, smem, st>>>(a, p);
    return cudaGetLastError();
 }
 
@@ -32,8 +43,8 @@ template <int R> static cudaError_t launch1(int levels, int bsmode, bool skip, i
 }
 
 // rows: R of the pattern's kernel shape (parts == 1); levels = tau + 1 (1..3)
-cudaError_t sqb_launch_bitslice_wm(int rows, int levels, int bsmode, bool skip, int grid, cudaStream_t st,
-                                   const K2BsArgs &a, const BsPattern &p)
+cudaError_t SQB_WM_ENTRY(int rows, int levels, int bsmode, bool skip, int grid, cudaStream_t st,
+                         const K2BsArgs &a, const BsPattern &p)
 {
    switch (rows) {
    case 8: return launch1<8>(levels, bsmode, skip, grid, st, a, p);

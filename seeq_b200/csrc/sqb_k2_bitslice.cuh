@@ -43,11 +43,6 @@ constexpr int kBsBlock   = 4;                       // columns per prefetch bloc
 #ifndef SQB_PACK_CTAS
 #define SQB_PACK_CTAS 4                             // CTAs per SM of k15_pack (A/B knob: 5 -> 51 registers, 6 -> 42)
 #endif
-#ifndef SQB_PLANE_PAIRS
-#define SQB_PLANE_PAIRS 0                           // A/B build: planes of a tile laid out
-#endif                                              // [pair of groups][column][2 groups] instead of [column][32 groups]:
-                                                    // the pack's stores coalesce (8 columns x 32 B side by side = 2 data-pipe
-                                                    // wavefronts per STG.64 instead of 8), the matcher's lanes read 32-B pieces
 #ifndef SQB_G2_BLOCK
 #define SQB_G2_BLOCK 6                              // prefetch block of the multi-part matcher (r1y, r1z: 2 -12 %, 6 +1.5 %, 8 -10 %)
 #endif
@@ -57,6 +52,14 @@ constexpr int kBsBlock   = 4;                       // columns per prefetch bloc
 #ifndef SQB_G2_CTAS
 #define SQB_G2_CTAS 3                               // CTAs per SM of the multi-part matcher with R <= 24 (A/B knob)
 #endif
+
+// one group of 32 lines of the fused tokenise + pack kernel (sqb_k12_fused.cuh)
+struct GroupDesc {
+   uint32_t tile;       // K1 tile the lines start in
+   uint32_t first;      // local entry index of slot 0 (consecutive entries) / index into gent (line filter)
+   uint32_t meta;       // lines in the group (1..32) | columns << 8
+   uint32_t poff;       // first uint4 of the group's planes: [block of 4 columns][plane 0..2][4 columns] words
+};
 
 struct BsPrepArgs {
    const uint32_t *ls;
@@ -294,7 +297,6 @@ static __global__ void __launch_bounds__(kThreads, SQB_PACK_CTAS) k15_pack(const
       //   even lanes: group g0,     planes (j&2), (j&2)+1 of column j>>2
       //   odd  lanes: group g0 + 1, the same planes
       const uint32_t slot16 = (g0 + (uint32_t)(lane & 1)) * 2u + (uint32_t)((lane >> 1) & 1);   // in 8-byte units
-      (void)slot16;                                     // (unused in the SQB_PLANE_PAIRS build)
       for (uint32_t c0 = 0; c0 < ncols; c0 += 32) {
          uint32_t wa[4], wb[4];
          sa.next(wa);
@@ -312,13 +314,7 @@ static __global__ void __launch_bounds__(kThreads, SQB_PACK_CTAS) k15_pack(const
             const uint32_t got = __shfl_xor_sync(kFull, give, 1);
             const uint2 v = (lane & 1) ? make_uint2(got, tb) : make_uint2(ta, got);
             const uint32_t col = c0 + 8u * (uint32_t)k + (uint32_t)(lane >> 2);
-#if SQB_PLANE_PAIRS
-            // (g0 is even: the warp's pair of groups is pair g0 / 2 of the tile)
-            if (col < ncols)
-               reinterpret_cast<uint2 *>(out + ((size_t)(g0 >> 1) * ncols + col) * 2u)[(lane & 1) * 2 + ((lane >> 1) & 1)] = v;
-#else
             if (col < ncols) reinterpret_cast<uint2 *>(out + (size_t)col * 32u)[slot16] = v;
-#endif
          }
       }
    }
@@ -338,6 +334,11 @@ struct K2BsArgs {
    uint8_t *segstop;              // out: followed segments that ran into a STOP (the rest of the line is dead)
    uint32_t wup;                  // a continuation reports the events that end after its warm-up
    const uint32_t *act;           // line filter: slot -> entry of ls (nullptr: identity)
+   // fused tokenise + pack (sqb_k12_fused.cuh): the planes come per GROUP of 32 lines, described by gdesc
+   const GroupDesc *gdesc;        // nullptr: planes[tile][column][group] of k15_pack
+   uint32_t gdesc_cap;
+   const uint16_t *gent;          // line filter: local entry index of every slot (or nullptr: consecutive)
+   const uint32_t *k1_tile_base;  // first ls entry of every K1 tile (k1_scan_tiles)
 };
 
 struct BsWarpSmem {
@@ -365,11 +366,12 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 //
 // WM > 0 selects the NFA-level automaton (bs_wm_step, tau = WM - 1 <= 2, G == 1)
 // instead of Myers' delta encoding: fewer logic ops per column for small tau.
-template <int R, int G, int MODE, bool SKIP, int WM = 0>
+template <int R, int G, int MODE, bool SKIP, int WM = 0, bool FUSED = false>
 __global__ void __launch_bounds__(kBsThreads, WM ? (R * WM <= 24 ? 6 : (R * WM <= 48 ? 4 : 3)) : (G > 1 ? (R <= 24 ? SQB_G2_CTAS : 2) : (R <= 16 ? 4 : 3)))
 k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
 {
    static_assert(WM == 0 || G == 1, "the NFA-level automaton is single-part");
+   static_assert(!FUSED || G == 1, "the fused tokenise + pack kernel serves single-part automata");
    using Smem = typename std::conditional<MODE == BS_ALL, BsWarpSmemAll, BsWarpSmem>::type;
    using State = typename std::conditional<WM != 0, BsWmState<R, (WM ? WM : 1)>, BsState<R, G>>::type;
    extern __shared__ __align__(128) uint8_t dyn[];
@@ -389,7 +391,12 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
    Smem &sm = reinterpret_cast<Smem *>(dyn)[warp];
    const uint32_t nlines = bs_nslots(a.ctr, a.act, a.max_lines);
    const uint32_t ntiles = (nlines + kBsTileLines - 1) / kBsTileLines;
-   const uint32_t nitems = ntiles * (uint32_t)G;          // (tile, quarter) pairs
+   // fused tokenise + pack (single-part automata only): the work items are 32 GROUPS each
+   // (FUSED is a template parameter: as a run-time branch the two fetch paths cost the tight instances
+   // -- 80 registers at 6 CTAs per SM -- a few spills)
+   constexpr bool fused = FUSED;
+   const uint32_t ngroups_f = fused ? (uint32_t)min(a.ctr[C_NGROUPS], (unsigned long long)a.gdesc_cap) : 0u;
+   const uint32_t nitems = fused ? (ngroups_f + 31u) / 32u : ntiles * (uint32_t)G;          // (tile, quarter) pairs
 
    sm.slots[0][BS_ONES][lane] = ~0u;
    sm.slots[1][BS_ONES][lane] = ~0u;
@@ -416,68 +423,107 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
       const uint32_t tile = item / (uint32_t)G, q = item % (uint32_t)G;
       const uint32_t group = q * (uint32_t)NG + (uint32_t)gl;           // group of the tile served by this lane
       const uint32_t line0 = tile * kBsTileLines;
-      const uint32_t left = nlines - line0;                              // > 0
-      const uint32_t mine = left > group * 32u ? min(left - group * 32u, 32u) : 0u;
+      uint32_t mine, ncols, my_ncols = 0u, gent0 = 0u;
+      uint32_t slot0 = line0 + group * 32u, ent0;
+      bool consecutive = true;
+      const uint4 *col;
+      if (fused) {
+         // lane = one group of the fused kernel: its descriptor says where the lines and the planes are
+         const uint32_t gi = item * 32u + (uint32_t)lane;
+         GroupDesc d{0u, 0u, 0u, 0u};
+         if (gi < ngroups_f) d = a.gdesc[gi];
+         mine = d.meta & 0xffu;
+         my_ncols = d.meta >> 8;
+         gent0 = d.first;
+         ent0 = mine ? a.k1_tile_base[d.tile] + (a.gent ? 0u : d.first) : 0u;
+         col = a.planes + d.poff;
+         ncols = __reduce_max_sync(kFull, my_ncols);
+      } else {
+         const uint32_t left = nlines - line0;                              // > 0
+         mine = left > group * 32u ? min(left - group * 32u, 32u) : 0u;
+         // slot -> entry of ls.  With the line filter the 32 slots of a lane usually map to
+         // consecutive entries when the filter drops nothing around them: one look-up per
+         // tile then serves every event of the lane
+         ent0 = slot0;
+         if (a.act && mine > 0u) {
+            ent0 = a.act[slot0];
+            consecutive = a.act[slot0 + mine - 1u] - ent0 == mine - 1u;
+         }
+         ncols = a.tile_cols[tile];
+         col = a.planes + (size_t)a.tile_off[tile] * 32u + group;
+      }
       State st;
       if constexpr (WM != 0) bs_wm_reset(st, pat, mine == 32u ? ~0u : ((1u << mine) - 1u));
       else bs_reset(st, pat, mine == 32u ? ~0u : ((1u << mine) - 1u), part);
       if (MODE == BS_ALL) {
 #pragma unroll
          for (int i = 0; i < 32; i++) static_cast<BsWarpSmemAll &>(sm).cnt[i * 32 + lane] = 0u;
+         __syncwarp();            // lane g counts in cnt[g * 32 + r]: words other lanes have just cleared (racecheck, r3a)
       }
       uint32_t lane_events = 0;
-      // slot -> entry of ls.  With the line filter the 32 slots of a lane usually map to
-      // consecutive entries when the filter drops nothing around them: one look-up per
-      // tile then serves every event of the lane
-      const uint32_t slot0 = line0 + group * 32u;
-      uint32_t ent0 = slot0;
-      bool consecutive = true;
-      if (a.act && mine > 0u) {
-         ent0 = a.act[slot0];
-         consecutive = a.act[slot0 + mine - 1u] - ent0 == mine - 1u;
-      }
-      auto entry_of = [&](uint32_t r) -> uint32_t { return consecutive ? ent0 + r : a.act[slot0 + r]; };
+      auto entry_of = [&](uint32_t r) -> uint32_t {
+         if (fused) return a.gent ? ent0 + (uint32_t)a.gent[gent0 + r] : ent0 + r;
+         return consecutive ? ent0 + r : a.act[slot0 + r];
+      };
       uint32_t qmask = 0u, fmask = 0u;
       if (has_cuts) {
          qmask = a.gmask[tile * 32u + group];
          fmask = a.gfollow[tile * 32u + group];
       }
-      const uint32_t ncols = a.tile_cols[tile];
       const uint32_t niter = ncols + (uint32_t)(G - 1);
-#if SQB_PLANE_PAIRS
-      const uint4 *col = a.planes + (size_t)a.tile_off[tile] * 32u + (size_t)(group >> 1) * ncols * 2u + (group & 1u);
-#else
-      const uint4 *col = a.planes + (size_t)a.tile_off[tile] * 32u + group;
-#endif
 
       // columns are consumed in blocks of kBsBlock; the next block is in flight while
       // this one is matched (global latency >> one column of work).  Iteration t of
       // part p is column t - p; before the line start that is a NULL column.
       auto fetch = [&](uint32_t t) {
          const int c = (int)t - part;
-         uint4 v = col[(size_t)min((uint32_t)max(c, 0), ncols - 1u) * (SQB_PLANE_PAIRS ? 2u : 32u)];          // ncols >= 1
+         uint4 v = col[(size_t)min((uint32_t)max(c, 0), ncols - 1u) * 32u];          // ncols >= 1
          if (G > 1 && c < 0) v = make_uint4(~0u, ~0u, ~0u, 0u);
          return v;
       };
+      // fused layout: block b of the lane's own group = three uint4 {p0, p1, p2 of 4 columns}; a lane
+      // without a group (or past its last block) re-reads a valid block: its lines are dead by then
+      const uint32_t my_last = ((my_ncols + 3u) >> 2) - (my_ncols ? 1u : 0u);
+      auto fetchb = [&](uint32_t b, uint4 &q0, uint4 &q1, uint4 &q2) {
+         const uint4 *p = col + (size_t)min(b, my_last) * 3u;
+         q0 = p[0];
+         q1 = p[1];
+         q2 = p[2];
+      };
       uint4 nxt[kBsBlock];
+      if (fused) {
+         fetchb(0u, nxt[0], nxt[1], nxt[2]);
+      } else {
 #pragma unroll
-      for (int k = 0; k < kBsBlock; k++) nxt[k] = fetch((uint32_t)k);
+         for (int k = 0; k < kBsBlock; k++) nxt[k] = fetch((uint32_t)k);
+      }
       uint32_t ph_prev = 0u, mh_prev = 0u;               // what this part handed upwards one iteration ago
 #pragma unroll 1
       for (uint32_t t0 = 0; t0 < niter; t0 += kBsBlock) {
          if (!__any_sync(kFull, st.alive != 0u)) break;
-         uint4 blk[kBsBlock];
+         uint32_t P0[kBsBlock], P1[kBsBlock], P2[kBsBlock];
+         if constexpr (fused) {
+            {
+               const uint4 q0 = nxt[0], q1 = nxt[1], q2 = nxt[2];
+               P0[0] = q0.x; P0[1] = q0.y; P0[2] = q0.z; P0[3] = q0.w;
+               P1[0] = q1.x; P1[1] = q1.y; P1[2] = q1.z; P1[3] = q1.w;
+               P2[0] = q2.x; P2[1] = q2.y; P2[2] = q2.z; P2[3] = q2.w;
+               fetchb(t0 / (uint32_t)kBsBlock + 1u, nxt[0], nxt[1], nxt[2]);
+            }
+         } else {
 #pragma unroll
-         for (int k = 0; k < kBsBlock; k++) {
-            blk[k] = nxt[k];
-            nxt[k] = fetch(t0 + kBsBlock + (uint32_t)k);
+            for (int k = 0; k < kBsBlock; k++) {
+               P0[k] = nxt[k].x;
+               P1[k] = nxt[k].y;
+               P2[k] = nxt[k].z;
+               nxt[k] = fetch(t0 + kBsBlock + (uint32_t)k);
+            }
          }
 #pragma unroll
          for (int k = 0; k < kBsBlock; k++) {
          // iterations >= niter: every line is dead, nothing happens
          const uint32_t c = t0 + (uint32_t)k - (uint32_t)part;       // column of this lane (last part: >= 0 while alive)
-         const uint4 cur = blk[k];
-         const uint32_t p0 = cur.x, p1 = cur.y, p2 = cur.z;
+         const uint32_t p0 = P0[k], p1 = P1[k], p2 = P2[k];
          uint32_t anybase, stop, skip;
          {
             const uint32_t na = ~p2 & ~p1 & ~p0, nc = ~p2 & ~p1 & p0, ng = ~p2 & p1 & ~p0, nt = ~p2 & p1 & p0;
@@ -569,10 +615,21 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
       for (uint32_t ss = st.stopped & fmask; ss; ss &= ss - 1u) a.segstop[entry_of((uint32_t)(__ffs(ss) - 1))] = 1;
       if (MODE == BS_ALL && !a.count_only) {
          __syncwarp();
+         if (fused) {
+            // lane L writes the count of slot L of group i: the group's whereabouts come from lane i
 #pragma unroll 4
-         for (int i = 0; i < NG; i++) {
-            const uint32_t slot = line0 + (q * (uint32_t)NG + (uint32_t)i) * 32u + (uint32_t)lane;
-            if (slot < nlines) a.cnt[a.act ? a.act[slot] : slot] = static_cast<BsWarpSmemAll &>(sm).cnt[i * 32 + lane];
+            for (int i = 0; i < 32; i++) {
+               const uint32_t e0 = __shfl_sync(kFull, ent0, i), g0 = __shfl_sync(kFull, gent0, i), mi = __shfl_sync(kFull, mine, i);
+               if ((uint32_t)lane < mi)
+                  a.cnt[a.gent ? e0 + (uint32_t)a.gent[g0 + (uint32_t)lane] : e0 + (uint32_t)lane] =
+                     static_cast<BsWarpSmemAll &>(sm).cnt[i * 32 + lane];
+            }
+         } else {
+#pragma unroll 4
+            for (int i = 0; i < NG; i++) {
+               const uint32_t slot = line0 + (q * (uint32_t)NG + (uint32_t)i) * 32u + (uint32_t)lane;
+               if (slot < nlines) a.cnt[a.act ? a.act[slot] : slot] = static_cast<BsWarpSmemAll &>(sm).cnt[i * 32 + lane];
+            }
          }
          __syncwarp();
       }

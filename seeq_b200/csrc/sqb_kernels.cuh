@@ -62,7 +62,10 @@ enum Counter {
    C_NCUTS = 11,     // segment cuts made by K1
    C_NZ_CORR = 12,   // SQ_ALL with cuts: segments with events beyond the first of their line
    C_NACTIVE = 13,   // line filter: entries of ls the matcher has to look at
-   C_COUNT = 16
+   C_NGROUPS = 14,   // fused tokenise + pack: groups of 32 lines allocated (may exceed the capacity)
+   C_PLANE_UNITS = 15,// fused: uint4 units of bit-planes allocated (may exceed the capacity)
+   C_FUSED_OVF = 16, // fused: a tile met something the fused kernel does not handle (the host re-runs the scan)
+   C_COUNT = 24
 };
 
 struct Event {        // SQ_ALL: one forward event, unordered
@@ -465,6 +468,12 @@ struct K1ScanArgs {
    uint32_t *tile_abase;          // index in act[] of the first live entry of tile t; total -> ctr[C_NACTIVE]
    int fastq;                     // the live entries are the sequence lines of 4-line records (entry index 1 mod 4):
                                   // tile_alive is computed here, from tile_base and tile_cnt
+   // fused tokenise + pack (sqb_k12_fused.cuh): this kernel also makes the matcher decision k15_scan makes on
+   // the two-kernel path -- ctr[C_BS_SELECTED] = 1 bit-sliced scan, 0 too few lines (word-parallel kernels),
+   // 2 plane / group buffers too small (ctr[C_BS_COLS] = plane units needed), 4 the fused kernel gave up
+   int fused;
+   uint32_t planes_cap, gdesc_cap;
+   BsGate gate;
 };
 
 static __global__ void __launch_bounds__(1024) k1_scan_tiles(const K1ScanArgs a)
@@ -490,6 +499,12 @@ static __global__ void __launch_bounds__(1024) k1_scan_tiles(const K1ScanArgs a)
          a.ctr[C_NPSEUDO] = total;
          a.ctr[C_NLINES] = total;
          a.ctr[C_NACTIVE] = alive;
+         if (a.fused) {
+            const unsigned long long units = a.ctr[C_PLANE_UNITS], ng = a.ctr[C_NGROUPS];
+            a.ctr[C_BS_COLS] = units;
+            a.ctr[C_BS_SELECTED] = a.ctr[C_FUSED_OVF] != 0ull ? 4ull
+                                   : (total < a.gate.min_lines ? 0ull : ((units > a.planes_cap || ng > a.gdesc_cap) ? 2ull : 1ull));
+         }
       }
       return;
    }
@@ -637,8 +652,10 @@ static __global__ void __launch_bounds__(kThreads) k1_gather(const K1GatherArgs 
             if (ok) {
                a.ls[dst + j] = a.fastq ? raw : (raw & ~kDeadBit);
                if (a.res_init && dst + j + 1u < a.ls_cap) a.res_init[dst + j] = kNoMatch;
-               a.lflags[dst + j] = live ? 0 : 1;
-               if (live) a.act[nact + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = dst + j;
+               if (a.act) {                 // (the fused path has its own slot tables: ls only)
+                  a.lflags[dst + j] = live ? 0 : 1;
+                  if (live) a.act[nact + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = dst + j;
+               }
             }
             nact += (uint32_t)__popc(bal);
          }
@@ -1053,7 +1070,7 @@ template <int W> __device__ __forceinline__ void rev_tables_load(RevTables<W> &t
 }
 
 #ifndef SQB_REV_WINDOW
-#define SQB_REV_WINDOW 0
+#define SQB_REV_WINDOW 1                   // r3a: k34_finish_lines 0.200 -> 0.179 ms on cfg2 (A/B against =0)
 #endif
 
 template <int W, int kChunk = 8>
@@ -1069,7 +1086,7 @@ __device__ __forceinline__ uint32_t reverse_start(const uint8_t *__restrict__ te
    const uint8_t *p = text + line_begin + end;           // the pass reads p[-1], p[-2], ...
    bool more = end > 0;
 #if SQB_REV_WINDOW
-   // A/B build (-DSQB_REV_WINDOW=1, not the default): the last 16 bytes in front of `end` in
+   // (-DSQB_REV_WINDOW=0 removes it.)  The last 16 bytes in front of `end` in
    // ONE round trip -- the two aligned 16-byte vectors that hold them, realigned in registers -- instead of up to
    // four rounds of byte loads; a pass that is not over after 16 bytes carries on in the loop below.
    if (more && line_begin + end >= 16u) {

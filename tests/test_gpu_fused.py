@@ -1,0 +1,172 @@
+"""GPU parity of the fused tokenise + pack kernel (k12_scan_pack, sqb_k12_fused.cuh) and of the matcher that
+reads its group planes: ragged lines across tile boundaries, lines beyond the staged overlap (one re-run with
+the wide overlap, then the two-kernel path), more line starts per tile than the kernel lists, the line
+filter, buffers without a final newline, NUL bytes -- each against the oracle, and the fused path against
+the two-kernel path on the same bytes."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle.pyoracle import SQ_ALL, SQ_BEST, SQ_CONVERT, SQ_FAIL, SQ_FIRST, SQ_IGNORE
+
+pytestmark = pytest.mark.gpu
+
+MATCH = [SQ_FIRST, SQ_BEST, SQ_ALL]
+NONDNA = [SQ_FAIL, SQ_CONVERT, SQ_IGNORE]
+FUSED, BITSLICE = 2, 1
+
+
+@pytest.fixture(scope="module")
+def B():
+    from seeq_b200 import binding
+    binding.lib()
+    return binding
+
+
+@pytest.fixture(autouse=True)
+def lifted_thresholds(monkeypatch):
+    monkeypatch.setenv("SEEQ_B200_MATCHER", "bitslice")      # small buffers take the production kernels
+    monkeypatch.delenv("SEEQ_B200_FUSED", raising=False)
+
+
+def ragged(rng, nlines, lo, hi, pattern, alphabet="ACGT", junk=0.0, final_newline=True):
+    lines = []
+    for _ in range(nlines):
+        n = rng.randint(lo, hi)
+        s = [rng.choice(alphabet) for _ in range(n)]
+        if n > len(pattern) + 2 and rng.random() < 0.5:
+            at = rng.randrange(n - len(pattern))
+            inst = list(pattern)
+            if rng.random() < 0.6:
+                inst[rng.randrange(len(inst))] = rng.choice("ACGT")
+            s[at:at + len(inst)] = inst
+        if junk:
+            for k in range(n):
+                if rng.random() < junk:
+                    s[k] = rng.choice("NnXa-u\x00")
+        lines.append("".join(s))
+    buf = "\n".join(lines)
+    if final_newline:
+        buf += "\n"
+    return buf.encode("latin-1")
+
+
+def scan(B, oracle, pattern, tau, buf, opt, extra=0):
+    sq = B.Seeq(pattern, tau)
+    st = B.StatsT()
+    recs = sq.batch(buf, opt | extra, B.SQ_ANY, st)
+    exp, nl, nm = oracle.buffer_scan(buf, sq.keys, tau, opt)
+    got = [(int(r["line"]) + 1, int(r["start"]), int(r["end"]), int(r["dist"])) for r in recs]
+    assert (st.nlines, st.nmatched) == (nl, nm), (pattern, tau, opt, st.path)
+    assert got == [tuple(int(x) for x in row) for row in exp], (pattern, tau, opt, st.path)
+    sq.close()
+    return st
+
+
+@pytest.mark.parametrize("pattern,tau", [("A[CG]TNNGATC", 1), ("GATCGGAAGAGC", 2), ("ACGTTGCAAGCTTAGGCATCGATC", 3),
+                                         ("GATTACAGATTACAGATTACAGATTACAGA", 0)])
+def test_ragged_lines_all_modes(B, oracle, pattern, tau):
+    rng = random.Random(len(pattern) * 31 + tau)
+    plain = pattern.replace("[CG]", "C").replace("N", "A")
+    buf = ragged(rng, 2600, 0, 330, plain, junk=0.004)            # ~ 430 KB: a dozen tiles, lines across every boundary
+    for mo in MATCH:
+        for nd in NONDNA:
+            st = scan(B, oracle, pattern, tau, buf, mo | nd)
+            assert st.path & BITSLICE and st.path & FUSED, (mo, nd, st.path)
+    buf = ragged(rng, 900, 100, 160, plain, final_newline=False)
+    st = scan(B, oracle, pattern, tau, buf, SQ_BEST)
+    assert st.path & FUSED
+
+
+def test_lines_beyond_the_overlap(B, oracle):
+    """Lines of up to 3000 bytes run past the 512 bytes staged behind a tile: the scan is repeated once with the
+    4096-byte overlap; lines of 9000 bytes send the engine to the two-kernel path for good.  Same records."""
+    rng = random.Random(5)
+    pattern = "GATCGGAAGAGC"
+    buf = ragged(rng, 600, 0, 3000, pattern)
+    sq = B.Seeq(pattern, 2)
+    for it in range(2):
+        st = B.StatsT()
+        recs = sq.batch(buf, SQ_ALL, B.SQ_ANY, st)
+        exp, nl, nm = oracle.buffer_scan(buf, sq.keys, 2, SQ_ALL)
+        assert [(int(r["line"]) + 1, int(r["start"]), int(r["end"]), int(r["dist"])) for r in recs] == \
+            [tuple(int(x) for x in row) for row in exp]
+        assert st.path & FUSED and st.reruns == (1 if it == 0 else 0), (it, st.path, st.reruns)
+    sq.close()
+    buf = ragged(rng, 200, 0, 9000, pattern)
+    for mo in MATCH:
+        st = scan(B, oracle, pattern, 2, buf, mo)
+        assert not (st.path & FUSED) and st.reruns >= 1
+
+
+def test_more_line_starts_than_a_tile_lists(B, oracle):
+    rng = random.Random(6)
+    buf = ragged(rng, 60000, 0, 12, "ACGTA")                      # ~ 5000 line starts per 32 KiB tile
+    for mo in MATCH:
+        st = scan(B, oracle, "ACGTA", 1, buf, mo | SQ_CONVERT)
+        assert not (st.path & FUSED)
+    buf = ragged(rng, 30000, 10, 40, "ACGTACG")                   # ~ 1250 per tile: listed
+    for mo in MATCH:
+        st = scan(B, oracle, "ACGTACG", 1, buf, mo)
+        assert st.path & FUSED
+
+
+def test_line_filter(B, oracle, monkeypatch):
+    monkeypatch.setenv("SEEQ_B200_FILTER", "2")
+    g = B.make_gen(seed=5, line_len=150, plant="GATCGGAAGAGC", plant_per_1024=307, max_edits=2, fastq=True)
+    buf = B.gen_host(g, 6000)
+    for mo in MATCH:
+        st = scan(B, oracle, "GATCGGAAGAGC", 2, buf, mo)
+        assert st.path & FUSED and st.path & 8, st.path
+    rng = random.Random(8)
+    mixed = ragged(rng, 3000, 0, 200, "GATCGGAAGAGC", alphabet="ACGT", junk=0.02)      # dead lines scattered about
+    for mo in MATCH:
+        st = scan(B, oracle, "GATCGGAAGAGC", 2, mixed, mo)
+        assert st.path & FUSED
+
+
+def test_fused_equals_two_kernel_path(B, monkeypatch):
+    g = B.make_gen(seed=2, line_len=150, n_per_1024=5)
+    buf = B.gen_host(g, 200000)
+    out = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("SEEQ_B200_FUSED", fused)
+        for pattern, tau, opt in (("A[CG]TNNGATC", 1, SQ_BEST), ("GATCGGAAGAGC", 2, SQ_ALL), ("TTGACAGCTAGCTCAGTCCT", 2, SQ_FIRST)):
+            sq = B.Seeq(pattern, tau)
+            st = B.StatsT()
+            recs = sq.batch(buf, opt, B.SQ_ANY, st)
+            assert bool(st.path & FUSED) == (fused == "1")
+            out.setdefault((pattern, opt), []).append((recs.copy(), st.nlines, st.nmatched, st.nrecs))
+            n = sq.batch(buf, opt, B.SQ_COUNTLINES)
+            assert n == st.nmatched
+            sq.close()
+    for key, (a, b) in out.items():
+        assert a[1:] == b[1:], key
+        assert np.array_equal(a[0], b[0]), key
+
+
+def test_device_chunks_with_an_unaligned_start(B, oracle):
+    """sqbScanDeviceLarge hands K12 chunks that start `skip` < 16 bytes into their aligned address."""
+    import ctypes as C
+    g = B.make_gen(seed=9, line_len=97, plant="GATCGGAAGAGC", plant_per_1024=200, max_edits=2)
+    buf = B.gen_host(g, 40000)
+    L = B.lib()
+    d = L.sqbDeviceAlloc(buf.size + 64)
+    assert L.sqbMemcpyH2D(d, buf.ctypes.data, buf.size) == 0
+    sq = B.Seeq("GATCGGAAGAGC", 2)
+    eng = B.Engine.borrowed(sq.engine())
+    import os
+    os.environ["SEEQ_B200_DEVICE_CHUNK_MB"] = "1"
+    try:
+        st = eng.scan_device_large(d, buf.size, SQ_BEST)
+    finally:
+        del os.environ["SEEQ_B200_DEVICE_CHUNK_MB"]
+    recs = eng.host_records()
+    exp, nl, nm = oracle.buffer_scan(buf, sq.keys, 2, SQ_BEST)
+    assert (st.nlines, st.nmatched) == (nl, nm)
+    assert [(int(r["line"]) + 1, int(r["start"]), int(r["end"]), int(r["dist"])) for r in recs] == \
+        [tuple(int(x) for x in row) for row in exp]
+    assert st.path & FUSED
+    L.sqbDeviceFree(d)
+    sq.close()

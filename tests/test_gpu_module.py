@@ -66,7 +66,7 @@ def test_match_objects(seeq, oracle):
             if len(exp) == 0:
                 assert got is None
             else:
-                assert [tuple(int(x) for x in t) for t in got.matches] == [tuple(int(x) for x in e[1:]) for e in exp]
+                assert [tuple(int(x) for x in t) for t in got.matchlist] == [tuple(int(x) for x in e[1:]) for e in exp]
 
 
 @pytest.mark.parametrize("mode,opt", [("first", SQ_FIRST), ("best", SQ_BEST), ("all", SQ_ALL)])
