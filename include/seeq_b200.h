@@ -136,6 +136,12 @@ int sqbFetchLineStarts (sqb_engine_t * e, uint32_t * dst, uint64_t first, uint64
 int sqbScanHost (sqb_engine_t * e, const char * text, size_t nbytes,
                  int options, sqb_stats_t * stats);
 const sqb_rec_t * sqbHostRecords    (sqb_engine_t * e, uint64_t * count);
+/* $SEEQ_B200_DEVICES = "all" or a count: sqbScanHost -- and with it seeqBatchMatch, seeqFileMatch, seeq() --
+ * shards the buffer by newline-aligned byte ranges over that many GPUs of the box, one host thread and
+ * engine per device inside this ONE process; results are those of the single-device scan (stats.devices
+ * says how many took part).  Shards below $SEEQ_B200_MIN_SHARD_MB (16) MiB are not made.
+ * A number that changes whenever a scan rewrites the arrays sqbHostRecords / sqbHostLineStarts return: */
+unsigned long long sqbScanGeneration (sqb_engine_t * e);
 /* byte offset of every counted line of the last sqbScanHost (on request) */
 int               sqbHostLineStarts (sqb_engine_t * e, const uint64_t ** starts, uint64_t * count);
 

@@ -102,6 +102,7 @@ SYMBOLS = {
     "sqbFetchLineStarts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "sqbScanHost": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(StatsT)]),
     "sqbHostRecords": (C.c_void_p, [C.c_void_p, _u64p]),
+    "sqbScanGeneration": (C.c_ulonglong, [C.c_void_p]),
     "sqbHostLineStarts": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _u64p]),
     "sqbHostAlloc": (C.c_void_p, [C.c_size_t]),
     "sqbHostFree": (None, [C.c_void_p]),

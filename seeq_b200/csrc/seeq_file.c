@@ -20,6 +20,7 @@
 #include "sqb_private.h"
 
 #include <errno.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -59,13 +60,26 @@ seeqfile_t *seeqOpen(const char *file)
 
 static void release_buffers(sqb_file_t *f)
 {
-   if (f->buf) {
-      if (f->pinned) sqbHostFree(f->buf);
-      else free(f->buf);
+   if (f->thread_started) {
+      /* the reader may sit in fread() on a pipe that never delivers: cancel it there */
+      pthread_mutex_lock(&f->mu);
+      f->stop = 1;
+      pthread_cond_broadcast(&f->cv);
+      pthread_mutex_unlock(&f->mu);
+      pthread_cancel(f->thread);
+      pthread_join(f->thread, NULL);
+      pthread_mutex_destroy(&f->mu);
+      pthread_cond_destroy(&f->cv);
+      f->thread_started = 0;
    }
-   free(f->recs);
-   free(f->lines);
+   for (int k = 0; k < 2; k++) {
+      if (f->chunk[k].buf) sqbHostFree(f->chunk[k].buf);
+      f->chunk[k].buf = NULL;
+      f->chunk[k].cap = 0;
+   }
+   free(f->carry);
    free(f->last_header);
+   f->carry = NULL;
    f->buf = NULL;
    f->recs = NULL;
    f->lines = NULL;
@@ -91,12 +105,20 @@ int seeqClose(seeqfile_t *sqfile)
 /* ------------------------------------------------------------------------ */
 /* chunk reader                                                              */
 /* ------------------------------------------------------------------------ */
+/* bytes per chunk: $SEEQ_B200_FILE_CHUNK_MB (64) MiB per GPU that sqbScanHost will use ($SEEQ_B200_DEVICES) */
 static size_t chunk_target(FILE *in)
 {
    const char *env = getenv("SEEQ_B200_FILE_CHUNK_MB");
    size_t mb = env ? (size_t)atol(env) : 64;
    if (mb < 1) mb = 1;
    if (mb > 1024) mb = 1024;
+   const char *devs = getenv("SEEQ_B200_DEVICES");
+   if (devs && *devs) {
+      int nd = strcmp(devs, "all") == 0 ? sqbDeviceCount() : atoi(devs);
+      if (nd > sqbDeviceCount()) nd = sqbDeviceCount();
+      if (nd > 1) mb *= (size_t)nd;
+      if (mb > 2048) mb = 2048;
+   }
    size_t target = mb << 20;
    /* do not pin 64 MiB for a tiny regular file */
    struct stat st;
@@ -109,23 +131,83 @@ static size_t chunk_target(FILE *in)
    return target;
 }
 
-static int buffer_reserve(sqb_file_t *f, size_t need)
+/* (reader thread) room for `need` bytes in a chunk buffer, contents kept */
+static int chunk_reserve(sqb_chunk_t *c, size_t keep, size_t need)
 {
-   if (need <= f->cap) return 0;
-   size_t cap = f->cap ? f->cap : 4096;
+   if (need <= c->cap) return 0;
+   size_t cap = c->cap ? c->cap : 4096;
    while (cap < need) cap *= 2;
    char *nb = sqbHostAlloc(cap);
-   if (nb == NULL) {
-      fprintf(stderr, "seeq-b200: %s\n", sqbLastError());
-      errno = ENODEV;
-      return -1;
-   }
-   if (f->fill) memcpy(nb, f->buf, f->fill);
-   if (f->buf) sqbHostFree(f->buf);
-   f->buf = nb;
-   f->cap = cap;
-   f->pinned = 1;
+   if (nb == NULL) return -1;
+   if (keep) memcpy(nb, c->buf, keep);
+   if (c->buf) sqbHostFree(c->buf);
+   c->buf = nb;
+   c->cap = cap;
    return 0;
+}
+
+static void reader_fail(sqb_file_t *f, int err)
+{
+   pthread_mutex_lock(&f->mu);
+   f->reader_errno = err ? err : EIO;
+   pthread_cond_broadcast(&f->cv);
+   pthread_mutex_unlock(&f->mu);
+}
+
+/* The reader: fills chunk 0, 1, 0, ... -- each starts with the partial line left behind the chunk before
+ * it, then takes `target` bytes of the stream (more while no newline has been seen: a line longer than
+ * the chunk) and ends after its last newline; the rest is carried to the next chunk. */
+static void *reader_main(void *arg)
+{
+   sqb_file_t *f = arg;
+   for (int k = 0;; k ^= 1) {
+      pthread_mutex_lock(&f->mu);
+      while (f->state[k] != SQB_CH_FREE && !f->stop) pthread_cond_wait(&f->cv, &f->mu);
+      const int stop = f->stop;
+      pthread_mutex_unlock(&f->mu);
+      if (stop) break;
+      sqb_chunk_t *c = &f->chunk[k];
+      size_t fill = f->carry_len;
+      if (chunk_reserve(c, 0, fill + f->target + 16)) { reader_fail(f, ENODEV); break; }
+      if (fill) memcpy(c->buf, f->carry, fill);
+      f->carry_len = 0;
+      int eof = 0, bad = 0;
+      for (;;) {
+         if (chunk_reserve(c, fill, fill + f->target + 16)) { bad = ENODEV; break; }
+         const size_t got = fread(c->buf + fill, 1, f->target, f->in);
+         const int newline = got && memrchr(c->buf + fill, '\n', got) != NULL;
+         fill += got;
+         if (got < f->target) {
+            if (ferror(f->in)) { bad = errno ? errno : EIO; break; }
+            eof = 1;
+            break;
+         }
+         if (newline) break;
+      }
+      if (bad) { reader_fail(f, bad); break; }
+      size_t len = fill;
+      if (!eof) {
+         const char *nl = memrchr(c->buf, '\n', fill);
+         len = (size_t)(nl - c->buf) + 1;
+         const size_t tail = fill - len;
+         if (tail > f->carry_cap) {
+            char *nc = realloc(f->carry, tail + tail / 2 + 64);
+            if (nc == NULL) { reader_fail(f, ENOMEM); break; }
+            f->carry = nc;
+            f->carry_cap = tail + tail / 2 + 64;
+         }
+         if (tail) memcpy(f->carry, c->buf + len, tail);
+         f->carry_len = tail;
+      }
+      c->len = len;
+      c->last = eof;
+      pthread_mutex_lock(&f->mu);
+      f->state[k] = SQB_CH_READY;
+      pthread_cond_broadcast(&f->cv);
+      pthread_mutex_unlock(&f->mu);
+      if (eof) break;
+   }
+   return NULL;
 }
 
 /* start of the line that ends just before position `end` (end > 0) */
@@ -161,46 +243,56 @@ static int remember_last_header(sqb_file_t *f)
 /* Makes the next chunk resident.  1 = a chunk is resident, 0 = end of input. */
 static int chunk_load(sqb_file_t *f)
 {
-   FILE *in = f->pub.fdi;
    if (f->started) {
-      if ((f->pub.flags & 1) && remember_last_header(f)) return -1;
-      f->line_base += f->nlines;
+      if (f->buf != NULL) {
+         if ((f->pub.flags & 1) && remember_last_header(f)) return -1;
+         f->line_base += f->nlines;
+         /* hand the buffer back to the reader */
+         pthread_mutex_lock(&f->mu);
+         f->state[f->cur] = SQB_CH_FREE;
+         pthread_cond_broadcast(&f->cv);
+         pthread_mutex_unlock(&f->mu);
+         f->cur ^= 1;
+      }
    } else {
-      f->target = chunk_target(in);
+      f->in = f->pub.fdi;
+      f->target = chunk_target(f->in);
+      f->cur = 0;
+      pthread_mutex_init(&f->mu, NULL);
+      pthread_cond_init(&f->cv, NULL);
+      if (pthread_create(&f->thread, NULL, reader_main, f) != 0) {
+         pthread_mutex_destroy(&f->mu);
+         pthread_cond_destroy(&f->cv);
+         return -1;                                       /* errno tells */
+      }
+      f->thread_started = 1;
       f->started = 1;
    }
-   /* carry the partial line to the front */
-   const size_t carry = f->fill - f->len;
-   if (carry && f->len) memmove(f->buf, f->buf + f->len, carry);
-   f->fill = carry;
+   f->buf = NULL;
    f->len = 0;
    f->cur_line = f->cur_rec = 0;
    f->nlines = f->nrecs = 0;
+   f->recs = NULL;
+   f->lines = NULL;
    f->res_valid = 0;
    f->hdr_scan = f->hdr_off = 0;
    f->hdr_seen = 0;
    f->hdr_dirty = 1;
-   if (f->eof && carry == 0) return 0;
+   if (f->eof) return 0;
 
-   size_t want = f->target;
-   while (!f->eof) {
-      if (buffer_reserve(f, f->fill + want + 16)) return -1;
-      const size_t got = fread(f->buf + f->fill, 1, want, in);
-      f->fill += got;
-      if (got < want) {
-         if (ferror(in)) { seeqerr = 0; return -1; }      /* errno tells */
-         f->eof = 1;
-         break;
-      }
-      if (memrchr(f->buf, '\n', f->fill) != NULL) break;
-      /* a line longer than the chunk: keep reading */
+   pthread_mutex_lock(&f->mu);
+   while (f->state[f->cur] != SQB_CH_READY && f->reader_errno == 0) pthread_cond_wait(&f->cv, &f->mu);
+   const int err = f->state[f->cur] == SQB_CH_READY ? 0 : f->reader_errno;
+   pthread_mutex_unlock(&f->mu);
+   if (err) {
+      if (err == ENODEV) fprintf(stderr, "seeq-b200: %s\n", sqbLastError());
+      seeqerr = 0;
+      errno = err;                                        /* errno tells */
+      return -1;
    }
-   if (f->eof) {
-      f->len = f->fill;                                   /* last line may lack '\n' */
-   } else {
-      const char *nl = memrchr(f->buf, '\n', f->fill);
-      f->len = (size_t)(nl - f->buf) + 1;
-   }
+   f->buf = f->chunk[f->cur].buf;
+   f->len = f->chunk[f->cur].len;
+   f->eof = f->chunk[f->cur].last;
    return f->len > 0 ? 1 : 0;
 }
 
@@ -210,9 +302,10 @@ static int chunk_load(sqb_file_t *f)
 static int ensure_results(sqb_file_t *f, seeq_t *sq, int opt)
 {
    const sqb_seeq_t *p = (const sqb_seeq_t *)sq;
-   if (f->res_valid && f->res_uid == p->uid && f->res_opt == opt) return 0;
    sqb_engine_t *eng = seeqEngine(sq);
    if (eng == NULL) return -1;
+   if (f->res_valid && f->res_uid == p->uid && f->res_opt == opt && f->res_eng == eng &&
+       f->res_gen == sqbScanGeneration(eng)) return 0;
    const int flags = opt | SQB_KEEP_LINES | ((f->pub.flags & 1) ? SQB_FASTA : 0);
    sqb_stats_t st;
    if (sqbScanHost(eng, f->buf, f->len, flags, &st)) {
@@ -220,28 +313,17 @@ static int ensure_results(sqb_file_t *f, seeq_t *sq, int opt)
       errno = EIO;
       return -1;
    }
+   /* the engine's own arrays serve the iterator: they stay as they are until the next scan of this engine,
+    * which changes its generation (then the chunk is scanned again) */
    uint64_t nr = 0, nl = 0;
-   const sqb_rec_t *recs = sqbHostRecords(eng, &nr);
-   const uint64_t *lines = NULL;
-   sqbHostLineStarts(eng, &lines, &nl);
-   if (nr > f->rec_cap) {
-      free(f->recs);
-      f->rec_cap = (size_t)nr + (size_t)nr / 4 + 16;
-      f->recs = malloc(f->rec_cap * sizeof(sqb_rec_t));
-      if (f->recs == NULL) { f->rec_cap = 0; return -1; }
-   }
-   if (nl > f->line_cap) {
-      free(f->lines);
-      f->line_cap = (size_t)nl + (size_t)nl / 4 + 16;
-      f->lines = malloc(f->line_cap * sizeof(uint64_t));
-      if (f->lines == NULL) { f->line_cap = 0; return -1; }
-   }
-   if (nr) memcpy(f->recs, recs, (size_t)nr * sizeof(sqb_rec_t));
-   if (nl) memcpy(f->lines, lines, (size_t)nl * sizeof(uint64_t));
+   f->recs = sqbHostRecords(eng, &nr);
+   sqbHostLineStarts(eng, &f->lines, &nl);
    f->nrecs = (size_t)nr;
    f->nlines = (size_t)nl;
    f->res_uid = p->uid;
    f->res_opt = opt;
+   f->res_eng = eng;
+   f->res_gen = sqbScanGeneration(eng);
    f->res_valid = 1;
    /* first record at or after the line to hand out next */
    size_t lo = 0, hi = f->nrecs;

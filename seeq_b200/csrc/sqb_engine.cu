@@ -24,7 +24,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <set>
+#include <string>
 #include <utility>
 #include <vector>
 
@@ -180,6 +182,10 @@ struct sqb_engine {
    unsigned long long *d_word = nullptr, *h_word = nullptr;     // device_cuts: one word each
    cudaStream_t big_stream = nullptr;                           // sqbScanDeviceLarge: the kernels of all chunks
    bool graphs = true;                                          // SEEQ_B200_GRAPHS=0 disables graph replay
+   // sqbScanHost over several GPUs from ONE process ($SEEQ_B200_DEVICES): engines of the same pattern on the
+   // other devices, created on first use and owned by this engine; one host thread drives each
+   std::vector<sqb_engine *> peers;
+   unsigned long long scan_generation = 0;                      // bumped by every scan that rewrites the host results
    unsigned long long version = 1;                              // bumped whenever a capacity guess or a mode changes
 };
 
@@ -237,7 +243,9 @@ struct NumaScope {
    {
       static int cache[64];
       static bool known[64];
+      static std::mutex mu;
       if (device < 0 || device >= 64) return -1;
+      std::lock_guard<std::mutex> lock(mu);
       if (known[device]) return cache[device];
       int node = -1;
       const char *env = getenv("SEEQ_B200_NUMA");
@@ -299,7 +307,8 @@ static cudaError_t pinned_alloc(void **p, size_t bytes)
    int device = 0;
    if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); device = 0; }
    NumaScope scope(device);
-   return cudaMallocHost(p, bytes);
+   // portable: every device of the process may DMA out of / into it (multi-GPU sqbScanHost)
+   return cudaHostAlloc(p, bytes, cudaHostAllocPortable);
 }
 
 // ---------------------------------------------------------------------------
@@ -527,7 +536,7 @@ static int launch_bitslice(const sqb_engine *e, int mode, int options, size_t ma
       return 0;
    }
 #define SQB_SHAPE(RR, GG) if (R == RR && G == GG) return launch_bs1<RR, GG>(bsmode, skip, grid, st, a, e->bs_pat);
-   SQB_SHAPE(8, 1) SQB_SHAPE(10, 1) SQB_SHAPE(12, 1) SQB_SHAPE(16, 1) SQB_SHAPE(24, 1) SQB_SHAPE(32, 1)
+   SQB_SHAPE(8, 1) SQB_SHAPE(10, 1) SQB_SHAPE(12, 1) SQB_SHAPE(16, 1) SQB_SHAPE(20, 1) SQB_SHAPE(24, 1) SQB_SHAPE(32, 1)
    SQB_SHAPE(20, 2) SQB_SHAPE(24, 2) SQB_SHAPE(32, 2)
    SQB_SHAPE(20, 4) SQB_SHAPE(24, 4) SQB_SHAPE(26, 4) SQB_SHAPE(28, 4) SQB_SHAPE(32, 4)
 #undef SQB_SHAPE
@@ -1027,6 +1036,8 @@ sqb_engine_t *sqbEngineNew(const unsigned char *keys, int m, int tau, int device
 void sqbEngineFree(sqb_engine_t *e)
 {
    if (e == NULL) return;
+   for (sqb_engine *p : e->peers) sqbEngineFree(p);
+   e->peers.clear();
    cudaSetDevice(e->device);
    for (auto &s : e->slot) slot_free(s);
    if (e->host_recs) cudaFreeHost(e->host_recs);
@@ -1370,10 +1381,152 @@ static int scan_chunks(sqb_engine **engs, int P, const char *text, size_t nbytes
    return 0;
 }
 
+// ---- several GPUs from one process ------------------------------------------------
+// $SEEQ_B200_DEVICES = "all" or a count: sqbScanHost (and with it seeqBatchMatch, seeqFileMatch and seeq())
+// cuts the buffer into newline-aligned shards (sqbShardRange), one per device, and drives every device from
+// a host thread of its own -- each with its own engine, streams and chunk pipeline, so every PCIe link
+// carries its shard at the same time.  No collective: the line bases are prefix-summed on the host and
+// the records of the shards are concatenated in shard order.  The reference is single-threaded
+// (seeq.c:293-392); its "N cores" baseline runs N processes over the same kind of shards.
+static int host_devices(const sqb_engine *e, size_t nbytes, int options)
+{
+   if (options & (SQB_SINGLE_LINE | SQB_DEVICE_RESULTS)) return 1;
+   const char *env = getenv("SEEQ_B200_DEVICES");
+   if (env == nullptr || *env == 0) return 1;
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); return 1; }
+   int want = strcmp(env, "all") == 0 ? ndev : atoi(env);
+   want = std::max(1, std::min(want, ndev));
+   // a shard below 16 MiB does not pay for its launches
+   const size_t min_shard = getenv("SEEQ_B200_MIN_SHARD_MB") ? (size_t)atol(getenv("SEEQ_B200_MIN_SHARD_MB")) << 20 : (size_t)16 << 20;
+   while (want > 1 && nbytes / (size_t)want < std::max<size_t>(min_shard, 1)) want--;
+   (void)e;
+   return want;
+}
+
+static int scan_host_multi(sqb_engine *e, int nd, const char *text, size_t nbytes, int options, sqb_stats_t *stats)
+{
+   int ndev = 0;
+   CU(cudaGetDeviceCount(&ndev));
+   while ((int)e->peers.size() < nd - 1) {
+      const int dev = (e->device + 1 + (int)e->peers.size()) % ndev;
+      sqb_engine *p = sqbEngineNew(e->keys, e->m, e->tau, dev);
+      if (p == nullptr) return -1;
+      p->cuts = e->cuts; p->filter = e->filter; p->fused = e->fused; p->bs_ok = e->bs_ok;
+      p->bs_gate = e->bs_gate; p->bs_min_bytes = e->bs_min_bytes;
+      e->peers.push_back(p);
+   }
+   CU(cudaSetDevice(e->device));
+   std::vector<sqb_engine *> eng((size_t)nd);
+   eng[0] = e;
+   for (int r = 1; r < nd; r++) eng[(size_t)r] = e->peers[(size_t)r - 1];
+   // shards: newline-aligned, and at record boundaries with SQB_FASTQ
+   std::vector<size_t> cut((size_t)nd + 1, 0);
+   for (int r = 0; r < nd; r++) {
+      size_t b, en;
+      sqbShardRange(text, nbytes, r, nd, &b, &en);
+      cut[(size_t)r] = b;
+      cut[(size_t)r + 1] = en;
+   }
+   if (options & SQB_FASTQ) {
+      for (int r = 1; r < nd; r++) {
+         if (cut[(size_t)r] >= nbytes) continue;
+         const size_t q = fastq_record_start(text, cut[(size_t)r - 1], cut[(size_t)r], nbytes);
+         if (q == (size_t)-1 || q < cut[(size_t)r - 1]) { set_err("SQB_FASTQ: no record boundary near byte %zu", cut[(size_t)r]); return -1; }
+         cut[(size_t)r] = q;
+      }
+   }
+   std::vector<sqb_stats_t> st((size_t)nd);
+   std::vector<int> rc((size_t)nd, 0);
+   std::vector<std::string> errs((size_t)nd);
+   auto work = [&](int r) {
+      sqb_engine *er = eng[(size_t)r];
+      rc[(size_t)r] = scan_chunks(&er, 1, text + cut[(size_t)r], cut[(size_t)r + 1] - cut[(size_t)r], options, &st[(size_t)r],
+                                  false, nullptr);
+      if (rc[(size_t)r]) errs[(size_t)r] = g_err;
+   };
+   {
+      std::vector<std::thread> th;
+      for (int r = 1; r < nd; r++) th.emplace_back(work, r);
+      work(0);
+      for (auto &t : th) t.join();
+   }
+   CU(cudaSetDevice(e->device));
+   for (int r = 0; r < nd; r++)
+      if (rc[(size_t)r]) { set_err("device %d: %s", eng[(size_t)r]->device, errs[(size_t)r].c_str()); return -1; }
+   // ---- merge: line bases, records in shard order, line offsets -------------------------
+   std::vector<uint64_t> line_base((size_t)nd, 0), rec_off((size_t)nd, 0);
+   uint64_t lines = 0, recs = 0;
+   for (int r = 0; r < nd; r++) {
+      line_base[(size_t)r] = lines;
+      rec_off[(size_t)r] = recs;
+      lines += st[(size_t)r].nlines;
+      recs += (options & SQB_COUNT_ONLY) ? 0 : eng[(size_t)r]->host_recs_n;
+   }
+   if (!(options & SQB_COUNT_ONLY) && recs > e->host_recs_n) {
+      if (recs > e->host_recs_cap) {
+         sqb_rec_t *bigger = nullptr;
+         const size_t cap = (size_t)recs + (size_t)recs / 4 + (1u << 16);
+         CU(pinned_alloc((void **)&bigger, cap * sizeof(sqb_rec_t)));
+         if (e->host_recs_n) memcpy(bigger, e->host_recs, e->host_recs_n * sizeof(sqb_rec_t));
+         if (e->host_recs) CU(cudaFreeHost(e->host_recs));
+         e->host_recs = bigger;
+         e->host_recs_cap = cap;
+      }
+      // every shard's records are copied (line numbers rebased) by a thread of their own
+      auto copy = [&](int r) {
+         const sqb_engine *er = eng[(size_t)r];
+         sqb_rec_t *dst = e->host_recs + rec_off[(size_t)r];
+         const uint32_t base = (uint32_t)line_base[(size_t)r];
+         for (size_t i = 0; i < er->host_recs_n; i++) {
+            sqb_rec_t x = er->host_recs[i];
+            x.line += base;
+            dst[i] = x;
+         }
+      };
+      std::vector<std::thread> th;
+      for (int r = 2; r < nd; r++) th.emplace_back(copy, r);
+      copy(1);
+      for (auto &t : th) t.join();
+      e->host_recs_n = (size_t)recs;
+   }
+   if (options & SQB_KEEP_LINES_INTERNAL) {
+      for (int r = 1; r < nd; r++) {
+         const sqb_engine *er = eng[(size_t)r];
+         const size_t old = e->host_lines.size();
+         e->host_lines.resize(old + er->host_lines.size());
+         for (size_t i = 0; i < er->host_lines.size(); i++) e->host_lines[old + i] = er->host_lines[i] + cut[(size_t)r];
+      }
+   }
+   sqb_stats_t acc;
+   memset(&acc, 0, sizeof acc);
+   for (int r = 0; r < nd; r++) {
+      const sqb_stats_t &x = st[(size_t)r];
+      acc.nlines += x.nlines;
+      acc.nmatched += x.nmatched;
+      acc.nrecs += x.nrecs;
+      acc.launches += x.launches;
+      acc.reruns += x.reruns;
+      acc.device_ms = std::max(acc.device_ms, x.device_ms);
+      for (int k = 0; k < 8; k++) acc.kernel_ms[k] = std::max(acc.kernel_ms[k], x.kernel_ms[k]);
+      acc.path |= x.path;
+   }
+   acc.nbytes = nbytes;
+   acc.devices = (uint32_t)nd;
+   e->last_stats = acc;
+   if (stats) *stats = acc;
+   return 0;
+}
+
 int sqbScanHost(sqb_engine_t *e, const char *text, size_t nbytes, int options, sqb_stats_t *stats)
 {
+   e->scan_generation++;
+   const int nd = host_devices(e, nbytes, options);
+   if (nd > 1) return scan_host_multi(e, nd, text, nbytes, options, stats);
    return scan_chunks(&e, 1, text, nbytes, options, stats, false, nullptr);
 }
+
+unsigned long long sqbScanGeneration(sqb_engine_t *e) { return e->scan_generation; }
 
 int sqbScanDeviceLarge(sqb_engine_t *e, const void *d_text, size_t nbytes, int options, void *stream,
                        sqb_stats_t *stats)

@@ -39,6 +39,7 @@ cudaError_t sqb_launch_bitslice_myers_fused(int rows, int bsmode, bool skip, int
    case 10: return launch1<10>(bsmode, skip, grid, st, a, p);
    case 12: return launch1<12>(bsmode, skip, grid, st, a, p);
    case 16: return launch1<16>(bsmode, skip, grid, st, a, p);
+   case 20: return launch1<20>(bsmode, skip, grid, st, a, p);
    case 24: return launch1<24>(bsmode, skip, grid, st, a, p);
    case 32: return launch1<32>(bsmode, skip, grid, st, a, p);
    default: return cudaErrorInvalidValue;

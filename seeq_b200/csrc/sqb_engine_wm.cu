@@ -51,6 +51,7 @@ cudaError_t SQB_WM_ENTRY(int rows, int levels, int bsmode, bool skip, int grid, 
    case 10: return launch1<10>(levels, bsmode, skip, grid, st, a, p);
    case 12: return launch1<12>(levels, bsmode, skip, grid, st, a, p);
    case 16: return launch1<16>(levels, bsmode, skip, grid, st, a, p);
+   case 20: return launch1<20>(levels, bsmode, skip, grid, st, a, p);
    case 24: return launch1<24>(levels, bsmode, skip, grid, st, a, p);
    case 32: return launch1<32>(levels, bsmode, skip, grid, st, a, p);
    default: return cudaErrorInvalidValue;

@@ -31,27 +31,38 @@ typedef struct {
    sqb_shadow_t   shadow[2];
 } sqb_seeq_t;
 
-/* one resident chunk of the input file and its batch results */
+/* The input file is read in large chunks that end on a line boundary, by a READER THREAD that fills one
+ * pinned buffer while the batch of the other is matched and handed out (seeq.c:361 reads line by line with
+ * getline).  The resident chunk and its batch results: */
+#include <pthread.h>
+
+typedef struct {
+   char         * buf;          /* pinned; buf[0..len) holds whole lines (the last one may lack '\n' only at end of input) */
+   size_t         cap, len;
+   int            last;         /* no chunk follows */
+} sqb_chunk_t;
+
+enum { SQB_CH_FREE = 0, SQB_CH_READY = 1 };
+
 typedef struct {
    seeqfile_t     pub;          /* must be first */
    unsigned long long magic;
-   /* chunk text: buf[0..len) holds whole lines (the last one may lack '\n'
-    * only at end of input); buf[len..fill) is the partial line carried over */
+   /* the resident chunk (one of chunk[]) */
    char         * buf;
-   size_t         cap, len, fill;
-   int            pinned;
-   int            eof;
+   size_t         len;
+   int            eof;          /* the resident chunk is the last one */
    int            started;      /* at least one chunk was loaded */
-   /* batch results for (res_sq, res_opt) over the resident chunk */
-   unsigned long long res_uid;
+   /* batch results for (res_uid, res_opt) over the resident chunk: the engine's own arrays, valid while the
+    * engine's scan generation is res_gen (a seeqStringMatch on the same seeq_t in between re-scans the chunk) */
+   unsigned long long res_uid, res_gen;
+   sqb_engine_t * res_eng;
    int            res_opt;
    int            res_valid;
-   sqb_rec_t    * recs;         size_t nrecs, rec_cap;
-   uint64_t     * lines;        size_t nlines, line_cap;   /* offsets of counted lines */
+   const sqb_rec_t * recs;      size_t nrecs;
+   const uint64_t * lines;      size_t nlines;             /* offsets of counted lines */
    size_t         cur_line;     /* next counted line of the chunk to hand out */
    size_t         cur_rec;      /* first record with line >= cur_line         */
    size_t         line_base;    /* counted lines before the resident chunk    */
-   size_t         target;       /* bytes to read per chunk                    */
    char         * last_header;  /* FASTA: last header seen before the chunk   */
    /* FASTA: forward cursor over the headers of the resident chunk.  Lines are handed out in increasing
     * order, so the header in force for a line is found by walking on from the previous line served:
@@ -60,6 +71,20 @@ typedef struct {
    size_t         hdr_off;      /* offset of the last header line before hdr_scan          */
    int            hdr_seen;     /* 1: hdr_off is valid (else the header is last_header)    */
    int            hdr_dirty;    /* 1: pub.info does not show the header in force           */
+   /* reader thread */
+   pthread_t      thread;
+   int            thread_started;
+   pthread_mutex_t mu;
+   pthread_cond_t cv;
+   sqb_chunk_t    chunk[2];
+   int            state[2];     /* SQB_CH_* (under mu) */
+   int            cur;          /* index of the resident chunk */
+   int            stop;         /* seeqClose: the reader is to give up */
+   int            reader_errno; /* != 0: the reader failed (under mu) */
+   FILE         * in;
+   size_t         target;       /* bytes to read per chunk */
+   char         * carry;        /* partial line behind the last chunk (reader only) */
+   size_t         carry_len, carry_cap;
 } sqb_file_t;
 
 int  sqb_parse_pattern (const char * text, char * keys);

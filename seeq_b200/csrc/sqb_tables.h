@@ -58,7 +58,7 @@ static inline void build_class_table(int options, ClassTable *t)
 // the kernel instance (R rows per part, G parts) that serves a pattern of m
 // positions; false if there is none (m > 128)
 struct BsShape { int rows, parts; };
-static const BsShape kBsShapes[] = {{8, 1}, {10, 1}, {12, 1}, {16, 1}, {24, 1}, {32, 1},   // m <= 32: one lane per group
+static const BsShape kBsShapes[] = {{8, 1}, {10, 1}, {12, 1}, {16, 1}, {20, 1}, {24, 1}, {32, 1},   // m <= 32: one lane per group
                                     {20, 2}, {24, 2}, {32, 2},                       // m <= 64: two lanes
                                     {20, 4}, {24, 4}, {26, 4}, {28, 4}, {32, 4}};    // m <= 128: four lanes
 static inline bool bs_shape_for(int m, BsShape *out)

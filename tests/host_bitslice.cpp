@@ -111,7 +111,7 @@ extern "C" long bs_host_scan(const char *buf, size_t n, const unsigned char *key
    for (size_t l0 = 0; l0 < begin.size(); l0 += 32) {
       const size_t l1 = std::min(begin.size(), l0 + 32);
 #define SHAPE(R, G) if (p.rows == R && p.parts == G) run_rows<R, G>(mode, skip, cls, n, begin, l0, l1, p, ev);
-      SHAPE(8, 1) SHAPE(10, 1) SHAPE(12, 1) SHAPE(16, 1) SHAPE(24, 1) SHAPE(32, 1)
+      SHAPE(8, 1) SHAPE(10, 1) SHAPE(12, 1) SHAPE(16, 1) SHAPE(20, 1) SHAPE(24, 1) SHAPE(32, 1)
       SHAPE(20, 2) SHAPE(24, 2) SHAPE(32, 2)
       SHAPE(20, 4) SHAPE(24, 4) SHAPE(26, 4) SHAPE(28, 4) SHAPE(32, 4)
 #undef SHAPE
@@ -264,7 +264,7 @@ extern "C" long bs_host_scan_cut(const char *buf, size_t n, const unsigned char 
       if (mode == BS_BEST) run_group_cut<R, G, BS_BEST>(cls, n, segs, l0, l1, wup, p, per_seg, segstop);     \
       if (mode == BS_ALL) run_group_cut<R, G, BS_ALL>(cls, n, segs, l0, l1, wup, p, per_seg, segstop);       \
    }
-      SHAPE(8, 1) SHAPE(10, 1) SHAPE(12, 1) SHAPE(16, 1) SHAPE(24, 1) SHAPE(32, 1)
+      SHAPE(8, 1) SHAPE(10, 1) SHAPE(12, 1) SHAPE(16, 1) SHAPE(20, 1) SHAPE(24, 1) SHAPE(32, 1)
       SHAPE(20, 2) SHAPE(24, 2) SHAPE(32, 2)
       SHAPE(20, 4) SHAPE(24, 4) SHAPE(26, 4) SHAPE(28, 4) SHAPE(32, 4)
 #undef SHAPE
@@ -412,7 +412,7 @@ extern "C" long bs_host_scan_wm(const char *buf, size_t n, const unsigned char *
    }
 #define WM2(R, T) if (p.rows == R && tau + 1 == T) { WM3(R, T, BS_FIRST) WM3(R, T, BS_BEST) WM3(R, T, BS_ALL) }
 #define WM1(R) WM2(R, 1) WM2(R, 2) WM2(R, 3)
-      WM1(8) WM1(10) WM1(12) WM1(16) WM1(24) WM1(32)
+      WM1(8) WM1(10) WM1(12) WM1(16) WM1(20) WM1(24) WM1(32)
 #undef WM1
 #undef WM2
 #undef WM3

@@ -92,7 +92,8 @@ def test_lines_beyond_the_overlap(B, oracle):
         exp, nl, nm = oracle.buffer_scan(buf, sq.keys, 2, SQ_ALL)
         assert [(int(r["line"]) + 1, int(r["start"]), int(r["end"]), int(r["dist"])) for r in recs] == \
             [tuple(int(x) for x in row) for row in exp]
-        assert st.path & FUSED and st.reruns == (1 if it == 0 else 0), (it, st.path, st.reruns)
+        # (first pass: the overlap re-run, and possibly one for the plane capacity guess)
+        assert st.path & FUSED and (1 <= st.reruns <= 2 if it == 0 else st.reruns == 0), (it, st.path, st.reruns)
     sq.close()
     buf = ragged(rng, 200, 0, 9000, pattern)
     for mo in MATCH:
