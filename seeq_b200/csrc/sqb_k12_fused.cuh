@@ -59,9 +59,12 @@ struct K12Args {
    uint32_t planes_cap;           // uint4 units
 };
 
+// dynamic shared memory: the text stage, the nibble array, the class table, the tile's lists
+__host__ __device__ constexpr uint32_t k12_text_bytes(uint32_t ov) { return (kK1Tile + ov + 16u + 127u) & ~127u; }
+__host__ __device__ constexpr uint32_t k12_nib_bytes(uint32_t ov) { return ((kK1Tile + ov) / 2u + 16u + 127u) & ~127u; }
 __host__ __device__ constexpr uint32_t k12_smem_bytes(uint32_t ov)
 {
-   return ((kK1Tile + ov + 16u + 127u) & ~127u) + 256u + (kFMaxEntries + 4u) * 4u + kFMaxEntries * 2u;
+   return k12_text_bytes(ov) + k12_nib_bytes(ov) + 256u + (kFMaxEntries + 4u) * 4u + kFMaxEntries * 2u;
 }
 
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr)
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, co
 {
    extern __shared__ __align__(128) uint8_t dyn[];
    __shared__ uint64_t bar;
-   __shared__ uint32_t s_next, s_base, s_ovnl, s_nlive, s_pbase, s_gbase, s_skip, s_alive;
+   __shared__ uint32_t s_tile[2], s_base, s_ovnl, s_nlive, s_pbase, s_gbase, s_skip, s_alive;
    __shared__ uint32_t s_wsum[kWarps];
    __shared__ uint32_t s_gcols[kFMaxGroups];
    __shared__ __align__(16) uint32_t s_out[kWarps][2][96];     // planes of 32 columns of one group, two buffers
@@ -158,8 +161,9 @@ __global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, co
    const uint32_t ntiles = (n + kK1Tile - 1) / kK1Tile;
    const uint32_t n16 = (n + 15u) & ~15u;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-   uint8_t *buf = dyn;
-   uint8_t *lut = dyn + ((stage + 16u + 127u) & ~127u);
+   uint8_t *buf = dyn;                                          // the text of the tile (TMA)
+   uint8_t *nib = dyn + k12_text_bytes(ov);                     // its class nibbles, one contiguous array
+   uint8_t *lut = nib + k12_nib_bytes(ov);
    uint32_t *lst = reinterpret_cast<uint32_t *>(lut + 256);     // [entries + 1] offset in the stage | kDeadBit
    uint16_t *live = reinterpret_cast<uint16_t *>(lst + kFMaxEntries + 4u);   // FILTER: entries that are alive
    const uint32_t rot = (uint32_t)lane & 7u;
@@ -181,31 +185,35 @@ __global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, co
    }
    const uint32_t sel16 = (lane & 16) ? 0x3276u : 0x5410u, sel8 = (lane & 8) ? 0x3715u : 0x6240u;
 
+   auto issue = [&](uint32_t t) {          // (tid 0) TMA of tile t into the text stage
+      const uint32_t start = t * kK1Tile;
+      uint32_t bytes = n16 - start;
+      if (bytes > stage) bytes = stage;
+      mbar_expect_tx(&bar, bytes);
+      bulk_g2s(buf, a.text + start, bytes, &bar);
+   };
    lut[tid] = ct.code[tid];
    if (tid == 0) {
       mbar_init(&bar, 1);
       mbar_fence_init();
-      s_next = (uint32_t)atomicAdd(&a.ctr[C_TICKET_K1], 1ull);
+      const uint32_t t = (uint32_t)atomicAdd(&a.ctr[C_TICKET_K1], 1ull);
+      s_tile[0] = t;
+      s_ovnl = 0xffffffffu;
+      if (t < ntiles) issue(t);
    }
+   __syncthreads();
    uint32_t phase = 0;
    bool out_pending = false;              // lane 0: bulk stores of this warp may still read s_out
    uint32_t oit = 0;                      // blocks of 32 columns this warp has staged so far (buffer = oit & 1)
 
-   for (;;) {
-      fence_proxy_async();                // this thread's accesses to buf come before the refill by TMA
-      __syncthreads();                    // T: nobody reads buf any more; s_next is visible
-      const uint32_t tile = s_next;
+   // The text stage is free again as soon as every lane holds its text in registers (barrier A): the TMA
+   // of the NEXT tile is issued there and runs under the emit and pack phases of this one.  The tile
+   // numbers travel through s_tile[iteration parity]; every shared scalar is rewritten between two
+   // barriers that all its readers of the round before have passed.
+   for (uint32_t iter = 0;; iter++) {
+      const uint32_t tile = s_tile[iter & 1u];
       if (tile >= ntiles) break;
       const uint32_t tile0 = tile * kK1Tile;
-      if (tid == 0) {
-         s_ovnl = 0xffffffffu;
-         s_skip = 0u;
-         s_alive = 0u;
-         uint32_t bytes = n16 - tile0;
-         if (bytes > stage) bytes = stage;
-         mbar_expect_tx(&bar, bytes);
-         bulk_g2s(buf, a.text + tile0, bytes, &bar);
-      }
       mbar_wait(&bar, phase);
       phase ^= 1u;
 
@@ -282,6 +290,7 @@ __global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, co
          if (lane >= d) inc += t;
       }
       if (lane == 31) s_wsum[warp] = inc;
+      fence_proxy_async();                   // this thread's reads of the text stage come before its refill by TMA
       __syncthreads();                       // A: the text is in registers, s_wsum and s_ovnl are complete
       uint32_t before = 0, tile_total = 0;
 #pragma unroll
@@ -291,7 +300,12 @@ __global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, co
          tile_total += x;
       }
       if (tid == 0) {
-         s_next = (uint32_t)atomicAdd(&a.ctr[C_TICKET_K1], 1ull);      // (everyone has read its tile)
+         const uint32_t ovnl = s_ovnl;
+         s_ovnl = 0xffffffffu;
+         s_alive = 0u;
+         const uint32_t nt = (uint32_t)atomicAdd(&a.ctr[C_TICKET_K1], 1ull);
+         s_tile[(iter + 1u) & 1u] = nt;
+         if (nt < ntiles) issue(nt);
          const uint32_t at = (uint32_t)atomicAdd(&a.ctr[C_LS_CURSOR], (unsigned long long)tile_total);
          a.tile_cnt[tile] = tile_total;
          a.tile_off[tile] = at;
@@ -299,20 +313,21 @@ __global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, co
          // where the tile's last line ends (exclusive, with its terminator): the first newline of the
          // overlap, or one STOP column behind the end of the buffer
          uint32_t end = 0xffffffffu;
-         if (s_ovnl != 0xffffffffu) end = s_ovnl + 1u;
+         if (ovnl != 0xffffffffu) end = ovnl + 1u;
          if (tile0 + stage > n) end = min(end, n - tile0 + 1u);
          if (tile_total > kFMaxEntries || (tile_total != 0u && end == 0xffffffffu)) {
             s_skip = 1u;
             atomicMax(&a.ctr[C_FUSED_OVF], 1ull);
          } else {
+            s_skip = 0u;
             lst[tile_total] = end;
          }
       }
       // ---- class nibbles: one contiguous array over the tile's own text ----
 #pragma unroll
       for (int k = 0; k < 8; k++)
-         *reinterpret_cast<uint2 *>(buf + nib_off + ((((uint32_t)k + rot) & 7u) << 3)) = make_uint2(lo[k], hi[k]);
-      if (has_ov) *reinterpret_cast<uint2 *>(buf + (kK1Tile >> 1) + (uint32_t)tid * 8u) = make_uint2(olo, ohi);
+         *reinterpret_cast<uint2 *>(nib + nib_off + ((((uint32_t)k + rot) & 7u) << 3)) = make_uint2(lo[k], hi[k]);
+      if (has_ov) *reinterpret_cast<uint2 *>(nib + (kK1Tile >> 1) + (uint32_t)tid * 8u) = make_uint2(olo, ohi);
       __syncthreads();                       // B: nibbles, s_base, s_skip
       const bool skip_tile = s_skip != 0u;
 
@@ -324,8 +339,8 @@ __global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, co
          auto dead_flag = [&](uint32_t o) -> uint32_t {       // o = offset of the line start in the stage
             if (!FILTER) return 0u;
             const uint32_t a0 = (o >> 1) & ~3u;
-            const uint32_t w0 = *reinterpret_cast<const uint32_t *>(buf + a0);
-            const uint32_t w1 = *reinterpret_cast<const uint32_t *>(buf + a0 + 4u);
+            const uint32_t w0 = *reinterpret_cast<const uint32_t *>(nib + a0);
+            const uint32_t w1 = *reinterpret_cast<const uint32_t *>(nib + a0 + 4u);
             uint32_t win = __funnelshift_r(w0, w1, (o & 7u) * 4u);
             if (a.filter_k < 8u) win &= (1u << (4u * a.filter_k)) - 1u;
             const uint32_t y = (win ^ 0x55555555u) & 0x77777777u;
@@ -443,7 +458,7 @@ __global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, co
          if (FILTER) a.gent[(size_t)(gbase + g) * 32u + (uint32_t)lane] = (uint16_t)ent;
          uint4 *dst = a.planes + (size_t)pbase + before_units;
          SmemNibbleStream st;
-         st.open(smem_addr(buf), nib_chunks, begin, have);
+         st.open(smem_addr(nib), nib_chunks, begin, have);
          for (uint32_t c0 = 0; c0 < ncols; c0 += 32, oit++) {
             uint32_t w[4];
             st.next(w);

@@ -13,6 +13,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 # skip the generator + 3 warm-up steps, then capture one full step
 NK=${3:-14}
 if [ "$NK" = "0" ]; then exit 0; fi        # launch list only
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k1_|k15_|k2_|k34_|k_tile|k_off' \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k1_|k12_|k15_|k2_|k34_|k_tile|k_off' \
     -s $((3 * NK)) -c $NK -f -o $OUT/${TAG}_${WL}_full $BENCH > $OUT/${TAG}_${WL}_full.log 2>&1
 ls -la $OUT | tail -8
