@@ -661,14 +661,16 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
          if (dev_reserve(&s.d_planes, &s.planes_cap, want_units, 16)) return -1;
          K12Args ka{d_text, n, s.d_ls_raw, (uint32_t)s.line_cap, ctr, tile_cnt, tile_off, tile_alive,
                     (uint32_t)e->filter_k, skip, e->fused_ov, s.d_gdesc, (uint32_t)std::min<size_t>(s.gdesc_cap, 0xffffffffu),
-                    s.d_gent, s.d_planes, (uint32_t)std::min<size_t>(s.planes_cap, 0xffffffffu)};
+                    s.d_gent, s.d_planes, (uint32_t)std::min<size_t>(s.planes_cap, 0xffffffffu), 4u};
          if (first_use((const void *)k12_scan_pack<true>)) {
             CU(cudaFuncSetAttribute(k12_scan_pack<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k12_smem_bytes(kFMaxOverlap)));
             CU(cudaFuncSetAttribute(k12_scan_pack<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k12_smem_bytes(kFMaxOverlap)));
          }
          const size_t smem = k12_smem_bytes(e->fused_ov);
-         if (filter) k12_scan_pack<true><<<grid, kThreads, smem, st>>>(ka, ct);
-         else k12_scan_pack<false><<<grid, kThreads, smem, st>>>(ka, ct);
+         ClassTable32 ct32;
+         build_class_table32(ct, &ct32);
+         if (filter) k12_scan_pack<true><<<grid, kThreads, smem, st>>>(ka, ct32);
+         else k12_scan_pack<false><<<grid, kThreads, smem, st>>>(ka, ct32);
       } else {
       K1Args k1{d_text, n, s.d_ls_raw, (uint32_t)s.line_cap, want_codes ? (uint2 *)s.d_codes : nullptr, ctr,
                 tile_cnt, tile_off, tile_real, tile_last, tile_alive,
@@ -1029,7 +1031,7 @@ sqb_engine_t *sqbEngineNew(const unsigned char *keys, int m, int tau, int device
    if (const char *c = getenv("SEEQ_B200_NFA")) e->nfa_levels = atoi(c) != 0;
    if (const char *c = getenv("SEEQ_B200_GRAPHS")) e->graphs = atoi(c) != 0;
    if (const char *c = getenv("SEEQ_B200_FUSED")) e->fused = atoi(c) != 0;
-   if (const char *c = getenv("SEEQ_B200_FUSED_OV")) e->fused_ov = std::min<uint32_t>(kFMaxOverlap, std::max(16, atoi(c)) & ~15u);
+   if (const char *c = getenv("SEEQ_B200_FUSED_OV")) e->fused_ov = std::min<uint32_t>(kFMaxOverlap, std::max(32, atoi(c)) & ~31u);
    return e;
 }
 

@@ -5,14 +5,20 @@
 // 16-byte loads / 32-byte store pieces on the L1 data pipe.  Here a CTA stages one 32 KiB tile of text
 // (plus `ov` bytes of overlap so that the tile's last line is complete) with ONE TMA bulk copy and
 //
-//   1. classifies it exactly like K1 (one table look-up per byte, newline flags, warp-aggregated
-//      prefix, line starts allocated with one atomic per tile) -- the class nibbles stay in SHARED
-//      memory, written contiguously over the tile's own text;
+//   1. classifies it (one table look-up per byte, as K1) straight into TEXT-MAJOR BIT-PLANES in shared
+//      memory: the table entry of a byte holds its three class bits and its newline bit in four BYTES,
+//      one IMAD per text byte shifts it into place, and two rounds of PRMT turn the four accumulators of
+//      a 32-byte chunk into the words p0, p1, p2 (bit i = class bit of byte i) and NL (bit i = byte i
+//      is a newline).  NL is the line scan: popc, ONE warp-aggregated prefix, line starts allocated with
+//      one atomic per tile (ls_raw, as K1);
 //   2. forms GROUPS of 32 consecutive lines that start in the tile (tile-local: no CTA waits for
-//      another); a warp takes a group, lane r streams the nibbles of line r out of shared memory
-//      (16-byte LDS, funnel-shift realign), the warp transposes 32 lines x 32 columns with the
-//      shuffle butterfly of k15_pack and stages the three planes of the block in shared memory;
+//      another); a warp takes a group, lane r follows line r through the three plane streams (one LDS and
+//      one funnel shift per plane and 32 columns), the warp transposes 32 lines x 32 columns per plane
+//      with the shuffle butterfly of k15_pack (three transposes, not four: the newline bit stays behind)
+//      and stages the block in shared memory;
 //   3. one bulk (TMA) store per 32 columns writes the planes of the group to HBM.
+// The TMA of the next tile is issued as soon as every lane holds its text in registers and runs under
+// phases 2 and 3.
 //
 // Plane layout of a group (allocated with one atomic per tile, any order across tiles):
 //   [column block of 4][plane 0..2][4 columns] words = 48 bytes per 4 columns = 3 bits per text byte
@@ -37,7 +43,8 @@ namespace sqb {
 
 constexpr uint32_t kFMaxEntries = 2048;                 // line starts per tile the fused path handles
 constexpr uint32_t kFMaxGroups  = kFMaxEntries / 32;
-constexpr uint32_t kFMaxOverlap = kThreads * 16;        // one 16-byte vector per thread
+constexpr uint32_t kFMaxOverlap = 4096;                 // bytes; one 32-byte chunk per thread at most (256 * 32 = 8192)
+constexpr uint32_t kFWords      = kK1Tile / 32;         // plane words of a tile (1024)
 
 // (GroupDesc: sqb_k2_bitslice.cuh)
 
@@ -51,103 +58,98 @@ struct K12Args {
    uint32_t *tile_alive;          // out (FILTER): live entries per tile (statistics: C_NACTIVE)
    uint32_t filter_k;
    uint32_t skip;                 // as K1Args::skip
-   uint32_t ov;                   // overlap bytes staged behind a tile: multiple of 16, 16 .. kFMaxOverlap
+   uint32_t ov;                   // overlap bytes staged behind a tile: multiple of 32, 32 .. kFMaxOverlap
    GroupDesc *gdesc;              // out
    uint32_t gdesc_cap;
    uint16_t *gent;                // out (FILTER): [group * 32 + slot] local entry index
    uint4 *planes;                 // out
    uint32_t planes_cap;           // uint4 units
+   uint32_t four;                 // == 4, as a run-time value: table address = byte * four + base stays an IMAD (FMA
+                                  // pipe); with the literal the assembler makes it an LEA on the ALU pipe, which
+                                  // already carries one PRMT per text byte
 };
 
-// dynamic shared memory: the text stage, the nibble array, the class table, the tile's lists
-__host__ __device__ constexpr uint32_t k12_text_bytes(uint32_t ov) { return (kK1Tile + ov + 16u + 127u) & ~127u; }
-__host__ __device__ constexpr uint32_t k12_nib_bytes(uint32_t ov) { return ((kK1Tile + ov) / 2u + 16u + 127u) & ~127u; }
-__host__ __device__ constexpr uint32_t k12_smem_bytes(uint32_t ov)
+// byte -> {p0, p1, p2, newline} in the four bytes of a word (bit 0 of each)
+struct ClassTable32 {
+   uint32_t w[256];
+};
+static inline void build_class_table32(const ClassTable &ct, ClassTable32 *out)
 {
-   return k12_text_bytes(ov) + k12_nib_bytes(ov) + 256u + (kFMaxEntries + 4u) * 4u + kFMaxEntries * 2u;
+   for (int b = 0; b < 256; b++) {
+      const uint32_t c = ct.code[b];
+      out->w[b] = (c & 1u) | (((c >> 1) & 1u) << 8) | (((c >> 2) & 1u) << 16) | (((c >> 3) & 1u) << 24);
+   }
 }
 
-__device__ __forceinline__ uint4 lds_v4(uint32_t addr)
+// dynamic shared memory: the text stage, the plane words (3 planes), the class table, the tile's lists
+__host__ __device__ constexpr uint32_t k12_text_bytes(uint32_t ov) { return (kK1Tile + ov + 16u + 127u) & ~127u; }
+__host__ __device__ constexpr uint32_t k12_plane_words(uint32_t ov) { return kFWords + ov / 32u + 8u; }
+__host__ __device__ constexpr uint32_t k12_smem_bytes(uint32_t ov)
 {
-   uint4 v;
-   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+   return k12_text_bytes(ov) + 3u * 4u * k12_plane_words(ov) + 1024u + (kFMaxEntries + 4u) * 4u + kFMaxEntries * 2u;
+}
+
+// Where text word w (32 text bytes) of the tile lives in a plane array: thread tid owns the words
+// 4 tid .. 4 tid + 3 and stores word t of its four at t * 256 + tid -- lanes of a warp hit 32 banks; the
+// words of the overlap follow in text order.
+__device__ __forceinline__ uint32_t plane_slot(uint32_t w)
+{
+   return w < kFWords ? (((w & 3u) << 8) | (w >> 2)) : w;
+}
+
+__device__ __forceinline__ uint32_t lds_u32a(uint32_t addr)
+{
+   uint32_t v;
+   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+   return v;
+}
+// (not volatile: the class table is constant for the life of the kernel, the loads may be scheduled freely)
+__device__ __forceinline__ uint32_t lds_u32c(uint32_t addr)
+{
+   uint32_t v;
+   asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
    return v;
 }
 
-// nibble stream of one line out of the tile's nibble array in shared memory (cf. NibbleStream)
-struct SmemNibbleStream {
-   uint32_t base;                 // shared-memory address of the nibble array
-   uint32_t chunk, last;          // next 16-byte chunk, last valid chunk
-   uint32_t ws, bs;
-   uint4 prev, cur;
-   bool valid;
-
-   __device__ __forceinline__ uint4 load()
-   {
-      uint4 v = cur;
-      if (valid) v = lds_v4(base + (chunk << 4));
-      chunk = min(chunk + 1u, last);
-      return v;
-   }
-   __device__ __forceinline__ void open(uint32_t smem_base, uint32_t nchunks, uint32_t begin, bool ok)
-   {
-      base = smem_base;
-      last = nchunks - 1u;
-      valid = ok;
-      chunk = min(begin >> 5, last);
-      ws = (begin & 31u) >> 3;
-      bs = (begin & 7u) * 4u;
-      cur = make_uint4(0x55555555u, 0x55555555u, 0x55555555u, 0x55555555u);
-      prev = load();
-      cur = load();
-   }
-   __device__ __forceinline__ void next(uint32_t (&out)[4])
-   {
-      const uint32_t w[8] = {prev.x, prev.y, prev.z, prev.w, cur.x, cur.y, cur.z, cur.w};
-      uint32_t u[5];
-#pragma unroll
-      for (int i = 0; i < 5; i++) {
-         const uint32_t lo = (ws & 1u) ? w[i + 1] : w[i];
-         const uint32_t hi = (ws & 1u) ? w[i + 3] : w[i + 2];
-         u[i] = (ws & 2u) ? hi : lo;
-      }
-#pragma unroll
-      for (int i = 0; i < 4; i++) out[i] = __funnelshift_r(u[i], u[i + 1], bs);
-      prev = cur;
-      cur = load();
-   }
-};
-
-// class nibbles of one 16-byte vector: lo = bytes 0..7, hi = bytes 8..15 (nibble j = byte j)
-__device__ __forceinline__ void classify16(const uint4 v, const uint8_t *lut, uint32_t &lo, uint32_t &hi)
+// 32 text bytes -> p0, p1, p2, nl (bit i = byte i).  first = the vector of bytes 0..15
+// (lut = shared-memory ADDRESS of the table: the index is scaled and based by one IMAD on the FMA pipe --
+// the compiler's LEA would sit on the ALU pipe, which carries the PRMTs)
+__device__ __forceinline__ void classify32(const uint4 v0, const uint4 v1, const uint32_t lut, const uint32_t four,
+                                           uint32_t &p0, uint32_t &p1, uint32_t &p2, uint32_t &nl)
 {
-   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-   uint32_t l = 0, h = 0;
+   const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+   uint32_t acc[4] = {0u, 0u, 0u, 0u};                // [nl | p2 | p1 | p0] bytes of text bytes 8g .. 8g+7
 #pragma unroll
-   for (int j = 0; j < 8; j++) {
-      const uint32_t bx = __byte_perm(w[j >> 2], 0u, 0x4440u + (uint32_t)(j & 3));
-      const uint32_t by = __byte_perm(w[2 + (j >> 2)], 0u, 0x4440u + (uint32_t)(j & 3));
-      l = mad_u32((uint32_t)lut[bx], 1u << (4 * j), l);
-      h = mad_u32((uint32_t)lut[by], 1u << (4 * j), h);
+   for (int g = 0; g < 4; g++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+         const uint32_t b = __byte_perm(w[2 * g + (j >> 2)], 0u, 0x4440u + (uint32_t)(j & 3));
+         acc[g] = mad_u32(lds_u32c(mad_u32(b, four, lut)), 1u << j, acc[g]);
+      }
    }
-   lo = l;
-   hi = h;
+   const uint32_t t0 = __byte_perm(acc[0], acc[1], 0x5140u), t1 = __byte_perm(acc[2], acc[3], 0x5140u);
+   const uint32_t t2 = __byte_perm(acc[0], acc[1], 0x7362u), t3 = __byte_perm(acc[2], acc[3], 0x7362u);
+   p0 = __byte_perm(t0, t1, 0x5410u);
+   p1 = __byte_perm(t0, t1, 0x7632u);
+   p2 = __byte_perm(t2, t3, 0x5410u);
+   nl = __byte_perm(t2, t3, 0x7632u);
 }
 
-// nibbles of the bytes at positions >= n become STOP (never a newline); p = position of byte 0
-__device__ __forceinline__ void stop_beyond(uint32_t &lo, uint32_t &hi, uint32_t p, uint32_t n)
+// the bytes at positions >= n are STOP (p2 p1 p0 = 101) and never newlines; p = position of bit 0
+__device__ __forceinline__ void stop_beyond32(uint32_t &p0, uint32_t &p1, uint32_t &p2, uint32_t &nl, uint32_t p, uint32_t n)
 {
-#pragma unroll
-   for (int j = 0; j < 8; j++) {
-      if (p + (uint32_t)j >= n) lo = (lo & ~(0xFu << (4 * j))) | ((uint32_t)kClsStop << (4 * j));
-      if (p + 8u + (uint32_t)j >= n) hi = (hi & ~(0xFu << (4 * j))) | ((uint32_t)kClsStop << (4 * j));
-   }
+   if (p + 32u <= n) return;
+   const uint32_t valid = p >= n ? 0u : ((1u << (n - p)) - 1u);       // n - p in 1..31
+   p0 |= ~valid;
+   p1 &= valid;
+   p2 |= ~valid;
+   nl &= valid;
 }
 
 __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 template <bool FILTER>
-__global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, const __grid_constant__ ClassTable ct)
+__global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, const __grid_constant__ ClassTable32 ct)
 {
    extern __shared__ __align__(128) uint8_t dyn[];
    __shared__ uint64_t bar;
@@ -161,16 +163,19 @@ __global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, co
    const uint32_t ntiles = (n + kK1Tile - 1) / kK1Tile;
    const uint32_t n16 = (n + 15u) & ~15u;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const uint32_t pwords = k12_plane_words(ov);                 // words per plane array
    uint8_t *buf = dyn;                                          // the text of the tile (TMA)
-   uint8_t *nib = dyn + k12_text_bytes(ov);                     // its class nibbles, one contiguous array
-   uint8_t *lut = nib + k12_nib_bytes(ov);
-   uint32_t *lst = reinterpret_cast<uint32_t *>(lut + 256);     // [entries + 1] offset in the stage | kDeadBit
+   uint32_t *pl = reinterpret_cast<uint32_t *>(dyn + k12_text_bytes(ov));       // [3][pwords]
+   uint32_t *lut = pl + 3u * pwords;                            // [256]
+   uint32_t *lst = lut + 256;                                   // [entries + 1] offset in the stage | kDeadBit
    uint16_t *live = reinterpret_cast<uint16_t *>(lst + kFMaxEntries + 4u);   // FILTER: entries that are alive
-   const uint32_t rot = (uint32_t)lane & 7u;
+   // the lane's 128 bytes are four 32-byte chunks; slot q holds chunk (q + lane) & 3, so that the 16-byte
+   // loads of a quarter-warp fall into different bank groups two by two (one replay instead of seven)
+   const uint32_t crot = (uint32_t)lane & 3u;
    const uint32_t lane_off = (uint32_t)warp * kK1WarpBytes + (uint32_t)lane * kK1LaneBytes;
-   const uint32_t nib_off = lane_off >> 1;                      // this lane's nibbles in the contiguous array
-   const bool has_ov = (uint32_t)tid * 16u < ov;
-   const uint32_t nib_chunks = stage >> 5;                      // 16-byte chunks of the nibble array
+   const bool has_ov = (uint32_t)tid * 32u < ov;
+   const uint32_t last_word = kFWords + ov / 32u - 1u;          // last plane word with data
+   const uint32_t pl_addr = smem_addr(pl), lut_addr = smem_addr(lut);
 
    // transpose constants (k15_pack)
    uint32_t keep[5], rotc[5];
@@ -184,6 +189,8 @@ __global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, co
       }
    }
    const uint32_t sel16 = (lane & 16) ? 0x3276u : 0x5410u, sel8 = (lane & 8) ? 0x3715u : 0x6240u;
+   // where this lane's transposed words go in the staging block: lane = column; [column >> 2][plane][column & 3]
+   const uint32_t out_idx = ((uint32_t)lane >> 2) * 12u + ((uint32_t)lane & 3u);
 
    auto issue = [&](uint32_t t) {          // (tid 0) TMA of tile t into the text stage
       const uint32_t start = t * kK1Tile;
@@ -192,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, co
       mbar_expect_tx(&bar, bytes);
       bulk_g2s(buf, a.text + start, bytes, &bar);
    };
-   lut[tid] = ct.code[tid];
+   lut[tid] = ct.w[tid];
    if (tid == 0) {
       mbar_init(&bar, 1);
       mbar_fence_init();
@@ -206,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, co
    bool out_pending = false;              // lane 0: bulk stores of this warp may still read s_out
    uint32_t oit = 0;                      // blocks of 32 columns this warp has staged so far (buffer = oit & 1)
 
-   // The text stage is free again as soon as every lane holds its text in registers (barrier A): the TMA
+   // The text stage is free again as soon as every lane holds its planes in registers (barrier A): the TMA
    // of the NEXT tile is issued there and runs under the emit and pack phases of this one.  The tile
    // numbers travel through s_tile[iteration parity]; every shared scalar is rewritten between two
    // barriers that all its readers of the round before have passed.
@@ -219,65 +226,52 @@ __global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, co
 
       const uint32_t pos0 = tile0 + lane_off;                 // text position of this lane's first byte
 
-      // ---- classify: vector slot k holds text vector (k + rot) & 7 of the lane (as K1) ----
-      uint32_t lo[8], hi[8];
+      // ---- classify: slot q = chunk (q + crot) & 3 of the lane ----
+      uint32_t P0[4], P1[4], P2[4], NL[4];
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-         const uint4 v = *reinterpret_cast<const uint4 *>(buf + lane_off + ((((uint32_t)k + rot) & 7u) << 4));
-         classify16(v, lut, lo[k], hi[k]);
+      for (int q = 0; q < 4; q++) {
+         const uint32_t t = ((uint32_t)q + crot) & 3u;
+         const uint4 *src = reinterpret_cast<const uint4 *>(buf + lane_off + (t << 5));
+         classify32(src[0], src[1], lut_addr, a.four, P0[q], P1[q], P2[q], NL[q]);
       }
-      if (a.skip != 0u && pos0 == 0u) {     // the bytes in front of the buffer: STOP, the last one a newline
-         const uint32_t nl = a.skip - 1u;
-#pragma unroll
-         for (int j = 0; j < 8; j++) {
-            if ((uint32_t)j <= nl)
-               lo[0] = (lo[0] & ~(0xFu << (4 * j))) | ((uint32_t)(kClsStop | ((uint32_t)j == nl ? kClsNewline : 0)) << (4 * j));
-            if (8u + (uint32_t)j <= nl)
-               hi[0] = (hi[0] & ~(0xFu << (4 * j))) | ((uint32_t)(kClsStop | (8u + (uint32_t)j == nl ? kClsNewline : 0)) << (4 * j));
-         }
+      if (a.skip != 0u && pos0 == 0u) {     // the bytes in front of the buffer: STOP, the last one a newline (lane 0: crot == 0)
+         const uint32_t sm = (1u << a.skip) - 1u;
+         P0[0] |= sm;
+         P1[0] &= ~sm;
+         P2[0] |= sm;
+         NL[0] = (NL[0] & ~sm) | (1u << (a.skip - 1u));
       }
       if (pos0 + kK1LaneBytes > n) {
 #pragma unroll
-         for (int k = 0; k < 8; k++) stop_beyond(lo[k], hi[k], pos0 + ((((uint32_t)k + rot) & 7u) << 4), n);
+         for (int q = 0; q < 4; q++) stop_beyond32(P0[q], P1[q], P2[q], NL[q], pos0 + ((((uint32_t)q + crot) & 3u) << 5), n);
       }
-      // ---- the overlap behind the tile: one vector per thread; only its nibbles and the first
+      // ---- the overlap behind the tile: one 32-byte chunk per thread; only its planes and the first
       //      newline (= end of the tile's last line) are of interest ----
-      uint32_t olo = 0, ohi = 0;
+      uint32_t O0 = 0, O1 = 0, O2 = 0;
       if (has_ov) {
-         const uint32_t o = kK1Tile + (uint32_t)tid * 16u;
-         classify16(*reinterpret_cast<const uint4 *>(buf + o), lut, olo, ohi);
-         if (tile0 + o + 16u > n) stop_beyond(olo, ohi, tile0 + o, n);
-         const uint32_t fl = olo & 0x88888888u, fh = ohi & 0x88888888u;
-         if (fl | fh) atomicMin(&s_ovnl, o + (fl ? (uint32_t)(__ffs(fl) - 1) >> 2 : 8u + ((uint32_t)(__ffs(fh) - 1) >> 2)));
+         const uint32_t o = kK1Tile + (uint32_t)tid * 32u;
+         const uint4 *src = reinterpret_cast<const uint4 *>(buf + o);
+         uint32_t onl;
+         classify32(src[0], src[1], lut_addr, a.four, O0, O1, O2, onl);
+         stop_beyond32(O0, O1, O2, onl, tile0 + o, n);
+         if (onl) atomicMin(&s_ovnl, o + (uint32_t)(__ffs(onl) - 1));
       }
 
-      // ---- newline flags (as K1) ----
-      uint32_t f[8];
-      {
-         uint32_t g[8], h2[8];
-#pragma unroll
-         for (int k = 0; k < 8; k++) g[k] = ((lo[k] & 0x88888888u) >> 1) | (hi[k] & 0x88888888u);
-#pragma unroll
-         for (int v = 0; v < 8; v++) h2[v] = (rot & 1u) ? g[(v + 7) & 7] : g[v];
-#pragma unroll
-         for (int v = 0; v < 8; v++) g[v] = (rot & 2u) ? h2[(v + 6) & 7] : h2[v];
-#pragma unroll
-         for (int v = 0; v < 8; v++) f[v] = (rot & 4u) ? g[(v + 4) & 7] : g[v];
-      }
+      // ---- line starts: c[t] = newline flags of chunk t in TEXT order (bit i = byte i) ----
       uint32_t c[4];
+      {
+         uint32_t g[4];
 #pragma unroll
-      for (int q = 0; q < 4; q++) c[q] = (f[2 * q] >> 2) | f[2 * q + 1];
+         for (int t = 0; t < 4; t++) g[t] = (crot & 1u) ? NL[(t + 3) & 3] : NL[t];
+#pragma unroll
+         for (int t = 0; t < 4; t++) c[t] = (crot & 2u) ? g[(t + 2) & 3] : g[t];
+      }
       // a newline at p opens a line at p+1 only if p+1 < n
       if (pos0 + kK1LaneBytes + 1u > n) {
 #pragma unroll
-         for (int q = 0; q < 4; q++) {
-            uint32_t bits = c[q];
-            while (bits) {
-               const int b = __ffs(bits) - 1;
-               bits &= bits - 1;
-               const uint32_t byte = 32u * (uint32_t)q + 8u * (uint32_t)(b & 3) + (uint32_t)(b >> 2);
-               if (pos0 + byte + 1u >= n) c[q] &= ~(1u << b);
-            }
+         for (int t = 0; t < 4; t++) {
+            const uint32_t p = pos0 + 32u * (uint32_t)t;               // newline bit i opens a line at p + i + 1
+            if (p + 33u > n) c[t] &= (p + 1u >= n) ? 0u : ((1u << (n - p - 1u)) - 1u);
          }
       }
       const uint32_t first = (tile == 0 && tid == 0 && n > 0 && a.skip == 0u) ? 1u : 0u;
@@ -291,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, co
       }
       if (lane == 31) s_wsum[warp] = inc;
       fence_proxy_async();                   // this thread's reads of the text stage come before its refill by TMA
-      __syncthreads();                       // A: the text is in registers, s_wsum and s_ovnl are complete
+      __syncthreads();                       // A: the planes are in registers, s_wsum and s_ovnl are complete
       uint32_t before = 0, tile_total = 0;
 #pragma unroll
       for (int w2 = 0; w2 < kWarps; w2++) {
@@ -323,12 +317,20 @@ __global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, co
             lst[tile_total] = end;
          }
       }
-      // ---- class nibbles: one contiguous array over the tile's own text ----
+      // ---- the plane words of the tile (every reader of the round before has passed A) ----
 #pragma unroll
-      for (int k = 0; k < 8; k++)
-         *reinterpret_cast<uint2 *>(nib + nib_off + ((((uint32_t)k + rot) & 7u) << 3)) = make_uint2(lo[k], hi[k]);
-      if (has_ov) *reinterpret_cast<uint2 *>(nib + (kK1Tile >> 1) + (uint32_t)tid * 8u) = make_uint2(olo, ohi);
-      __syncthreads();                       // B: nibbles, s_base, s_skip
+      for (int q = 0; q < 4; q++) {
+         const uint32_t slot = ((((uint32_t)q + crot) & 3u) << 8) + (uint32_t)tid;
+         pl[slot] = P0[q];
+         pl[pwords + slot] = P1[q];
+         pl[2u * pwords + slot] = P2[q];
+      }
+      if (has_ov) {
+         pl[kFWords + (uint32_t)tid] = O0;
+         pl[pwords + kFWords + (uint32_t)tid] = O1;
+         pl[2u * pwords + kFWords + (uint32_t)tid] = O2;
+      }
+      __syncthreads();                       // B: planes, s_base, s_skip
       const bool skip_tile = s_skip != 0u;
 
       // ---- emit: ls_raw (global, ordered inside the tile) and the tile's own list ----
@@ -336,15 +338,15 @@ __global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, co
          uint32_t lidx = before + (inc - cnt);
          const uint32_t gbase = s_base;
          uint32_t myalive = 0;
-         auto dead_flag = [&](uint32_t o) -> uint32_t {       // o = offset of the line start in the stage
+         // FILTER: a STOP (101) among the first filter_k class codes of the line that starts at offset o
+         auto dead_flag = [&](uint32_t o) -> uint32_t {
             if (!FILTER) return 0u;
-            const uint32_t a0 = (o >> 1) & ~3u;
-            const uint32_t w0 = *reinterpret_cast<const uint32_t *>(nib + a0);
-            const uint32_t w1 = *reinterpret_cast<const uint32_t *>(nib + a0 + 4u);
-            uint32_t win = __funnelshift_r(w0, w1, (o & 7u) * 4u);
-            if (a.filter_k < 8u) win &= (1u << (4u * a.filter_k)) - 1u;
-            const uint32_t y = (win ^ 0x55555555u) & 0x77777777u;
-            const bool dead = ((y - 0x11111111u) & ~y & 0x88888888u) != 0u;
+            const uint32_t w = o >> 5, sh = o & 31u;
+            const uint32_t i0 = plane_slot(w), i1 = plane_slot(min(w + 1u, last_word));
+            const uint32_t w0 = __funnelshift_r(pl[i0], pl[i1], sh);
+            const uint32_t w1 = __funnelshift_r(pl[pwords + i0], pl[pwords + i1], sh);
+            const uint32_t w2 = __funnelshift_r(pl[2u * pwords + i0], pl[2u * pwords + i1], sh);
+            const bool dead = (w0 & ~w1 & w2 & ((1u << a.filter_k) - 1u)) != 0u;          // filter_k <= 8
             myalive += dead ? 0u : 1u;
             return dead ? kDeadBit : 0u;
          };
@@ -357,6 +359,7 @@ __global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, co
             put(lidx, 0u);
             lidx++;
          }
+         // one line start per lane and round, chunk by chunk in text order
          const uint32_t r1 = (uint32_t)__popc(c[0]), r2 = r1 + (uint32_t)__popc(c[1]), r3 = r2 + (uint32_t)__popc(c[2]);
          uint32_t w0 = c[0], w1 = c[1], w2 = c[2], w3 = c[3];
          for (uint32_t left = cnt - first; left != 0u; left--) {
@@ -364,14 +367,13 @@ __global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, co
             const uint32_t cur = w0 ? w0 : (w1 ? w1 : (w2 ? w2 : w3));
             const uint32_t orig = q == 0u ? c[0] : (q == 1u ? c[1] : (q == 2u ? c[2] : c[3]));
             const uint32_t rbase = q == 0u ? 0u : (q == 1u ? r1 : (q == 2u ? r2 : r3));
-            const uint32_t b = (uint32_t)__ffs(cur) - 1u, e = b & 3u;
+            const uint32_t b = (uint32_t)__ffs(cur) - 1u;
             const uint32_t rest = cur & (cur - 1u);
             if (q == 0u) w0 = rest;
             else if (q == 1u) w1 = rest;
             else if (q == 2u) w2 = rest;
             else w3 = rest;
-            const uint32_t before_b = (0x11111111u * ((1u << e) - 1u)) | ((0x11111111u << e) & ((1u << (b & ~3u)) - 1u));
-            put(lidx + rbase + (uint32_t)__popc(orig & before_b), lane_off + 32u * q + 1u + 8u * e + (b >> 2));
+            put(lidx + rbase + (uint32_t)__popc(orig & ((1u << b) - 1u)), lane_off + 32u * q + b + 1u);
          }
          if (FILTER) {
             const uint32_t wa = __reduce_add_sync(kFull, myalive);
@@ -457,23 +459,36 @@ __global__ void __launch_bounds__(kThreads, 3) k12_scan_pack(const K12Args a, co
          }
          if (FILTER) a.gent[(size_t)(gbase + g) * 32u + (uint32_t)lane] = (uint16_t)ent;
          uint4 *dst = a.planes + (size_t)pbase + before_units;
-         SmemNibbleStream st;
-         st.open(smem_addr(nib), nib_chunks, begin, have);
+         // lane r follows line r through the plane streams: 32 columns = bits sh.. of word w and the next
+         const uint32_t sh = begin & 31u;
+         uint32_t w = begin >> 5;
+         uint32_t a0, a1, a2;                                       // word w of the three planes
+         {
+            const uint32_t ad = pl_addr + (plane_slot(w) << 2);
+            a0 = lds_u32a(ad);
+            a1 = lds_u32a(ad + 4u * pwords);
+            a2 = lds_u32a(ad + 8u * pwords);
+         }
          for (uint32_t c0 = 0; c0 < ncols; c0 += 32, oit++) {
-            uint32_t w[4];
-            st.next(w);
+            w = min(w + 1u, last_word);
+            const uint32_t ad = pl_addr + (plane_slot(w) << 2);
+            const uint32_t b0 = lds_u32a(ad), b1 = lds_u32a(ad + 4u * pwords), b2 = lds_u32a(ad + 8u * pwords);
+            // a lane without a line feeds STOP columns (101)
+            const uint32_t x0c = have ? __funnelshift_r(a0, b0, sh) : ~0u;
+            const uint32_t x1c = have ? __funnelshift_r(a1, b1, sh) : 0u;
+            const uint32_t x2c = have ? __funnelshift_r(a2, b2, sh) : ~0u;
+            a0 = b0;
+            a1 = b1;
+            a2 = b2;
             uint32_t *out = s_out[warp][oit & 1u];
             if (oit >= 2u) {                                        // the store that read this buffer two rounds ago
                if (lane == 0) bulk_wait_read_1();
                __syncwarp();
             }
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-               const uint32_t t = warp_transpose32(w[k], keep, rotc, sel16, sel8);
-               // lane holds plane (lane & 3) of column c0 + 8k + (lane >> 2)
-               const uint32_t cc = 8u * (uint32_t)k + ((uint32_t)lane >> 2);
-               if ((lane & 3) != 3) out[(cc >> 2) * 12u + ((uint32_t)lane & 3u) * 4u + (cc & 3u)] = t;
-            }
+            // after the transpose lane j holds column c0 + j of the plane, bit r = line r
+            out[out_idx] = warp_transpose32(x0c, keep, rotc, sel16, sel8);
+            out[out_idx + 4u] = warp_transpose32(x1c, keep, rotc, sel16, sel8);
+            out[out_idx + 8u] = warp_transpose32(x2c, keep, rotc, sel16, sel8);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
