@@ -165,7 +165,7 @@ struct sqb_engine {
    // two-kernel path serves this engine)
    int fused = 1;
    uint32_t fused_ov = 512;               // overlap staged behind a tile; 4096 after a scan met longer lines
-   double units_per_byte = 0.0255;        // plane units (16 B) per text byte: 3 bits per byte + padding
+   double units_per_byte = 0.028;         // plane units (16 B) per text byte: 3 bits per byte + padding to 32 columns
    BsPattern bs_pat;
    Slot slot[2];
    // lines / events per byte seen so far (capacity guesses)
@@ -652,7 +652,7 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
       const uint32_t ntiles = (uint32_t)div_up(n, kK1Tile);
       ClassTable ct;
       build_class_table(options, &ct);
-      const int grid = (int)std::min<size_t>(div_up(n, kK1Tile), (size_t)e->sms * 3);
+      const int grid = (int)std::min<size_t>(div_up(n, kK1Tile), (size_t)e->sms * (fused ? SQB_K12_CTAS : 3));
       if (fused) {
          // groups: 32 lines each, plus one partial group per K1 tile at most
          if (dev_reserve(&s.d_gdesc, &s.gdesc_cap, s.line_cap / 32 + k1_tiles + 64, 64)) return -1;
@@ -661,7 +661,7 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
          if (dev_reserve(&s.d_planes, &s.planes_cap, want_units, 16)) return -1;
          K12Args ka{d_text, n, s.d_ls_raw, (uint32_t)s.line_cap, ctr, tile_cnt, tile_off, tile_alive,
                     (uint32_t)e->filter_k, skip, e->fused_ov, s.d_gdesc, (uint32_t)std::min<size_t>(s.gdesc_cap, 0xffffffffu),
-                    s.d_gent, s.d_planes, (uint32_t)std::min<size_t>(s.planes_cap, 0xffffffffu), 4u};
+                    s.d_gent, s.d_planes, (uint32_t)std::min<size_t>(s.planes_cap, 0xffffffffu)};
          if (first_use((const void *)k12_scan_pack<true>)) {
             CU(cudaFuncSetAttribute(k12_scan_pack<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k12_smem_bytes(kFMaxOverlap)));
             CU(cudaFuncSetAttribute(k12_scan_pack<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k12_smem_bytes(kFMaxOverlap)));

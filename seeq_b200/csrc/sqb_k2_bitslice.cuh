@@ -58,7 +58,7 @@ struct GroupDesc {
    uint32_t tile;       // K1 tile the lines start in
    uint32_t first;      // local entry index of slot 0 (consecutive entries) / index into gent (line filter)
    uint32_t meta;       // lines in the group (1..32) | columns << 8
-   uint32_t poff;       // first uint4 of the group's planes: [block of 4 columns][plane 0..2][4 columns] words
+   uint32_t poff;       // first uint4 of the group's planes: [block of 32 columns][plane 0..2][32 columns] words
 };
 
 struct BsPrepArgs {
@@ -481,14 +481,16 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
          if (G > 1 && c < 0) v = make_uint4(~0u, ~0u, ~0u, 0u);
          return v;
       };
-      // fused layout: block b of the lane's own group = three uint4 {p0, p1, p2 of 4 columns}; a lane
-      // without a group (or past its last block) re-reads a valid block: its lines are dead by then
+      // fused layout: [block of 32 columns][plane][32 columns] words; block b of four columns of the lane's own
+      // group = three uint4 {p0, p1, p2 of 4 columns}, 128 bytes apart; a lane without a group (or past its last
+      // block) re-reads a valid block: its lines are dead by then
       const uint32_t my_last = ((my_ncols + 3u) >> 2) - (my_ncols ? 1u : 0u);
       auto fetchb = [&](uint32_t b, uint4 &q0, uint4 &q1, uint4 &q2) {
-         const uint4 *p = col + (size_t)min(b, my_last) * 3u;
+         const uint32_t bb = min(b, my_last);
+         const uint4 *p = col + (size_t)(bb >> 3) * 24u + (bb & 7u);
          q0 = p[0];
-         q1 = p[1];
-         q2 = p[2];
+         q1 = p[8];
+         q2 = p[16];
       };
       uint4 nxt[kBsBlock];
       if (fused) {

@@ -103,11 +103,11 @@ def test_lines_beyond_the_overlap(B, oracle):
 
 def test_more_line_starts_than_a_tile_lists(B, oracle):
     rng = random.Random(6)
-    buf = ragged(rng, 60000, 0, 12, "ACGTA")                      # ~ 5000 line starts per 32 KiB tile
+    buf = ragged(rng, 60000, 0, 12, "ACGTA")                      # ~ 5000 line starts per 32 KiB tile (1024 are listed)
     for mo in MATCH:
         st = scan(B, oracle, "ACGTA", 1, buf, mo | SQ_CONVERT)
         assert not (st.path & FUSED)
-    buf = ragged(rng, 30000, 10, 40, "ACGTACG")                   # ~ 1250 per tile: listed
+    buf = ragged(rng, 30000, 30, 60, "ACGTACG")                   # ~ 700 per tile: listed
     for mo in MATCH:
         st = scan(B, oracle, "ACGTACG", 1, buf, mo)
         assert st.path & FUSED
