@@ -661,14 +661,14 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
          if (dev_reserve(&s.d_planes, &s.planes_cap, want_units, 16)) return -1;
          K12Args ka{d_text, n, s.d_ls_raw, (uint32_t)s.line_cap, ctr, tile_cnt, tile_off, tile_alive,
                     (uint32_t)e->filter_k, skip, e->fused_ov, s.d_gdesc, (uint32_t)std::min<size_t>(s.gdesc_cap, 0xffffffffu),
-                    s.d_gent, s.d_planes, (uint32_t)std::min<size_t>(s.planes_cap, 0xffffffffu)};
-         if (first_use((const void *)k12_scan_pack<true>)) {
-            CU(cudaFuncSetAttribute(k12_scan_pack<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k12_smem_bytes(kFMaxOverlap)));
-            CU(cudaFuncSetAttribute(k12_scan_pack<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k12_smem_bytes(kFMaxOverlap)));
-         }
-         const size_t smem = k12_smem_bytes(e->fused_ov);
+                    s.d_gent, s.d_planes, (uint32_t)std::min<size_t>(s.planes_cap, 0xffffffffu), 4u};
          ClassTable32 ct32;
          build_class_table32(ct, &ct32);
+         if (first_use((const void *)k12_scan_pack<true>)) {
+            CU(cudaFuncSetAttribute(k12_scan_pack<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k12_smem_bytes(kFMaxOverlap, true)));
+            CU(cudaFuncSetAttribute(k12_scan_pack<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k12_smem_bytes(kFMaxOverlap, false)));
+         }
+         const size_t smem = k12_smem_bytes(e->fused_ov, filter);
          if (filter) k12_scan_pack<true><<<grid, kThreads, smem, st>>>(ka, ct32);
          else k12_scan_pack<false><<<grid, kThreads, smem, st>>>(ka, ct32);
       } else {

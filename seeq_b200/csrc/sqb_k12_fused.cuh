@@ -10,14 +10,25 @@
 //      them with warp-aggregated prefix sums and writes the tile's ordered list of line starts: into
 //      shared memory for step 2 and -- allocated with one atomic per tile -- into ls_raw (as K1);
 //   2. forms GROUPS of 32 consecutive lines that start in the tile (tile-local: no CTA waits for
-//      another) and builds their bit-planes ALREADY TRANSPOSED: a warp takes a group, LANE = TEXT
-//      COLUMN, and walks the 32 lines of the group: one LDS.U8 fetches byte (line r, column c), one
-//      table look-up turns it into {p0, p1, p2} spread over three bytes of a word, and one multiply-add
-//      drops the three class bits into bit r & 7 of the line-octet's accumulator.  After 32 lines four
-//      accumulators hold the three plane words of column c (bit r = line r): 9 PRMT put them together.
-//      No transpose, no shuffles, no funnel shifts: 4 instructions per text byte (the three-kernel
-//      version before this one: 12), two of them on the shared-memory pipe, which bounds the kernel;
-//   3. stores the plane words with fully coalesced 128-byte stores (lane = column).
+//      another) and builds their bit-planes ALREADY TRANSPOSED.  A block of 32 lines x 32 columns is
+//      the work of eight lanes: a lane takes four neighbouring columns and walks the 32 lines; per line ONE
+//      aligned 32-bit load fetches its four text bytes, every byte goes through the 256-entry class table
+//      in shared memory, whose entry holds {p0, p1, p2} in three bytes of a word, and one multiply-add drops
+//      the three class bits of (line r, column c) into bit r & 7 of the column's accumulator of that line
+//      octet.  After 32 lines seven PRMT per column put the plane words together (bit r = line r).  No
+//      transpose across lanes, no shuffles, no funnel shifts.  Per four text bytes: 5.5 accesses to shared
+//      memory, 9 multiply-adds (FMA pipe), 5 logic ops -- the three pipes are loaded about evenly.  (A lane per
+//      column with one LDS.U8 per byte: twice the shared-memory accesses, bound by that pipe at 0.8 of its
+//      peak.  Classifying four bytes at a time in registers -- the low three bits of a byte are a perfect hash
+//      of the alphabet, PRMT is a 4-way look-up in an 8-byte register table -- needs no table in memory but
+//      15 logic ops per four bytes on the half-rate ALU pipe: measured slower.)
+//   3. stores the plane words as 16-byte pieces, 128 contiguous bytes per plane and block.
+//
+// Lines start at any byte, 32-bit loads do not: a line is read from the aligned word at or in front of its
+// start, and its planes begin with lead = start & 3 NULL columns (class 7: all three planes set, by OR-ing the
+// group's lead masks into the first columns).  A NULL column leaves an automaton that is still in its reset
+// state untouched (sqb_bitslice.h), so the matcher only has to subtract the lead from the end columns of
+// the events it reports (the two bits of every line's lead travel in the group descriptor).
 //
 // Plane layout of a group (allocated with one atomic per tile, any order across tiles):
 //   [block of 32 columns][plane 0..2][32 columns] words = 384 bytes per 32 columns = 3 bits per text byte
@@ -45,12 +56,23 @@ namespace sqb {
 constexpr uint32_t kFMaxEntries = 1024;                 // line starts per tile the fused path handles (lines of 32 bytes on average)
 constexpr uint32_t kFMaxGroups  = kFMaxEntries / 32;
 #ifndef SQB_K12_CTAS
-#define SQB_K12_CTAS 4                                  // CTAs per SM: 64 registers, 42 KB of shared memory each
+#define SQB_K12_CTAS 3                                  // CTAs per SM: 80 registers, 71 KB of shared memory each
 #endif
 constexpr uint32_t kFMaxOverlap = 4096;                 // bytes staged behind a tile at most = longest line of the fused path
-constexpr uint32_t kFChunks     = kK1Tile / 32;         // 32-byte chunks of a tile (1024): four per thread
 
 // (GroupDesc: sqb_k2_bitslice.cuh)
+
+// byte -> {p0, p1, p2, newline} in the four bytes of a word (bit 0 of each)
+struct ClassTable32 {
+   uint32_t w[256];
+};
+static inline void build_class_table32(const ClassTable &ct, ClassTable32 *out)
+{
+   for (int b = 0; b < 256; b++) {
+      const uint32_t c = ct.code[b];
+      out->w[b] = (c & 1u) | (((c >> 1) & 1u) << 8) | (((c >> 2) & 1u) << 16) | (((c >> 3) & 1u) << 24);
+   }
+}
 
 struct K12Args {
    const uint8_t *text;
@@ -68,26 +90,18 @@ struct K12Args {
    uint16_t *gent;                // out (FILTER): [group * 32 + slot] local entry index
    uint4 *planes;                 // out
    uint32_t planes_cap;           // uint4 units
+   uint32_t four;                 // == 4, as a run-time value: table address = byte * four + base stays an IMAD (FMA
+                                  // pipe); with the literal the assembler makes it an LEA on the ALU pipe, which
+                                  // carries the byte extraction
 };
 
-// byte -> {p0, p1, p2, newline} in the four bytes of a word (bit 0 of each)
-struct ClassTable32 {
-   uint32_t w[256];
-};
-static inline void build_class_table32(const ClassTable &ct, ClassTable32 *out)
-{
-   for (int b = 0; b < 256; b++) {
-      const uint32_t c = ct.code[b];
-      out->w[b] = (c & 1u) | (((c >> 1) & 1u) << 8) | (((c >> 2) & 1u) << 16) | (((c >> 3) & 1u) << 24);
-   }
-}
-
-// dynamic shared memory: the text stage (+ 32 columns read past the longest line, + the STOP byte behind the
-// buffer), the class table, the tile's list of line starts, the live entries, the line starts of every warp's group
+// dynamic shared memory: two text stages (+ 35 columns read past the longest line, + the STOP byte behind the
+// buffer), the class table, the tile's line starts (all of them; those of the grouped lines, padded to whole groups),
+// the live entries
 __host__ __device__ constexpr uint32_t k12_text_bytes(uint32_t ov) { return (kK1Tile + ov + 64u + 127u) & ~127u; }
-__host__ __device__ constexpr uint32_t k12_smem_bytes(uint32_t ov)
+__host__ __device__ constexpr uint32_t k12_smem_bytes(uint32_t ov, bool filter)
 {
-   return k12_text_bytes(ov) + 1024u + (kFMaxEntries + 4u) * 4u + kFMaxEntries * 2u + (uint32_t)kWarps * 32u * 4u;
+   return 2u * k12_text_bytes(ov) + 1024u + (kFMaxEntries + 8u) * 2u + (kFMaxEntries + 32u) * 2u + (filter ? kFMaxEntries * 2u : 0u);
 }
 // plane units (uint4) of a group of `ncols` columns
 __host__ __device__ constexpr uint32_t k12_group_units(uint32_t ncols) { return ((ncols + 31u) >> 5) * 24u; }
@@ -99,9 +113,25 @@ __device__ __forceinline__ uint32_t nl_flags(uint32_t w)
    return ~(t | w) & 0x80808080u;                                         // ... and bit 7 of the byte itself is clear
 }
 
-// The flags of a 32-byte chunk live in ONE word: the flags of text word k (0..7) rotated left by k, so byte b of
-// word k sits at bit (8 b + 7 + k) & 31.  In "u-space" (the word rotated right by 7) that is bit u = 8 b + k.
-// u-space mask of the bytes in front of byte index v = 4 k + b (v = 0..32) in TEXT order:
+// (not volatile: the class table is constant for the life of the kernel, the loads may be scheduled freely)
+__device__ __forceinline__ uint32_t lds_u32c(uint32_t addr)
+{
+   uint32_t v;
+   asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+   return v;
+}
+
+// hi32(a * b) + c on the FMA pipe: a >> s for b = 2^(32 - s), added to c
+__device__ __forceinline__ uint32_t mad_hi_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+   uint32_t d;
+   asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+   return d;
+}
+
+// The flags of a 32-byte chunk live in ONE word ("u-space"): the flag of byte b of text word k (0..7) sits at
+// bit u = 8 b + k -- the flags of word k shifted right by 7 - k, one multiply-add (high half) each.
+// Mask of the bytes in front of byte index v = 4 k + b (v = 0..32) in TEXT order:
 __device__ __forceinline__ uint32_t chunk_before(uint32_t v)
 {
    if (v >= 32u) return ~0u;
@@ -109,92 +139,91 @@ __device__ __forceinline__ uint32_t chunk_before(uint32_t v)
    return (((1u << k) - 1u) * 0x01010101u) | ((0x01010101u << k) & ((1u << (8u * b)) - 1u));
 }
 
-__device__ __forceinline__ uint32_t chunk_flags(const uint8_t *p, uint32_t h)
+__device__ __forceinline__ uint32_t chunk_flags(const uint8_t *p)
 {
-   // the half of the chunk a lane loads first alternates every four lanes: the 16-byte loads of a
-   // quarter-warp (eight lanes, 32 bytes apart) then cover all 32 banks once
-   const uint4 va = *reinterpret_cast<const uint4 *>(p + 16u * h);
-   const uint4 vb = *reinterpret_cast<const uint4 *>(p + 16u * (h ^ 1u));
-   const uint32_t ra = 4u * h, rb = 4u * (h ^ 1u);
-   uint32_t f, acc;
-   f = nl_flags(va.x); acc = __funnelshift_l(f, f, ra);
-   f = nl_flags(va.y); acc |= __funnelshift_l(f, f, ra + 1u);
-   f = nl_flags(va.z); acc |= __funnelshift_l(f, f, ra + 2u);
-   f = nl_flags(va.w); acc |= __funnelshift_l(f, f, ra + 3u);
-   f = nl_flags(vb.x); acc |= __funnelshift_l(f, f, rb);
-   f = nl_flags(vb.y); acc |= __funnelshift_l(f, f, rb + 1u);
-   f = nl_flags(vb.z); acc |= __funnelshift_l(f, f, rb + 2u);
-   f = nl_flags(vb.w); acc |= __funnelshift_l(f, f, rb + 3u);
-   return __funnelshift_r(acc, acc, 7);          // u-space
+   const uint4 va = *reinterpret_cast<const uint4 *>(p);
+   const uint4 vb = *reinterpret_cast<const uint4 *>(p + 16);
+   uint32_t acc = nl_flags(vb.w);                                  // k = 7: in place
+   acc = mad_hi_u32(nl_flags(va.x), 1u << 25, acc);
+   acc = mad_hi_u32(nl_flags(va.y), 1u << 26, acc);
+   acc = mad_hi_u32(nl_flags(va.z), 1u << 27, acc);
+   acc = mad_hi_u32(nl_flags(va.w), 1u << 28, acc);
+   acc = mad_hi_u32(nl_flags(vb.x), 1u << 29, acc);
+   acc = mad_hi_u32(nl_flags(vb.y), 1u << 30, acc);
+   acc = mad_hi_u32(nl_flags(vb.z), 1u << 31, acc);
+   return acc;
 }
 
 template <bool FILTER>
 __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K12Args a, const __grid_constant__ ClassTable32 ct)
 {
    extern __shared__ __align__(128) uint8_t dyn[];
-   __shared__ uint64_t bar;
-   __shared__ uint32_t s_tile[2], s_base, s_ovnl, s_nlive, s_pbase, s_gbase, s_skip;
-   __shared__ uint32_t s_wsum[4][kWarps];                      // line starts per (pass, warp)
+   __shared__ uint64_t bar[2];
+   __shared__ uint32_t s_tile[2], s_base, s_ovnl, s_pbase, s_gbase, s_skip, s_nlive, s_stores, s_ready;
+   __shared__ uint32_t s_wsum[4 * kWarps];                     // line starts per (pass, warp)
    __shared__ uint32_t s_gcols[kFMaxGroups];
-   __shared__ uint32_t s_gpre[kFMaxGroups];                    // plane units of the tile's groups in front of each
+   __shared__ uint32_t s_glong[kFMaxGroups];                   // longest line of every group
+   __shared__ uint32_t s_glead[kFMaxGroups][3];                // lines of the group whose lead is >= 1, >= 2, == 3
 
    const uint32_t n = a.n, ov = a.ov;
    const uint32_t stage = kK1Tile + ov;                         // text bytes staged per tile
    const uint32_t ntiles = (n + kK1Tile - 1) / kK1Tile;
    const uint32_t n16 = (n + 15u) & ~15u;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-   uint8_t *buf = dyn;                                          // the text of the tile (TMA)
-   uint32_t *lut = reinterpret_cast<uint32_t *>(dyn + k12_text_bytes(ov));   // [256]
-   uint32_t *lst = lut + 256;                                   // [entries + 1] offset in the stage | kDeadBit
-   uint16_t *live = reinterpret_cast<uint16_t *>(lst + kFMaxEntries + 4u);   // FILTER: entries that are alive
-   uint32_t *gl = reinterpret_cast<uint32_t *>(live + kFMaxEntries) + warp * 32;   // line starts of this warp's group
-   const uint32_t half = ((uint32_t)lane >> 2) & 1u;
+   const uint32_t tbytes = k12_text_bytes(ov);
+   uint32_t *lut = reinterpret_cast<uint32_t *>(dyn + 2u * tbytes);          // [256]
+   uint16_t *lst = reinterpret_cast<uint16_t *>(lut + 256);     // [entries + 1] offset of every line start in the stage
+   uint16_t *lsg = lst + kFMaxEntries + 8u;                     // [groups * 32] the same of the grouped lines, padded
+   uint16_t *live = lsg + kFMaxEntries + 32u;                   // FILTER: dead flags, then the live entries
    const bool has_ov = (uint32_t)tid * 32u < ov;
 
-   auto issue = [&](uint32_t t) {          // (tid 0) TMA of tile t into the text stage
+   auto issue = [&](uint32_t st, uint32_t t) {   // (tid 0) TMA of tile t into text stage st
       const uint32_t start = t * kK1Tile;
       uint32_t bytes = n16 - start;
       if (bytes > stage) bytes = stage;
-      mbar_expect_tx(&bar, bytes);
-      bulk_g2s(buf, a.text + start, bytes, &bar);
+      mbar_expect_tx(&bar[st], bytes);
+      bulk_g2s(dyn + st * tbytes, a.text + start, bytes, &bar[st]);
    };
    lut[tid] = ct.w[tid];
    if (tid == 0) {
-      mbar_init(&bar, 1);
+      mbar_init(&bar[0], 1);
+      mbar_init(&bar[1], 1);
       mbar_fence_init();
       const uint32_t t = (uint32_t)atomicAdd(&a.ctr[C_TICKET_K1], 1ull);
       s_tile[0] = t;
       s_ovnl = 0xffffffffu;
-      if (t < ntiles) issue(t);
+      s_ready = 0u;
+      if (t < ntiles) issue(0u, t);
    }
    __syncthreads();
-   uint32_t phase = 0;
+   uint32_t phases = 0;                   // bit st = parity to wait for on stage st
 
-   // One text stage: the TMA of the next tile is issued when every warp is done with this one (barrier F);
-   // the other CTAs of the SM compute meanwhile.  The tile numbers travel through s_tile[iteration parity]:
-   // the next one is drawn before barrier A of this iteration.
+   // Two text stages.  Iteration j works on stage j & 1; behind its barrier A every warp is done with the tile
+   // before (stage (j + 1) & 1), so thread 0 draws the next tile there and sends its TMA into that stage: the copy
+   // runs under the rest of this iteration.  Three CTA barriers per tile (A, B, E); every shared scalar is rewritten
+   // between two barriers that all its readers of the round before have passed.
    for (uint32_t iter = 0;; iter++) {
-      const uint32_t tile = s_tile[iter & 1u];
+      const uint32_t st = iter & 1u;
+      const uint32_t tile = s_tile[st];
       if (tile >= ntiles) break;
       const uint32_t tile0 = tile * kK1Tile;
-      uint32_t next_tile = 0xffffffffu;                        // tid 0
-      mbar_wait(&bar, phase);
-      phase ^= 1u;
+      uint8_t *buf = dyn + st * tbytes;                         // the text of the tile
+      mbar_wait(&bar[st], (phases >> st) & 1u);
+      phases ^= 1u << st;
 
-      if (tid == 0) {
-         next_tile = (uint32_t)atomicAdd(&a.ctr[C_TICKET_K1], 1ull);
-         s_tile[(iter + 1u) & 1u] = next_tile;
-         // the bytes in front of the buffer are not looked at (this thread scans them itself, below)
-         if (tile == 0u)
-            for (uint32_t i = 0; i < a.skip; i++) buf[i] = 'A';
-      }
+      // the next tile's number: drawn now, needed behind barrier A (the atomic's round trip hides under the scan)
+      unsigned long long nt64 = 0ull;
+      if (tid == 0) nt64 = atomicAdd(&a.ctr[C_TICKET_K1], 1ull);
+      // the bytes in front of the buffer are not looked at (thread 0 scans them itself, below)
+      if (tid == 0 && tile == 0u)
+         for (uint32_t i = 0; i < a.skip; i++) buf[i] = 'A';
 
       // ---- line scan: chunk tid of the four 8 KiB passes; the overlap: one chunk per thread ----
       uint32_t c[4];
 #pragma unroll
       for (int i = 0; i < 4; i++) {
          const uint32_t o = (uint32_t)i * (kK1Tile / 4u) + (uint32_t)tid * 32u;
-         c[i] = chunk_flags(buf + o, half);
+         c[i] = chunk_flags(buf + o);
          // a newline at p opens a line at p + 1 only if p + 1 < n
          const uint32_t p = tile0 + o;
          if (p + 33u > n) c[i] &= chunk_before(p + 1u >= n ? 0u : n - 1u - p);
@@ -202,7 +231,7 @@ __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K1
       if (has_ov) {
          // only the first newline (= end of the tile's last line) is of interest; the last byte of the buffer counts
          const uint32_t o = kK1Tile + (uint32_t)tid * 32u;
-         uint32_t x = chunk_flags(buf + o, half);
+         uint32_t x = chunk_flags(buf + o);
          const uint32_t p = tile0 + o;
          if (p + 32u > n) x &= chunk_before(p >= n ? 0u : n - p);
          uint32_t best = 32u;
@@ -227,39 +256,46 @@ __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K1
          }
       }
       if (lane == 31) {
-         s_wsum[0][warp] = x01 & 0xffffu;
-         s_wsum[1][warp] = x01 >> 16;
-         s_wsum[2][warp] = x23 & 0xffffu;
-         s_wsum[3][warp] = x23 >> 16;
+         s_wsum[warp] = x01 & 0xffffu;
+         s_wsum[kWarps + warp] = x01 >> 16;
+         s_wsum[2 * kWarps + warp] = x23 & 0xffffu;
+         s_wsum[3 * kWarps + warp] = x23 >> 16;
       }
-      __syncthreads();                       // A: s_wsum, s_ovnl, the STOP byte
-      uint32_t base[4], tile_total = 0;
+      fence_proxy_async();                   // this thread's reads of the OTHER stage (the tile before) come before its refill
+      __syncthreads();                       // A: s_wsum, s_ovnl; every warp is done with the tile before
+      // where the line starts of every (pass, warp) go: an exclusive scan of the 32 sums, by every warp for itself
+      uint32_t base[4], tile_total;
+      {
+         static_assert(4 * kWarps == 32, "one (pass, warp) sum per lane");
+         const uint32_t v = s_wsum[lane];
+         uint32_t x = v;
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-         uint32_t before = 0, tot = 0;
-#pragma unroll
-         for (int w2 = 0; w2 < kWarps; w2++) {
-            const uint32_t x = s_wsum[i][w2];
-            if (w2 < warp) before += x;
-            tot += x;
+         for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, x, d);
+            if (lane >= d) x += t;
          }
-         base[i] = tile_total + before;
-         tile_total += tot;
+         tile_total = __shfl_sync(kFull, x, 31);
+         const uint32_t ex = x - v;
+#pragma unroll
+         for (int i = 0; i < 4; i++) base[i] = __shfl_sync(kFull, ex, i * kWarps + warp);
       }
       base[0] += (x01 & 0xffffu) - c0n;
       base[1] += (x01 >> 16) - c1n;
       base[2] += (x23 & 0xffffu) - c2n;
       base[3] += (x23 >> 16) - c3n;
+      unsigned long long at64 = 0ull;        // (tid 0) the tile's place in ls_raw: used behind the emit loops
       if (tid == 0) {
+         // the next tile: its TMA into the stage of the tile before
+         const uint32_t nt = (uint32_t)nt64;
+         s_tile[st ^ 1u] = nt;
+         if (nt < ntiles) issue(st ^ 1u, nt);
+         at64 = atomicAdd(&a.ctr[C_LS_CURSOR], (unsigned long long)tile_total);
          const uint32_t ovnl = s_ovnl;
          s_ovnl = 0xffffffffu;
          // one STOP byte behind the end of the buffer closes a last line without a newline (every scanning
          // thread is past the stage; the filter and the classification read it after barrier B)
          if (n - tile0 < stage + 32u) buf[n - tile0] = 0;
-         const uint32_t at = (uint32_t)atomicAdd(&a.ctr[C_LS_CURSOR], (unsigned long long)tile_total);
          a.tile_cnt[tile] = tile_total;
-         a.tile_off[tile] = at;
-         s_base = at;
          // where the tile's last line ends (exclusive, with its terminator): the first newline of the
          // overlap, or one STOP column behind the end of the buffer
          uint32_t end = 0xffffffffu;
@@ -270,12 +306,12 @@ __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K1
             atomicMax(&a.ctr[C_FUSED_OVF], 1ull);
          } else {
             s_skip = 0u;
-            lst[tile_total] = end;
+            lst[tile_total] = (uint16_t)end;                  // <= kK1Tile + ov + 1 < 65536
          }
       }
       // ---- the tile's list of line starts, in text order ----
       if (first) {
-         lst[0] = a.skip;
+         lst[0] = (uint16_t)a.skip;
          base[0] += 1u;
       }
 #pragma unroll
@@ -287,46 +323,34 @@ __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K1
             x &= x - 1u;
             const uint32_t v = 4u * (u & 7u) + (u >> 3);                       // byte index of the newline in its chunk
             const uint32_t idx = base[i] + (uint32_t)__popc(c[i] & chunk_before(v));
-            if (idx < kFMaxEntries) lst[idx] = o + v;
+            if (idx < kFMaxEntries) lst[idx] = (uint16_t)(o + v);
          }
+      }
+      if (tid == 0) {
+         a.tile_off[tile] = (uint32_t)at64;
+         s_base = (uint32_t)at64;
       }
       __syncthreads();                       // B: the list, s_base, s_skip
       const bool skip_tile = s_skip != 0u;   // (uniform) the host repeats the scan on the two-kernel path
-      uint32_t ngroups = 0, nlive = 0;
-      if (!skip_tile) {
-         // ---- ls_raw (coalesced); FILTER: a STOP among the first filter_k class codes of a line kills it;
-         //      no filter: the columns of every group = its longest line with the terminator ----
-         const uint32_t gbase_ls = s_base;
-         for (uint32_t j0 = (uint32_t)warp * 32u; j0 < tile_total; j0 += (uint32_t)kThreads) {
-            const uint32_t j = j0 + (uint32_t)lane;
-            uint32_t len = 0;
-            if (j < tile_total) {
+      uint32_t nlive = tile_total;
+      if (FILTER) {
+         // a STOP among the first filter_k class codes of a line kills it; ls_raw (coalesced)
+         if (!skip_tile) {
+            const uint32_t gbase_ls = s_base;
+            for (uint32_t j = (uint32_t)tid; j < tile_total; j += (uint32_t)kThreads) {
                const uint32_t o = lst[j];
                uint32_t fl = 0u;
-               if (FILTER) {
-                  for (uint32_t i = 0; i < a.filter_k; i++) {                  // filter_k <= 8
-                     const uint32_t e = lut[buf[o + i]];
-                     if ((e & 0x00010101u) == 0x00010001u) {                   // STOP = 101
-                        fl = kDeadBit;
-                        break;
-                     }
+               for (uint32_t i = 0; i < a.filter_k; i++) {                     // filter_k <= 8
+                  if ((lut[buf[o + i]] & 0x00010101u) == 0x00010001u) {        // STOP = 101
+                     fl = kDeadBit;
+                     break;
                   }
-                  if (fl) live[j] = 1;                                         // (flags for the compaction below)
-                  else live[j] = 0;
-               } else {
-                  len = lst[j + 1u] - o;
                }
+               live[j] = fl ? 1 : 0;                                           // (flags for the compaction below)
                if (gbase_ls + j < a.ls_cap) a.ls_raw[gbase_ls + j] = (tile0 + o) | fl;
             }
-            if (!FILTER) {
-               len = __reduce_max_sync(kFull, len);
-               if (lane == 0) s_gcols[j0 >> 5] = len;
-            }
          }
-         nlive = tile_total;
-      }
-      __syncthreads();                       // C: (no filter) the group columns; (filter) the dead flags
-      if (FILTER) {
+         __syncthreads();                    // C: the dead flags
          // the entries that are alive, in order (one warp; a few rounds).  The flags sit in live[] itself:
          // entry i is read in round i / 32 and the compacted list never overtakes the reader
          if (!skip_tile && warp == 0) {
@@ -341,115 +365,214 @@ __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K1
                run += (uint32_t)__popc(bal);
             }
             if (lane == 0) {
-               s_nlive = run;
                a.tile_alive[tile] = run;
+               s_nlive = run;
             }
          }
          if (skip_tile && tid == 0) a.tile_alive[tile] = 0u;
-         __syncthreads();                    // C2
-         if (!skip_tile) {
-            nlive = s_nlive;
-            const uint32_t ng = (nlive + 31u) >> 5;
-            for (uint32_t g = (uint32_t)warp; g < ng; g += kWarps) {
-               const uint32_t j = g * 32u + (uint32_t)lane;
-               uint32_t len = 0;
-               if (j < nlive) {
-                  const uint32_t i = (uint32_t)live[j];
-                  len = lst[i + 1u] - lst[i];
-               }
-               len = __reduce_max_sync(kFull, len);
-               if (lane == 0) s_gcols[g] = len;
-            }
-         }
-         __syncthreads();                    // D
+         __syncthreads();                    // C2: the live entries
+         if (!skip_tile) nlive = s_nlive;
       }
-      ngroups = (nlive + 31u) >> 5;
-      // plane units (uint4) of the groups in front of every group of the tile, the tile's room in the plane
-      // buffer and its group numbers: one warp
-      if (!skip_tile && warp == 0) {
-         uint32_t tot = 0, longest = 0;
-         for (uint32_t g0 = 0; g0 < ngroups; g0 += 32) {
-            const uint32_t g = g0 + (uint32_t)lane;
-            const uint32_t cols = g < ngroups ? s_gcols[g] : 0u;
-            const uint32_t u = k12_group_units(cols);
-            uint32_t x = u;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-               const uint32_t t = __shfl_up_sync(kFull, x, d);
-               if (lane >= d) x += t;
-            }
-            if (g < ngroups) s_gpre[g] = tot + x - u;
-            tot += __shfl_sync(kFull, x, 31);
-            longest = max(longest, __reduce_max_sync(kFull, cols));
-         }
-         if (lane == 0) {
-            if (longest > ov) {
-               // a line longer than the overlap: its group would read beyond the staged text
-               s_skip = 1u;
-               atomicMax(&a.ctr[C_FUSED_OVF], 1ull);
-            } else {
-               const uint32_t pb = (uint32_t)min(atomicAdd(&a.ctr[C_PLANE_UNITS], (unsigned long long)tot), 0xffffffffull);
-               const uint32_t gb = (uint32_t)atomicAdd(&a.ctr[C_NGROUPS], (unsigned long long)ngroups);
-               s_pbase = pb;
-               s_gbase = gb;
-               // beyond a capacity nothing is stored; the counters go on counting and the host repeats the scan
-               if ((unsigned long long)pb + tot > a.planes_cap || gb + ngroups > a.gdesc_cap) s_skip = 1u;
-            }
-         }
-      }
-      __syncthreads();                       // E
-      if (!skip_tile && s_skip == 0u) {
-         const uint32_t pbase = s_pbase, gbase = s_gbase;
-         // ---- classify + transpose: one group per warp and round, lane = column ----
-         for (uint32_t g = (uint32_t)warp; g < ngroups; g += kWarps) {
-            const uint32_t ncols = s_gcols[g];
+      const uint32_t ngroups = (nlive + 31u) >> 5;
+      if (!skip_tile) {
+         // ---- the tables of the groups, one group per warp and round: its columns (the longest line with the lead in
+         //      front and the terminator), its longest line, its lead masks, the aligned starts of its lines ----
+         for (uint32_t g = (uint32_t)warp; g < ngroups; g += (uint32_t)kWarps) {
             const uint32_t j = g * 32u + (uint32_t)lane;
-            const bool have = j < nlive;
-            const uint32_t ent = have ? (FILTER ? (uint32_t)live[j] : j) : 0u;
-            const uint32_t begin = lst[have ? ent : (FILTER ? (uint32_t)live[g * 32u] : g * 32u)];     // a lane without a line re-reads slot 0
+            uint32_t len = 0, lead = 0, begin;
+            if (j < nlive) {
+               const uint32_t i = FILTER ? (uint32_t)live[j] : j;
+               begin = lst[i];
+               len = (uint32_t)lst[i + 1u] - begin;
+               lead = begin & 3u;
+            } else {
+               begin = lst[FILTER ? (uint32_t)live[g * 32u] : g * 32u];      // a slot without a line re-reads slot 0
+            }
+            lsg[j] = (uint16_t)(begin & ~3u);
+            const uint32_t mx = __reduce_max_sync(kFull, len + lead), lg = __reduce_max_sync(kFull, len);
+            const uint32_t m1 = __ballot_sync(kFull, lead >= 1u), m2 = __ballot_sync(kFull, lead >= 2u), m3 = __ballot_sync(kFull, lead == 3u);
             if (lane == 0) {
+               s_gcols[g] = mx;
+               s_glong[g] = lg;
+               s_glead[g][0] = m1;
+               s_glead[g][1] = m2;
+               s_glead[g][2] = m3;
+            }
+         }
+         if (!FILTER) {
+            const uint32_t gbase_ls = s_base;
+            for (uint32_t j = (uint32_t)tid; j < tile_total; j += (uint32_t)kThreads)
+               if (gbase_ls + j < a.ls_cap) a.ls_raw[gbase_ls + j] = tile0 + (uint32_t)lst[j];
+         }
+      }
+      __syncthreads();                       // E: the group tables
+      if (skip_tile) continue;
+      // the blocks of 32 columns in front of every group (lane = group): every warp for itself
+      const uint32_t my_cols = (uint32_t)lane < ngroups ? s_gcols[lane] : 0u;
+      const uint32_t my_nb = (my_cols + 31u) >> 5;
+      uint32_t my_gblk = my_nb;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+         const uint32_t t = __shfl_up_sync(kFull, my_gblk, d);
+         if (lane >= d) my_gblk += t;
+      }
+      const uint32_t nblocks = __shfl_sync(kFull, my_gblk, 31);
+      my_gblk = (uint32_t)lane < ngroups ? my_gblk - my_nb : 0xffffffffu;
+      if (__reduce_max_sync(kFull, (uint32_t)lane < ngroups ? s_glong[lane] : 0u) > ov) {
+         // (uniform) a line longer than the overlap: its group would read beyond the staged text
+         if (tid == 0) atomicMax(&a.ctr[C_FUSED_OVF], 1ull);
+         continue;
+      }
+      // The tile's room in the plane buffer and its group numbers: thread 0 asks for them now and publishes them
+      // when it needs them itself, in front of its first store -- the round trip of the atomics hides under the
+      // classification of the first blocks.  The other warps wait for s_ready in front of THEIR first store.
+      unsigned long long pb64 = 0ull, gb64 = 0ull;
+      if (tid == 0) {
+         pb64 = atomicAdd(&a.ctr[C_PLANE_UNITS], (unsigned long long)nblocks * 24ull);
+         gb64 = atomicAdd(&a.ctr[C_NGROUPS], (unsigned long long)ngroups);
+      }
+      bool ready = false;
+      uint32_t pbase = 0;
+      bool stores = false;
+      auto room = [&]() {                    // (warp-uniform call) pbase / stores are valid on return
+         if (ready) return;
+         if (warp == 0) {
+            uint32_t pb = 0, gb = 0, ok = 0;
+            if (lane == 0) {
+               pb = (uint32_t)min(pb64, 0xffffffffull);
+               gb = (uint32_t)gb64;
+               // beyond a capacity nothing is stored; the counters go on counting and the host repeats the scan
+               ok = (pb64 + (unsigned long long)nblocks * 24ull <= a.planes_cap && gb64 + ngroups <= a.gdesc_cap) ? 1u : 0u;
+            }
+            pb = __shfl_sync(kFull, pb, 0);
+            gb = __shfl_sync(kFull, gb, 0);
+            ok = __shfl_sync(kFull, ok, 0);
+            if (ok && (uint32_t)lane < ngroups) {          // the descriptors of the groups: lane = group
                GroupDesc d;
                d.tile = tile;
-               d.first = FILTER ? (gbase + g) * 32u : g * 32u;
-               d.meta = min(nlive - g * 32u, 32u) | (ncols << 8);
-               d.poff = pbase + s_gpre[g];
-               a.gdesc[gbase + g] = d;
+               d.first = FILTER ? (gb + (uint32_t)lane) * 32u : (uint32_t)lane * 32u;
+               d.meta = min(nlive - (uint32_t)lane * 32u, 32u) | (my_cols << 8);
+               d.poff = pb + my_gblk * 24u;
+               d.lead_lo = s_glead[lane][0] ^ s_glead[lane][1] ^ s_glead[lane][2];
+               d.lead_hi = s_glead[lane][1];
+               d.pad0 = d.pad1 = 0u;
+               a.gdesc[gb + (uint32_t)lane] = d;
             }
-            if (FILTER) a.gent[(size_t)(gbase + g) * 32u + (uint32_t)lane] = (uint16_t)ent;
-            __syncwarp();
-            gl[lane] = begin;
-            __syncwarp();
-            uint32_t L[32];                                          // the 32 line starts (the same in every lane)
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-               const uint4 v = reinterpret_cast<const uint4 *>(gl)[q];
-               L[4 * q] = v.x;
-               L[4 * q + 1] = v.y;
-               L[4 * q + 2] = v.z;
-               L[4 * q + 3] = v.w;
+            if (lane == 0) {
+               s_pbase = pb;
+               s_gbase = gb;
+               s_stores = ok;
+               __threadfence_block();
+               *reinterpret_cast<volatile uint32_t *>(&s_ready) = iter + 1u;
             }
-            uint32_t *out = reinterpret_cast<uint32_t *>(a.planes + (size_t)pbase + s_gpre[g]) + lane;
-            const uint8_t *col = buf + lane;
-            for (uint32_t c0 = 0; c0 < ncols; c0 += 32) {
-               uint32_t acc[4] = {0u, 0u, 0u, 0u};                   // [- | p2 | p1 | p0] bytes of the lines 8q .. 8q+7
+            pbase = pb;
+            stores = ok != 0u;
+         } else {
+            while (*reinterpret_cast<volatile uint32_t *>(&s_ready) != iter + 1u) {}
+            __threadfence_block();
+            pbase = *reinterpret_cast<volatile uint32_t *>(&s_pbase);
+            stores = *reinterpret_cast<volatile uint32_t *>(&s_stores) != 0u;
+         }
+         ready = true;
+      };
+      const uint32_t lut_addr = smem_addr(lut);
+      // ---- classify + transpose.  The blocks (32 lines x 32 columns) of the tile are numbered group by group.
+      //      Whole rounds of 32 blocks: a warp takes four neighbouring blocks, eight lanes each, lane = (block, four
+      //      columns).  The blocks that are left: one per warp, lane = column (a quarter of the work per round, so
+      //      the warps that get none wait a quarter as long) ----
+      const uint32_t nfull = nblocks & ~31u;
+      const uint32_t cq = (uint32_t)lane & 7u;
+      for (uint32_t b0 = (uint32_t)warp * 4u; b0 < nfull; b0 += (uint32_t)kWarps * 4u) {
+         const uint32_t blk = b0 + ((uint32_t)lane >> 3);
+         // the group of the block: the last one that starts at or before it
+         uint32_t g = 0;
 #pragma unroll
-               for (int r = 0; r < 32; r++) {
-                  const uint32_t e = lut[col[L[r]]];
-                  acc[r >> 3] = mad_u32(e, 1u << (r & 7), acc[r >> 3]);
+         for (int q = 0; q < 4; q++) {
+            const uint32_t m = __ballot_sync(kFull, my_gblk <= b0 + (uint32_t)q);
+            if (((uint32_t)lane >> 3) == (uint32_t)q) g = 31u - (uint32_t)__clz(m);
+         }
+         const uint32_t cb = blk - __shfl_sync(kFull, my_gblk, g);
+         const uint16_t *ls = lsg + g * 32u;
+         const uint8_t *col = buf + cb * 32u + cq * 4u;
+         uint32_t P[3][4];                                        // plane words of the lane's four columns
+         {
+            uint32_t A[4][4];                                     // [column][line octet]: bytes [- | p2 | p1 | p0], bit = line
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+#pragma unroll
+               for (int j = 0; j < 4; j++) A[j][q] = 0u;
+#pragma unroll
+               for (int i = 0; i < 8; i++) {
+                  const uint32_t w = *reinterpret_cast<const uint32_t *>(col + ls[8 * q + i]);
+                  const uint32_t x0 = w & 0xffu, x1 = __byte_perm(w, 0u, 0x4441u), x2 = __byte_perm(w, 0u, 0x4442u), x3 = w >> 24;
+                  A[0][q] = mad_u32(lds_u32c(mad_u32(x0, a.four, lut_addr)), 1u << i, A[0][q]);
+                  A[1][q] = mad_u32(lds_u32c(mad_u32(x1, a.four, lut_addr)), 1u << i, A[1][q]);
+                  A[2][q] = mad_u32(lds_u32c(mad_u32(x2, a.four, lut_addr)), 1u << i, A[2][q]);
+                  A[3][q] = mad_u32(lds_u32c(mad_u32(x3, a.four, lut_addr)), 1u << i, A[3][q]);
                }
-               const uint32_t t0 = __byte_perm(acc[0], acc[1], 0x5140u), t1 = __byte_perm(acc[2], acc[3], 0x5140u);
-               const uint32_t t2 = __byte_perm(acc[0], acc[1], 0x7362u), t3 = __byte_perm(acc[2], acc[3], 0x7362u);
-               out[0] = __byte_perm(t0, t1, 0x5410u);
-               out[32] = __byte_perm(t0, t1, 0x7632u);
-               out[64] = __byte_perm(t2, t3, 0x5410u);
-               out += 96;
-               col += 32;
+            }
+            // per column: the bytes p of the four octets make the word of plane p
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+               const uint32_t u0 = __byte_perm(A[j][0], A[j][1], 0x5140u), u1 = __byte_perm(A[j][2], A[j][3], 0x5140u);
+               const uint32_t u2 = __byte_perm(A[j][0], A[j][1], 0x7362u), u3 = __byte_perm(A[j][2], A[j][3], 0x7362u);
+               P[0][j] = __byte_perm(u0, u1, 0x5410u);
+               P[1][j] = __byte_perm(u0, u1, 0x7632u);
+               P[2][j] = __byte_perm(u2, u3, 0x5410u);
             }
          }
+         if (cb == 0u && cq == 0u) {
+            // the columns in front of a line's first byte are NULL columns (111)
+            const uint32_t m1 = s_glead[g][0], m2 = s_glead[g][1], m3 = s_glead[g][2];
+#pragma unroll
+            for (int p = 0; p < 3; p++) {
+               P[p][0] |= m1;
+               P[p][1] |= m2;
+               P[p][2] |= m3;
+            }
+         }
+         room();
+         if (stores) {
+            uint4 *out = a.planes + (size_t)pbase + (size_t)blk * 24u + cq;
+            out[0] = make_uint4(P[0][0], P[0][1], P[0][2], P[0][3]);
+            out[8] = make_uint4(P[1][0], P[1][1], P[1][2], P[1][3]);
+            out[16] = make_uint4(P[2][0], P[2][1], P[2][2], P[2][3]);
+         }
       }
-      fence_proxy_async();                   // this thread's reads of the text stage come before its refill by TMA
-      __syncthreads();                       // F: the stage, the lists and the group tables are free
-      if (tid == 0 && next_tile < ntiles) issue(next_tile);
+      for (uint32_t blk = nfull + (uint32_t)warp; blk < nblocks; blk += (uint32_t)kWarps) {
+         const uint32_t g = 31u - (uint32_t)__clz(__ballot_sync(kFull, my_gblk <= blk));
+         const uint32_t cb = blk - __shfl_sync(kFull, my_gblk, g);
+         const uint16_t *ls = lsg + g * 32u;
+         const uint8_t *col = buf + cb * 32u + (uint32_t)lane;
+         uint32_t acc[4] = {0u, 0u, 0u, 0u};                      // [- | p2 | p1 | p0] bytes of the lines 8q .. 8q+7
+#pragma unroll
+         for (int r = 0; r < 32; r++) {
+            const uint32_t e = lds_u32c(mad_u32((uint32_t)col[ls[r]], a.four, lut_addr));
+            acc[r >> 3] = mad_u32(e, 1u << (r & 7), acc[r >> 3]);
+         }
+         const uint32_t t0 = __byte_perm(acc[0], acc[1], 0x5140u), t1 = __byte_perm(acc[2], acc[3], 0x5140u);
+         const uint32_t t2 = __byte_perm(acc[0], acc[1], 0x7362u), t3 = __byte_perm(acc[2], acc[3], 0x7362u);
+         uint32_t P0 = __byte_perm(t0, t1, 0x5410u), P1 = __byte_perm(t0, t1, 0x7632u), P2 = __byte_perm(t2, t3, 0x5410u);
+         if (cb == 0u && lane < 3) {
+            const uint32_t m = s_glead[g][lane];
+            P0 |= m;
+            P1 |= m;
+            P2 |= m;
+         }
+         room();
+         if (stores) {
+            uint32_t *out = reinterpret_cast<uint32_t *>(a.planes + (size_t)pbase + (size_t)blk * 24u) + lane;
+            out[0] = P0;
+            out[32] = P1;
+            out[64] = P2;
+         }
+      }
+      room();                                // (a warp without a block; thread 0 must publish in any case)
+      if (FILTER && stores) {
+         const uint32_t gbase = *reinterpret_cast<volatile uint32_t *>(&s_gbase);
+         for (uint32_t j = (uint32_t)tid; j < ngroups * 32u; j += (uint32_t)kThreads)
+            a.gent[(size_t)gbase * 32u + j] = j < nlive ? live[j] : (uint16_t)0;
+      }
    }
 }
 

@@ -59,6 +59,8 @@ struct GroupDesc {
    uint32_t first;      // local entry index of slot 0 (consecutive entries) / index into gent (line filter)
    uint32_t meta;       // lines in the group (1..32) | columns << 8
    uint32_t poff;       // first uint4 of the group's planes: [block of 32 columns][plane 0..2][32 columns] words
+   uint32_t lead_lo, lead_hi;   // bit r: bits 0 / 1 of the NULL columns in front of line r (its start & 3)
+   uint32_t pad0, pad1;
 };
 
 struct BsPrepArgs {
@@ -425,18 +427,21 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
       const uint32_t line0 = tile * kBsTileLines;
       uint32_t mine, ncols, my_ncols = 0u, gent0 = 0u;
       uint32_t slot0 = line0 + group * 32u, ent0;
+      uint32_t lead_lo = 0u, lead_hi = 0u;                // fused: NULL columns in front of the lines (two bits each)
       bool consecutive = true;
       const uint4 *col;
       if (fused) {
          // lane = one group of the fused kernel: its descriptor says where the lines and the planes are
          const uint32_t gi = item * 32u + (uint32_t)lane;
-         GroupDesc d{0u, 0u, 0u, 0u};
+         GroupDesc d{0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
          if (gi < ngroups_f) d = a.gdesc[gi];
          mine = d.meta & 0xffu;
          my_ncols = d.meta >> 8;
          gent0 = d.first;
          ent0 = mine ? a.k1_tile_base[d.tile] + (a.gent ? 0u : d.first) : 0u;
          col = a.planes + d.poff;
+         lead_lo = d.lead_lo;
+         lead_hi = d.lead_hi;
          ncols = __reduce_max_sync(kFull, my_ncols);
       } else {
          const uint32_t left = nlines - line0;                              // > 0
@@ -465,6 +470,7 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
          if (fused) return a.gent ? ent0 + (uint32_t)a.gent[gent0 + r] : ent0 + r;
          return consecutive ? ent0 + r : a.act[slot0 + r];
       };
+      auto lead_of = [&](int r) -> uint32_t { return ((lead_lo >> r) & 1u) | (((lead_hi >> r) & 1u) << 1); };
       uint32_t qmask = 0u, fmask = 0u;
       if (has_cuts) {
          qmask = a.gmask[tile * 32u + group];
@@ -596,7 +602,7 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
                   const uint32_t line = entry_of((uint32_t)r);
                   const uint32_t rank = static_cast<BsWarpSmemAll &>(sm).cnt[gl * 32 + r]++;
                   if (!a.count_only) {
-                     if (idx < a.ev_cap) a.ev[idx] = Event{line, rank, c, value_of(streak, r)};
+                     if (idx < a.ev_cap) a.ev[idx] = Event{line, rank, c - lead_of(r), value_of(streak, r)};
                      idx++;
                   }
                }
@@ -607,7 +613,7 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
             while (e) {
                const int r = __ffs(e) - 1;
                e &= e - 1;
-               a.res[entry_of((uint32_t)r)] = ((unsigned long long)value_of(streak, r) << 32) | c;
+               a.res[entry_of((uint32_t)r)] = ((unsigned long long)value_of(streak, r) << 32) | (c - lead_of(r));
             }
          }
          }
