@@ -669,8 +669,8 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
             CU(cudaFuncSetAttribute(k12_scan_pack<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k12_smem_bytes(kFMaxOverlap, false)));
          }
          const size_t smem = k12_smem_bytes(e->fused_ov, filter);
-         if (filter) k12_scan_pack<true><<<grid, kThreads, smem, st>>>(ka, ct32);
-         else k12_scan_pack<false><<<grid, kThreads, smem, st>>>(ka, ct32);
+         if (filter) k12_scan_pack<true><<<grid, kFThreads, smem, st>>>(ka, ct32);
+         else k12_scan_pack<false><<<grid, kFThreads, smem, st>>>(ka, ct32);
       } else {
       K1Args k1{d_text, n, s.d_ls_raw, (uint32_t)s.line_cap, want_codes ? (uint2 *)s.d_codes : nullptr, ctr,
                 tile_cnt, tile_off, tile_real, tile_last, tile_alive,

@@ -55,9 +55,23 @@ namespace sqb {
 
 constexpr uint32_t kFMaxEntries = 1024;                 // line starts per tile the fused path handles (lines of 32 bytes on average)
 constexpr uint32_t kFMaxGroups  = kFMaxEntries / 32;
-#ifndef SQB_K12_CTAS
-#define SQB_K12_CTAS 3                                  // CTAs per SM: 80 registers, 71 KB of shared memory each
+#ifndef SQB_K12_THREADS
+#define SQB_K12_THREADS 256                             // threads per CTA: 256 (four 8 KiB scan passes) or 512 (two 16 KiB passes)
 #endif
+#ifndef SQB_K12_STAGES
+#define SQB_K12_STAGES 1                                // text stages: 1, or 2 (the next tile's copy runs under this tile)
+#endif
+// CTAs per SM.  The kernel is a chain of short phases between CTA barriers, so what keeps the SM busy is the NUMBER of
+// independent CTAs, not the copy / compute overlap inside one (measured, cfg2, r4i): two stages, 3 CTAs (80 registers,
+// 72 KB) 0.70 ms; one stage, 4 CTAs (64 registers) 0.67 ms; one stage, 5 CTAs (48 registers, 39 KB) 0.64 ms; 512
+// threads, two stages, 2 CTAs 0.90 ms.
+#ifndef SQB_K12_CTAS
+#define SQB_K12_CTAS (SQB_K12_STAGES == 1 ? 5 : (SQB_K12_THREADS == 256 ? 3 : 2))
+#endif
+constexpr uint32_t kFStages = SQB_K12_STAGES;
+constexpr int kFThreads = SQB_K12_THREADS, kFWarps = kFThreads / 32;
+constexpr int kFPasses = (int)(kK1Tile / 32u) / kFThreads;          // 32-byte chunks per thread and tile
+static_assert(kFPasses * kFWarps == 32 && (kFPasses == 2 || kFPasses == 4), "one (pass, warp) sum per lane");
 constexpr uint32_t kFMaxOverlap = 4096;                 // bytes staged behind a tile at most = longest line of the fused path
 
 // (GroupDesc: sqb_k2_bitslice.cuh)
@@ -101,7 +115,7 @@ struct K12Args {
 __host__ __device__ constexpr uint32_t k12_text_bytes(uint32_t ov) { return (kK1Tile + ov + 64u + 127u) & ~127u; }
 __host__ __device__ constexpr uint32_t k12_smem_bytes(uint32_t ov, bool filter)
 {
-   return 2u * k12_text_bytes(ov) + 1024u + (kFMaxEntries + 8u) * 2u + (kFMaxEntries + 32u) * 2u + (filter ? kFMaxEntries * 2u : 0u);
+   return kFStages * k12_text_bytes(ov) + 1024u + (kFMaxEntries + 8u) * 2u + (kFMaxEntries + 32u) * 2u + (filter ? kFMaxEntries * 2u : 0u);
 }
 // plane units (uint4) of a group of `ncols` columns
 __host__ __device__ constexpr uint32_t k12_group_units(uint32_t ncols) { return ((ncols + 31u) >> 5) * 24u; }
@@ -155,12 +169,12 @@ __device__ __forceinline__ uint32_t chunk_flags(const uint8_t *p)
 }
 
 template <bool FILTER>
-__global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K12Args a, const __grid_constant__ ClassTable32 ct)
+__global__ void __launch_bounds__(kFThreads, SQB_K12_CTAS) k12_scan_pack(const K12Args a, const __grid_constant__ ClassTable32 ct)
 {
    extern __shared__ __align__(128) uint8_t dyn[];
    __shared__ uint64_t bar[2];
    __shared__ uint32_t s_tile[2], s_base, s_ovnl, s_pbase, s_gbase, s_skip, s_nlive, s_stores, s_ready;
-   __shared__ uint32_t s_wsum[4 * kWarps];                     // line starts per (pass, warp)
+   __shared__ uint32_t s_wsum[32];                             // line starts per (pass, warp)
    __shared__ uint32_t s_gcols[kFMaxGroups];
    __shared__ uint32_t s_glong[kFMaxGroups];                   // longest line of every group
    __shared__ uint32_t s_glead[kFMaxGroups][3];                // lines of the group whose lead is >= 1, >= 2, == 3
@@ -171,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K1
    const uint32_t n16 = (n + 15u) & ~15u;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const uint32_t tbytes = k12_text_bytes(ov);
-   uint32_t *lut = reinterpret_cast<uint32_t *>(dyn + 2u * tbytes);          // [256]
+   uint32_t *lut = reinterpret_cast<uint32_t *>(dyn + kFStages * tbytes);    // [256]
    uint16_t *lst = reinterpret_cast<uint16_t *>(lut + 256);     // [entries + 1] offset of every line start in the stage
    uint16_t *lsg = lst + kFMaxEntries + 8u;                     // [groups * 32] the same of the grouped lines, padded
    uint16_t *live = lsg + kFMaxEntries + 32u;                   // FILTER: dead flags, then the live entries
@@ -184,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K1
       mbar_expect_tx(&bar[st], bytes);
       bulk_g2s(dyn + st * tbytes, a.text + start, bytes, &bar[st]);
    };
-   lut[tid] = ct.w[tid];
+   if (tid < 256) lut[tid] = ct.w[tid];
    if (tid == 0) {
       mbar_init(&bar[0], 1);
       mbar_init(&bar[1], 1);
@@ -203,13 +217,13 @@ __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K1
    // runs under the rest of this iteration.  Three CTA barriers per tile (A, B, E); every shared scalar is rewritten
    // between two barriers that all its readers of the round before have passed.
    for (uint32_t iter = 0;; iter++) {
-      const uint32_t st = iter & 1u;
+      const uint32_t st = iter & 1u, sb = kFStages == 2u ? st : 0u;          // tile-number slot, text stage
       const uint32_t tile = s_tile[st];
       if (tile >= ntiles) break;
       const uint32_t tile0 = tile * kK1Tile;
-      uint8_t *buf = dyn + st * tbytes;                         // the text of the tile
-      mbar_wait(&bar[st], (phases >> st) & 1u);
-      phases ^= 1u << st;
+      uint8_t *buf = dyn + sb * tbytes;                         // the text of the tile
+      mbar_wait(&bar[sb], (phases >> sb) & 1u);
+      phases ^= 1u << sb;
 
       // the next tile's number: drawn now, needed behind barrier A (the atomic's round trip hides under the scan)
       unsigned long long nt64 = 0ull;
@@ -218,11 +232,11 @@ __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K1
       if (tid == 0 && tile == 0u)
          for (uint32_t i = 0; i < a.skip; i++) buf[i] = 'A';
 
-      // ---- line scan: chunk tid of the four 8 KiB passes; the overlap: one chunk per thread ----
-      uint32_t c[4];
+      // ---- line scan: chunk tid of every pass; the overlap: one chunk per thread ----
+      uint32_t c[kFPasses];
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-         const uint32_t o = (uint32_t)i * (kK1Tile / 4u) + (uint32_t)tid * 32u;
+      for (int i = 0; i < kFPasses; i++) {
+         const uint32_t o = (uint32_t)i * (kK1Tile / (uint32_t)kFPasses) + (uint32_t)tid * 32u;
          c[i] = chunk_flags(buf + o);
          // a newline at p opens a line at p + 1 only if p + 1 < n
          const uint32_t p = tile0 + o;
@@ -243,30 +257,33 @@ __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K1
          if (best < 32u) atomicMin(&s_ovnl, o + best);
       }
       const uint32_t first = (tile == 0u && tid == 0 && n > a.skip) ? 1u : 0u;     // the line at the start of the buffer
-      const uint32_t c0n = (uint32_t)__popc(c[0]) + first, c1n = (uint32_t)__popc(c[1]);
-      const uint32_t c2n = (uint32_t)__popc(c[2]), c3n = (uint32_t)__popc(c[3]);
-      // two packed inclusive warp scans (a lane has at most 33 starts per pass: 16 bits hold a warp's sum)
-      uint32_t x01 = c0n | (c1n << 16), x23 = c2n | (c3n << 16);
+      uint32_t cn[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int i = 0; i < kFPasses; i++) cn[i] = (uint32_t)__popc(c[i]) + (i == 0 ? first : 0u);
+      // packed inclusive warp scans, two passes each (a lane has at most 33 starts per pass: 16 bits hold a warp's sum)
+      uint32_t x01 = cn[0] | (cn[1] << 16), x23 = cn[2] | (cn[3] << 16);
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-         const uint32_t t01 = __shfl_up_sync(kFull, x01, d), t23 = __shfl_up_sync(kFull, x23, d);
-         if (lane >= d) {
-            x01 += t01;
-            x23 += t23;
+         const uint32_t t01 = __shfl_up_sync(kFull, x01, d);
+         if (lane >= d) x01 += t01;
+         if (kFPasses > 2) {
+            const uint32_t t23 = __shfl_up_sync(kFull, x23, d);
+            if (lane >= d) x23 += t23;
          }
       }
       if (lane == 31) {
          s_wsum[warp] = x01 & 0xffffu;
-         s_wsum[kWarps + warp] = x01 >> 16;
-         s_wsum[2 * kWarps + warp] = x23 & 0xffffu;
-         s_wsum[3 * kWarps + warp] = x23 >> 16;
+         s_wsum[kFWarps + warp] = x01 >> 16;
+         if (kFPasses > 2) {
+            s_wsum[2 * kFWarps + warp] = x23 & 0xffffu;
+            s_wsum[3 * kFWarps + warp] = x23 >> 16;
+         }
       }
       fence_proxy_async();                   // this thread's reads of the OTHER stage (the tile before) come before its refill
       __syncthreads();                       // A: s_wsum, s_ovnl; every warp is done with the tile before
       // where the line starts of every (pass, warp) go: an exclusive scan of the 32 sums, by every warp for itself
-      uint32_t base[4], tile_total;
+      uint32_t base[kFPasses], tile_total;
       {
-         static_assert(4 * kWarps == 32, "one (pass, warp) sum per lane");
          const uint32_t v = s_wsum[lane];
          uint32_t x = v;
 #pragma unroll
@@ -277,18 +294,20 @@ __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K1
          tile_total = __shfl_sync(kFull, x, 31);
          const uint32_t ex = x - v;
 #pragma unroll
-         for (int i = 0; i < 4; i++) base[i] = __shfl_sync(kFull, ex, i * kWarps + warp);
+         for (int i = 0; i < kFPasses; i++) base[i] = __shfl_sync(kFull, ex, i * kFWarps + warp);
       }
-      base[0] += (x01 & 0xffffu) - c0n;
-      base[1] += (x01 >> 16) - c1n;
-      base[2] += (x23 & 0xffffu) - c2n;
-      base[3] += (x23 >> 16) - c3n;
+      base[0] += (x01 & 0xffffu) - cn[0];
+      base[1] += (x01 >> 16) - cn[1];
+      if (kFPasses > 2) {
+         base[kFPasses > 2 ? 2 : 0] += (x23 & 0xffffu) - cn[2];
+         base[kFPasses > 2 ? 3 : 0] += (x23 >> 16) - cn[3];
+      }
       unsigned long long at64 = 0ull;        // (tid 0) the tile's place in ls_raw: used behind the emit loops
       if (tid == 0) {
          // the next tile: its TMA into the stage of the tile before
          const uint32_t nt = (uint32_t)nt64;
          s_tile[st ^ 1u] = nt;
-         if (nt < ntiles) issue(st ^ 1u, nt);
+         if (kFStages == 2u && nt < ntiles) issue(st ^ 1u, nt);
          at64 = atomicAdd(&a.ctr[C_LS_CURSOR], (unsigned long long)tile_total);
          const uint32_t ovnl = s_ovnl;
          s_ovnl = 0xffffffffu;
@@ -315,8 +334,8 @@ __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K1
          base[0] += 1u;
       }
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-         const uint32_t o = (uint32_t)i * (kK1Tile / 4u) + (uint32_t)tid * 32u + 1u;
+      for (int i = 0; i < kFPasses; i++) {
+         const uint32_t o = (uint32_t)i * (kK1Tile / (uint32_t)kFPasses) + (uint32_t)tid * 32u + 1u;
          uint32_t x = c[i];
          while (x) {
             const uint32_t u = (uint32_t)__ffs(x) - 1u;
@@ -337,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K1
          // a STOP among the first filter_k class codes of a line kills it; ls_raw (coalesced)
          if (!skip_tile) {
             const uint32_t gbase_ls = s_base;
-            for (uint32_t j = (uint32_t)tid; j < tile_total; j += (uint32_t)kThreads) {
+            for (uint32_t j = (uint32_t)tid; j < tile_total; j += (uint32_t)kFThreads) {
                const uint32_t o = lst[j];
                uint32_t fl = 0u;
                for (uint32_t i = 0; i < a.filter_k; i++) {                     // filter_k <= 8
@@ -377,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K1
       if (!skip_tile) {
          // ---- the tables of the groups, one group per warp and round: its columns (the longest line with the lead in
          //      front and the terminator), its longest line, its lead masks, the aligned starts of its lines ----
-         for (uint32_t g = (uint32_t)warp; g < ngroups; g += (uint32_t)kWarps) {
+         for (uint32_t g = (uint32_t)warp; g < ngroups; g += (uint32_t)kFWarps) {
             const uint32_t j = g * 32u + (uint32_t)lane;
             uint32_t len = 0, lead = 0, begin;
             if (j < nlive) {
@@ -401,12 +420,23 @@ __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K1
          }
          if (!FILTER) {
             const uint32_t gbase_ls = s_base;
-            for (uint32_t j = (uint32_t)tid; j < tile_total; j += (uint32_t)kThreads)
+            for (uint32_t j = (uint32_t)tid; j < tile_total; j += (uint32_t)kFThreads)
                if (gbase_ls + j < a.ls_cap) a.ls_raw[gbase_ls + j] = tile0 + (uint32_t)lst[j];
          }
       }
       __syncthreads();                       // E: the group tables
-      if (skip_tile) continue;
+      // one text stage: the next tile's copy starts when every warp is done with this one
+      auto end_of_tile = [&]() {
+         if (kFStages == 1u) {
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0 && (uint32_t)nt64 < ntiles) issue(0u, (uint32_t)nt64);
+         }
+      };
+      if (skip_tile) {
+         end_of_tile();
+         continue;
+      }
       // the blocks of 32 columns in front of every group (lane = group): every warp for itself
       const uint32_t my_cols = (uint32_t)lane < ngroups ? s_gcols[lane] : 0u;
       const uint32_t my_nb = (my_cols + 31u) >> 5;
@@ -421,6 +451,7 @@ __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K1
       if (__reduce_max_sync(kFull, (uint32_t)lane < ngroups ? s_glong[lane] : 0u) > ov) {
          // (uniform) a line longer than the overlap: its group would read beyond the staged text
          if (tid == 0) atomicMax(&a.ctr[C_FUSED_OVF], 1ull);
+         end_of_tile();
          continue;
       }
       // The tile's room in the plane buffer and its group numbers: thread 0 asks for them now and publishes them
@@ -482,7 +513,7 @@ __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K1
       //      the warps that get none wait a quarter as long) ----
       const uint32_t nfull = nblocks & ~31u;
       const uint32_t cq = (uint32_t)lane & 7u;
-      for (uint32_t b0 = (uint32_t)warp * 4u; b0 < nfull; b0 += (uint32_t)kWarps * 4u) {
+      for (uint32_t b0 = (uint32_t)warp * 4u; b0 < nfull; b0 += (uint32_t)kFWarps * 4u) {
          const uint32_t blk = b0 + ((uint32_t)lane >> 3);
          // the group of the block: the last one that starts at or before it
          uint32_t g = 0;
@@ -539,7 +570,7 @@ __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K1
             out[16] = make_uint4(P[2][0], P[2][1], P[2][2], P[2][3]);
          }
       }
-      for (uint32_t blk = nfull + (uint32_t)warp; blk < nblocks; blk += (uint32_t)kWarps) {
+      for (uint32_t blk = nfull + (uint32_t)warp; blk < nblocks; blk += (uint32_t)kFWarps) {
          const uint32_t g = 31u - (uint32_t)__clz(__ballot_sync(kFull, my_gblk <= blk));
          const uint32_t cb = blk - __shfl_sync(kFull, my_gblk, g);
          const uint16_t *ls = lsg + g * 32u;
@@ -570,9 +601,10 @@ __global__ void __launch_bounds__(kThreads, SQB_K12_CTAS) k12_scan_pack(const K1
       room();                                // (a warp without a block; thread 0 must publish in any case)
       if (FILTER && stores) {
          const uint32_t gbase = *reinterpret_cast<volatile uint32_t *>(&s_gbase);
-         for (uint32_t j = (uint32_t)tid; j < ngroups * 32u; j += (uint32_t)kThreads)
+         for (uint32_t j = (uint32_t)tid; j < ngroups * 32u; j += (uint32_t)kFThreads)
             a.gent[(size_t)gbase * 32u + j] = j < nlive ? live[j] : (uint16_t)0;
       }
+      end_of_tile();
    }
 }
 
