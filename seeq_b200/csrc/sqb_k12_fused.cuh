@@ -337,11 +337,12 @@ __global__ void __launch_bounds__(kFThreads, SQB_K12_CTAS) k12_scan_pack(const K
       for (int i = 0; i < kFPasses; i++) {
          const uint32_t o = (uint32_t)i * (kK1Tile / (uint32_t)kFPasses) + (uint32_t)tid * 32u + 1u;
          uint32_t x = c[i];
+         const bool several = (x & (x - 1u)) != 0u;                             // (lines of 32 bytes and more: never)
          while (x) {
             const uint32_t u = (uint32_t)__ffs(x) - 1u;
             x &= x - 1u;
             const uint32_t v = 4u * (u & 7u) + (u >> 3);                       // byte index of the newline in its chunk
-            const uint32_t idx = base[i] + (uint32_t)__popc(c[i] & chunk_before(v));
+            const uint32_t idx = base[i] + (several ? (uint32_t)__popc(c[i] & chunk_before(v)) : 0u);
             if (idx < kFMaxEntries) lst[idx] = (uint16_t)(o + v);
          }
       }
@@ -499,7 +500,7 @@ __global__ void __launch_bounds__(kFThreads, SQB_K12_CTAS) k12_scan_pack(const K
             pbase = pb;
             stores = ok != 0u;
          } else {
-            while (*reinterpret_cast<volatile uint32_t *>(&s_ready) != iter + 1u) {}
+            while (*reinterpret_cast<volatile uint32_t *>(&s_ready) != iter + 1u) __nanosleep(40);   // (a tight loop took 13 % of the kernel's issue slots)
             __threadfence_block();
             pbase = *reinterpret_cast<volatile uint32_t *>(&s_pbase);
             stores = *reinterpret_cast<volatile uint32_t *>(&s_stores) != 0u;
