@@ -39,7 +39,8 @@ namespace sqb {
 // class codes of the tokenizer (K1), three bit-planes p2 p1 p0
 //   0 A   1 C   2 G   3 T/U   4 N   5 STOP   6 SKIP   7 NULL
 // Eq slots of one text column
-enum BsSlot { BS_A = 0, BS_C, BS_G, BS_T, BS_N, BS_ANY, BS_CUSTOM0, BS_CUSTOM1, BS_ONES, BS_SLOTS };
+constexpr int kBsMaxCustom = 6;          // bracket classes other than a single base, N and "any" a pattern may use
+enum BsSlot { BS_A = 0, BS_C, BS_G, BS_T, BS_N, BS_ANY, BS_CUSTOM0, BS_CUSTOM1, BS_ONES = BS_CUSTOM0 + kBsMaxCustom, BS_SLOTS };
 
 enum BsMode { BS_FIRST = 0, BS_BEST = 1, BS_ALL = 2 };
 
@@ -56,10 +57,10 @@ struct BsPattern {
    int32_t  m, tau;
    int32_t  rows;                       // R: rows per part of the kernel instance
    int32_t  parts;                      // G: 1, 2 or 4;  R * G >= m
-   int32_t  ncustom;                    // custom classes in use (0..2)
+   int32_t  ncustom;                    // custom classes in use (0..kBsMaxCustom)
    uint8_t  slot[kBsMaxRows];           // Eq slot of every row (pad rows: BS_ONES)
    uint32_t slot_off[kBsMaxRows];       // the same as byte offset slot * 32 lanes * 4 (kernel smem layout)
-   uint32_t custom[2][5];               // custom classes: all-ones where A,C,G,T,N belongs to the class
+   uint32_t custom[kBsMaxCustom][5];    // custom classes: all-ones where A,C,G,T,N belongs to the class
    uint32_t tau_plane[8];               // bit k of tau, replicated: 0 or ~0
    uint32_t m_plane[8];                 // bit k of m
    uint32_t best_plane[kBsBestBits];    // bit k of tau + 1
@@ -114,10 +115,9 @@ SQB_BS_HD void bs_classes(uint32_t p0, uint32_t p1, uint32_t p2, const BsPattern
    slots[BS_N] = n;
    anybase = ~p2 | n;
    slots[BS_ANY] = anybase;
-   slots[BS_CUSTOM0] = (a & p.custom[0][0]) | (c & p.custom[0][1]) | (g & p.custom[0][2]) | (t & p.custom[0][3]) |
-                       (n & p.custom[0][4]);
-   slots[BS_CUSTOM1] = (a & p.custom[1][0]) | (c & p.custom[1][1]) | (g & p.custom[1][2]) | (t & p.custom[1][3]) |
-                       (n & p.custom[1][4]);
+   for (int k = 0; k < kBsMaxCustom; k++)
+      slots[BS_CUSTOM0 + k] = (a & p.custom[k][0]) | (c & p.custom[k][1]) | (g & p.custom[k][2]) | (t & p.custom[k][3]) |
+                              (n & p.custom[k][4]);
    slots[BS_ONES] = ~0u;
    stop = p2 & ~p1 & p0;
    skip = p2 & p1 & ~p0;

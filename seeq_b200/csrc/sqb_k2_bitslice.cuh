@@ -546,12 +546,11 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
             sl[BS_T][lane] = nt;
             sl[BS_N][lane] = nn;
             sl[BS_ANY][lane] = anybase;
-            if (pat.ncustom > 0)
-               sl[BS_CUSTOM0][lane] = (na & pat.custom[0][0]) | (nc & pat.custom[0][1]) | (ng & pat.custom[0][2]) |
-                                      (nt & pat.custom[0][3]) | (nn & pat.custom[0][4]);
-            if (pat.ncustom > 1)
-               sl[BS_CUSTOM1][lane] = (na & pat.custom[1][0]) | (nc & pat.custom[1][1]) | (ng & pat.custom[1][2]) |
-                                      (nt & pat.custom[1][3]) | (nn & pat.custom[1][4]);
+#pragma unroll
+            for (int q = 0; q < kBsMaxCustom; q++)
+               if (pat.ncustom > q)                     // (uniform)
+                  sl[BS_CUSTOM0 + q][lane] = (na & pat.custom[q][0]) | (nc & pat.custom[q][1]) | (ng & pat.custom[q][2]) |
+                                             (nt & pat.custom[q][3]) | (nn & pat.custom[q][4]);
          }
          uint32_t ph = 0u, mh = 0u;
          if (G > 1) {

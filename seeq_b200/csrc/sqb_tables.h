@@ -86,7 +86,7 @@ constexpr uint32_t kCutWindow = 256;
 static inline uint32_t bs_warmup(int m, int tau) { return (uint32_t)(m + 2 * tau + 2); }
 
 // keys: one class byte per pattern position (bit0 A .. bit3 T, 0x1F = N).
-// Returns false if the pattern needs more than two custom classes or does not
+// Returns false if the pattern needs more than kBsMaxCustom custom classes or does not
 // fit (the caller then uses the word-parallel kernels).
 static inline bool build_bs_pattern(const unsigned char *keys, int m, int tau, BsPattern *p)
 {
@@ -100,7 +100,7 @@ static inline bool build_bs_pattern(const unsigned char *keys, int m, int tau, B
    const int R = shape.rows * shape.parts;        // rows of the whole automaton
    const int pad = R - m;
    int ncustom = 0;
-   unsigned char custom_key[2] = {0, 0};
+   unsigned char custom_key[kBsMaxCustom] = {0};
    for (int j = 0; j < R; j++) {
       if (j < pad) { p->slot[j] = BS_ONES; continue; }     // entries beyond R stay 0 (unused)
       const unsigned char k = keys[j - pad] & 0x1F;
@@ -115,7 +115,7 @@ static inline bool build_bs_pattern(const unsigned char *keys, int m, int tau, B
       default:
          for (int c = 0; c < ncustom; c++) if (custom_key[c] == k) slot = BS_CUSTOM0 + c;
          if (slot < 0) {
-            if (ncustom == 2) return false;
+            if (ncustom == kBsMaxCustom) return false;
             custom_key[ncustom] = k;
             for (int b = 0; b < 5; b++) p->custom[ncustom][b] = (k >> b) & 1 ? ~0u : 0u;
             slot = BS_CUSTOM0 + ncustom++;

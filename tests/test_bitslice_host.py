@@ -39,7 +39,7 @@ def harness(tmp_path_factory):
 
 def rand_pattern(rng, mmin, mmax, custom=True):
     m = rng.randint(mmin, mmax)
-    brackets = [rng.sample("ACGT", rng.randint(2, 3)) for _ in range(2)]
+    brackets = [rng.sample("ACGT", rng.randint(2, 3)) for _ in range(rng.randint(1, 5))]     # up to kBsMaxCustom = 6 classes
     out = []
     for _ in range(m):
         r = rng.random()
@@ -93,7 +93,7 @@ def test_bitsliced_events_equal_oracle(harness, oracle, mrange):
                 n = harness.bs_host_scan(buf, len(buf), keys, len(keys), tau, mo | nd,
                                          out.ctypes.data_as(C.POINTER(C.c_uint64)), out.shape[0])
                 if n == -1:
-                    continue              # more than two custom classes: not a bit-sliced pattern
+                    continue              # more than kBsMaxCustom custom classes: not a bit-sliced pattern
                 assert n >= 0
                 exp, _, _ = oracle.buffer_scan(buf, keys, tau, mo | nd)
                 exp = exp[:, [0, 2, 3]]

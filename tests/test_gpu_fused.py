@@ -171,3 +171,17 @@ def test_device_chunks_with_an_unaligned_start(B, oracle):
     assert st.path & FUSED
     L.sqbDeviceFree(d)
     sq.close()
+
+
+def test_many_bracket_classes_stay_bit_sliced(B, oracle):
+    """Up to six bracket classes (other than single bases, N and "any") have an Eq slot of their own: a pattern
+    with four or six of them runs on the bit-sliced kernels like any other (it used to fall back to the
+    word-parallel ones beyond two); a seventh class does fall back -- same records either way."""
+    rng = random.Random(11)
+    buf = ragged(rng, 3000, 20, 200, "ACGTTAGGCATT", junk=0.003)
+    for pattern, sliced in (("A[CG]T[AT]NG[ACG]TC[GT]A", True), ("[AC][AG][AT][CG][CT][GT]ACGT", True),
+                            ("[AC][AG][AT][CG][CT][GT][ACG]ACG", False)):
+        for mo in MATCH:
+            for nd in (SQ_FAIL, SQ_CONVERT):
+                st = scan(B, oracle, pattern, 2, buf, mo | nd)
+                assert bool(st.path & BITSLICE) == sliced, (pattern, st.path)

@@ -9,7 +9,7 @@ import sys
 
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 NAMES = (("k2_bitslice", "k2_matcher"), ("k2_forward", "k2_matcher"), ("k15_pack", "k15_pack"),
-         ("k1_scan_classify", "k1_scan_classify"), ("k34_finish", "k34_finish"))
+         ("k1_scan_classify", "k1_scan_classify"), ("k12_scan_pack", "k12_scan_pack"), ("k34_finish", "k34_finish"))
 
 
 def main():
