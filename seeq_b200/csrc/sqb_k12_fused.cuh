@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(kFThreads, SQB_K12_CTAS) k12_scan_pack(const K
 {
    extern __shared__ __align__(128) uint8_t dyn[];
    __shared__ uint64_t bar[2];
-   __shared__ uint32_t s_tile[2], s_base, s_ovnl, s_pbase, s_gbase, s_skip, s_nlive, s_stores, s_ready;
+   __shared__ uint64_t bar_alloc;                              // the tile's plane / group allocation has been published
+   __shared__ uint32_t s_tile[2], s_base, s_ovnl, s_pbase, s_gbase, s_skip, s_nlive, s_stores;
    __shared__ uint32_t s_wsum[32];                             // line starts per (pass, warp)
    __shared__ uint32_t s_gcols[kFMaxGroups];
    __shared__ uint32_t s_glong[kFMaxGroups];                   // longest line of every group
@@ -202,15 +203,16 @@ __global__ void __launch_bounds__(kFThreads, SQB_K12_CTAS) k12_scan_pack(const K
    if (tid == 0) {
       mbar_init(&bar[0], 1);
       mbar_init(&bar[1], 1);
+      mbar_init(&bar_alloc, 1);
       mbar_fence_init();
       const uint32_t t = (uint32_t)atomicAdd(&a.ctr[C_TICKET_K1], 1ull);
       s_tile[0] = t;
       s_ovnl = 0xffffffffu;
-      s_ready = 0u;
       if (t < ntiles) issue(0u, t);
    }
    __syncthreads();
    uint32_t phases = 0;                   // bit st = parity to wait for on stage st
+   uint32_t alloc_phase = 0;              // parity to wait for on bar_alloc
 
    // Two text stages.  Iteration j works on stage j & 1; behind its barrier A every warp is done with the tile
    // before (stage (j + 1) & 1), so thread 0 draws the next tile there and sends its TMA into that stage: the copy
@@ -457,14 +459,14 @@ __global__ void __launch_bounds__(kFThreads, SQB_K12_CTAS) k12_scan_pack(const K
       }
       // The tile's room in the plane buffer and its group numbers: thread 0 asks for them now and publishes them
       // when it needs them itself, in front of its first store -- the round trip of the atomics hides under the
-      // classification of the first blocks.  The other warps wait for s_ready in front of THEIR first store.
+      // classification of the first blocks.  The other warps wait for the mbarrier bar_alloc in front of THEIR first store.
       unsigned long long pb64 = 0ull, gb64 = 0ull;
       if (tid == 0) {
          pb64 = atomicAdd(&a.ctr[C_PLANE_UNITS], (unsigned long long)nblocks * 24ull);
          gb64 = atomicAdd(&a.ctr[C_NGROUPS], (unsigned long long)ngroups);
       }
       bool ready = false;
-      uint32_t pbase = 0;
+      uint32_t pbase = 0, gbase = 0;
       bool stores = false;
       auto room = [&]() {                    // (warp-uniform call) pbase / stores are valid on return
          if (ready) return;
@@ -494,17 +496,18 @@ __global__ void __launch_bounds__(kFThreads, SQB_K12_CTAS) k12_scan_pack(const K
                s_pbase = pb;
                s_gbase = gb;
                s_stores = ok;
-               __threadfence_block();
-               *reinterpret_cast<volatile uint32_t *>(&s_ready) = iter + 1u;
+               mbar_arrive(&bar_alloc);                       // (release: the three words are visible to whoever sees the phase flip)
             }
             pbase = pb;
+            gbase = gb;
             stores = ok != 0u;
          } else {
-            while (*reinterpret_cast<volatile uint32_t *>(&s_ready) != iter + 1u) __nanosleep(40);   // (a tight loop took 13 % of the kernel's issue slots)
-            __threadfence_block();
-            pbase = *reinterpret_cast<volatile uint32_t *>(&s_pbase);
-            stores = *reinterpret_cast<volatile uint32_t *>(&s_stores) != 0u;
+            mbar_wait(&bar_alloc, alloc_phase);              // (a spin on a flag took 13 % of the kernel's issue slots)
+            pbase = s_pbase;
+            gbase = s_gbase;
+            stores = s_stores != 0u;
          }
+         alloc_phase ^= 1u;                                  // every warp passes here exactly once per tile that gets this far
          ready = true;
       };
       const uint32_t lut_addr = smem_addr(lut);
@@ -601,7 +604,6 @@ __global__ void __launch_bounds__(kFThreads, SQB_K12_CTAS) k12_scan_pack(const K
       }
       room();                                // (a warp without a block; thread 0 must publish in any case)
       if (FILTER && stores) {
-         const uint32_t gbase = *reinterpret_cast<volatile uint32_t *>(&s_gbase);
          for (uint32_t j = (uint32_t)tid; j < ngroups * 32u; j += (uint32_t)kFThreads)
             a.gent[(size_t)gbase * 32u + j] = j < nlive ? live[j] : (uint16_t)0;
       }

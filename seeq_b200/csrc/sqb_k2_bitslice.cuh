@@ -546,11 +546,13 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
             sl[BS_T][lane] = nt;
             sl[BS_N][lane] = nn;
             sl[BS_ANY][lane] = anybase;
+            if (pat.ncustom > 0) {                      // (uniform; most patterns have none: one branch per column)
 #pragma unroll
-            for (int q = 0; q < kBsMaxCustom; q++)
-               if (pat.ncustom > q)                     // (uniform)
-                  sl[BS_CUSTOM0 + q][lane] = (na & pat.custom[q][0]) | (nc & pat.custom[q][1]) | (ng & pat.custom[q][2]) |
-                                             (nt & pat.custom[q][3]) | (nn & pat.custom[q][4]);
+               for (int q = 0; q < kBsMaxCustom; q++)
+                  if (pat.ncustom > q)
+                     sl[BS_CUSTOM0 + q][lane] = (na & pat.custom[q][0]) | (nc & pat.custom[q][1]) | (ng & pat.custom[q][2]) |
+                                                (nt & pat.custom[q][3]) | (nn & pat.custom[q][4]);
+            }
          }
          uint32_t ph = 0u, mh = 0u;
          if (G > 1) {
