@@ -460,7 +460,9 @@ static bool use_bitslice(const sqb_engine *e, int options, uint32_t n)
 static bool cuts_allowed(const sqb_engine *e, int options, uint32_t n)
 {
    if (!use_bitslice(e, options, n) || e->cuts == 0) return false;
-   if (options & (SQB_FASTA | SQB_FASTQ | SQB_COUNT_ONLY | SQB_KEEP_LINES_INTERNAL)) return false;
+   // (SQB_KEEP_LINES -- every seeqFileMatch call -- takes cuts too: the line starts handed back are the entries of
+   // ls that open a line, see scan_one_chunk)
+   if (options & (SQB_FASTA | SQB_FASTQ | SQB_COUNT_ONLY)) return false;
    if ((options & OPT_NONDNA) == OPT_IGNORE) return false;
    return bs_warmup(e->m, e->tau) <= kCutWindow;
 }
@@ -480,6 +482,11 @@ static bool use_fused(const sqb_engine *e, int options, uint32_t n)
 {
    if (!e->fused || !use_bitslice(e, options, n) || e->bs_pat.parts != 1) return false;
    if (options & (SQB_FASTA | SQB_FASTQ)) return false;
+   // with the line filter the two-kernel path is the faster one (cfg5, r4r: 1145 against 1092 GB/s): K12's groups are local
+   // to a tile, and the 104 lines of a 32 KiB tile that survive the filter fill the matcher's lanes to 81 %
+   // (SEEQ_B200_FUSED=2: fused all the same -- the tests of that path)
+   // (a scan that only PROBES the filter -- the first of an engine -- stays fused: the fused kernel counts the live lines too)
+   if (e->fused < 2 && use_filter(e, options, n) && (e->filter == 2 || e->filter_state == 1)) return false;
    return !use_cuts(e, options, n);
 }
 
@@ -520,7 +527,7 @@ static int launch_bitslice(const sqb_engine *e, int mode, int options, size_t ma
    const int R = e->bs_pat.rows, G = e->bs_pat.parts;
    const bool nfa = G == 1 && e->tau <= 2 && e->nfa_levels;
    int per_sm = G > 1 ? (R <= 24 ? SQB_G2_CTAS : 2) : (R <= 16 ? 4 : 3);
-   if (nfa) per_sm = R * (e->tau + 1) <= 24 ? 6 : (R * (e->tau + 1) <= 48 ? 4 : 3);      // = the kernels' launch bounds
+   if (nfa) per_sm = R * (e->tau + 1) <= 24 ? 6 : (R * (e->tau + 1) <= SQB_WM_4CTA_ROWS ? 4 : 3);      // = the kernels' launch bounds
    if (const char *c = getenv("SEEQ_B200_BS_CTAS")) per_sm = std::max(1, atoi(c));
    // work items = (tile, 1/G of its groups), one warp each
    const int grid = (int)std::max<size_t>(1, std::min<size_t>(div_up(div_up(max_lines, kBsTileLines) * G, kBsWarps),
@@ -1030,7 +1037,7 @@ sqb_engine_t *sqbEngineNew(const unsigned char *keys, int m, int tau, int device
    if (const char *c = getenv("SEEQ_B200_FILTER")) e->filter = atoi(c);
    if (const char *c = getenv("SEEQ_B200_NFA")) e->nfa_levels = atoi(c) != 0;
    if (const char *c = getenv("SEEQ_B200_GRAPHS")) e->graphs = atoi(c) != 0;
-   if (const char *c = getenv("SEEQ_B200_FUSED")) e->fused = atoi(c) != 0;
+   if (const char *c = getenv("SEEQ_B200_FUSED")) e->fused = std::max(0, std::min(2, atoi(c)));
    if (const char *c = getenv("SEEQ_B200_FUSED_OV")) e->fused_ov = std::min<uint32_t>(kFMaxOverlap, std::max(32, atoi(c)) & ~31u);
    return e;
 }
@@ -1180,16 +1187,29 @@ static int host_collect(sqb_engine *e, Slot &s, int options, uint64_t *line_base
       }
       CU(cudaMemcpyAsync(e->host_recs + e->host_recs_n, s.d_recs, st.nrecs * sizeof(Rec), cudaMemcpyDeviceToHost, s.stream));
    }
+   // with segment cuts the entries of ls are segments: the line starts are the entries whose line differs from the one
+   // before (lid), picked out on the host
+   const bool keep_cut = (options & SQB_KEEP_LINES_INTERNAL) && s.h_ctr[C_NCUTS] != 0ull;
+   const size_t nent = keep_cut ? (size_t)s.h_ctr[C_NPSEUDO] : (size_t)st.nlines;
    if ((options & SQB_KEEP_LINES_INTERNAL) && st.nlines > 0) {
-      if (pin_reserve(&s.h_ls, &s.h_ls_cap, (size_t)st.nlines)) return -1;
-      CU(cudaMemcpyAsync(s.h_ls, s.d_ls, st.nlines * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+      if (pin_reserve(&s.h_ls, &s.h_ls_cap, nent * (keep_cut ? 2 : 1))) return -1;
+      CU(cudaMemcpyAsync(s.h_ls, s.d_ls, nent * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+      if (keep_cut) CU(cudaMemcpyAsync(s.h_ls + nent, s.d_lid, nent * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
    }
    CU(cudaStreamSynchronize(s.stream));
    if (!count_only && !on_device && st.nrecs > 0) e->host_recs_n += (size_t)st.nrecs;
    if ((options & SQB_KEEP_LINES_INTERNAL) && st.nlines > 0) {
       const size_t old = e->host_lines.size();
       e->host_lines.resize(old + st.nlines);
-      for (uint64_t k = 0; k < st.nlines; k++) e->host_lines[old + k] = (uint64_t)s.chunk_off + s.h_ls[k];
+      if (!keep_cut) {
+         for (uint64_t k = 0; k < st.nlines; k++) e->host_lines[old + k] = (uint64_t)s.chunk_off + s.h_ls[k];
+      } else {
+         const uint32_t *lid = s.h_ls + nent;
+         size_t w = 0;
+         for (size_t k = 0; k < nent; k++)
+            if ((k == 0 || lid[k] != lid[k - 1]) && w < (size_t)st.nlines) e->host_lines[old + w++] = (uint64_t)s.chunk_off + s.h_ls[k];
+         if (w != (size_t)st.nlines) { set_err("segment cuts: %zu line starts for %llu lines", w, (unsigned long long)st.nlines); return -1; }
+      }
    }
    *line_base += st.nlines;
    acc->nbytes += st.nbytes;

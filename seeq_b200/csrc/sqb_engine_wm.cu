@@ -19,8 +19,13 @@ using namespace sqb;
 template <int R, int T, int MODE> static cudaError_t launch3(bool skip, int grid, cudaStream_t st, const K2BsArgs &a, const BsPattern &p)
 {
    const size_t smem = (MODE == BS_ALL ? sizeof(BsWarpSmemAll) : sizeof(BsWarpSmem)) * kBsWarps;      // < 48 KiB
-   if (skip) k2_bitslice<R, 1, MODE, true, T, SQB_WM_FUSED != 0><<<grid, kBsThreads, smem, st>>>(a, p);
-   else k2_bitslice<R, 1, MODE, false, T, SQB_WM_FUSED != 0><<<grid, kBsThreads, smem, st>>>(a, p);
+   if (p.ncustom > 0) {
+      if (skip) k2_bitslice<R, 1, MODE, true, T, SQB_WM_FUSED != 0, true><<<grid, kBsThreads, smem, st>>>(a, p);
+      else k2_bitslice<R, 1, MODE, false, T, SQB_WM_FUSED != 0, true><<<grid, kBsThreads, smem, st>>>(a, p);
+   } else {
+      if (skip) k2_bitslice<R, 1, MODE, true, T, SQB_WM_FUSED != 0, false><<<grid, kBsThreads, smem, st>>>(a, p);
+      else k2_bitslice<R, 1, MODE, false, T, SQB_WM_FUSED != 0, false><<<grid, kBsThreads, smem, st>>>(a, p);
+   }
    return cudaGetLastError();
 }
 

@@ -49,6 +49,9 @@ constexpr int kBsBlock   = 4;                       // columns per prefetch bloc
 #ifndef SQB_G2_RADDR_SMEM
 #define SQB_G2_RADDR_SMEM 0                         // 1: Eq slot addresses of the multi-part matcher from shared memory
 #endif                                              //    instead of R registers (A/B knob)
+#ifndef SQB_WM_4CTA_ROWS
+#define SQB_WM_4CTA_ROWS 60                         // NFA-level instances of up to this many state planes run 4 CTAs per SM (128 registers; m = 20, tau = 2: 0.524 -> 0.515 ms, r4v)
+#endif
 #ifndef SQB_G2_CTAS
 #define SQB_G2_CTAS 3                               // CTAs per SM of the multi-part matcher with R <= 24 (A/B knob)
 #endif
@@ -368,8 +371,10 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 //
 // WM > 0 selects the NFA-level automaton (bs_wm_step, tau = WM - 1 <= 2, G == 1)
 // instead of Myers' delta encoding: fewer logic ops per column for small tau.
-template <int R, int G, int MODE, bool SKIP, int WM = 0, bool FUSED = false>
-__global__ void __launch_bounds__(kBsThreads, WM ? (R * WM <= 24 ? 6 : (R * WM <= 48 ? 4 : 3)) : (G > 1 ? (R <= 24 ? SQB_G2_CTAS : 2) : (R <= 16 ? 4 : 3)))
+// CUSTOM = false: an instance for patterns without bracket classes (single-part automata only).  The code of the
+// bracket classes costs such patterns 8 % when it is merely SKIPPED at run time (metric shape, r4t: 0.571 against 0.525 ms).
+template <int R, int G, int MODE, bool SKIP, int WM = 0, bool FUSED = false, bool CUSTOM = true>
+__global__ void __launch_bounds__(kBsThreads, WM ? (R * WM <= 24 ? 6 : (R * WM <= SQB_WM_4CTA_ROWS ? 4 : 3)) : (G > 1 ? (R <= 24 ? SQB_G2_CTAS : 2) : (R <= 16 ? 4 : 3)))
 k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
 {
    static_assert(WM == 0 || G == 1, "the NFA-level automaton is single-part");
@@ -529,6 +534,7 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
          }
 #pragma unroll
          for (int k = 0; k < kBsBlock; k++) {
+         const int kk = k;
          // iterations >= niter: every line is dead, nothing happens
          const uint32_t c = t0 + (uint32_t)k - (uint32_t)part;       // column of this lane (last part: >= 0 while alive)
          const uint32_t p0 = P0[k], p1 = P1[k], p2 = P2[k];
@@ -539,19 +545,27 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
             anybase = ~p2 | nn;
             stop = p2 & ~p1 & p0;
             skip = p2 & p1 & ~p0;
-            auto &sl = sm.slots[G == 1 ? (k & 1) : 0];
+            auto &sl = sm.slots[G == 1 ? (kk & 1) : 0];
             sl[BS_A][lane] = na;
             sl[BS_C][lane] = nc;
             sl[BS_G][lane] = ng;
             sl[BS_T][lane] = nt;
             sl[BS_N][lane] = nn;
             sl[BS_ANY][lane] = anybase;
-            if (pat.ncustom > 0) {                      // (uniform; most patterns have none: one branch per column)
-#pragma unroll
-               for (int q = 0; q < kBsMaxCustom; q++)
-                  if (pat.ncustom > q)
+            // bracket classes beyond the single bases: the first two inline, the others in a ROLLED loop (uniform trip
+            // count) -- unrolled for all six they made every instance 7 % slower whether a pattern had one or not (r4q:
+            // code size), and a rolled loop from the first class on cost the patterns with one class 6 % (r4r)
+            if (CUSTOM && pat.ncustom > 0) {
+               sl[BS_CUSTOM0][lane] = (na & pat.custom[0][0]) | (nc & pat.custom[0][1]) | (ng & pat.custom[0][2]) |
+                                      (nt & pat.custom[0][3]) | (nn & pat.custom[0][4]);
+               if (pat.ncustom > 1) {
+                  sl[BS_CUSTOM1][lane] = (na & pat.custom[1][0]) | (nc & pat.custom[1][1]) | (ng & pat.custom[1][2]) |
+                                         (nt & pat.custom[1][3]) | (nn & pat.custom[1][4]);
+#pragma unroll 1
+                  for (int q = 2; q < pat.ncustom; q++)
                      sl[BS_CUSTOM0 + q][lane] = (na & pat.custom[q][0]) | (nc & pat.custom[q][1]) | (ng & pat.custom[q][2]) |
                                                 (nt & pat.custom[q][3]) | (nn & pat.custom[q][4]);
+               }
             }
          }
          uint32_t ph = 0u, mh = 0u;
@@ -566,7 +580,7 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
                return lds_u32(raddr[(G > 1 && !SQB_G2_RADDR_SMEM) ? j : 0]);
             }
             return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(slot_base) +
-                                                       (k & 1) * (int)sizeof(sm.slots[0]) + pat.slot_off[j]);
+                                                       (kk & 1) * (int)sizeof(sm.slots[0]) + pat.slot_off[j]);
          };
          uint32_t streak[B];
          uint32_t evt;

@@ -226,3 +226,28 @@ def test_sharded_scan_equals_unsharded(B, oracle, matcher):
         exp = np.stack([whole["line"], whole["start"], whole["end"], whole["dist"]], axis=1).astype(np.int64)
         assert np.array_equal(got, exp), world
     sq.close()
+
+
+def test_long_lines_through_the_line_keeping_scan_are_cut(B, oracle, monkeypatch):
+    """seeqFileMatch scans with SQB_KEEP_LINES (it serves the lines one call at a time).  Lines of 10 kb are cut into
+    segments there too: the line starts handed back are the entries of the segment list that open a line."""
+    import numpy as np
+    monkeypatch.setenv("SEEQ_B200_MATCHER", "bitslice")      # (lifts the size thresholds: 400 lines take the production kernels)
+    monkeypatch.setenv("SEEQ_B200_CUTS", "2")                 # ... and with them the on-demand trigger: cut from the first scan
+    pattern = "ACGTTGCAAGCTTAGGCATCGATCGGATCAGCTAGCTAGC"
+    g = B.make_gen(seed=3, line_len=10000, plant=pattern, plant_per_1024=1024, max_edits=4)
+    buf = B.gen_host(g, 400)
+    sq = B.Seeq(pattern, 4)
+    for mo in (B.SQ_FIRST, B.SQ_BEST, B.SQ_ALL):
+        for it in range(2):                                   # the first scan of an engine finds the long lines and repeats itself
+            st = B.StatsT()
+            recs = sq.batch(buf, mo | B.SQB_KEEP_LINES, B.SQ_ANY, st)
+            exp, nl, nm = oracle.buffer_scan(buf, sq.keys, 4, mo)
+            got = [(int(r["line"]) + 1, int(r["start"]), int(r["end"]), int(r["dist"])) for r in recs]
+            assert got == [tuple(int(x) for x in row) for row in exp]
+            assert (st.nlines, st.nmatched) == (nl, nm)
+            assert st.path & 4, st.path                        # SQB_PATH_CUTS
+            starts = B.Engine.borrowed(sq.engine()).host_line_starts()
+            nlpos = np.flatnonzero(np.frombuffer(buf, np.uint8) == 10)
+            assert np.array_equal(starts, np.concatenate([[0], nlpos[:-1] + 1]).astype(np.uint64))
+    sq.close()

@@ -115,6 +115,7 @@ def test_more_line_starts_than_a_tile_lists(B, oracle):
 
 def test_line_filter(B, oracle, monkeypatch):
     monkeypatch.setenv("SEEQ_B200_FILTER", "2")
+    monkeypatch.setenv("SEEQ_B200_FUSED", "2")               # filtered scans take the two-kernel path by default (it is faster)
     g = B.make_gen(seed=5, line_len=150, plant="GATCGGAAGAGC", plant_per_1024=307, max_edits=2, fastq=True)
     buf = B.gen_host(g, 6000)
     for mo in MATCH:
