@@ -15,4 +15,13 @@ NK=${3:-14}
 if [ "$NK" = "0" ]; then exit 0; fi        # launch list only
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k1_|k12_|k15_|k2_|k34_|k_tile|k_off' \
     -s $((3 * NK)) -c $NK -f -o $OUT/${TAG}_${WL}_full $BENCH > $OUT/${TAG}_${WL}_full.log 2>&1
+# gpurun copies back at most 64 MiB: summarise here (tools/summarise_ncu.py only needs `ncu -i`), keep the per-instruction
+# source page of the largest kernels as CSV, and drop the report itself when it is too large to travel
+python tools/summarise_ncu.py $OUT/${TAG}_${WL}_full.ncu-rep $OUT/${TAG}_${WL} --launches $OUT/${TAG}_${WL}_launches.csv \
+    --note "ncu --set full --clock-control none of one step of bench.py --workload $WL (tools/gpu_profile.sh $TAG)" > /dev/null 2>&1
+for k in k12_scan_pack k2_bitslice; do
+  ncu -i $OUT/${TAG}_${WL}_full.ncu-rep --page source --csv --kernel-name regex:$k 2>/dev/null | cut -d, -f1-12 | gzip > $OUT/${TAG}_${WL}_${k}_source.csv.gz
+done
+SZ=$(du -sm $OUT | cut -f1)
+if [ "$SZ" -gt 55 ]; then rm -f $OUT/${TAG}_${WL}_full.ncu-rep; fi
 ls -la $OUT | tail -8
