@@ -462,7 +462,9 @@ static bool cuts_allowed(const sqb_engine *e, int options, uint32_t n)
    if (!use_bitslice(e, options, n) || e->cuts == 0) return false;
    // (SQB_KEEP_LINES -- every seeqFileMatch call -- takes cuts too: the line starts handed back are the entries of
    // ls that open a line, see scan_one_chunk)
-   if (options & (SQB_FASTA | SQB_FASTQ | SQB_COUNT_ONLY)) return false;
+   // ... and so do the count-only scans: slot_enqueue runs them as SQ_FIRST / SQ_ALL scans without the finish kernels
+   // (matched lines and events are counted per LINE behind k_seg_reduce, not per segment in the matcher)
+   if (options & (SQB_FASTA | SQB_FASTQ)) return false;
    if ((options & OPT_NONDNA) == OPT_IGNORE) return false;
    return bs_warmup(e->m, e->tau) <= kCutWindow;
 }
@@ -565,16 +567,23 @@ static cudaError_t record_event(cudaEvent_t ev, cudaStream_t st)
 // front != nullptr: the slot of ANOTHER engine that has scanned (or is scanning, earlier on the same
 // stream) the same text with the same options; its line starts, line filter and bit-planes are read
 // instead of being computed again (several patterns over one pass of the text).
-static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n, int options, cudaStream_t st,
+static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t n, const int options_asked, cudaStream_t st,
                         uint32_t skip, const Slot *front)
 {
+   // A count-only scan of long lines is cut into segments like any other; the matcher would then count segments, so the
+   // scan runs as a plain SQ_FIRST / SQ_ALL scan up to the per-tile sums (which leave the counts of matched LINES and of
+   // events in the counters) and stops in front of K3 / K4.
+   int options = options_asked;
+   const bool count_cut = (options & SQB_COUNT_ONLY) && !(options & SQB_SINGLE_LINE) && front == nullptr &&
+                          use_cuts(e, options, n);
+   if (count_cut) options &= ~SQB_COUNT_ONLY;
    const int mode = mode_of(options);
    const bool single = options & SQB_SINGLE_LINE;
    const bool timing = options & SQB_TIMING;
    s.cur_text = d_text;
    s.cur_n = n;
    s.cur_skip = skip;
-   s.cur_options = options;
+   s.cur_options = options_asked;
    s.cur_stream = st;
    s.cur_front = front;
    s.launches = 0;
@@ -800,7 +809,9 @@ static int slot_enqueue(sqb_engine *e, Slot &s, const uint8_t *d_text, uint32_t 
       k_tile_sums<<<gsum, kThreads, 0, st>>>(ts);
       k_tile_scan<<<1, 1024, 0, st>>>(ts);
       const int gtile = (int)std::max<size_t>(1, std::min<size_t>(div_up(max_lines, kFinTile), (size_t)e->sms * 8));
-      if (!all) {
+      if (count_cut) {
+         s.launches += 2;                     // the counts are in place: no records wanted
+      } else if (!all) {
          if (launch_finish(e, false, gtile, st, fa, rev)) return -1;
          s.launches += 3;
       } else {

@@ -236,6 +236,28 @@ def test_counts(B, oracle, matcher):
         sq.close()
 
 
+def test_counts_of_long_lines_are_cut(B, oracle, monkeypatch):
+    """Count-only scans (seeq -c, SQ_COUNTLINES / SQ_COUNTMATCH) of 10-kb lines take segment cuts too: they run as plain
+    scans up to the per-tile sums, so that lines and events are counted per LINE, not per segment."""
+    monkeypatch.setenv("SEEQ_B200_MATCHER", "bitslice")
+    pattern = "ACGTTGCAAGCTTAGGCATCGATCGGATCAGCTAGCTAGC"
+    g = B.make_gen(seed=3, line_len=10000, plant=pattern, plant_per_1024=700, max_edits=4)
+    buf = bytes(B.gen_host(g, 300)).replace(b"ACGTACGT", b"ACGT\x00CGT", 40)      # a few STOP bytes: dead segments behind them
+    keys, _ = oracle.parse(pattern)
+    r_all, _, _ = oracle.buffer_scan(buf, keys, 4, SQ_ALL)
+    _, _, nm = oracle.buffer_scan(buf, keys, 4, SQ_FIRST)
+    for cuts in ("0", "2"):
+        monkeypatch.setenv("SEEQ_B200_CUTS", cuts)
+        sq = B.Seeq(pattern, 4)
+        for it in range(2):
+            st = B.StatsT()
+            assert sq.batch(buf, 0, SQ_COUNTMATCH, st) == len(r_all)
+            assert bool(st.path & 4) == (cuts == "2"), (cuts, st.path)
+            assert sq.batch(buf, 0, SQ_COUNTLINES, st) == nm
+            assert bool(st.path & 4) == (cuts == "2"), (cuts, st.path)
+        sq.close()
+
+
 def test_string_api_fuzz(B, oracle):
     rng = random.Random(17)
     for it in range(60):
