@@ -61,6 +61,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
        "WAIT_%=:\n"
        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
        "@p bra DONE_%=;\n"
+       "nanosleep.u32 32;\n"          // (a bare retry loop took 15 % of K12's issued instructions, profiles/r4y)
        "bra WAIT_%=;\n"
        "DONE_%=:\n"
        "}\n" ::"r"(smem_addr(bar)),

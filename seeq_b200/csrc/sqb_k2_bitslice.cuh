@@ -555,7 +555,13 @@ k2_bitslice(const K2BsArgs a, const __grid_constant__ BsPattern pat)
             // bracket classes beyond the single bases: the first two inline, the others in a ROLLED loop (uniform trip
             // count) -- unrolled for all six they made every instance 7 % slower whether a pattern had one or not (r4q:
             // code size), and a rolled loop from the first class on cost the patterns with one class 6 % (r4r)
-            if (CUSTOM && pat.ncustom > 0) {
+            if (G > 1) {
+               // (multi-part instances: every class through the rolled loop -- the inline code cost cfg4 3.5 %, r5b)
+#pragma unroll 1
+               for (int q = 0; q < pat.ncustom; q++)
+                  sl[BS_CUSTOM0 + q][lane] = (na & pat.custom[q][0]) | (nc & pat.custom[q][1]) | (ng & pat.custom[q][2]) |
+                                             (nt & pat.custom[q][3]) | (nn & pat.custom[q][4]);
+            } else if (CUSTOM && pat.ncustom > 0) {
                sl[BS_CUSTOM0][lane] = (na & pat.custom[0][0]) | (nc & pat.custom[0][1]) | (ng & pat.custom[0][2]) |
                                       (nt & pat.custom[0][3]) | (nn & pat.custom[0][4]);
                if (pat.ncustom > 1) {
