@@ -186,3 +186,64 @@ def test_many_bracket_classes_stay_bit_sliced(B, oracle):
             for nd in (SQ_FAIL, SQ_CONVERT):
                 st = scan(B, oracle, pattern, 2, buf, mo | nd)
                 assert bool(st.path & BITSLICE) == sliced, (pattern, st.path)
+
+
+def test_tile_and_buffer_boundaries(B, oracle):
+    """The fused kernel works on 32 KiB tiles with 512 bytes of overlap and masks everything at and behind the end of
+    the buffer by hand: newlines on the last byte of a tile, lines that start on a tile's first byte, buffers that end
+    exactly on a tile boundary / one byte before / one byte after it, with and without a final newline, and a line that
+    ends on the very last byte of the staged overlap."""
+    rng = random.Random(17)
+    pattern, tau = "GATCGGAAGAGC", 2
+    tile = 32768
+
+    def lines_to(total, final_newline):
+        """ragged lines whose bytes add up to exactly `total` (newlines included)"""
+        out, left = [], total
+        while left > 0:
+            n = min(rng.randint(0, 120), left - 1)
+            s = [rng.choice("ACGT") for _ in range(n)]
+            if n > 14 and rng.random() < 0.5:
+                at = rng.randrange(n - 12)
+                s[at:at + 12] = pattern
+            out.append("".join(s) + "\n")
+            left -= n + 1
+        buf = "".join(out)
+        assert len(buf) == total
+        return (buf if final_newline else buf[:-1] + "A").encode()
+
+    sizes = [tile - 1, tile, tile + 1, 2 * tile - 1, 2 * tile, 2 * tile + 1, 3 * tile + 511, 3 * tile + 512, 3 * tile + 513, 5 * tile]
+    for total in sizes:
+        for final_newline in (True, False):
+            buf = lines_to(total, final_newline)
+            for mo in (SQ_BEST, SQ_ALL):
+                st = scan(B, oracle, pattern, tau, buf, mo)
+                assert st.path & FUSED, (total, st.path)
+    # a newline exactly on the last byte of the first tile, the next line starting on the first byte of the second; a line
+    # of exactly 512 bytes (terminator included) that starts on the last byte of a tile: it ends on the last staged byte
+    body = lines_to(tile, True)
+    assert body[tile - 1:tile] == b"\n"
+    exact = ("A" * 200 + pattern + "C" * (511 - 200 - 12)).encode() + b"\n"          # 512 bytes with the newline
+    head = lines_to(tile - 1, True)
+    for buf in (body + lines_to(1000, True), head + exact + lines_to(3000, True), head + exact):
+        for mo in MATCH:
+            st = scan(B, oracle, pattern, tau, buf, mo)
+            assert st.path & FUSED, st.path
+
+
+def test_fused_path_against_the_compiled_reference(B, reference):
+    """The records of the CUDA path against the UNMODIFIED reference (oracle/_ref, compiled from /root/reference in the
+    build container and carried to the GPU box), not only against the oracle port: 60 000 reads, three modes."""
+    g = B.make_gen(seed=12, line_len=150, plant="TTGACAGCTAGCTCAGTCCT", plant_per_1024=200, max_edits=2, n_per_1024=3)
+    buf = B.gen_host(g, 60000)
+    for pattern, tau in (("TTGACAGCTAGCTCAGTCCT", 2), ("A[CG]TNNGATC", 1)):
+        sq = B.Seeq(pattern, tau)
+        for mo in MATCH:
+            st = B.StatsT()
+            recs = sq.batch(buf, mo, B.SQ_ANY, st)
+            exp, nl, nm = reference.buffer_scan(buf, pattern, tau, mo, cap=max(1024, 4 * 60000))
+            got = np.stack([recs["line"].astype(np.uint64) + 1, recs["start"], recs["end"], recs["dist"]], axis=1).astype(np.uint64)
+            assert st.path & FUSED
+            assert (st.nlines, st.nmatched) == (nl, nm)
+            assert np.array_equal(got, exp), (pattern, mo)
+        sq.close()
