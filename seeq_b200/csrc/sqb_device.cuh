@@ -53,6 +53,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
 
+// (A nanosleep back-off in this loop was tried: the retries are 15 % of K12's issued instructions, profiles/r4y, but they sit
+// in otherwise idle issue slots -- 0.632 -> 0.626 ms -- and under compute-sanitizer racecheck the sleeping waiters of
+// k2_forward_thread did not finish within 25 minutes, r5e.  try_wait already suspends the warp for a hardware time limit.)
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
    asm volatile(
@@ -61,7 +64,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
        "WAIT_%=:\n"
        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
        "@p bra DONE_%=;\n"
-       "nanosleep.u32 32;\n"          // (a bare retry loop took 15 % of K12's issued instructions, profiles/r4y)
        "bra WAIT_%=;\n"
        "DONE_%=:\n"
        "}\n" ::"r"(smem_addr(bar)),

@@ -20,7 +20,18 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k1_
 python tools/summarise_ncu.py $OUT/${TAG}_${WL}_full.ncu-rep $OUT/${TAG}_${WL} --launches $OUT/${TAG}_${WL}_launches.csv \
     --note "ncu --set full --clock-control none of one step of bench.py --workload $WL (tools/gpu_profile.sh $TAG)" > /dev/null 2>&1
 for k in k12_scan_pack k2_bitslice; do
-  ncu -i $OUT/${TAG}_${WL}_full.ncu-rep --page source --csv --kernel-name regex:$k 2>/dev/null | cut -d, -f1-12 | gzip > $OUT/${TAG}_${WL}_${k}_source.csv.gz
+  ncu -i $OUT/${TAG}_${WL}_full.ncu-rep --page source --csv --kernel-name regex:$k 2>/dev/null | python -c "
+import csv, sys
+keep = None
+w = csv.writer(sys.stdout)
+for r in csv.reader(sys.stdin):
+    if r and r[0] == 'Address':
+        want = ('Address', 'Source', '# Samples', 'Instructions Executed', 'Thread Instructions Executed', 'L1 Wavefronts Shared',
+                'stall_barrier', 'stall_long_sb', 'stall_short_sb', 'stall_math', 'stall_mio', 'stall_wait', 'stall_not_selected',
+                'stall_selected', 'stall_branch_resolving', 'stall_no_inst', 'stall_lg')
+        keep = [i for i, h in enumerate(r) if h in want]
+    w.writerow([r[i] for i in keep if i < len(r)] if keep and len(r) > 8 else r)
+" | gzip > $OUT/${TAG}_${WL}_${k}_source.csv.gz
 done
 SZ=$(du -sm $OUT | cut -f1)
 if [ "$SZ" -gt 55 ]; then rm -f $OUT/${TAG}_${WL}_full.ncu-rep; fi
