@@ -49,6 +49,7 @@
 // and the translate step of seeqStringMatch (libseeq.c:250-264).
 #pragma once
 
+#include "sqb_k12_arith.h"
 #include "sqb_k2_bitslice.cuh"
 
 namespace sqb {
@@ -76,17 +77,7 @@ constexpr uint32_t kFMaxOverlap = 4096;                 // bytes staged behind a
 
 // (GroupDesc: sqb_k2_bitslice.cuh)
 
-// byte -> {p0, p1, p2, newline} in the four bytes of a word (bit 0 of each)
-struct ClassTable32 {
-   uint32_t w[256];
-};
-static inline void build_class_table32(const ClassTable &ct, ClassTable32 *out)
-{
-   for (int b = 0; b < 256; b++) {
-      const uint32_t c = ct.code[b];
-      out->w[b] = (c & 1u) | (((c >> 1) & 1u) << 8) | (((c >> 2) & 1u) << 16) | (((c >> 3) & 1u) << 24);
-   }
-}
+// (ClassTable32, nl_flags, chunk_before, the plane assembly: sqb_k12_arith.h -- host-compilable, pinned on the CPU)
 
 struct K12Args {
    const uint8_t *text;
@@ -117,15 +108,6 @@ __host__ __device__ constexpr uint32_t k12_smem_bytes(uint32_t ov, bool filter)
 {
    return kFStages * k12_text_bytes(ov) + 1024u + (kFMaxEntries + 8u) * 2u + (kFMaxEntries + 32u) * 2u + (filter ? kFMaxEntries * 2u : 0u);
 }
-// plane units (uint4) of a group of `ncols` columns
-__host__ __device__ constexpr uint32_t k12_group_units(uint32_t ncols) { return ((ncols + 31u) >> 5) * 24u; }
-
-// Newline flags of four text bytes: bit 7 of every byte that is '\n' (exact: no carry crosses a byte).
-__device__ __forceinline__ uint32_t nl_flags(uint32_t w)
-{
-   const uint32_t t = ((w ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;     // bit 7: the low seven bits differ from '\n'
-   return ~(t | w) & 0x80808080u;                                         // ... and bit 7 of the byte itself is clear
-}
 
 // (not volatile: the class table is constant for the life of the kernel, the loads may be scheduled freely)
 __device__ __forceinline__ uint32_t lds_u32c(uint32_t addr)
@@ -143,16 +125,7 @@ __device__ __forceinline__ uint32_t mad_hi_u32(uint32_t a, uint32_t b, uint32_t 
    return d;
 }
 
-// The flags of a 32-byte chunk live in ONE word ("u-space"): the flag of byte b of text word k (0..7) sits at
-// bit u = 8 b + k -- the flags of word k shifted right by 7 - k, one multiply-add (high half) each.
-// Mask of the bytes in front of byte index v = 4 k + b (v = 0..32) in TEXT order:
-__device__ __forceinline__ uint32_t chunk_before(uint32_t v)
-{
-   if (v >= 32u) return ~0u;
-   const uint32_t k = v >> 2, b = v & 3u;
-   return (((1u << k) - 1u) * 0x01010101u) | ((0x01010101u << k) & ((1u << (8u * b)) - 1u));
-}
-
+// the flag word of a 32-byte chunk (u-space, sqb_k12_arith.h): one multiply-add (high half) per text word
 __device__ __forceinline__ uint32_t chunk_flags(const uint8_t *p)
 {
    const uint4 va = *reinterpret_cast<const uint4 *>(p);
@@ -254,7 +227,7 @@ __global__ void __launch_bounds__(kFThreads, SQB_K12_CTAS) k12_scan_pack(const K
          while (x) {
             const uint32_t u = (uint32_t)__ffs(x) - 1u;
             x &= x - 1u;
-            best = min(best, 4u * (u & 7u) + (u >> 3));
+            best = min(best, chunk_byte_of(u));
          }
          if (best < 32u) atomicMin(&s_ovnl, o + best);
       }
@@ -343,7 +316,7 @@ __global__ void __launch_bounds__(kFThreads, SQB_K12_CTAS) k12_scan_pack(const K
          while (x) {
             const uint32_t u = (uint32_t)__ffs(x) - 1u;
             x &= x - 1u;
-            const uint32_t v = 4u * (u & 7u) + (u >> 3);                       // byte index of the newline in its chunk
+            const uint32_t v = chunk_byte_of(u);                               // byte index of the newline in its chunk
             const uint32_t idx = base[i] + (several ? (uint32_t)__popc(c[i] & chunk_before(v)) : 0u);
             if (idx < kFMaxEntries) lst[idx] = (uint16_t)(o + v);
          }
@@ -548,13 +521,7 @@ __global__ void __launch_bounds__(kFThreads, SQB_K12_CTAS) k12_scan_pack(const K
             }
             // per column: the bytes p of the four octets make the word of plane p
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-               const uint32_t u0 = __byte_perm(A[j][0], A[j][1], 0x5140u), u1 = __byte_perm(A[j][2], A[j][3], 0x5140u);
-               const uint32_t u2 = __byte_perm(A[j][0], A[j][1], 0x7362u), u3 = __byte_perm(A[j][2], A[j][3], 0x7362u);
-               P[0][j] = __byte_perm(u0, u1, 0x5410u);
-               P[1][j] = __byte_perm(u0, u1, 0x7632u);
-               P[2][j] = __byte_perm(u2, u3, 0x5410u);
-            }
+            for (int j = 0; j < 4; j++) k12_planes_of_column(A[j], P[0][j], P[1][j], P[2][j]);
          }
          if (cb == 0u && cq == 0u) {
             // the columns in front of a line's first byte are NULL columns (111)
@@ -585,9 +552,8 @@ __global__ void __launch_bounds__(kFThreads, SQB_K12_CTAS) k12_scan_pack(const K
             const uint32_t e = lds_u32c(mad_u32((uint32_t)col[ls[r]], a.four, lut_addr));
             acc[r >> 3] = mad_u32(e, 1u << (r & 7), acc[r >> 3]);
          }
-         const uint32_t t0 = __byte_perm(acc[0], acc[1], 0x5140u), t1 = __byte_perm(acc[2], acc[3], 0x5140u);
-         const uint32_t t2 = __byte_perm(acc[0], acc[1], 0x7362u), t3 = __byte_perm(acc[2], acc[3], 0x7362u);
-         uint32_t P0 = __byte_perm(t0, t1, 0x5410u), P1 = __byte_perm(t0, t1, 0x7632u), P2 = __byte_perm(t2, t3, 0x5410u);
+         uint32_t P0, P1, P2;
+         k12_planes_of_column(acc, P0, P1, P2);
          if (cb == 0u && lane < 3) {
             const uint32_t m = s_glead[g][lane];
             P0 |= m;

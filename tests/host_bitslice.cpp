@@ -461,3 +461,74 @@ extern "C" int bs_parse_cpulist(const char *s, unsigned char *cpus, int maxcpus)
 {
    return sqb::parse_cpulist(s, cpus, maxcpus);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The arithmetic of the fused tokenise + pack kernel (seeq_b200/csrc/sqb_k12_arith.h) on the host
+// ---------------------------------------------------------------------------------------------------------------
+#include "sqb_k12_arith.h"
+
+extern "C" uint32_t k12_nl_flags(uint32_t w) { return sqb::nl_flags(w); }
+extern "C" uint32_t k12_chunk_before(uint32_t v) { return sqb::chunk_before(v); }
+extern "C" uint32_t k12_chunk_byte_of(uint32_t u) { return sqb::chunk_byte_of(u); }
+extern "C" uint32_t k12_chunk_flags(const unsigned char *p32)
+{
+   uint32_t w[8];
+   memcpy(w, p32, 32);
+   return sqb::chunk_flags_words(w);
+}
+extern "C" void k12_table32(int options, uint32_t *out256)
+{
+   sqb::ClassTable ct;
+   sqb::ClassTable32 t;
+   sqb::build_class_table(options, &ct);
+   sqb::build_class_table32(ct, &t);
+   memcpy(out256, t.w, sizeof t.w);
+}
+
+// One group of up to 32 lines the way k12_scan_pack builds its planes: every line is read from the aligned word at or
+// in front of its start (`text` must be 4-byte aligned and readable up to 35 + 32 bytes past the longest line), four
+// columns per "lane", one table look-up and one multiply-add per byte into the accumulator of its column and line octet,
+// PRMT assembly, lead (NULL) columns OR-ed in.  planes: [block of 32 columns][plane][32 columns].  Returns the columns.
+extern "C" uint32_t k12_host_group(const unsigned char *text, const uint32_t *starts, const uint32_t *lens, int nlines, int options,
+                                   uint32_t *planes, uint32_t planes_cap_words)
+{
+   sqb::ClassTable ct;
+   sqb::ClassTable32 t;
+   sqb::build_class_table(options, &ct);
+   sqb::build_class_table32(ct, &t);
+   uint32_t aligned[32], lead[32], ncols = 0, m1 = 0, m2 = 0, m3 = 0;
+   for (int r = 0; r < 32; r++) {
+      const int rr = r < nlines ? r : 0;                       // a slot without a line re-reads slot 0
+      aligned[r] = starts[rr] & ~3u;
+      lead[r] = r < nlines ? (starts[rr] & 3u) : 0u;
+      if (r < nlines) ncols = std::max(ncols, lens[r] + lead[r]);
+      if (lead[r] >= 1) m1 |= 1u << r;
+      if (lead[r] >= 2) m2 |= 1u << r;
+      if (lead[r] == 3) m3 |= 1u << r;
+   }
+   const uint32_t nblk = (ncols + 31u) >> 5;
+   if (nblk * 96u > planes_cap_words) return 0xffffffffu;
+   for (uint32_t cb = 0; cb < nblk; cb++)
+      for (uint32_t cq = 0; cq < 8; cq++) {                    // one lane of the kernel
+         uint32_t A[4][4], P[3][4];
+         for (int q = 0; q < 4; q++) {
+            for (int j = 0; j < 4; j++) A[j][q] = 0;
+            for (int i = 0; i < 8; i++) {
+               uint32_t w;
+               memcpy(&w, text + aligned[8 * q + i] + cb * 32u + cq * 4u, 4);
+               const uint32_t x[4] = {w & 0xffu, sqb::k12_prmt(w, 0u, 0x4441u), sqb::k12_prmt(w, 0u, 0x4442u), w >> 24};
+               for (int j = 0; j < 4; j++) A[j][q] = t.w[x[j]] * (1u << i) + A[j][q];
+            }
+         }
+         for (int j = 0; j < 4; j++) sqb::k12_planes_of_column(A[j], P[0][j], P[1][j], P[2][j]);
+         if (cb == 0 && cq == 0)
+            for (int p = 0; p < 3; p++) {
+               P[p][0] |= m1;
+               P[p][1] |= m2;
+               P[p][2] |= m3;
+            }
+         for (int p = 0; p < 3; p++)
+            for (int j = 0; j < 4; j++) planes[cb * 96u + (uint32_t)p * 32u + cq * 4u + (uint32_t)j] = P[p][j];
+      }
+   return ncols;
+}
