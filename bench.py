@@ -3,8 +3,9 @@
 
   python bench.py --gpus 1 --steps K --warmup W [--workload metric] [--reads R] [--impl reference]
 
-A *step* is one pass of the hot path (K1 line scan + class coding -> bit-plane pack -> K2 forward
-matcher -> K3 reverse pass / K4 ordered compaction) over one batch of synthetic reads.
+A *step* is one pass of the hot path (K12: line scan + class coding + bit-plane pack in one kernel -- or K1
+and the pack kernel for multi-part automata, cut lines and filtered scans -> K2 forward matcher -> K3
+reverse pass / K4 ordered compaction) over one batch of synthetic reads.
 
 Default workload = `metric`: BASELINE.json's metric is quoted on "d=2, 20-nt pattern": `seeq -b -l -p -k
 -d 2 <20-mer>` (best match + positions, the flags of configs[1]) over 10 M synthetic 150-nt reads, 1.51 GB
