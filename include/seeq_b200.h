@@ -152,6 +152,35 @@ void   sqbDeviceFree  (void * p);
 int    sqbMemcpyH2D (void * dst, const void * src, size_t nbytes);
 int    sqbMemcpyD2H (void * dst, const void * src, size_t nbytes);
 
+/* ---- BGZF (bgzip) input, inflated on the device -------------------------------------- */
+/* The reference reads plain text (seeq.c:201-256, getline at :361).  A BGZF file (bgzip: gzip members of at most
+ * 64 KiB of text, each with its compressed size in a "BC" extra sub-field) is indexed on the host without decoding,
+ * crosses the PCIe link COMPRESSED, is inflated by one warp per member (k0_inflate_bgzf) into one text buffer in
+ * HBM and scanned where it lies.  Plain gzip (no "BC" sub-field) is refused: it cannot be cut without decoding.
+ * CRC-32 is not checked; ISIZE, code validity and the bounds of every member are (sqbLastError names the member). */
+typedef struct {
+   uint64_t in_off;     /* first byte of the member's deflate stream in the buffer   */
+   uint32_t in_len;     /* bytes of deflate stream                                   */
+   uint32_t isize;      /* bytes of text (ISIZE)                                     */
+   uint64_t out_off;    /* offset of the member's text in the inflated buffer        */
+} sqb_bgzf_member_t;
+/* Host only: the members of gz[0..nbytes) that carry text (the empty end-of-file member is dropped) and the size
+ * of the inflated text.  members may be NULL (count only).  -1: not BGZF / truncated. */
+int sqbBgzfIndex (const void * gz, size_t nbytes, sqb_bgzf_member_t * members, uint64_t cap,
+                  uint64_t * count, uint64_t * text_bytes);
+/* Inflates `count` members of a DEVICE-resident compressed buffer (d_gz: readable 16 bytes past its end) into
+ * d_text; members is a HOST array.  Blocks until done; kernel_ms (may be NULL) = CUDA-event time of the kernel. */
+int sqbBgzfInflateDevice (int device, const void * d_gz, const sqb_bgzf_member_t * members, uint64_t count,
+                          void * d_text, void * stream, double * kernel_ms);
+/* sqbScanHost for a BGZF buffer in host memory (pinned is faster): compressed slices of $SEEQ_B200_BGZF_SLICE_MB
+ * (32) MiB go to the device, slice k is inflated while slice k+1 is on the link, then the text is scanned like
+ * sqbScanDeviceLarge does.  stats->nbytes counts TEXT bytes; records / line starts as after sqbScanHost.
+ * One device (that of the engine). */
+int sqbScanHostBgzf (sqb_engine_t * e, const void * gz, size_t nbytes, int options, sqb_stats_t * stats);
+/* the inflated text of the last sqbScanHostBgzf on the engine's device (valid until the next one there) */
+const void * sqbBgzfDeviceText (sqb_engine_t * e, uint64_t * nbytes);
+int sqbEngineDevice (sqb_engine_t * e);
+
 /* ---- seeq_t level batch entry (the batched analogue of seeqStringMatch) ---- */
 struct seeq_t;
 /* Matches every line of a host buffer against the pattern of `sq` in one GPU

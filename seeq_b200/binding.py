@@ -58,6 +58,10 @@ class StatsT(C.Structure):
 SQB_PATH_BITSLICE, SQB_PATH_FUSED, SQB_PATH_CUTS, SQB_PATH_FILTER = 1, 2, 4, 8
 
 
+class BgzfMemberT(C.Structure):
+    _fields_ = [("in_off", C.c_uint64), ("in_len", C.c_uint32), ("isize", C.c_uint32), ("out_off", C.c_uint64)]
+
+
 class GenT(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("line_len", C.c_uint32), ("plant_per_1024", C.c_uint32),
                 ("max_edits", C.c_uint32), ("n_per_1024", C.c_uint32), ("junk_per_1024", C.c_uint32),
@@ -119,6 +123,12 @@ SYMBOLS = {
     "seeqBatchMatch": (C.c_long, [_SEEQ, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                   C.POINTER(C.c_void_p), C.POINTER(StatsT)]),
     "seeqEngine": (C.c_void_p, [_SEEQ]),
+    "sqbBgzfIndex": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(BgzfMemberT), C.c_uint64, _u64p, _u64p]),
+    "sqbBgzfInflateDevice": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(BgzfMemberT), C.c_uint64, C.c_void_p,
+                                       C.c_void_p, C.POINTER(C.c_double)]),
+    "sqbScanHostBgzf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(StatsT)]),
+    "sqbBgzfDeviceText": (C.c_void_p, [C.c_void_p, _u64p]),
+    "sqbEngineDevice": (C.c_int, [C.c_void_p]),
     "sqbShardRange": (None, [C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                              C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "sqbGenBytes": (C.c_size_t, [C.POINTER(GenT), C.c_uint64, C.c_uint64]),
@@ -286,6 +296,26 @@ class Engine:
             raise RuntimeError("sqbScanHost failed: " + last_error())
         return st
 
+    def scan_host_bgzf(self, buf, options: int) -> StatsT:
+        """sqbScanHostBgzf: `buf` is a BGZF (bgzip) buffer; results as after scan_host of the inflated text."""
+        addr, n, keep = _ptr(buf)
+        return self.scan_host_bgzf_ptr(addr, n, options)
+
+    def scan_host_bgzf_ptr(self, addr: int, n: int, options: int) -> StatsT:
+        st = StatsT()
+        if self.L.sqbScanHostBgzf(self.e, addr, n, options, C.byref(st)):
+            raise RuntimeError("sqbScanHostBgzf failed: " + last_error())
+        return st
+
+    def bgzf_text(self) -> np.ndarray:
+        """the inflated text of the last scan_host_bgzf, copied back from the device"""
+        n = C.c_uint64(0)
+        p = self.L.sqbBgzfDeviceText(self.e, C.byref(n))
+        out = np.empty(n.value, dtype=np.uint8)
+        if n.value and self.L.sqbMemcpyD2H(out.ctypes.data, p, n.value):
+            raise RuntimeError("sqbMemcpyD2H failed: " + last_error())
+        return out
+
     def host_records(self) -> np.ndarray:
         n = C.c_uint64(0)
         p = self.L.sqbHostRecords(self.e, C.byref(n))
@@ -390,6 +420,43 @@ def gen_host(g: GenT, nreads: int, first: int = 0, out: np.ndarray | None = None
     assert out.size >= nbytes
     L.sqbGenHost(C.byref(g), first, nreads, out.ctypes.data)
     return out[:nbytes]
+
+
+def bgzf_index(buf):
+    """sqbBgzfIndex -> (array of BgzfMemberT, bytes of text); host only"""
+    addr, n, keep = _ptr(buf)
+    L = lib()
+    cnt, tb = C.c_uint64(0), C.c_uint64(0)
+    if L.sqbBgzfIndex(addr, n, None, 0, C.byref(cnt), C.byref(tb)):
+        raise ValueError("sqbBgzfIndex failed: " + last_error())
+    members = (BgzfMemberT * max(1, cnt.value))()
+    if L.sqbBgzfIndex(addr, n, members, cnt.value, C.byref(cnt), C.byref(tb)):
+        raise ValueError("sqbBgzfIndex failed: " + last_error())
+    return members, cnt.value, tb.value
+
+
+def bgzf_inflate_device(buf, device: int = 0):
+    """A BGZF buffer inflated on the device (H2D, sqbBgzfInflateDevice, D2H) -> (text as uint8 array, kernel ms)."""
+    addr, n, keep = _ptr(buf)
+    L = lib()
+    members, cnt, tb = bgzf_index(buf)
+    d_gz = L.sqbDeviceAlloc(n + 64)
+    d_text = L.sqbDeviceAlloc(tb + 64)
+    if not d_gz or not d_text:
+        raise RuntimeError("sqbDeviceAlloc failed: " + last_error())
+    try:
+        if n and L.sqbMemcpyH2D(d_gz, addr, n):
+            raise RuntimeError("sqbMemcpyH2D failed: " + last_error())
+        ms = C.c_double(0)
+        if L.sqbBgzfInflateDevice(device, d_gz, members, cnt, d_text, None, C.byref(ms)):
+            raise RuntimeError("sqbBgzfInflateDevice failed: " + last_error())
+        out = np.empty(tb, dtype=np.uint8)
+        if tb and L.sqbMemcpyD2H(out.ctypes.data, d_text, tb):
+            raise RuntimeError("sqbMemcpyD2H failed: " + last_error())
+        return out, ms.value
+    finally:
+        L.sqbDeviceFree(d_gz)
+        L.sqbDeviceFree(d_text)
 
 
 def shard_range(buf: np.ndarray, rank: int, world: int):

@@ -32,7 +32,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CU_UNITS = [("sqb_engine.cu", [], "sqb_engine.cu.o"),
             ("sqb_engine_wm.cu", ["-DSQB_WM_FUSED=0"], "sqb_engine_wm.cu.o"),
             ("sqb_engine_wm.cu", ["-DSQB_WM_FUSED=1"], "sqb_engine_wmf.cu.o"),
-            ("sqb_engine_bsf.cu", [], "sqb_engine_bsf.cu.o")]
+            ("sqb_engine_bsf.cu", [], "sqb_engine_bsf.cu.o"),
+            ("sqb_bgzf.cu", [], "sqb_bgzf.cu.o")]
 C_SOURCES = ["seeq_api.c", "seeq_file.c"]
 HEADERS = sorted(os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".h", ".cuh"))) + \
           [os.path.join(INC, h) for h in ("libseeq.h", "seeq.h", "seeq_b200.h")]

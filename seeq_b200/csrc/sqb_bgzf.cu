@@ -1,0 +1,518 @@
+// sqb_bgzf.cu -- BGZF (bgzip) read sets inflated on the device, in front of the scan.
+//
+// The reference opens plain text (seeq.c:201-256) and reads it line by line (seeq.c:361); a compressed read set
+// has to be inflated by another process first.  Here the COMPRESSED bytes cross the PCIe link (DNA text deflates to
+// 0.25-0.3 of its size), one warp per BGZF member inflates them into one HBM text buffer (k0_inflate_bgzf), and the
+// scan kernels (K12 / K1, matcher, finish) run over that buffer where it lies: sqbScanHostBgzf is sqbScanHost for
+// a .gz buffer.  Everything a lane computes is in sqb_inflate.h and is pinned on the CPU against zlib
+// (tests/test_inflate_host.py); this file adds the warp: shuffles, table entries 32 apart, warp-wide match copies.
+//
+// Only the public C-ABI of the engine is used from here (sqbScanDeviceLarge): the scan path does not change.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "seeq_b200.h"
+#include "sqb_inflate.h"
+
+using namespace sqb;
+
+extern "C" void sqb_set_error(const char *msg);          // sqb_engine.cu: the text behind sqbLastError()
+extern "C" int sqbEngineDevice(sqb_engine_t *e);
+
+namespace {
+
+constexpr uint32_t kFull = 0xffffffffu;
+
+// Two members per warp, one per half-warp.  Lanes 0 and 16 decode symbols (sqb_inflate.h: run_symbols) side by side:
+// with one decoding lane per warp the kernel is bound by the issue slots of the SM -- a warp instruction costs its
+// slot whatever the number of active lanes -- and two lanes that run the same loop share theirs.  Literals are stored
+// as they are decoded; matches are queued, 16 per member, and copied by the sixteen lanes of the half -- one lane per
+// short match, all sixteen on a long one, in as few rounds as their dependencies allow (match_ready).  The halves
+// also build their tables (entries 16 apart) and copy stored blocks.  The warp runs as ONE sequence of phases (block
+// header, tables, symbols, queue): every shuffle, vote and barrier is warp-wide, a half with nothing to do in a
+// phase sits it out.  Text bytes are written straight to HBM: the 126 MB L2 merges the byte stores of the ~4700
+// members in flight into full sectors before they reach DRAM.
+constexpr int kPairWarps = 4;                            // 8 members per CTA: 8 x 6 KB of tables and queue; 4 CTAs =
+                                                         // 32 members per SM
+constexpr uint32_t kPairQueue = 16;
+enum : uint32_t { ST_HEADER = 0, ST_SYMBOLS = 1, ST_DONE = 2 };
+
+__global__ void __launch_bounds__(kPairWarps * 32, 4)
+k0_inflate_bgzf_pair(const uint8_t *__restrict__ gz, const inf::Member *__restrict__ members, uint32_t first,
+                     uint32_t count, uint8_t *text, uint32_t *__restrict__ status,
+                     unsigned long long *__restrict__ first_error)
+{
+   __shared__ inf::Tables s_tables[2 * kPairWarps];
+   __shared__ inf::MatchQueue s_queue[2 * kPairWarps];
+   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+   const uint32_t hl = lane & 15u, hbase = lane & 16u;   // lane in the half, first lane of the half
+   const uint32_t slot = warp * 2u + (lane >> 4);
+   const uint32_t idx = (blockIdx.x * kPairWarps + warp) * 2u + (lane >> 4);
+   if ((blockIdx.x * kPairWarps + warp) * 2u >= count) return;       // the whole warp
+   const bool have = idx < count;                        // the upper half of the last warp may have no member
+   inf::Member mb;
+   mb.in_off = 0; mb.in_len = 0; mb.isize = 0; mb.out_off = 0;
+   if (have) mb = members[first + idx];
+   inf::Tables &t = s_tables[slot];
+   inf::MatchQueue &q = s_queue[slot];
+   uint8_t *out = text + mb.out_off;
+   const uint32_t oend = mb.isize;
+
+   inf::BitReader br;
+   br.init(gz + mb.in_off, mb.in_len);                  // every lane holds a reader; only the decoding lane's advances
+   uint32_t pos = 0, err = inf::OK, final_block = 0, type = 0;
+   uint32_t st = have ? ST_HEADER : ST_DONE;            // the same in all lanes of a half
+
+   while (__any_sync(kFull, st != ST_DONE)) {
+      // ---- block header: the decoding lane; stored blocks and tables: the half ----
+      const bool hdr = st == ST_HEADER;
+      if (__any_sync(kFull, hdr)) {
+         uint32_t len = 0;
+         unsigned long long src = 0;
+         if (hdr && hl == 0) {
+            err = inf::read_block_header(br, t, &type, &final_block);
+            if (err == inf::OK && type == 0) {           // stored: LEN, ~LEN, bytes
+               br.align_byte();
+               const bool over = br.refill();
+               len = br.take(16);
+               const uint32_t nlen = br.take(16);
+               const uint8_t *sp = br.byte_ptr();
+               if (over || len != (~nlen & 0xffffu)) err = inf::ERR_HEADER;
+               else if (sp + len > br.src_end()) err = inf::ERR_INPUT;
+               else if (len > oend - pos) err = inf::ERR_OUTPUT;
+               src = (unsigned long long)(uintptr_t)sp;
+               if (err == inf::OK) br.init(sp + len, (uint32_t)(br.src_end() - (sp + len)));
+            }
+         }
+         __syncwarp();                                   // counts and sorted symbols are the decoding lane's: publish
+         err = __shfl_sync(kFull, err, hbase);
+         type = __shfl_sync(kFull, type, hbase);
+         final_block = __shfl_sync(kFull, final_block, hbase);
+         len = __shfl_sync(kFull, len, hbase);
+         src = __shfl_sync(kFull, src, hbase);
+         if (hdr && err == inf::OK) {
+            if (type == 0) {
+               const uint8_t *sp = (const uint8_t *)(uintptr_t)src;
+               for (uint32_t j = hl; j < len; j += 16) out[pos + j] = sp[j];
+               pos += len;
+               st = final_block ? ST_DONE : ST_HEADER;
+            } else {
+               // the scratch arrays of the header alias t.lit: every lane has passed the barrier, nobody reads them
+               for (uint32_t e = hl; e < inf::kLitN; e += 16) t.lit[e] = inf::make_lit_entry(t.lcnt, t.lsym, e);
+               for (uint32_t e = hl; e < inf::kDistN; e += 16) t.dist[e] = inf::make_dist_entry(t.dcnt, t.dsym, e);
+               st = ST_SYMBOLS;
+            }
+         } else if (hdr) st = ST_DONE;
+         __syncwarp();                                   // tables and stored bytes: visible
+      }
+
+      // ---- symbols: the decoding lane until its queue is full or the block ends; the queue: the half ----
+      const bool sym = st == ST_SYMBOLS;
+      if (__any_sync(kFull, sym)) {
+         uint32_t nq = 0;
+         int r = inf::R_EOB;
+         if (sym && hl == 0) r = inf::run_symbols(br, t, out, pos, oend, q, kPairQueue, &nq);
+         __syncwarp();                                   // literal stores and queue entries: visible
+         r = __shfl_sync(kFull, r, hbase);
+         nq = __shfl_sync(kFull, nq, hbase);
+         pos = __shfl_sync(kFull, pos, hbase);
+         // resolve the queues (sqb_inflate.h: match_ready): lane i of a half owns match i of its member
+         uint32_t mp = 0, ml = 0, md = 0;
+         const bool owner = sym && hl < nq;
+         if (owner) { const inf::MatchQueue::Entry qe = q.e[hl]; mp = qe.pos; ml = qe.ld & 0xffffu; md = qe.ld >> 16; }
+         uint32_t pending = __ballot_sync(kFull, owner);
+         while (pending) {
+            const uint32_t hp = (pending >> hbase) & 0xffffu;
+            const uint32_t f = hp ? (uint32_t)__ffs((int)hp) - 1u + hbase : lane;
+            const uint32_t P = __shfl_sync(kFull, mp, f);
+            const bool ready = ((pending >> lane) & 1u) && (lane == f || inf::match_ready(mp, ml, md, P));
+            const bool mine = ready && inf::match_by_lane(ml, md);
+            const uint32_t rmask = __ballot_sync(kFull, ready);
+            uint32_t wide = __ballot_sync(kFull, ready && !mine);
+            if (mine) inf::copy_by_lane(out, mp, ml, md);
+            while (wide) {                               // long or self-overlapping: the half copies it
+               const uint32_t hw = (wide >> hbase) & 0xffffu;
+               const uint32_t i = hw ? (uint32_t)__ffs((int)hw) - 1u + hbase : lane;
+               const uint32_t bp = __shfl_sync(kFull, mp, i), bl = __shfl_sync(kFull, ml, i), bd = __shfl_sync(kFull, md, i);
+               if (hw) {
+                  if (bd >= bl) for (uint32_t j = hl; j < bl; j += 16) out[bp + j] = out[bp - bd + j];
+                  else for (uint32_t j = hl; j < bl; j += 16) out[bp + j] = out[inf::match_src(bp, bd, j)];
+               }
+               const uint32_t lo = wide & 0xffffu, hi = wide & 0xffff0000u;
+               wide = (lo & (lo - 1u)) | (hi & (hi - 1u));          // the lowest bit of either half is done
+            }
+            pending &= ~rmask;
+            __syncwarp();                                // this round's text is final for the next round
+         }
+         if (sym) {
+            if (r >= inf::R_ERR) { err = (uint32_t)(r - inf::R_ERR); st = ST_DONE; }
+            else if (r == inf::R_EOB) st = final_block ? ST_DONE : ST_HEADER;
+         }
+      }
+   }
+
+   if (have && hl == 0) {
+      if (err == inf::OK && br.overrun() > 0) err = inf::ERR_INPUT;
+      if (err == inf::OK && pos != oend) err = inf::ERR_SHORT;
+      status[first + idx] = err;
+      if (err != inf::OK) atomicMin(first_error, ((unsigned long long)(first + idx) << 8) | err);
+   }
+}
+
+// One member per warp: lane 0 decodes, the warp resolves queues of 32 matches.  The first form of the kernel, kept
+// as the plain statement of the scheme and for A/B runs (SEEQ_B200_BGZF_KERNEL=single); tests run both.
+constexpr int kWarps = 8;                                // members per CTA; 4 CTAs = 32 members per SM
+
+__global__ void __launch_bounds__(kWarps * 32, 4)
+k0_inflate_bgzf(const uint8_t *__restrict__ gz, const inf::Member *__restrict__ members, uint32_t first,
+                uint32_t count, uint8_t *text, uint32_t *__restrict__ status,
+                unsigned long long *__restrict__ first_error)
+{
+   __shared__ inf::Tables s_tables[kWarps];
+   __shared__ inf::MatchQueue s_queue[kWarps];
+   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+   const uint32_t idx = blockIdx.x * kWarps + warp;
+   if (idx >= count) return;
+   const inf::Member mb = members[first + idx];
+   inf::Tables &t = s_tables[warp];
+   inf::MatchQueue &q = s_queue[warp];
+   uint8_t *out = text + mb.out_off;
+   const uint32_t oend = mb.isize;
+
+   inf::BitReader br;
+   br.init(gz + mb.in_off, mb.in_len);                  // every lane holds a reader; only lane 0's advances
+   uint32_t pos = 0, err = inf::OK, final_block = 0;
+
+   while (!final_block && err == inf::OK) {
+      uint32_t type = 0;
+      if (lane == 0) err = inf::read_block_header(br, t, &type, &final_block);
+      err = __shfl_sync(kFull, err, 0);
+      type = __shfl_sync(kFull, type, 0);
+      final_block = __shfl_sync(kFull, final_block, 0);
+      if (err != inf::OK) break;
+
+      if (type == 0) {                                   // stored: LEN, ~LEN, bytes
+         uint32_t len = 0;
+         unsigned long long src = 0;
+         if (lane == 0) {
+            br.align_byte();
+            const bool over = br.refill();
+            len = br.take(16);
+            const uint32_t nlen = br.take(16);
+            const uint8_t *sp = br.byte_ptr();
+            if (over || len != (~nlen & 0xffffu)) err = inf::ERR_HEADER;
+            else if (sp + len > br.src_end()) err = inf::ERR_INPUT;
+            else if (len > oend - pos) err = inf::ERR_OUTPUT;
+            src = (unsigned long long)(uintptr_t)sp;
+         }
+         err = __shfl_sync(kFull, err, 0);
+         if (err != inf::OK) break;
+         len = __shfl_sync(kFull, len, 0);
+         src = __shfl_sync(kFull, src, 0);
+         const uint8_t *sp = (const uint8_t *)(uintptr_t)src;
+         for (uint32_t j = lane; j < len; j += 32) out[pos + j] = sp[j];
+         pos += len;
+         if (lane == 0) br.init(sp + len, (uint32_t)(br.src_end() - (sp + len)));
+         __syncwarp();
+         continue;
+      }
+
+      __syncwarp();                                      // counts and sorted symbols are lane 0's: publish
+      // the scratch arrays alias t.lit: every lane has passed the barrier, nobody reads them any more
+      for (uint32_t e = lane; e < inf::kLitN; e += 32) t.lit[e] = inf::make_lit_entry(t.lcnt, t.lsym, e);
+      for (uint32_t e = lane; e < inf::kDistN; e += 32) t.dist[e] = inf::make_dist_entry(t.dcnt, t.dsym, e);
+      __syncwarp();
+
+      for (;;) {
+         uint32_t nq = 0;
+         int r = inf::R_EOB;
+         if (lane == 0) r = inf::run_symbols(br, t, out, pos, oend, q, inf::kQueue, &nq);
+         r = __shfl_sync(kFull, r, 0);
+         nq = __shfl_sync(kFull, nq, 0);
+         __syncwarp();                                   // lane 0's literal stores and queue entries: visible
+         // resolve the queue (sqb_inflate.h: match_ready): lane i owns match i
+         uint32_t mp = 0, ml = 0, md = 0;
+         if (lane < nq) { const inf::MatchQueue::Entry qe = q.e[lane]; mp = qe.pos; ml = qe.ld & 0xffffu; md = qe.ld >> 16; }
+         uint32_t pending = __ballot_sync(kFull, lane < nq);
+         while (pending) {
+            const int f = __ffs((int)pending) - 1;
+            const uint32_t P = __shfl_sync(kFull, mp, f);
+            const bool ready = ((pending >> lane) & 1u) && ((int)lane == f || inf::match_ready(mp, ml, md, P));
+            const bool mine = ready && inf::match_by_lane(ml, md);
+            const uint32_t rmask = __ballot_sync(kFull, ready);
+            uint32_t wide = __ballot_sync(kFull, ready && !mine);
+            if (mine) inf::copy_by_lane(out, mp, ml, md);
+            while (wide) {                               // long or self-overlapping: the warp copies it
+               const int i = __ffs((int)wide) - 1;
+               wide &= wide - 1u;
+               const uint32_t bp = __shfl_sync(kFull, mp, i), bl = __shfl_sync(kFull, ml, i), bd = __shfl_sync(kFull, md, i);
+               if (bd >= bl) for (uint32_t j = lane; j < bl; j += 32) out[bp + j] = out[bp - bd + j];
+               else for (uint32_t j = lane; j < bl; j += 32) out[bp + j] = out[inf::match_src(bp, bd, j)];
+            }
+            pending &= ~rmask;
+            __syncwarp();                                // this round's text is final for the next round
+         }
+         if (r >= inf::R_ERR) err = (uint32_t)(r - inf::R_ERR);
+         if (r != inf::R_FULL) break;
+      }
+      if (err != inf::OK) break;
+      pos = __shfl_sync(kFull, pos, 0);
+      __syncwarp();                                      // the tables are rewritten by the next header
+   }
+
+   if (lane == 0) {
+      if (err == inf::OK && br.overrun() > 0) err = inf::ERR_INPUT;
+      if (err == inf::OK && pos != oend) err = inf::ERR_SHORT;
+      status[first + idx] = err;
+      if (err != inf::OK) atomicMin(first_error, ((unsigned long long)(first + idx) << 8) | err);
+   }
+}
+
+// ---- per-device state: the compressed bytes, the text and the member list in HBM ----------------------------------
+struct BgzfState {
+   std::mutex mu;
+   uint8_t *d_gz = nullptr;        size_t gz_cap = 0;
+   uint8_t *d_text = nullptr;      size_t text_cap = 0;
+   inf::Member *d_members = nullptr; size_t members_cap = 0;
+   uint32_t *d_status = nullptr;   size_t status_cap = 0;
+   unsigned long long *d_first = nullptr, *h_first = nullptr;
+   cudaStream_t copy = nullptr, work = nullptr;
+   std::vector<cudaEvent_t> ev;
+   cudaEvent_t t0 = nullptr, t1 = nullptr;
+   uint64_t text_bytes = 0;        // of the last sqbScanHostBgzf
+   bool ready = false;
+};
+BgzfState g_state[64];
+
+void fail(const char *fmt, ...)
+{
+   char buf[480];
+   va_list ap;
+   va_start(ap, fmt);
+   vsnprintf(buf, sizeof buf, fmt, ap);
+   va_end(ap);
+   sqb_set_error(buf);
+}
+
+#define CUB(call)                                                                                             \
+   do {                                                                                                       \
+      cudaError_t e_ = (call);                                                                                \
+      if (e_ != cudaSuccess) {                                                                                \
+         fail("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call);              \
+         return -1;                                                                                           \
+      }                                                                                                       \
+   } while (0)
+
+template <class T> int grow(T **p, size_t *cap, size_t need)
+{
+   if (*cap >= need) return 0;
+   if (*p) cudaFree(*p);
+   *p = nullptr;
+   *cap = 0;
+   const size_t want = need + need / 8 + 256;
+   CUB(cudaMalloc((void **)p, want * sizeof(T)));
+   *cap = want;
+   return 0;
+}
+
+int state_init(BgzfState &s)
+{
+   if (s.ready) return 0;
+   CUB(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
+   CUB(cudaStreamCreateWithFlags(&s.work, cudaStreamNonBlocking));
+   CUB(cudaMalloc((void **)&s.d_first, sizeof(unsigned long long)));
+   CUB(cudaMallocHost((void **)&s.h_first, sizeof(unsigned long long)));
+   CUB(cudaEventCreate(&s.t0));
+   CUB(cudaEventCreate(&s.t1));
+   s.ready = true;
+   return 0;
+}
+
+const char *err_text(uint32_t code)
+{
+   switch (code) {
+   case inf::ERR_INPUT: return "the deflate stream runs past the member's data";
+   case inf::ERR_OUTPUT: return "more text than ISIZE announces";
+   case inf::ERR_CODE: return "invalid code";
+   case inf::ERR_DIST: return "distance reaches in front of the member";
+   case inf::ERR_HEADER: return "invalid block header";
+   case inf::ERR_SHORT: return "less text than ISIZE announces";
+   }
+   return "?";
+}
+
+// members [first, first + count) on stream st
+void launch_inflate(BgzfState &s, const uint8_t *d_gz, uint32_t first, uint32_t count, uint8_t *d_text, cudaStream_t st)
+{
+   if (count == 0) return;
+   const char *env = getenv("SEEQ_B200_BGZF_KERNEL");
+   if (env && strcmp(env, "single") == 0) {
+      const uint32_t grid = (count + kWarps - 1) / kWarps;
+      k0_inflate_bgzf<<<grid, kWarps * 32, 0, st>>>(d_gz, s.d_members, first, count, d_text, s.d_status, s.d_first);
+   } else {
+      const uint32_t per = 2 * kPairWarps;
+      const uint32_t grid = (count + per - 1) / per;
+      k0_inflate_bgzf_pair<<<grid, kPairWarps * 32, 0, st>>>(d_gz, s.d_members, first, count, d_text, s.d_status, s.d_first);
+   }
+}
+
+int index_members(const uint8_t *gz, size_t nbytes, std::vector<inf::Member> &out, uint64_t *text_bytes)
+{
+   uint64_t off = 0, o = 0;
+   out.clear();
+   while (off < nbytes) {
+      inf::Member m;
+      const uint64_t next = inf::parse_member(gz, nbytes, off, &m);
+      if (next == 0) {
+         fail("not a BGZF member at byte %llu of %llu (plain gzip has no block index: recompress with bgzip)",
+              (unsigned long long)off, (unsigned long long)nbytes);
+         return -1;
+      }
+      if (m.isize > 65536u) { fail("BGZF member at byte %llu announces %u bytes of text (> 64 KiB)", (unsigned long long)off, m.isize); return -1; }
+      m.out_off = o;
+      if (m.isize) out.push_back(m);                   // the empty end-of-file member carries nothing
+      o += m.isize;
+      off = next;
+   }
+   *text_bytes = o;
+   return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sqbBgzfIndex(const void *gz, size_t nbytes, sqb_bgzf_member_t *members, uint64_t cap, uint64_t *count,
+                 uint64_t *text_bytes)
+{
+   static_assert(sizeof(sqb_bgzf_member_t) == sizeof(inf::Member), "member layout");
+   std::vector<inf::Member> v;
+   uint64_t tb = 0;
+   if (gz == NULL && nbytes) { fail("sqbBgzfIndex: no buffer"); return -1; }
+   if (index_members((const uint8_t *)gz, nbytes, v, &tb)) return -1;
+   if (count) *count = v.size();
+   if (text_bytes) *text_bytes = tb;
+   if (members) {
+      if (cap < v.size()) { fail("sqbBgzfIndex: room for %llu members, %llu found", (unsigned long long)cap, (unsigned long long)v.size()); return -1; }
+      if (!v.empty()) memcpy(members, v.data(), v.size() * sizeof(inf::Member));
+   }
+   return 0;
+}
+
+int sqbBgzfInflateDevice(int device, const void *d_gz, const sqb_bgzf_member_t *members, uint64_t count,
+                         void *d_text, void *stream, double *kernel_ms)
+{
+   if (device < 0 || device >= 64) { fail("sqbBgzfInflateDevice: device %d", device); return -1; }
+   if (count > 0xffffffffull) { fail("sqbBgzfInflateDevice: too many members"); return -1; }
+   if (count == 0) { if (kernel_ms) *kernel_ms = 0; return 0; }
+   if (d_gz == NULL || members == NULL || d_text == NULL) { fail("sqbBgzfInflateDevice: invalid arguments"); return -1; }
+   CUB(cudaSetDevice(device));
+   BgzfState &s = g_state[device];
+   std::lock_guard<std::mutex> lock(s.mu);
+   if (state_init(s)) return -1;
+   cudaStream_t st = stream ? (cudaStream_t)stream : s.work;
+   if (grow(&s.d_members, &s.members_cap, (size_t)count)) return -1;
+   if (grow(&s.d_status, &s.status_cap, (size_t)count)) return -1;
+   *s.h_first = ~0ull;
+   CUB(cudaMemcpyAsync(s.d_first, s.h_first, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+   CUB(cudaMemcpyAsync(s.d_members, members, (size_t)count * sizeof(inf::Member), cudaMemcpyHostToDevice, st));
+   CUB(cudaEventRecord(s.t0, st));
+   launch_inflate(s, (const uint8_t *)d_gz, 0, (uint32_t)count, (uint8_t *)d_text, st);
+   CUB(cudaGetLastError());
+   CUB(cudaEventRecord(s.t1, st));
+   CUB(cudaMemcpyAsync(s.h_first, s.d_first, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+   CUB(cudaStreamSynchronize(st));
+   if (kernel_ms) {
+      float ms = 0;
+      CUB(cudaEventElapsedTime(&ms, s.t0, s.t1));
+      *kernel_ms = ms;
+   }
+   if (*s.h_first != ~0ull) {
+      const unsigned long long w = *s.h_first;
+      fail("BGZF member %llu (text offset %llu): %s", w >> 8, (unsigned long long)members[w >> 8].out_off, err_text((uint32_t)(w & 0xff)));
+      return -1;
+   }
+   return 0;
+}
+
+// sqbScanHost for a BGZF buffer: the compressed bytes go to the device in slices, the members of slice k are
+// inflated while slice k+1 is on the link, the scan runs over the inflated text in HBM.
+int sqbScanHostBgzf(sqb_engine_t *e, const void *gz, size_t nbytes, int options, sqb_stats_t *stats)
+{
+   if (e == NULL || (gz == NULL && nbytes)) { fail("sqbScanHostBgzf: invalid arguments"); return -1; }
+   const int device = sqbEngineDevice(e);
+   if (device < 0 || device >= 64) { fail("sqbScanHostBgzf: device %d", device); return -1; }
+   std::vector<inf::Member> mem;
+   uint64_t text_bytes = 0;
+   if (index_members((const uint8_t *)gz, nbytes, mem, &text_bytes)) return -1;
+   if (mem.size() > 0xffffffffull) { fail("sqbScanHostBgzf: too many members"); return -1; }
+   CUB(cudaSetDevice(device));
+   BgzfState &s = g_state[device];
+   std::lock_guard<std::mutex> lock(s.mu);
+   if (state_init(s)) return -1;
+   if (grow(&s.d_gz, &s.gz_cap, nbytes + 64)) return -1;
+   if (grow(&s.d_text, &s.text_cap, (size_t)text_bytes + 64)) return -1;
+   if (grow(&s.d_members, &s.members_cap, mem.size() + 1)) return -1;
+   if (grow(&s.d_status, &s.status_cap, mem.size() + 1)) return -1;
+
+   const char *env = getenv("SEEQ_B200_BGZF_SLICE_MB");
+   const long mb = env ? atol(env) : 32;
+   const size_t slice_bytes = (size_t)(mb > 0 ? mb : 32) << 20;
+   *s.h_first = ~0ull;
+   CUB(cudaMemcpyAsync(s.d_first, s.h_first, sizeof(unsigned long long), cudaMemcpyHostToDevice, s.work));
+   if (!mem.empty())
+      CUB(cudaMemcpyAsync(s.d_members, mem.data(), mem.size() * sizeof(inf::Member), cudaMemcpyHostToDevice, s.work));
+   // slices end where a member ends (the bytes between two members -- headers, trailers -- travel with them)
+   size_t m0 = 0, b0 = 0, k = 0;
+   while (m0 < mem.size()) {
+      size_t m1 = m0;
+      size_t b1 = b0;
+      while (m1 < mem.size() && (b1 - b0 < slice_bytes || m1 == m0)) {
+         b1 = (size_t)(mem[m1].in_off + mem[m1].in_len + 8);
+         m1++;
+      }
+      if (m1 == mem.size()) b1 = nbytes;
+      if (k >= s.ev.size()) {
+         cudaEvent_t ev;
+         CUB(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+         s.ev.push_back(ev);
+      }
+      CUB(cudaMemcpyAsync(s.d_gz + b0, (const uint8_t *)gz + b0, b1 - b0, cudaMemcpyHostToDevice, s.copy));
+      CUB(cudaEventRecord(s.ev[k], s.copy));
+      CUB(cudaStreamWaitEvent(s.work, s.ev[k], 0));
+      launch_inflate(s, s.d_gz, (uint32_t)m0, (uint32_t)(m1 - m0), s.d_text, s.work);
+      CUB(cudaGetLastError());
+      m0 = m1;
+      b0 = b1;
+      k++;
+   }
+   CUB(cudaMemcpyAsync(s.h_first, s.d_first, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.work));
+   CUB(cudaStreamSynchronize(s.work));
+   if (*s.h_first != ~0ull) {
+      const unsigned long long w = *s.h_first;
+      fail("BGZF member %llu (text offset %llu): %s", w >> 8, (unsigned long long)mem[w >> 8].out_off, err_text((uint32_t)(w & 0xff)));
+      return -1;
+   }
+   s.text_bytes = text_bytes;
+   const int rc = sqbScanDeviceLarge(e, s.d_text, (size_t)text_bytes, options, NULL, stats);
+   if (rc == 0 && stats) stats->launches += (uint32_t)k;
+   return rc;
+}
+
+// the inflated text of the last sqbScanHostBgzf on the engine's device (valid until the next BGZF call there)
+const void *sqbBgzfDeviceText(sqb_engine_t *e, uint64_t *nbytes)
+{
+   const int device = sqbEngineDevice(e);
+   if (device < 0 || device >= 64) return NULL;
+   if (nbytes) *nbytes = g_state[device].text_bytes;
+   return g_state[device].d_text;
+}
+
+}  // extern "C"

@@ -990,6 +990,8 @@ static __global__ void k_find_newline(const uint8_t *text, unsigned long long lo
 extern "C" {
 
 const char *sqbLastError(void) { return g_err; }
+void sqb_set_error(const char *msg) { set_err("%s", msg); }      // for the other translation units (sqb_bgzf.cu)
+int sqbEngineDevice(sqb_engine_t *e) { return e ? e->device : -1; }
 
 int sqbDeviceCount(void)
 {

@@ -1,0 +1,18 @@
+#!/bin/bash
+# tools/gpu_bgzf.sh TAG -- run on the GPU box (under gpurun): the BGZF tests, the BGZF bench line, one ncu capture of
+# the inflate kernel.  Outputs land in gpurun_out/.
+TAG=${1:-r6a}
+OUT=gpurun_out
+mkdir -p $OUT
+timeout 150 python -m pytest tests/test_gpu_bgzf.py -q -p no:cacheprovider > $OUT/${TAG}_pytest_bgzf.log 2>&1
+echo "pytest rc=$?"; tail -3 $OUT/${TAG}_pytest_bgzf.log
+timeout 120 python tools/bgzf_bench.py --out $OUT/${TAG}_bgzf.json > $OUT/${TAG}_bgzf.log 2>&1
+echo "bench rc=$?"; tail -c 1500 $OUT/${TAG}_bgzf.log
+if [ "$2" != "noncu" ]; then
+timeout 120 ncu --set full --clock-control none --import-source on -k regex:k0_inflate -c 1 -f -o $OUT/${TAG}_bgzf_full \
+    python tools/bgzf_bench.py --mb 32 --copies 4 --inflate-only > $OUT/${TAG}_bgzf_ncu.log 2>&1
+echo "ncu rc=$?"
+ncu -i $OUT/${TAG}_bgzf_full.ncu-rep --page raw --csv > $OUT/${TAG}_bgzf_raw.csv 2>/dev/null
+ncu -i $OUT/${TAG}_bgzf_full.ncu-rep --page source --csv 2>/dev/null | gzip > $OUT/${TAG}_bgzf_source.csv.gz
+ls -la $OUT | grep ${TAG}
+fi
