@@ -39,12 +39,13 @@ constexpr uint32_t kFull = 0xffffffffu;
 // header, tables, symbols, queue): every shuffle, vote and barrier is warp-wide, a half with nothing to do in a
 // phase sits it out.  Text bytes are written straight to HBM: the 126 MB L2 merges the byte stores of the ~4700
 // members in flight into full sectors before they reach DRAM.
-constexpr int kPairWarps = 4;                            // 8 members per CTA: 8 x 6 KB of tables and queue; 4 CTAs =
-                                                         // 32 members per SM
+constexpr int kPairWarps = 4;                            // 8 members per CTA: 8 x 3.9 KB of tables and queue, 72 registers:
+constexpr int kPairCtas = 7;                             // 7 CTAs = 56 members per SM (the kernel is bound by the latency
+                                                         // of the decoding lanes' chains: the more of them, the better)
 constexpr uint32_t kPairQueue = 16;
 enum : uint32_t { ST_HEADER = 0, ST_SYMBOLS = 1, ST_DONE = 2 };
 
-__global__ void __launch_bounds__(kPairWarps * 32, 4)
+__global__ void __launch_bounds__(kPairWarps * 32, kPairCtas)
 k0_inflate_bgzf_pair(const uint8_t *__restrict__ gz, const inf::Member *__restrict__ members, uint32_t first,
                      uint32_t count, uint8_t *text, uint32_t *__restrict__ status,
                      unsigned long long *__restrict__ first_error)
@@ -276,6 +277,7 @@ k0_inflate_bgzf(const uint8_t *__restrict__ gz, const inf::Member *__restrict__ 
 }
 
 // ---- per-device state: the compressed bytes, the text and the member list in HBM ----------------------------------
+constexpr int kLanes = 4;
 struct BgzfState {
    std::mutex mu;
    uint8_t *d_gz = nullptr;        size_t gz_cap = 0;
@@ -284,8 +286,10 @@ struct BgzfState {
    uint32_t *d_status = nullptr;   size_t status_cap = 0;
    unsigned long long *d_first = nullptr, *h_first = nullptr;
    cudaStream_t copy = nullptr, work = nullptr;
+   cudaStream_t lanes[kLanes] = {};                     // the slices of one buffer are inflated side by side
+   cudaEvent_t lane_done[kLanes] = {};
    std::vector<cudaEvent_t> ev;
-   cudaEvent_t t0 = nullptr, t1 = nullptr;
+   cudaEvent_t t0 = nullptr, t1 = nullptr, begin = nullptr;
    uint64_t text_bytes = 0;        // of the last sqbScanHostBgzf
    bool ready = false;
 };
@@ -331,6 +335,11 @@ int state_init(BgzfState &s)
    CUB(cudaMallocHost((void **)&s.h_first, sizeof(unsigned long long)));
    CUB(cudaEventCreate(&s.t0));
    CUB(cudaEventCreate(&s.t1));
+   CUB(cudaEventCreateWithFlags(&s.begin, cudaEventDisableTiming));
+   for (int i = 0; i < kLanes; i++) {
+      CUB(cudaStreamCreateWithFlags(&s.lanes[i], cudaStreamNonBlocking));
+      CUB(cudaEventCreateWithFlags(&s.lane_done[i], cudaEventDisableTiming));
+   }
    s.ready = true;
    return 0;
 }
@@ -352,6 +361,9 @@ const char *err_text(uint32_t code)
 void launch_inflate(BgzfState &s, const uint8_t *d_gz, uint32_t first, uint32_t count, uint8_t *d_text, cudaStream_t st)
 {
    if (count == 0) return;
+   // 7 CTAs of 32.5 KB need the whole shared-memory carve-out of the SM (per device and kernel; a hint, cheap)
+   cudaFuncSetAttribute(k0_inflate_bgzf_pair, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+   cudaFuncSetAttribute(k0_inflate_bgzf, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
    const char *env = getenv("SEEQ_B200_BGZF_KERNEL");
    if (env && strcmp(env, "single") == 0) {
       const uint32_t grid = (count + kWarps - 1) / kWarps;
@@ -463,13 +475,17 @@ int sqbScanHostBgzf(sqb_engine_t *e, const void *gz, size_t nbytes, int options,
    if (grow(&s.d_status, &s.status_cap, mem.size() + 1)) return -1;
 
    const char *env = getenv("SEEQ_B200_BGZF_SLICE_MB");
-   const long mb = env ? atol(env) : 32;
-   const size_t slice_bytes = (size_t)(mb > 0 ? mb : 32) << 20;
+   const long mb = env ? atol(env) : 16;
+   const size_t slice_bytes = (size_t)(mb > 0 ? mb : 16) << 20;
    *s.h_first = ~0ull;
    CUB(cudaMemcpyAsync(s.d_first, s.h_first, sizeof(unsigned long long), cudaMemcpyHostToDevice, s.work));
    if (!mem.empty())
       CUB(cudaMemcpyAsync(s.d_members, mem.data(), mem.size() * sizeof(inf::Member), cudaMemcpyHostToDevice, s.work));
-   // slices end where a member ends (the bytes between two members -- headers, trailers -- travel with them)
+   CUB(cudaEventRecord(s.begin, s.work));
+   for (int i = 0; i < kLanes; i++) CUB(cudaStreamWaitEvent(s.lanes[i], s.begin, 0));
+   // slices end where a member ends (the bytes between two members -- headers, trailers -- travel with them); slice k
+   // is inflated on stream k mod 4: a slice alone does not fill the device (one CTA per 8 members), and a slice
+   // that has arrived need not wait for the one in front of it
    size_t m0 = 0, b0 = 0, k = 0;
    while (m0 < mem.size()) {
       size_t m1 = m0;
@@ -486,12 +502,16 @@ int sqbScanHostBgzf(sqb_engine_t *e, const void *gz, size_t nbytes, int options,
       }
       CUB(cudaMemcpyAsync(s.d_gz + b0, (const uint8_t *)gz + b0, b1 - b0, cudaMemcpyHostToDevice, s.copy));
       CUB(cudaEventRecord(s.ev[k], s.copy));
-      CUB(cudaStreamWaitEvent(s.work, s.ev[k], 0));
-      launch_inflate(s, s.d_gz, (uint32_t)m0, (uint32_t)(m1 - m0), s.d_text, s.work);
+      CUB(cudaStreamWaitEvent(s.lanes[k % kLanes], s.ev[k], 0));
+      launch_inflate(s, s.d_gz, (uint32_t)m0, (uint32_t)(m1 - m0), s.d_text, s.lanes[k % kLanes]);
       CUB(cudaGetLastError());
       m0 = m1;
       b0 = b1;
       k++;
+   }
+   for (int i = 0; i < kLanes; i++) {
+      CUB(cudaEventRecord(s.lane_done[i], s.lanes[i]));
+      CUB(cudaStreamWaitEvent(s.work, s.lane_done[i], 0));
    }
    CUB(cudaMemcpyAsync(s.h_first, s.d_first, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.work));
    CUB(cudaStreamSynchronize(s.work));

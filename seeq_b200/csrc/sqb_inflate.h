@@ -35,10 +35,39 @@
 #endif
 #define SQB_INF_RARE(x) __builtin_expect(!!(x), 0)
 
+// Table look-ups and queue entries of the symbol loop.  On the device they go through 32-bit shared-memory addresses
+// taken once in front of the loop: a generic pointer to shared memory is rebuilt from the CTA's shared window when
+// registers are short (an S2R in the loop).
+#ifdef __CUDA_ARCH__
+namespace sqb { namespace inf {
+__device__ __forceinline__ uint32_t smem_addr(const void *p)
+{
+   uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+   asm volatile("" : "+r"(a));                // opaque: kept in a register, not recomputed in the loop
+   return a;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+   uint32_t v;
+   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+   return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y)
+{
+   asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+} }
+#endif
+
+#ifndef SQB_INF_TB
+#define SQB_INF_TB 9       /* 512 entries: 2 KiB.  Measured on the CPU (tests/host_inflate.cpp counts the symbols that leave
+                              the fast path): 1.5 % of the symbols of deflated DNA and FASTQ text with 9 bits as with 10 */
+#endif
+
 namespace sqb {
 namespace inf {
 
-constexpr int TB = 10;                       // index bits of the literal/length table
+constexpr int TB = SQB_INF_TB;                      // index bits of the literal/length table
 constexpr int TBD = 8;                       // index bits of the distance table
 constexpr uint32_t kLitN = 1u << TB;
 constexpr uint32_t kDistN = 1u << TBD;
@@ -83,6 +112,8 @@ struct Scratch {                             // aliases Tables::lit
    uint16_t clsym[20];
    uint16_t offs[16];
 };
+
+static_assert(sizeof(Scratch) <= sizeof(Tables::lit), "the header's scratch arrays alias the literal/length table");
 
 // ---- bit reader: LSB-first, 64-bit window, aligned 32-bit loads, the next word already on its way ---------------
 struct BitReader {
@@ -312,15 +343,25 @@ SQB_INF_HD int run_symbols(BitReader &br, const Tables &t, uint8_t *out, uint32_
 {
    uint32_t n = 0, pos = pos_io;
    int ret;
+#ifdef __CUDA_ARCH__
+   const uint32_t s_lit = smem_addr(t.lit), s_dist = smem_addr(t.dist), s_q = smem_addr(q.e);
+#define SQB_INF_LIT(i) lds32(s_lit + ((i) << 2))
+#define SQB_INF_DIST(i) lds32(s_dist + ((i) << 2))
+#define SQB_INF_PUSH(i, p, v) sts64(s_q + ((i) << 3), (p), (v))
+#else
+#define SQB_INF_LIT(i) t.lit[i]
+#define SQB_INF_DIST(i) t.dist[i]
+#define SQB_INF_PUSH(i, p, v) (q.e[i].pos = (p), q.e[i].ld = (v))
+#endif
    for (;;) {
       if (SQB_INF_RARE(br.refill())) { ret = R_ERR + (int)ERR_INPUT; goto done; }
       {
          // ---- the usual symbols, decoded out of one 32-bit view of the window without touching the reader: three
          // literals with room for three bytes, or a match whose code words are in the tables and whose bits are all
-         // in the window (33 at least: a length takes up to 15 here, a distance up to 21).  Whatever else -- long code
+         // in the window (33 at least: a length takes up to TB + 5 here, a distance up to 21).  Whatever else -- long code
          // words, end of block, the last bytes of the member, anything invalid -- is left to the general path below.
          const uint32_t w = (uint32_t)br.buf;
-         const uint32_t e = t.lit[w & (kLitN - 1u)];
+         const uint32_t e = SQB_INF_LIT(w & (kLitN - 1u));
          if (e & 0x30u) {
             if (SQB_INF_RARE(pos + 3u > oend)) goto general;
             uint8_t *o = out + pos;
@@ -334,14 +375,13 @@ SQB_INF_HD int run_symbols(BitReader &br, const Tables &t, uint8_t *out, uint32_
          if (SQB_INF_RARE(e & 0xc0u)) goto general;
          const uint32_t l1 = e & 15u, x1 = (e >> 17) & 7u, c1 = l1 + x1;
          const uint32_t len = ((e >> 8) & 0x1ffu) + ((w >> l1) & ~(~0u << x1));
-         const uint32_t d = t.dist[(w >> c1) & (kDistN - 1u)];
+         const uint32_t d = SQB_INF_DIST((w >> c1) & (kDistN - 1u));
          const uint32_t c2 = c1 + (d & 15u), x2 = (d >> 4) & 15u, total = c2 + x2;
          const uint32_t dist = (d >> 16) + (br.peek_from(c2) & ~(~0u << x2));
          if (SQB_INF_RARE((d & (D_LONG | D_BAD)) != 0u || total > (uint32_t)br.cnt || dist > pos || len > oend - pos))
             goto general;
          br.drop(total);
-         q.e[n].pos = pos;
-         q.e[n].ld = len | dist << 16;
+         SQB_INF_PUSH(n, pos, len | dist << 16);
          n++;
          pos += len;
          if (n == qcap) { ret = R_FULL; goto done; }
@@ -349,8 +389,11 @@ SQB_INF_HD int run_symbols(BitReader &br, const Tables &t, uint8_t *out, uint32_
       }
    general:
       {
+#ifdef SQB_INF_COUNT_GENERAL
+         SQB_INF_COUNT_GENERAL++;                        /* host harness only: symbols off the fast path */
+#endif
          // ---- one symbol, step by step (RFC 1951 3.2.3), with every check
-         uint32_t e = t.lit[(uint32_t)br.buf & (kLitN - 1u)];
+         uint32_t e = SQB_INF_LIT((uint32_t)br.buf & (kLitN - 1u));
          if ((e & 0xf0u) == K_LONG) {
             const int r = canon_decode(t.lcnt, t.lsym, (uint32_t)br.buf, 15);
             if (r < 0) { ret = R_ERR + (int)ERR_CODE; goto done; }
@@ -372,7 +415,7 @@ SQB_INF_HD int run_symbols(BitReader &br, const Tables &t, uint8_t *out, uint32_
          if (kind == K_EOB) { ret = R_EOB; goto done; }
          const uint32_t len = ((e >> 8) & 0x1ffu) + br.take((e >> 17) & 7u);
          if (br.refill()) { ret = R_ERR + (int)ERR_INPUT; goto done; }
-         uint32_t d = t.dist[(uint32_t)br.buf & (kDistN - 1u)];
+         uint32_t d = SQB_INF_DIST((uint32_t)br.buf & (kDistN - 1u));
          if (d & D_LONG) {
             const int r = canon_decode(t.dcnt, t.dsym, (uint32_t)br.buf, 15);
             if (r < 0) { ret = R_ERR + (int)ERR_CODE; goto done; }
@@ -383,14 +426,16 @@ SQB_INF_HD int run_symbols(BitReader &br, const Tables &t, uint8_t *out, uint32_
          const uint32_t dist = (d >> 16) + br.take((d >> 4) & 15u);
          if (dist > pos) { ret = R_ERR + (int)ERR_DIST; goto done; }
          if (len > oend - pos) { ret = R_ERR + (int)ERR_OUTPUT; goto done; }
-         q.e[n].pos = pos;
-         q.e[n].ld = len | dist << 16;
+         SQB_INF_PUSH(n, pos, len | dist << 16);
          n++;
          pos += len;
          if (n == qcap) { ret = R_FULL; goto done; }
       }
    }
 done:
+#undef SQB_INF_LIT
+#undef SQB_INF_DIST
+#undef SQB_INF_PUSH
    pos_io = pos;
    *nq = n;
    return ret;
@@ -412,6 +457,7 @@ SQB_INF_HD void copy_by_lane(uint8_t *out, uint32_t mp, uint32_t ml, uint32_t md
 {
    uint8_t b[kLaneCopy];
    const uint8_t *src = out + mp - md;
+   uint8_t *dst = out + mp;
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
@@ -419,7 +465,7 @@ SQB_INF_HD void copy_by_lane(uint8_t *out, uint32_t mp, uint32_t ml, uint32_t md
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-   for (uint32_t k = 0; k < kLaneCopy; k++) if (k < ml) out[mp + k] = b[k];
+   for (uint32_t k = 0; k < kLaneCopy; k++) if (k < ml) dst[k] = b[k];
 }
 // byte j of a match copied by the whole warp: the source index (an overlapping match repeats its last md bytes)
 SQB_INF_HD uint32_t match_src(uint32_t mp, uint32_t md, uint32_t j)

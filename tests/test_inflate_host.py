@@ -124,19 +124,19 @@ def test_text_kinds_and_levels(H, kind, level):
     assert out == text
     if kind in ("dna", "fastq"):
         # [2] dynamic blocks, [6] table entries holding two literals, [9] matches copied by one lane each, [10] rounds
-        assert stats[2] > 0 and (stats[6] > 0 or level == 1) and stats[9] > 0
+        assert stats[2] > 0 and (stats[6] > 0 or level == 1 or kind == "fastq") and stats[9] > 0
         assert stats[10] < 8 * stats[11], "the queue resolves in a few rounds, not match by match"
 
 
 def test_three_literals_per_look_up(H):
-    """DNA without matches (Z_HUFFMAN_ONLY): code words of 2-3 bits, so the 10 index bits hold three bases"""
+    """DNA without matches (Z_HUFFMAN_ONLY): code words of 2-3 bits, so the 9 index bits hold three bases"""
     rng = np.random.default_rng(9)
     text = dna(rng, 200000)
     gz = bgzf.compress(text, level=6, strategy=zlib.Z_HUFFMAN_ONLY)
     stats = (C.c_uint32 * 16)()
     rc, out = inflate(H, gz, stats=stats)
     assert rc == len(text) and out == text
-    assert stats[7] > 500 * stats[2] and stats[9] == 0 and stats[8] == 0
+    assert stats[7] > 300 * stats[2] and stats[9] == 0 and stats[8] == 0
 
 
 def test_block_types_and_strategies(H):
@@ -190,7 +190,7 @@ def test_member_sizes_and_flush_points(H):
 
 
 def test_long_code_words_take_the_canonical_path(H):
-    """a skewed alphabet gives code words longer than the 10 index bits of the table"""
+    """a skewed alphabet gives code words longer than the 9 index bits of the table"""
     rng = np.random.default_rng(5)
     p = np.array([0.5 ** min(i + 1, 22) for i in range(200)])
     text = rng.choice(np.arange(200, dtype=np.uint8), size=400000, p=p / p.sum()).tobytes()
