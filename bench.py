@@ -29,6 +29,8 @@ One JSON line is printed by rank 0:
   cpu_baseline the unmodified reference (oracle/_ref) on the host cores, on a bounded sample of the same
                workload; "parity": the GPU's records of that very sample against the reference's count and
                record checksum (line, start, end, dist of every record)
+  bgzf         (one GPU) the same scan fed with a BGZF (bgzip) buffer in pinned host memory through sqbScanHostBgzf:
+               GB/s of TEXT end to end, the inflate kernel alone, the bound of the link at this compression ratio
 `--impl reference` times the reference's own CPU implementation instead.
 """
 from __future__ import annotations
@@ -419,6 +421,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the extra BASELINE configs (one GPU only)")
+    ap.add_argument("--no-bgzf", action="store_true", help="skip the BGZF (bgzip) input line (one GPU only)")
     args = ap.parse_args()
     # six warm-up steps at least: a scan slot replays its step as a CUDA graph once it has been asked for
     # the same scan three times (third time: capture), and there are two slots
@@ -539,6 +542,31 @@ def main():
                              "path": x["path"], "reruns": x["reruns"]}
             x["sq"].close()
 
+    # ---------------- the same scan fed with a BGZF (bgzip) buffer (one GPU) ----
+    # the compressed bytes cross the link, k0_inflate_bgzf_pair inflates them in HBM, the scan runs
+    # there.  1 GiB of the workload's reads, deflated by zlib at level 6; GB/s are of TEXT; text and counts are checked.
+    bgzf = None
+    if world == 1 and not args.no_bgzf and not args.no_e2e and not args.reads and not w["count"]:
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("bgzf_bench", os.path.join(ROOT, "tools", "bgzf_bench.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            z = mod.measure(workload=args.workload, sweep=False)
+            bgzf = {"e2e": {"value": z["e2e_bgzf_GBps_of_text"], "unit": "GB/s of text",
+                            "h2d_bytes_per_step": z["bgzf_bytes"], "d2h_bytes_per_step": 16 * z["nrecs"] + 64,
+                            "api": z["api"]},
+                    "e2e_plain_text_GBps": z["e2e_plain_GBps"], "text_bytes": z["text_bytes"], "bgzf_bytes": z["bgzf_bytes"],
+                    "ratio": z["ratio"], "members": z["members"], "zlib_level": z["zlib_level"],
+                    "inflate_kernel_GBps_of_text": z["inflate_kernel_GBps_of_text"],
+                    "inflate_kernel_ms": min(z["inflate_kernel_ms"]),
+                    "link_bound_GBps_of_text": z["link_bound_GBps_of_text"],
+                    "parity": {"checked": "inflated text byte for byte against the input of the deflater; line, match and "
+                                          "record counts against sqbScanHost of the plain text",
+                               "ok": bool(z["same_counts"] and z["same_text"])}}
+        except Exception as exc:           # reported, the line still prints
+            bgzf = {"error": repr(exc)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -584,7 +612,7 @@ def main():
                    "kernel_path": ("fused tokenise+pack" if r["path"] & 2 else "K1 + pack") +
                                   (", bit-sliced matcher" if r["path"] & 1 else ", word-parallel matcher")},
            "roofline": roofline, "cpu_baseline": cpu, "e2e": r["e2e"], "gpu_launches": r["launches"],
-           "scan_reruns": r["reruns"], "clocks": r["clocks"], "configs": configs}
+           "scan_reruns": r["reruns"], "clocks": r["clocks"], "configs": configs, "bgzf": bgzf}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

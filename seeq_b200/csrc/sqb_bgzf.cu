@@ -277,7 +277,7 @@ k0_inflate_bgzf(const uint8_t *__restrict__ gz, const inf::Member *__restrict__ 
 }
 
 // ---- per-device state: the compressed bytes, the text and the member list in HBM ----------------------------------
-constexpr int kLanes = 4;
+constexpr int kLanes = 32;
 struct BgzfState {
    std::mutex mu;
    uint8_t *d_gz = nullptr;        size_t gz_cap = 0;
@@ -484,8 +484,8 @@ int sqbScanHostBgzf(sqb_engine_t *e, const void *gz, size_t nbytes, int options,
    CUB(cudaEventRecord(s.begin, s.work));
    for (int i = 0; i < kLanes; i++) CUB(cudaStreamWaitEvent(s.lanes[i], s.begin, 0));
    // slices end where a member ends (the bytes between two members -- headers, trailers -- travel with them); slice k
-   // is inflated on stream k mod 4: a slice alone does not fill the device (one CTA per 8 members), and a slice
-   // that has arrived need not wait for the one in front of it
+   // is inflated on stream k mod 32.  A member is one serial chain of 2-5 ms whatever the size of the grid: a slice
+   // must not wait for the slice in front of it, and the slices of a buffer fill the device together
    size_t m0 = 0, b0 = 0, k = 0;
    while (m0 < mem.size()) {
       size_t m1 = m0;
