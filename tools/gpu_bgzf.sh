@@ -23,3 +23,11 @@ d=json.loads(open('$OUT/${TAG}_bench_quick.json').read().strip().splitlines()[-1
 print('value',d['value'],'e2e',d['e2e']['value'],'bgzf',json.dumps(d['bgzf'])[:900])"
 fi
 ls -la $OUT | grep ${TAG}
+if [ "$4" = "sanitize" ]; then
+for tool in memcheck racecheck; do
+  extra=""
+  [ "$tool" = "racecheck" ] && extra="--racecheck-report all"
+  timeout 55 compute-sanitizer --tool $tool $extra --print-limit 20 python tools/sanitize_bgzf.py > $OUT/${TAG}_sanitize_bgzf_$tool.log 2>&1
+  echo "== $tool: exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize bgzf tour|MISMATCH" $OUT/${TAG}_sanitize_bgzf_$tool.log | tail -4
+done
+fi
