@@ -173,9 +173,11 @@ int sqbBgzfIndex (const void * gz, size_t nbytes, sqb_bgzf_member_t * members, u
 int sqbBgzfInflateDevice (int device, const void * d_gz, const sqb_bgzf_member_t * members, uint64_t count,
                           void * d_text, void * stream, double * kernel_ms);
 /* sqbScanHost for a BGZF buffer in host memory (pinned is faster): compressed slices of $SEEQ_B200_BGZF_SLICE_MB
- * (32) MiB go to the device, slice k is inflated while slice k+1 is on the link, then the text is scanned like
- * sqbScanDeviceLarge does.  stats->nbytes counts TEXT bytes; records / line starts as after sqbScanHost.
- * One device (that of the engine). */
+ * (32) MiB leave for the device at once, the members are indexed while they travel (by several threads:
+ * $SEEQ_B200_BGZF_INDEX_THREADS), the members of a slice are inflated as soon as it has arrived (k0_inflate_bgzf_pair,
+ * the slices side by side on 32 streams), then the text is scanned like sqbScanDeviceLarge does.  stats->nbytes counts
+ * TEXT bytes; records / line starts as after sqbScanHost.  One device (that of the engine).
+ * $SEEQ_B200_BGZF_TRACE=1: host wall time of the phases on stderr. */
 int sqbScanHostBgzf (sqb_engine_t * e, const void * gz, size_t nbytes, int options, sqb_stats_t * stats);
 /* the inflated text of the last sqbScanHostBgzf on the engine's device (valid until the next one there) */
 const void * sqbBgzfDeviceText (sqb_engine_t * e, uint64_t * nbytes);

@@ -100,7 +100,7 @@ def measure(mb=64, copies=16, steps=5, level=6, workload="metric", kernel="", in
     st_p, t_p = timed(lambda: eng.scan_host_ptr(h_text, n_text, opt))
     by_slice = {}
     slice0 = os.environ.get("SEEQ_B200_BGZF_SLICE_MB")
-    for smb in ((8, 32) if sweep else ()):
+    for smb in ((8, 16) if sweep else ()):
         os.environ["SEEQ_B200_BGZF_SLICE_MB"] = str(smb)
         _, t = timed(lambda: eng.scan_host_bgzf_ptr(h_gz, n_gz, opt))
         by_slice[str(smb)] = n_text / (sum(t) / len(t)) / 1e9
