@@ -12,7 +12,7 @@ import sys
 
 WANT = ("k12_scan_pack", "k2_bitslice<20, 1, 1, false, 3, true>", "k2_bitslice<10, 1, 1, false, 2, true>",
         "k2_bitslice<26, 4, 1, false, 0, false>", "k1_scan_classify<true, false, false>", "k15_pack", "k34_finish_lines<1, 4>",
-        "k1_gather", "k1_scan_tiles")
+        "k1_gather", "k1_scan_tiles", "k0_inflate_bgzf_pair", "k0_inflate_bgzf(")
 EVIDENCE = ("UBLKCP", "SYNCS", "LDS", "STS", "LDG", "STG", "PRMT", "LOP3", "IMAD", "SHFL", "VOTE", "ATOMG", "ATOMS", "REDUX",
             "BAR", "NANOSLEEP")
 
