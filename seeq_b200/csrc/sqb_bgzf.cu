@@ -22,6 +22,7 @@
 
 #include "seeq_b200.h"
 #include "sqb_inflate.h"
+#include "sqb_bgzf_warp.h"
 
 using namespace sqb;
 
@@ -44,8 +45,15 @@ constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kPairWarps = 4;                            // 8 members per CTA: 8 x 3.9 KB of tables and queue, 72 registers:
 constexpr int kPairCtas = 7;                             // 7 CTAs = 56 members per SM (the kernel is bound by the latency
                                                          // of the decoding lanes' chains: the more of them, the better)
-constexpr uint32_t kPairQueue = 16;
-enum : uint32_t { ST_HEADER = 0, ST_SYMBOLS = 1, ST_DONE = 2 };
+
+struct DeviceWarp {                                      // the warp's primitives as sqb_bgzf_warp.h names them
+   __device__ __forceinline__ uint32_t lane() const { return threadIdx.x & 31u; }
+   template <class T> __device__ __forceinline__ T shfl(T v, uint32_t src) const { return __shfl_sync(kFull, v, src); }
+   __device__ __forceinline__ uint32_t ballot(bool p) const { return __ballot_sync(kFull, p); }
+   __device__ __forceinline__ bool any(bool p) const { return __any_sync(kFull, p) != 0; }
+   __device__ __forceinline__ void sync() const { __syncwarp(); }
+   __device__ __forceinline__ void atomic_min(unsigned long long *p, unsigned long long v) const { atomicMin(p, v); }
+};
 
 __global__ void __launch_bounds__(kPairWarps * 32, kPairCtas)
 k0_inflate_bgzf_pair(const uint8_t *__restrict__ gz, const inf::Member *__restrict__ members, uint32_t first,
@@ -54,119 +62,11 @@ k0_inflate_bgzf_pair(const uint8_t *__restrict__ gz, const inf::Member *__restri
 {
    __shared__ inf::Tables s_tables[2 * kPairWarps];
    __shared__ inf::MatchQueue s_queue[2 * kPairWarps];
-   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-   const uint32_t hl = lane & 15u, hbase = lane & 16u;   // lane in the half, first lane of the half
-   const uint32_t slot = warp * 2u + (lane >> 4);
-   const uint32_t idx = (blockIdx.x * kPairWarps + warp) * 2u + (lane >> 4);
-   if ((blockIdx.x * kPairWarps + warp) * 2u >= count) return;       // the whole warp
-   const bool have = idx < count;                        // the upper half of the last warp may have no member
-   inf::Member mb;
-   mb.in_off = 0; mb.in_len = 0; mb.isize = 0; mb.out_off = 0;
-   if (have) mb = members[first + idx];
-   inf::Tables &t = s_tables[slot];
-   inf::MatchQueue &q = s_queue[slot];
-   uint8_t *out = text + mb.out_off;
-   const uint32_t oend = mb.isize;
-
-   inf::BitReader br;
-   br.init(gz + mb.in_off, mb.in_len);                  // every lane holds a reader; only the decoding lane's advances
-   uint32_t pos = 0, err = inf::OK, final_block = 0, type = 0;
-   uint32_t st = have ? ST_HEADER : ST_DONE;            // the same in all lanes of a half
-
-   while (__any_sync(kFull, st != ST_DONE)) {
-      // ---- block header: the decoding lane; stored blocks and tables: the half ----
-      const bool hdr = st == ST_HEADER;
-      if (__any_sync(kFull, hdr)) {
-         uint32_t len = 0;
-         unsigned long long src = 0;
-         if (hdr && hl == 0) {
-            err = inf::read_block_header(br, t, &type, &final_block);
-            if (err == inf::OK && type == 0) {           // stored: LEN, ~LEN, bytes
-               br.align_byte();
-               const bool over = br.refill();
-               len = br.take(16);
-               const uint32_t nlen = br.take(16);
-               const uint8_t *sp = br.byte_ptr();
-               if (over || len != (~nlen & 0xffffu)) err = inf::ERR_HEADER;
-               else if (sp + len > br.src_end()) err = inf::ERR_INPUT;
-               else if (len > oend - pos) err = inf::ERR_OUTPUT;
-               src = (unsigned long long)(uintptr_t)sp;
-               if (err == inf::OK) br.init(sp + len, (uint32_t)(br.src_end() - (sp + len)));
-            }
-         }
-         __syncwarp();                                   // counts and sorted symbols are the decoding lane's: publish
-         err = __shfl_sync(kFull, err, hbase);
-         type = __shfl_sync(kFull, type, hbase);
-         final_block = __shfl_sync(kFull, final_block, hbase);
-         len = __shfl_sync(kFull, len, hbase);
-         src = __shfl_sync(kFull, src, hbase);
-         if (hdr && err == inf::OK) {
-            if (type == 0) {
-               const uint8_t *sp = (const uint8_t *)(uintptr_t)src;
-               for (uint32_t j = hl; j < len; j += 16) out[pos + j] = sp[j];
-               pos += len;
-               st = final_block ? ST_DONE : ST_HEADER;
-            } else {
-               // the scratch arrays of the header alias t.lit: every lane has passed the barrier, nobody reads them
-               for (uint32_t e = hl; e < inf::kLitN; e += 16) t.lit[e] = inf::make_lit_entry(t.lcnt, t.lsym, e);
-               for (uint32_t e = hl; e < inf::kDistN; e += 16) t.dist[e] = inf::make_dist_entry(t.dcnt, t.dsym, e);
-               st = ST_SYMBOLS;
-            }
-         } else if (hdr) st = ST_DONE;
-         __syncwarp();                                   // tables and stored bytes: visible
-      }
-
-      // ---- symbols: the decoding lane until its queue is full or the block ends; the queue: the half ----
-      const bool sym = st == ST_SYMBOLS;
-      if (__any_sync(kFull, sym)) {
-         uint32_t nq = 0;
-         int r = inf::R_EOB;
-         if (sym && hl == 0) r = inf::run_symbols(br, t, out, pos, oend, q, kPairQueue, &nq);
-         __syncwarp();                                   // literal stores and queue entries: visible
-         r = __shfl_sync(kFull, r, hbase);
-         nq = __shfl_sync(kFull, nq, hbase);
-         pos = __shfl_sync(kFull, pos, hbase);
-         // resolve the queues (sqb_inflate.h: match_ready): lane i of a half owns match i of its member
-         uint32_t mp = 0, ml = 0, md = 0;
-         const bool owner = sym && hl < nq;
-         if (owner) { const inf::MatchQueue::Entry qe = q.e[hl]; mp = qe.pos; ml = qe.ld & 0xffffu; md = qe.ld >> 16; }
-         uint32_t pending = __ballot_sync(kFull, owner);
-         while (pending) {
-            const uint32_t hp = (pending >> hbase) & 0xffffu;
-            const uint32_t f = hp ? (uint32_t)__ffs((int)hp) - 1u + hbase : lane;
-            const uint32_t P = __shfl_sync(kFull, mp, f);
-            const bool ready = ((pending >> lane) & 1u) && (lane == f || inf::match_ready(mp, ml, md, P));
-            const bool mine = ready && inf::match_by_lane(ml, md);
-            const uint32_t rmask = __ballot_sync(kFull, ready);
-            uint32_t wide = __ballot_sync(kFull, ready && !mine);
-            if (mine) inf::copy_by_lane(out, mp, ml, md);
-            while (wide) {                               // long or self-overlapping: the half copies it
-               const uint32_t hw = (wide >> hbase) & 0xffffu;
-               const uint32_t i = hw ? (uint32_t)__ffs((int)hw) - 1u + hbase : lane;
-               const uint32_t bp = __shfl_sync(kFull, mp, i), bl = __shfl_sync(kFull, ml, i), bd = __shfl_sync(kFull, md, i);
-               if (hw) {
-                  if (bd >= bl) for (uint32_t j = hl; j < bl; j += 16) out[bp + j] = out[bp - bd + j];
-                  else for (uint32_t j = hl; j < bl; j += 16) out[bp + j] = out[inf::match_src(bp, bd, j)];
-               }
-               const uint32_t lo = wide & 0xffffu, hi = wide & 0xffff0000u;
-               wide = (lo & (lo - 1u)) | (hi & (hi - 1u));          // the lowest bit of either half is done
-            }
-            pending &= ~rmask;
-            __syncwarp();                                // this round's text is final for the next round
-         }
-         if (sym) {
-            if (r >= inf::R_ERR) { err = (uint32_t)(r - inf::R_ERR); st = ST_DONE; }
-            else if (r == inf::R_EOB) st = final_block ? ST_DONE : ST_HEADER;
-         }
-      }
-   }
-
-   if (have && hl == 0) {
-      if (err == inf::OK && br.overrun() > 0) err = inf::ERR_INPUT;
-      if (err == inf::OK && pos != oend) err = inf::ERR_SHORT;
-      status[first + idx] = err;
-      if (err != inf::OK) atomicMin(first_error, ((unsigned long long)(first + idx) << 8) | err);
-   }
+   const uint32_t warp = threadIdx.x >> 5;
+   const uint32_t pair = blockIdx.x * kPairWarps + warp;
+   if (pair * 2u >= count) return;                       // the whole warp
+   DeviceWarp w;
+   inf::inflate_pair(w, gz, members, first, count, pair, s_tables + 2 * warp, s_queue + 2 * warp, text, status, first_error);
 }
 
 // One member per warp: lane 0 decodes, the warp resolves queues of 32 matches.  The first form of the kernel, kept

@@ -130,3 +130,91 @@ extern "C" long long host_bgzf_index(const uint8_t *gz, uint64_t nbytes, uint64_
    *text_bytes = o;
    return n;
 }
+
+// ---- two members per warp: sqb_bgzf_warp.h (the body of k0_inflate_bgzf_pair) run by 32 host threads -------------
+// The warp's primitives over a barrier: every lane deposits its value, all meet, every lane reads what it needs, all
+// meet again (the slots are free for the next exchange).  Between two exchanges the lanes run truly side by side, in
+// whatever order the host schedules them: an ordering the kernel relies on without a barrier shows as wrong text.
+#include <pthread.h>
+
+#include <thread>
+
+#include "sqb_bgzf_warp.h"
+
+namespace {
+struct WarpShared {
+   pthread_barrier_t bar;
+   uint64_t slot[32];
+};
+struct HostWarp {
+   WarpShared *sh;
+   uint32_t id;
+   uint32_t lane() const { return id; }
+   void wait() { pthread_barrier_wait(&sh->bar); }
+   template <class T> T shfl(T v, uint32_t src)
+   {
+      sh->slot[id] = (uint64_t)v;
+      wait();
+      const T r = (T)sh->slot[src & 31u];
+      wait();
+      return r;
+   }
+   uint32_t ballot(bool p)
+   {
+      sh->slot[id] = p ? 1u : 0u;
+      wait();
+      uint32_t m = 0;
+      for (int i = 0; i < 32; i++) m |= (uint32_t)(sh->slot[i] & 1u) << i;
+      wait();
+      return m;
+   }
+   bool any(bool p) { return ballot(p) != 0; }
+   void sync() { wait(); }
+   void atomic_min(unsigned long long *p, unsigned long long v)
+   {
+      unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
+      while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+   }
+};
+}  // namespace
+
+// Inflates a BGZF buffer the way the grid of k0_inflate_bgzf_pair does, one warp after the other.  Returns the text
+// size, -1 (not BGZF), -2 (no room), or -(16 * (1 + member) + error) for the first bad member by index; status (may be
+// NULL) gets one word per member that carries text.
+extern "C" long long host_bgzf_inflate_pair(const uint8_t *gz, uint64_t nbytes, uint8_t *text, uint64_t cap, uint32_t *status)
+{
+   std::vector<uint8_t> copy(nbytes + 16, 0);
+   memcpy(copy.data(), gz, nbytes);
+   std::vector<inf::Member> mem;
+   uint64_t off = 0, o = 0;
+   while (off < nbytes) {
+      inf::Member m;
+      const uint64_t next = inf::parse_member(copy.data(), nbytes, off, &m);
+      if (next == 0) return -1;
+      m.out_off = o;
+      if (o + m.isize > cap) return -2;
+      if (m.isize) mem.push_back(m);
+      o += m.isize;
+      off = next;
+   }
+   const uint32_t count = (uint32_t)mem.size();
+   std::vector<uint32_t> st(count + 1, 0xffffffffu);
+   unsigned long long first_error = ~0ull;
+   static inf::Tables tables[2];
+   static inf::MatchQueue queues[2];
+   WarpShared sh;
+   pthread_barrier_init(&sh.bar, NULL, 32);
+   std::vector<std::thread> lanes;
+   for (uint32_t id = 0; id < 32; id++)
+      lanes.emplace_back([&, id] {
+         HostWarp w{&sh, id};
+         for (uint32_t pair = 0; pair * 2u < count; pair++)
+            inf::inflate_pair(w, copy.data(), mem.data(), 0u, count, pair, tables, queues, text, st.data(), &first_error);
+      });
+   for (std::thread &t : lanes) t.join();
+   pthread_barrier_destroy(&sh.bar);
+   if (status) memcpy(status, st.data(), count * sizeof(uint32_t));
+   if (first_error != ~0ull) return -(long long)(16ull * (1ull + (first_error >> 8)) + (first_error & 0xffull));
+   for (uint32_t i = 0; i < count; i++) if (st[i] != inf::OK) return -3;             // a member nobody reported
+   return (long long)o;
+}

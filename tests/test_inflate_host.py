@@ -20,9 +20,12 @@ CSRC = os.path.join(os.path.dirname(HERE), "seeq_b200", "csrc")
 @pytest.fixture(scope="module")
 def host_lib(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("inflate") / "host_inflate.so")
-    subprocess.run(["g++", "-std=c++17", "-O2", "-w", "-shared", "-fPIC", "-I" + CSRC,
+    subprocess.run(["g++", "-std=c++17", "-O2", "-w", "-shared", "-fPIC", "-pthread", "-I" + CSRC,
                     os.path.join(HERE, "host_inflate.cpp"), "-o", so], check=True)
-    return C.CDLL(so)
+    L = C.CDLL(so)
+    L.host_bgzf_inflate_pair.restype = C.c_longlong
+    L.host_bgzf_inflate_pair.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
+    return L
 
 
 @pytest.fixture(params=[32, 16], ids=["queue32", "queue16"])
@@ -249,3 +252,94 @@ def test_damaged_streams_are_refused(H):
     assert rc < 0
     # not BGZF: plain gzip
     assert H.host_bgzf_index(zlib.compress(text, 6, 31), 100, C.byref(C.c_uint64())) == -1
+
+
+def inflate_pair(L, gz, cap):
+    guard = 64
+    buf = (C.c_ubyte * (cap + 2 * guard))()
+    C.memset(buf, 0xA5, cap + 2 * guard)
+    status = (C.c_uint32 * 4096)()
+    rc = L.host_bgzf_inflate_pair(gz, len(gz), C.addressof(buf) + guard, cap, status)
+    raw = bytes(buf)
+    assert raw[:guard] == b"\xa5" * guard and raw[guard + cap:] == b"\xa5" * guard, "wrote outside the text buffer"
+    return rc, raw[guard:guard + cap], status
+
+
+def test_two_members_per_warp(host_lib):
+    """sqb_bgzf_warp.h -- the body of k0_inflate_bgzf_pair, the same source -- run by 32 host threads that meet at a
+    barrier wherever the lanes of the warp exchange something: block headers by the two decoding lanes, tables by the
+    half-warps, queues of 16 matches, stored blocks, members that end at different times, an odd number of members,
+    a half with a damaged member next to a sound one."""
+    rng = np.random.default_rng(23)
+    pieces = [dna(rng, 9000), fastq(rng, 25), rng.integers(0, 256, size=5000, dtype=np.uint8).tobytes(),
+              b"".join(bytes([int(rng.integers(65, 70))]) * int(rng.integers(1, 300)) for _ in range(60)),
+              dna(rng, 3000, line=60) * 3, b"A", dna(rng, 20000)]
+    parts, want = [], b""
+    for i, piece in enumerate(pieces):
+        if i == 3:
+            parts.append(bgzf.EOF_MEMBER)
+        strategy = zlib.Z_FIXED if i == 4 else zlib.Z_DEFAULT_STRATEGY
+        parts.append(bgzf.member(piece, level=(0 if i == 2 else 6), strategy=strategy))
+        want += piece
+    # several deflate blocks of all types in one member, next to a member of one block
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    piece = fastq(rng, 40)
+    cdata = co.compress(piece[:3000]) + co.flush(zlib.Z_FULL_FLUSH) + co.compress(piece[3000:3001]) + \
+        co.flush(zlib.Z_SYNC_FLUSH) + co.compress(piece[3001:]) + co.flush()
+    import struct
+    head = struct.pack("<BBBBIBBHBBHH", 0x1f, 0x8b, 8, 4, 0, 0, 0xff, 6, 0x42, 0x43, 2, len(cdata) + 25)
+    parts.append(head + cdata + struct.pack("<II", zlib.crc32(piece), len(piece)))
+    want += piece
+    gz = b"".join(parts) + bgzf.EOF_MEMBER
+    assert bgzf.decompress_cpu(gz) == want and len(pieces) % 2 == 1
+    rc, out, status = inflate_pair(host_lib, gz, len(want))
+    assert rc == len(want), rc
+    assert out == want
+    assert list(status[:len(pieces) + 1]) == [0] * (len(pieces) + 1)
+    # member 1 damaged (ISIZE one short), its neighbour in the warp and every other member are inflated all the same
+    bad = bytearray(gz)
+    off = len(parts[0])
+    end = off + len(parts[1])
+    bad[end - 4:end] = struct.pack("<I", len(pieces[1]) - 1)
+    rc, out, status = inflate_pair(host_lib, bytes(bad), len(want))
+    assert rc == -(16 * (1 + 1) + 2), rc                          # member 1: more text than ISIZE announces
+    assert status[0] == 0 and status[1] == 2 and list(status[2:len(pieces) + 1]) == [0] * (len(pieces) - 1)
+    assert out[:len(pieces[0])] == pieces[0]
+
+
+def test_two_members_per_warp_under_thread_sanitizer(tmp_path):
+    """The same host run of sqb_bgzf_warp.h under ThreadSanitizer: between two barriers of the warp no lane reads or
+    writes a byte -- of the tables, the queues or the TEXT -- that another lane writes.  (compute-sanitizer's racecheck
+    on the device sees shared memory only; the text lives in global memory.)"""
+    import glob
+    import sys
+    tsan = glob.glob("/usr/lib/gcc/x86_64-linux-gnu/*/libtsan.so") + glob.glob("/usr/lib/x86_64-linux-gnu/libtsan.so*")
+    if not tsan:
+        pytest.skip("no libtsan in this image")
+    so = str(tmp_path / "host_inflate_tsan.so")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-w", "-shared", "-fPIC", "-pthread", "-I" + CSRC,
+                        os.path.join(HERE, "host_inflate.cpp"), "-o", so], capture_output=True, text=True)
+    if r.returncode:
+        pytest.skip("g++ -fsanitize=thread does not build here: " + r.stderr[-200:])
+    code = """
+import ctypes as C, sys
+sys.path.insert(0, %r)
+import numpy as np
+from seeq_b200 import bgzf
+from tests.test_inflate_host import dna, fastq
+L = C.CDLL(%r)
+L.host_bgzf_inflate_pair.restype = C.c_longlong
+L.host_bgzf_inflate_pair.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
+rng = np.random.default_rng(2)
+text = dna(rng, 6000) + fastq(rng, 20) + rng.integers(0, 256, size=3000, dtype=np.uint8).tobytes() + dna(rng, 5000)
+gz = bgzf.compress(text, level=6, block=4000)
+out = (C.c_ubyte * len(text))()
+rc = L.host_bgzf_inflate_pair(gz, len(gz), out, len(text), None)
+print("RESULT", rc == len(text) and bytes(out) == text)
+""" % (os.path.dirname(HERE), so)
+    env = dict(os.environ, LD_PRELOAD=tsan[0], TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    if "RESULT" not in r.stdout:
+        pytest.skip("the interpreter does not run under LD_PRELOAD=libtsan here: " + r.stderr[-300:])
+    assert "RESULT True" in r.stdout
+    assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[-3000:]
