@@ -92,3 +92,18 @@ def test_damage_is_refused_by_every_walk(B, monkeypatch):
     with pytest.raises(ValueError, match="not a BGZF member"):
         B.bgzf_index(zlib.compress(bytes(10 << 20), 1, 31) * 40)                    # plain gzip, 10 MB of it
     assert B.bgzf_index(b"")[1:] == (0, 0) and B.bgzf_index(bgzf.EOF_MEMBER)[1:] == (0, 0)
+
+
+def test_inflating_fails_loudly_without_a_device(B):
+    """no CPU fallback: the inflater is CUDA only (zlib is the CHECKER of the tests, never the product)"""
+    if B.lib().sqbDeviceCount() > 0:
+        pytest.skip("a CUDA device is present")
+    gz = bgzf.compress(b"ACGT\n" * 1000)
+    with pytest.raises(RuntimeError, match="failed"):
+        B.bgzf_inflate_device(gz)
+    import ctypes as C
+    members, cnt, tb = B.bgzf_index(gz)
+    text = (C.c_ubyte * tb)()
+    rc = B.lib().sqbBgzfInflateDevice(0, gz, members, cnt, text, None, None)
+    assert rc == -1 and "CUDA" in B.last_error()
+    assert B.lib().sqbScanHostBgzf(None, gz, len(gz), 0, None) == -1
