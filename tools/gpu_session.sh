@@ -12,6 +12,7 @@
 #   ab WL LIB...       bench.py on workload WL with the stock library and every LIB (another build of the
 #                      library, e.g. nvcc ... -DSQB_PACK_CTAS=5 -> seeq_b200/libseeq_b200_p5.so; SEEQ_B200_LIB)
 #   sanitize           compute-sanitizer memcheck + racecheck over the reduced kernel tour (tools/sanitize_case.py)
+#   bgzf               the BGZF (bgzip) input path: tools/gpu_bgzf.sh (tests, bench line, ncu, sanitizers)
 #   scale N            (gpurun --gpus N) torchrun bench.py on N GPUs as the driver launches it, plus config 5 at
 #                      N x 12.7 GB and the reference arm when N = 8, plus one GPU of the same box
 TAG=${1:?tag}; shift
@@ -84,6 +85,9 @@ while [ $# -gt 0 ]; do
     show $OUT/${TAG}_bench_n1.json same_box ;;
   sanitize)
     bash tools/gpu_sanitize.sh $TAG memcheck racecheck ;;
+  bgzf)
+    # BGZF input: GPU tests, tools/bgzf_bench.py line, ncu of the inflate kernel, bench.py with the bgzf key, sanitizers
+    bash tools/gpu_bgzf.sh $TAG ncu bench sanitize ;;
   *) echo "unknown part $part"; exit 2 ;;
   esac
 done
