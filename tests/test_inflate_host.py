@@ -25,14 +25,7 @@ def host_lib(tmp_path_factory):
     L = C.CDLL(so)
     L.host_bgzf_inflate_pair.restype = C.c_longlong
     L.host_bgzf_inflate_pair.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
-    return L
-
-
-@pytest.fixture(params=[32, 16], ids=["queue32", "queue16"])
-def H(host_lib, request):
-    """matches per queue: 32 = one member per warp (k0_inflate_bgzf), 16 = two members per warp (k0_inflate_bgzf_pair)"""
-    L = host_lib
-    L.host_set_queue(request.param)
+    L.host_set_queue.argtypes = [C.c_uint32]
     L.host_bgzf_inflate.restype = C.c_longlong
     L.host_bgzf_inflate.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
     L.host_bgzf_index.restype = C.c_longlong
@@ -41,6 +34,14 @@ def H(host_lib, request):
     L.host_lit_entry_of.argtypes = [C.c_uint32, C.c_uint32]
     L.host_dist_entry_of.restype = C.c_uint32
     L.host_dist_entry_of.argtypes = [C.c_uint32, C.c_uint32]
+    return L
+
+
+@pytest.fixture(params=[32, 16], ids=["queue32", "queue16"])
+def H(host_lib, request):
+    """matches per queue: 32 = one member per warp (k0_inflate_bgzf), 16 = two members per warp (k0_inflate_bgzf_pair)"""
+    L = host_lib
+    L.host_set_queue(request.param)
     return L
 
 
@@ -343,3 +344,42 @@ print("RESULT", rc == len(text) and bytes(out) == text)
         pytest.skip("the interpreter does not run under LD_PRELOAD=libtsan here: " + r.stderr[-300:])
     assert "RESULT True" in r.stdout
     assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[-3000:]
+
+
+def test_fuzz_against_zlib(host_lib):
+    """hypothesis: texts of every texture (alphabet size, repeat structure, length up to a member and a bit), every
+    level and strategy, members cut anywhere -- the decoder reads what zlib reads, for both queue sizes"""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @st.composite
+    def texts(draw):
+        seed = draw(st.integers(0, 2 ** 32 - 1))
+        rng = np.random.default_rng(seed)
+        n = draw(st.sampled_from([0, 1, 2, 5, 300, 4000, 30000, 66000, 140000]))
+        alphabet = draw(st.sampled_from([1, 2, 4, 5, 20, 64, 256]))
+        base = rng.integers(0, alphabet, size=max(n, 1), dtype=np.uint8) + (0 if alphabet == 256 else 48)
+        period = draw(st.sampled_from([0, 1, 3, 17, 260, 5000, 40000]))
+        if period and n > period:                                    # repeats at a fixed distance, with a few edits
+            reps = -(-n // period)
+            base = np.tile(base[:period], reps)[:n].copy()
+            for at in rng.integers(0, n, size=n // 97 + 1):
+                base[at] ^= 1
+        return base[:n].tobytes()
+
+    @settings(max_examples=120, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(text=texts(), level=st.integers(0, 9),
+           strategy=st.sampled_from([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]),
+           block=st.sampled_from([1, 7, 500, 4097, 0xff00, 65536]), queue=st.sampled_from([16, 32]))
+    def run(text, level, strategy, block, queue):
+        if block < 500 and len(text) > 4000:
+            text = text[:4000]                                       # thousands of tiny members: keep it quick
+        try:
+            gz = bgzf.compress(text, level=level, block=block, strategy=strategy)
+        except AssertionError:                                       # 64 KiB that do not deflate do not fit a member
+            return
+        host_lib.host_set_queue(queue)
+        rc, out = inflate(host_lib, gz)
+        assert rc == len(text) and out == text
+
+    run()
+    host_lib.host_set_queue(32)
