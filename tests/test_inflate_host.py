@@ -297,6 +297,11 @@ def test_two_members_per_warp(host_lib):
     assert rc == len(want), rc
     assert out == want
     assert list(status[:len(pieces) + 1]) == [0] * (len(pieces) + 1)
+    # an odd number of members: the upper half of the last warp has none
+    odd = b"".join(parts[:-1]) + bgzf.EOF_MEMBER
+    rc, out, status = inflate_pair(host_lib, odd, len(want) - len(piece))
+    assert rc == len(want) - len(piece) and out == want[:-len(piece)]
+    assert list(status[:len(pieces)]) == [0] * len(pieces)
     # member 1 damaged (ISIZE one short), its neighbour in the warp and every other member are inflated all the same
     bad = bytearray(gz)
     off = len(parts[0])
